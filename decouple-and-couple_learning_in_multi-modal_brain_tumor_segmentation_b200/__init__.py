@@ -1,0 +1,16 @@
+"""dcl_b200 -- B200-native sliding-window ClsWiseFormer inference.
+
+Host side of the C ABI in ``include/dcl_b200.h``.  The arithmetic lives in ``libdcl_b200.so``
+(hand-written sm_100a CUDA, built from ``csrc/``); this package only marshals pointers.  There
+is no CPU or PyTorch fallback: importing works anywhere, every compute call raises
+``DclError`` unless the library is built and a CUDA device is present.
+
+The directory name is fixed by the project layout and is not a Python identifier; import the
+package as ``dcl_b200`` (alias module at the repository root) or through ``importlib``.
+"""
+from ._native import (DclError, Precision, StitchMode, abi_version, build_library, library_path, load_library,
+                      weight_catalogue, workspace_bytes)
+from .engine import Engine, patch_starts, reference_starts
+
+__all__ = ["DclError", "Precision", "StitchMode", "Engine", "abi_version", "build_library", "library_path",
+           "load_library", "weight_catalogue", "workspace_bytes", "patch_starts", "reference_starts"]

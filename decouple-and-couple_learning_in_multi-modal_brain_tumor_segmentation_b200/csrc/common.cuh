@@ -1,0 +1,118 @@
+// Shared declarations of the dcl_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+namespace dcl {
+
+// ---- error plumbing ------------------------------------------------------------------------
+void set_error(const std::string& msg);
+#define DCL_CUDA_OK(expr)                                                                      \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      ::dcl::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+      return -2;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return fmaxf(v, 0.f);
+  if (act == ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+// ---- convolution family (conv_simt.cu) -------------------------------------------------------
+// Input descriptor of a 3-D convolution: channels [0,c0) come from x0, [c0,c0+c1) from x1 (the
+// skip concat of DeUp_Cat / the edge branch is never materialised).  x0 may be a strided view
+// (patch of a volume); x1 is dense.  Optional per-channel instance-norm + activation is applied
+// while the tile is staged ("prologue fusion"); zero padding is applied after it.
+struct ConvSrc {
+  const float* x0;
+  const float* x1;
+  int c0, c1;
+  int64_t s0c, s0d, s0h;   // element strides of x0 (w stride is 1)
+  const float* mean;       // per input channel (c0+c1) or nullptr
+  const float* rstd;
+  int act;
+};
+
+struct ConvDst {
+  float* y;                // dense (cout, od, oh, ow)
+  const float* bias;       // cout or nullptr
+  const float* out_scale;  // per output channel multiplier applied after bias (dropout3d) or nullptr
+  const float* residual;   // dense, same shape as y, added last; or nullptr
+};
+
+// Packed k3 weights: [cin][27][cout_pad], cout_pad = round_up(cout, 16).
+int launch_conv3d_k3(const ConvSrc& src, const ConvDst& dst, const float* w_packed, int cout, int cout_pad,
+                     int in_d, int in_h, int in_w, int stride, cudaStream_t st);
+// Pointwise conv: packed weights [cin][cout]; optional softmax over cout (<= 4) in the epilogue.
+int launch_conv1x1(const ConvSrc& src, const ConvDst& dst, const float* w_packed, int cout, int64_t spatial,
+                   bool softmax, cudaStream_t st);
+// ConvTranspose3d k2 s2: packed weights [cin][8][cout] (tap = (kd*2+kh)*2+kw).
+int launch_convt_k2s2(const float* x, float* y, const float* w_packed, const float* bias, int cin, int cout,
+                      int in_d, int in_h, int in_w, cudaStream_t st);
+
+// ---- normalisation (norm.cu) ---------------------------------------------------------------
+// accum: 2*channels doubles, zeroed by the launcher; mean/rstd: floats (biased variance, eps 1e-5).
+int launch_instnorm_stats(const float* x, int channels, int64_t spatial, double* accum, float* mean, float* rstd,
+                          cudaStream_t st);
+// y = act((x - mean) * rstd) + residual
+int launch_norm_act_res(const float* x, const float* mean, const float* rstd, int act, const float* residual,
+                        float* y, int channels, int64_t spatial, cudaStream_t st);
+// tokens[(d/p0,h/p1,w/p2)][(c,p0,p1,p2)] = act(norm(x)); optional dense copy of act(norm(x)) too.
+int launch_norm_act_tokenise(const float* x, const float* mean, const float* rstd, int act, float* tokens,
+                             float* dense_or_null, int channels, int grid, int p0, int p1, int p2, cudaStream_t st);
+// y[c][d][h][w] = tokens[...] * class_token[(c,p0,p1,p2)]   (split_dim of a scaled token matrix)
+int launch_scale_untokenise(const float* tokens, const float* class_token, float* y, int channels, int grid, int p0,
+                            int p1, int p2, cudaStream_t st);
+
+// ---- token path (token.cu) -----------------------------------------------------------------
+constexpr int TOKEN_DIM = 512;
+constexpr int TOP_NUM = 128;
+constexpr int SEQ = TOP_NUM + 1;
+// idx_out[0..128) = indices of the 128 largest <token, feats[i]> in descending score order.
+int launch_select_topk(const float* token, const float* feats, int n_tokens, float* score_scratch, int* idx_out,
+                       cudaStream_t st);
+// seq[0] = class_token; seq[1+i] = feats[idx[i]] + pe_row
+int launch_build_sequence(const float* class_token, const float* feats, const int* idx, const float* pe_row,
+                          float* seq, cudaStream_t st);
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int rows, cudaStream_t st);
+// y[m][n] = sum_k x[m][k] * w[n][k] + bias[n]  (+gelu) (+residual[m][n]);  w is the PyTorch (N,K) matrix.
+int launch_linear(const float* x, const float* w, const float* bias, const float* residual, float* y, int m, int n,
+                  int k, bool gelu, cudaStream_t st);
+// 8 heads x 64; q: (mq,512), kv: (mk,1024) = [K | V]; out (mq,512)
+int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st);
+// feats[idx[i]] = rows[i]   (i < 128)
+int launch_scatter_rows(float* feats, const int* idx, const float* rows, int row_stride, cudaStream_t st);
+// y = a + b + c  (n elements)
+int launch_add3(const float* a, const float* b, const float* c, float* y, int64_t n, cudaStream_t st);
+
+struct Floats16 { float v[16]; };
+// dst[0..16) = v, passed by value (keeps the per-patch dropout scale off the memcpy path)
+int launch_fill16(float* dst, const Floats16& v, cudaStream_t st);
+
+// ---- aux heads (aux.cu) --------------------------------------------------------------------
+// x: (2, g,g,g) logits -> y: (2, g*s, g*s, g*s) = softmax_c(trilinear_upsample(x, align_corners=False))
+int launch_upsample_softmax2(const float* x, float* y, int g, int scale, cudaStream_t st);
+
+// ---- stitch / label tail (stitch.cu) -------------------------------------------------------
+struct StitchBox {      // one rectangular copy of the crop-and-overwrite plan
+  int dst[3];           // destination origin (global)
+  int ext[3];           // extent
+  int src[3];           // source origin (patch local)
+};
+int launch_stitch_copy(const float* probs, float* out, const StitchBox& box, int X, int Y, int Zout, cudaStream_t st);
+int launch_accumulate(const float* probs, const int start[3], int gaussian, float* acc, float* wsum, int X, int Y,
+                      int Z, cudaStream_t st);
+// probs (4 x total) [+ wsum] -> labels / normalised probs / 13 counters over voxels [v0, v0+nvox)
+int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, int64_t v0, int64_t nvox,
+                           float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                           cudaStream_t st);
+
+extern thread_local int64_t g_launches;   // incremented by every launcher
+}  // namespace dcl

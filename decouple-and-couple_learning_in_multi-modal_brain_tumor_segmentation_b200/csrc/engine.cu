@@ -1,0 +1,1018 @@
+// Host side of the C ABI (include/dcl_b200.h): handle, weight repacking, the per-patch forward
+// schedule and the sliding-window driver.  Every arithmetic step is a kernel from this library;
+// there is no CPU compute path.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dcl_b200.h"
+#include "common.cuh"
+#include "conv_tc.cuh"
+
+namespace dcl {
+
+thread_local std::string g_error;
+thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_error = msg; }
+
+#define DCL_TRY(expr)            \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Weight catalogue: the 222 state_dict tensors of the reference.
+// ---------------------------------------------------------------------------------------------
+enum WKind { W_RAW, W_CONV3, W_CONV1, W_CONVT };
+struct WSpec {
+  std::string name;
+  WKind kind;
+  int cout, cin;       // conv kinds
+  int64_t numel;
+  bool aux;            // only needed when want_aux
+};
+
+static void add_conv(std::vector<WSpec>& v, const std::string& n, WKind k, int cout, int cin, bool aux = false) {
+  int taps = k == W_CONV3 ? 27 : (k == W_CONVT ? 8 : 1);
+  v.push_back({n + ".weight", k, cout, cin, (int64_t)cout * cin * taps, aux});
+  v.push_back({n + ".bias", W_RAW, 0, 0, cout, aux});
+}
+
+static const char* const REGION_KEY[3] = {"01", "02", "04"};
+static const char* const REGION_NUM[3] = {"1", "2", "4"};
+
+static std::vector<WSpec> build_catalogue() {
+  std::vector<WSpec> v;
+  const int D = TOKEN_DIM;
+  for (int r = 0; r < 3; ++r)
+    v.push_back({std::string("label_") + REGION_KEY[r] + "_position_encoding.pe", W_RAW, 0, 0, 1024 * D, false});
+  auto transformer = [&](const std::string& t) {
+    std::string a = t + ".cross_attention_list.0.fn.";
+    v.push_back({a + "norm.weight", W_RAW, 0, 0, D, false});
+    v.push_back({a + "norm.bias", W_RAW, 0, 0, D, false});
+    v.push_back({a + "norm2.weight", W_RAW, 0, 0, D, false});
+    v.push_back({a + "norm2.bias", W_RAW, 0, 0, D, false});
+    v.push_back({a + "fn.out_proj.weight", W_RAW, 0, 0, (int64_t)D * D, false});
+    v.push_back({a + "fn.out_proj.bias", W_RAW, 0, 0, D, false});
+    v.push_back({a + "fn.qkv.weight", W_RAW, 0, 0, (int64_t)3 * D * D, false});
+    std::string f = t + ".cross_ffn_list.0.fn.";
+    v.push_back({f + "norm.weight", W_RAW, 0, 0, D, false});
+    v.push_back({f + "norm.bias", W_RAW, 0, 0, D, false});
+    v.push_back({f + "fn.net.0.weight", W_RAW, 0, 0, (int64_t)D * D, false});
+    v.push_back({f + "fn.net.0.bias", W_RAW, 0, 0, D, false});
+    v.push_back({f + "fn.net.3.weight", W_RAW, 0, 0, (int64_t)D * D, false});
+    v.push_back({f + "fn.net.3.bias", W_RAW, 0, 0, D, false});
+  };
+  for (int r = 0; r < 3; ++r) transformer(std::string("transformer_") + REGION_KEY[r]);
+  v.push_back({"fusion_label_pos.pe", W_RAW, 0, 0, 1024 * D, false});
+  transformer("fusion_transformer_1_2_4");
+  for (int r = 0; r < 3; ++r) add_conv(v, std::string("conv_semantic_") + REGION_NUM[r], W_CONV3, 128, 256);
+  for (int r = 0; r < 3; ++r) add_conv(v, std::string("conv_mid_fea_") + REGION_NUM[r], W_CONV3, 32, 96);
+  const std::string u = "Unet_list.";
+  add_conv(v, u + "InitConv.conv", W_CONV3, 16, 4);
+  auto block = [&](const std::string& n, int c, bool aux = false) {
+    add_conv(v, n + ".conv1", W_CONV3, c, c, aux);
+    add_conv(v, n + ".conv2", W_CONV3, c, c, aux);
+  };
+  block(u + "EnBlock1", 16); block(u + "EnBlock1_1", 16);
+  add_conv(v, u + "EnDown1.conv", W_CONV3, 32, 16);
+  block(u + "EnBlock2_1", 32); block(u + "EnBlock2_2", 32);
+  add_conv(v, u + "EnDown2.conv", W_CONV3, 64, 32);
+  block(u + "EnBlock3_1", 64); block(u + "EnBlock3_2", 64);
+  add_conv(v, u + "EnDown3.conv", W_CONV3, 128, 64);
+  block(u + "EnBlock4_1", 128); block(u + "EnBlock4_2", 128);
+  add_conv(v, u + "EnDown_4.conv", W_CONV3, 256, 128);
+  const std::string d = "decoder.";
+  add_conv(v, d + "down_channel", W_CONV1, 128, 256);
+  block(d + "Enblock8_1", 128); block(d + "Enblock8_2", 128);
+  auto up = [&](const std::string& n, int c) {   // c = in_channels, out = c/2
+    add_conv(v, n + ".conv1", W_CONV1, c / 2, c);
+    add_conv(v, n + ".conv2", W_CONVT, c / 2, c / 2);
+    add_conv(v, n + ".conv3", W_CONV1, c / 2, c);
+  };
+  up(d + "DeUp4", 128); block(d + "DeBlock4", 64); block(d + "DeBlock4_1", 64);
+  up(d + "DeUp3", 64);  block(d + "DeBlock3", 32); block(d + "DeBlock3_1", 32);
+  up(d + "DeUp2", 32);  block(d + "DeBlock2", 16); block(d + "DeBlock2_1", 16);
+  add_conv(v, d + "endconv", W_CONV1, 4, 16);
+  auto sem_head = [&](const std::string& n) {
+    for (int r = 0; r < 3; ++r) {
+      add_conv(v, n + ".supervise_label_" + REGION_NUM[r], W_CONV3, 32, 128, true);
+      add_conv(v, n + ".down_label_" + REGION_NUM[r], W_CONV3, 2, 32, true);
+    }
+  };
+  auto edge_head = [&](const std::string& n) {
+    for (int r = 0; r < 3; ++r) {
+      add_conv(v, n + ".edge_supervise_label_" + REGION_NUM[r], W_CONV3, 8, 32, true);
+      add_conv(v, n + ".edge_down_label_" + REGION_NUM[r], W_CONV3, 2, 8, true);
+    }
+  };
+  sem_head("supervise_label"); edge_head("edge_supervise_label");
+  sem_head("mid_supervise_label"); edge_head("mid_edge_supervise_label");
+  for (int r = 0; r < 3; ++r) {
+    v.push_back({std::string("e_token_") + REGION_KEY[r], W_RAW, 0, 0, D, false});
+    v.push_back({std::string("s_token_") + REGION_KEY[r], W_RAW, 0, 0, D, false});
+  }
+  add_conv(v, "sum_fusion", W_CONV3, 256, 128);
+  add_conv(v, "conv_64_to_32", W_CONV3, 32, 32);
+  return v;
+}
+
+static const std::vector<WSpec>& catalogue() {
+  static const std::vector<WSpec> c = build_catalogue();
+  return c;
+}
+
+// ---------------------------------------------------------------------------------------------
+struct ConvW {          // packed conv weights on the device
+  float* w = nullptr;   // k3: [cin][27][cout_pad]   k1: [cin][cout]   convT: [cin][8][cout]
+  float* b = nullptr;
+  float* raw = nullptr; // PyTorch layout (used by the tensor-core path, which packs its own operand tiles)
+  TcWeights tc;         // bf16 hi/lo canonical tiles (built when precision != FP32)
+  int cout = 0, cin = 0, cout_pad = 0;
+};
+
+struct Transformer {
+  float *n1w, *n1b, *n2w, *n2b, *wqkv, *wout, *bout, *fnw, *fnb, *w0, *b0, *w3, *b3;
+};
+
+struct StatSlot { float* mean; float* rstd; };
+
+}  // namespace dcl
+
+using namespace dcl;
+
+struct dcl_handle {
+  int device = -1;
+  dcl_config cfg{};
+  bool ready = false;
+  int64_t launches = 0;
+  std::vector<void*> allocs;
+  int64_t alloc_bytes = 0;
+  bool dry_run = false;    // size the workspace without touching the device
+
+  std::map<std::string, std::vector<float>> host_w;   // raw state_dict tensors as set
+  std::map<std::string, float*> dev_raw;               // device copies (PyTorch layout)
+  std::map<std::string, ConvW> conv;                   // by module name (without .weight)
+  ConvW edge_merged, sem_merged;
+  Transformer tr[4];
+  float *e_tok[3], *s_tok[3], *pe[4];
+
+  // ---- activations (all fp32, dense NCDHW unless noted) ----
+  float *l_t0[4], *l_a[4], *l_t1[4], *l_x[4];   // encoder levels 0..3: input, scratch, block-1 out, block-2 out (skip)
+  float* x4;                                     // (256,16^3)
+  float *e_down, *e_raw, *s_raw;                 // (32,32^3), (96,32^3), (384,16^3)
+  float *E[3], *S[3];                            // token matrices (2048,512) / (1024,512)
+  float *edge_dense[3], *sem_dense[3];           // dense IN+LeakyReLU outputs (stages / aux)
+  float *sup_edge[3], *sup_sem[3];               // aux-head inputs after the couplers
+  float *aux_t1, *aux_t2;                        // aux conv scratch
+  float* score;                                  // (2048)
+  int* topk;                                     // (13,128)
+  float* seq[4];                                 // 4 x (129,512)
+  float *ln_a, *ln_b, *qbuf, *kvbuf, *obuf;      // attention scratch
+  float *eqs, *sqe, *cross, *ffn_ln, *ffn_h;
+  float* coupler_out[4];                         // (258,512) x3, (129,512)
+  float *f_tok, *f_fea, *fused_dense, *enc;
+  float *d8_0, *d8_a, *d8_b, *d8_1, *d8_2;
+  float *up_u1[3], *up_u2[3], *dl_in[3], *dl_a[3], *dl_b[3], *dl_1[3], *dl_2[3];   // decoder levels (32^3, 64^3, 128^3)
+  float* probs;                                  // (4,128^3)
+  float* keep_dev;                               // (16)
+  double* stat_accum;                            // (2*512)
+  std::vector<StatSlot> stat_slots;
+  int stat_next = 0;
+
+  // ---- volume level ----
+  float* vol_probs = nullptr;  int64_t vol_probs_cap = 0;
+  float* vol_wsum = nullptr;   int64_t vol_wsum_cap = 0;
+  float* stage_vol = nullptr;  int64_t stage_vol_cap = 0;
+  float* stage_probs = nullptr; int64_t stage_probs_cap = 0;
+  uint8_t* stage_labels = nullptr; uint8_t* stage_target = nullptr; int64_t stage_lab_cap = 0;
+  unsigned long long* counts_dev = nullptr;
+
+  std::map<std::string, std::pair<const float*, int64_t>> stages;
+
+  // ---- per-class event timing (dcl_profile_*) ----
+  struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> event_pool;
+  cudaEvent_t prof_begin(cudaStream_t st) {
+    cudaEvent_t e;
+    if (!event_pool.empty()) { e = event_pool.back(); event_pool.pop_back(); } else cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    return e;
+  }
+  void prof_end(cudaEvent_t a, int cls, double work, cudaStream_t st) {
+    cudaEvent_t b;
+    if (!event_pool.empty()) { b = event_pool.back(); event_pool.pop_back(); } else cudaEventCreate(&b);
+    cudaEventRecord(b, st);
+    prof.push_back({a, b, cls, work});
+  }
+};
+
+namespace dcl {
+
+static int dev_alloc(dcl_handle* h, void** p, int64_t bytes) {
+  h->alloc_bytes += (bytes + 255) / 256 * 256;
+  if (h->dry_run) { *p = nullptr; return 0; }
+  DCL_CUDA_OK(cudaMalloc(p, (size_t)bytes));
+  h->allocs.push_back(*p);
+  return 0;
+}
+static int falloc(dcl_handle* h, float** p, int64_t numel) { return dev_alloc(h, (void**)p, numel * 4); }
+
+static const int64_t P3 = 128LL * 128 * 128;
+static const int LVL_C[4] = {16, 32, 64, 128};
+static const int LVL_G[4] = {128, 64, 32, 16};
+
+static int allocate_workspace(dcl_handle* h) {
+  for (int l = 0; l < 4; ++l) {
+    int64_t n = (int64_t)LVL_C[l] * LVL_G[l] * LVL_G[l] * LVL_G[l];
+    DCL_TRY(falloc(h, &h->l_t0[l], n)); DCL_TRY(falloc(h, &h->l_a[l], n));
+    DCL_TRY(falloc(h, &h->l_t1[l], n)); DCL_TRY(falloc(h, &h->l_x[l], n));
+  }
+  const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
+  DCL_TRY(falloc(h, &h->x4, 256 * g16));
+  DCL_TRY(falloc(h, &h->e_down, 32 * g32)); DCL_TRY(falloc(h, &h->e_raw, 96 * g32));
+  DCL_TRY(falloc(h, &h->s_raw, 384 * g16));
+  for (int r = 0; r < 3; ++r) {
+    DCL_TRY(falloc(h, &h->E[r], 2048 * 512)); DCL_TRY(falloc(h, &h->S[r], 1024 * 512));
+    DCL_TRY(falloc(h, &h->edge_dense[r], 32 * g32)); DCL_TRY(falloc(h, &h->sem_dense[r], 128 * g16));
+    DCL_TRY(falloc(h, &h->sup_edge[r], 32 * g32)); DCL_TRY(falloc(h, &h->sup_sem[r], 128 * g16));
+  }
+  DCL_TRY(falloc(h, &h->aux_t1, 32 * g32)); DCL_TRY(falloc(h, &h->aux_t2, 2 * g32));
+  DCL_TRY(falloc(h, &h->score, 2048));
+  DCL_TRY(dev_alloc(h, (void**)&h->topk, 13 * 128 * sizeof(int)));
+  for (int i = 0; i < 4; ++i) DCL_TRY(falloc(h, &h->seq[i], SEQ * 512));
+  DCL_TRY(falloc(h, &h->ln_a, 258 * 512)); DCL_TRY(falloc(h, &h->ln_b, 258 * 512));
+  DCL_TRY(falloc(h, &h->qbuf, 258 * 512)); DCL_TRY(falloc(h, &h->kvbuf, 258 * 1024));
+  DCL_TRY(falloc(h, &h->obuf, 258 * 512));
+  DCL_TRY(falloc(h, &h->eqs, SEQ * 512)); DCL_TRY(falloc(h, &h->sqe, SEQ * 512));
+  DCL_TRY(falloc(h, &h->cross, 258 * 512)); DCL_TRY(falloc(h, &h->ffn_ln, 258 * 512));
+  DCL_TRY(falloc(h, &h->ffn_h, 258 * 512));
+  for (int i = 0; i < 4; ++i) DCL_TRY(falloc(h, &h->coupler_out[i], 258 * 512));
+  DCL_TRY(falloc(h, &h->f_tok, 512)); DCL_TRY(falloc(h, &h->f_fea, 1024 * 512));
+  DCL_TRY(falloc(h, &h->fused_dense, 128 * g16)); DCL_TRY(falloc(h, &h->enc, 256 * g16));
+  DCL_TRY(falloc(h, &h->d8_0, 128 * g16)); DCL_TRY(falloc(h, &h->d8_a, 128 * g16));
+  DCL_TRY(falloc(h, &h->d8_b, 128 * g16)); DCL_TRY(falloc(h, &h->d8_1, 128 * g16));
+  DCL_TRY(falloc(h, &h->d8_2, 128 * g16));
+  for (int l = 0; l < 3; ++l) {   // decoder level l: channels 64/32/16 at 32/64/128
+    int c = 64 >> l, g = 32 << l;
+    int64_t n = (int64_t)c * g * g * g;
+    DCL_TRY(falloc(h, &h->up_u1[l], n / 8)); DCL_TRY(falloc(h, &h->up_u2[l], n));
+    DCL_TRY(falloc(h, &h->dl_in[l], n)); DCL_TRY(falloc(h, &h->dl_a[l], n)); DCL_TRY(falloc(h, &h->dl_b[l], n));
+    DCL_TRY(falloc(h, &h->dl_1[l], n)); DCL_TRY(falloc(h, &h->dl_2[l], n));
+  }
+  DCL_TRY(falloc(h, &h->probs, 4 * P3));
+  DCL_TRY(falloc(h, &h->keep_dev, 16));
+  DCL_TRY(dev_alloc(h, (void**)&h->stat_accum, 2 * 512 * sizeof(double)));
+  if (!h->dry_run) DCL_CUDA_OK(cudaMemset(h->stat_accum, 0, 2 * 512 * sizeof(double)));
+  h->stat_slots.resize(48);
+  for (auto& s : h->stat_slots) { DCL_TRY(falloc(h, &s.mean, 512)); DCL_TRY(falloc(h, &s.rstd, 512)); }
+  DCL_TRY(dev_alloc(h, (void**)&h->counts_dev, 16 * sizeof(unsigned long long)));
+  return 0;
+}
+
+static int64_t workspace_estimate(const dcl_config* cfg) {
+  dcl_handle tmp;
+  if (cfg) tmp.cfg = *cfg;
+  tmp.dry_run = true;
+  if (allocate_workspace(&tmp) != 0) return -1;
+  return tmp.alloc_bytes;
+}
+
+// ---- weight upload / packing ----------------------------------------------------------------
+static int upload(dcl_handle* h, const std::vector<float>& v, float** out) {
+  DCL_TRY(falloc(h, out, (int64_t)v.size()));
+  DCL_CUDA_OK(cudaMemcpy(*out, v.data(), v.size() * 4, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// srcs: list of (weight, bias) host tensors concatenated along cout.
+static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vector<float>*>& ws,
+                     const std::vector<const std::vector<float>*>& bs, int cout_each, int cin, ConvW* out) {
+  const int parts = (int)ws.size();
+  const int cout = cout_each * parts;
+  out->cout = cout; out->cin = cin;
+  std::vector<float> bias((size_t)cout);
+  for (int p = 0; p < parts; ++p)
+    for (int c = 0; c < cout_each; ++c) bias[p * cout_each + c] = (*bs[p])[c];
+  std::vector<float> packed, raw;
+  if (kind == W_CONV3) {
+    out->cout_pad = (cout + 15) / 16 * 16;
+    packed.assign((size_t)cin * 27 * out->cout_pad, 0.f);
+    raw.resize((size_t)cout * cin * 27);
+    for (int p = 0; p < parts; ++p)
+      for (int co = 0; co < cout_each; ++co)
+        for (int ci = 0; ci < cin; ++ci)
+          for (int t = 0; t < 27; ++t) {
+            float v = (*ws[p])[((size_t)co * cin + ci) * 27 + t];
+            packed[((size_t)ci * 27 + t) * out->cout_pad + p * cout_each + co] = v;
+            raw[((size_t)(p * cout_each + co) * cin + ci) * 27 + t] = v;
+          }
+  } else if (kind == W_CONV1) {
+    out->cout_pad = cout;
+    packed.resize((size_t)cin * cout);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci) packed[(size_t)ci * cout + co] = (*ws[0])[(size_t)co * cin + ci];
+  } else {   // ConvTranspose3d weight is (Cin, Cout, 2,2,2)
+    out->cout_pad = cout;
+    packed.resize((size_t)cin * 8 * cout);
+    for (int ci = 0; ci < cin; ++ci)
+      for (int co = 0; co < cout; ++co)
+        for (int t = 0; t < 8; ++t) packed[((size_t)ci * 8 + t) * cout + co] = (*ws[0])[((size_t)ci * cout + co) * 8 + t];
+  }
+  DCL_TRY(upload(h, packed, &out->w));
+  DCL_TRY(upload(h, bias, &out->b));
+  if (kind == W_CONV3 && h->cfg.precision != DCL_FP32) {
+    DCL_TRY(upload(h, raw, &out->raw));
+    DCL_TRY(tc_pack_weights(raw.data(), cout, cin, &out->tc));
+    h->allocs.push_back(out->tc.dev);
+  }
+  return 0;
+}
+
+static bool needed(const dcl_handle* h, const WSpec& s) { return !s.aux || h->cfg.want_aux; }
+
+static int prepare(dcl_handle* h) {
+  for (const auto& s : catalogue())
+    if (needed(h, s) && !h->host_w.count(s.name)) {
+      set_error("weight not set: " + s.name);
+      return DCL_ERR_WEIGHTS;
+    }
+  auto W = [&](const std::string& n) -> const std::vector<float>* { return &h->host_w.at(n); };
+  std::map<std::string, int> conv_modules;
+  for (const auto& s : catalogue())
+    if (s.kind != W_RAW) conv_modules[s.name.substr(0, s.name.size() - 7)] = 1;
+  for (const auto& s : catalogue()) {
+    if (!needed(h, s)) continue;
+    if (s.kind == W_RAW) {
+      if (s.name.size() > 5 && s.name.compare(s.name.size() - 5, 5, ".bias") == 0 &&
+          conv_modules.count(s.name.substr(0, s.name.size() - 5)))
+        continue;   // conv bias: packed together with its weight
+      if (s.numel == 1024 * TOKEN_DIM) {   // positional-encoding buffer: only row 0 is ever added
+        std::vector<float> row(h->host_w.at(s.name).begin(), h->host_w.at(s.name).begin() + TOKEN_DIM);
+        DCL_TRY(upload(h, row, &h->dev_raw[s.name]));
+      } else {
+        DCL_TRY(upload(h, h->host_w.at(s.name), &h->dev_raw[s.name]));
+      }
+    } else {
+      std::string mod = s.name.substr(0, s.name.size() - 7);
+      DCL_TRY(pack_conv(h, s.kind, {W(s.name)}, {W(mod + ".bias")}, s.cout, s.cin, &h->conv[mod]));
+    }
+  }
+  DCL_TRY(pack_conv(h, W_CONV3, {W("conv_mid_fea_1.weight"), W("conv_mid_fea_2.weight"), W("conv_mid_fea_4.weight")},
+                    {W("conv_mid_fea_1.bias"), W("conv_mid_fea_2.bias"), W("conv_mid_fea_4.bias")}, 32, 96,
+                    &h->edge_merged));
+  DCL_TRY(pack_conv(h, W_CONV3,
+                    {W("conv_semantic_1.weight"), W("conv_semantic_2.weight"), W("conv_semantic_4.weight")},
+                    {W("conv_semantic_1.bias"), W("conv_semantic_2.bias"), W("conv_semantic_4.bias")}, 128, 256,
+                    &h->sem_merged));
+  auto R = [&](const std::string& n) { return h->dev_raw.at(n); };
+  const char* tnames[4] = {"transformer_01", "transformer_02", "transformer_04", "fusion_transformer_1_2_4"};
+  for (int i = 0; i < 4; ++i) {
+    std::string a = std::string(tnames[i]) + ".cross_attention_list.0.fn.";
+    std::string f = std::string(tnames[i]) + ".cross_ffn_list.0.fn.";
+    Transformer& t = h->tr[i];
+    t.n1w = R(a + "norm.weight"); t.n1b = R(a + "norm.bias"); t.n2w = R(a + "norm2.weight"); t.n2b = R(a + "norm2.bias");
+    t.wqkv = R(a + "fn.qkv.weight"); t.wout = R(a + "fn.out_proj.weight"); t.bout = R(a + "fn.out_proj.bias");
+    t.fnw = R(f + "norm.weight"); t.fnb = R(f + "norm.bias");
+    t.w0 = R(f + "fn.net.0.weight"); t.b0 = R(f + "fn.net.0.bias");
+    t.w3 = R(f + "fn.net.3.weight"); t.b3 = R(f + "fn.net.3.bias");
+  }
+  for (int r = 0; r < 3; ++r) {
+    h->e_tok[r] = R(std::string("e_token_") + REGION_KEY[r]);
+    h->s_tok[r] = R(std::string("s_token_") + REGION_KEY[r]);
+    h->pe[r] = R(std::string("label_") + REGION_KEY[r] + "_position_encoding.pe");
+  }
+  h->pe[3] = R("fusion_label_pos.pe");
+  h->ready = true;
+  return 0;
+}
+
+// ---- forward schedule --------------------------------------------------------------------------
+struct Fwd {
+  dcl_handle* h;
+  cudaStream_t st;
+
+  StatSlot stats(const float* x, int c, int64_t spatial, int* rc) {
+    StatSlot s = h->stat_slots[h->stat_next++ % h->stat_slots.size()];
+    *rc = launch_instnorm_stats(x, c, spatial, h->stat_accum, s.mean, s.rstd, st);
+    return s;
+  }
+
+  // dense-input 3x3x3 conv with optional fused input norm/activation
+  int conv3(const float* x0, int c0, const float* x1, int c1, int g, const ConvW& w, int stride, const StatSlot* norm,
+            int act, const float* out_scale, const float* residual, float* y) {
+    ConvSrc s{x0, x1, c0, c1, (int64_t)g * g * g, (int64_t)g * g, g, norm ? norm->mean : nullptr,
+              norm ? norm->rstd : nullptr, act};
+    ConvDst d{y, w.b, out_scale, residual};
+    cudaEvent_t ev = nullptr;
+    if (h->profiling) ev = h->prof_begin(st);
+    int rc;
+    if (h->cfg.precision != DCL_FP32 && tc_conv_supported(c0 + c1, w.cout, g, stride) && x1 == nullptr)
+      rc = launch_conv3d_k3_tc(s, d, w.tc, w.cout, g, h->cfg.precision == DCL_BF16X3, st);
+    else
+      rc = launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, g, g, g, stride, st);
+    if (h->profiling) {
+      const double og = (double)((g - 1) / stride + 1);
+      h->prof_end(ev, 0, 2.0 * 27.0 * (c0 + c1) * w.cout * og * og * og, st);
+    }
+    return rc;
+  }
+
+  int conv1(const float* x0, int c0, const float* x1, int c1, int64_t spatial, const ConvW& w, float* y,
+            bool softmax = false) {
+    ConvSrc s{x0, x1, c0, c1, spatial, 0, 0, nullptr, nullptr, ACT_NONE};
+    ConvDst d{y, w.b, nullptr, nullptr};
+    return launch_conv1x1(s, d, w.w, w.cout, spatial, softmax, st);
+  }
+
+  // EnBlock (Unet_skipconnection.py:36-57): y = conv2(relu(IN(conv1(relu(IN(x)))))) + x
+  int en_block(const float* x, int c, int g, const std::string& name, float* a, float* y) {
+    int rc = 0;
+    int64_t sp = (int64_t)g * g * g;
+    StatSlot s1 = stats(x, c, sp, &rc); DCL_TRY(rc);
+    DCL_TRY(conv3(x, c, nullptr, 0, g, h->conv.at(name + ".conv1"), 1, &s1, ACT_RELU, nullptr, nullptr, a));
+    StatSlot s2 = stats(a, c, sp, &rc); DCL_TRY(rc);
+    DCL_TRY(conv3(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &s2, ACT_RELU, nullptr, x, y));
+    return 0;
+  }
+
+  // EnBlock2 / DeBlock (cls_wise_former.py:691-713, :732-754): y = lrelu(IN(conv2(lrelu(IN(conv1(x)))))) + x
+  int post_block(const float* x, int c, int g, const std::string& name, float* a, float* b, float* y) {
+    int rc = 0;
+    int64_t sp = (int64_t)g * g * g;
+    DCL_TRY(conv3(x, c, nullptr, 0, g, h->conv.at(name + ".conv1"), 1, nullptr, ACT_NONE, nullptr, nullptr, a));
+    StatSlot s1 = stats(a, c, sp, &rc); DCL_TRY(rc);
+    DCL_TRY(conv3(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &s1, ACT_LRELU, nullptr, nullptr, b));
+    StatSlot s2 = stats(b, c, sp, &rc); DCL_TRY(rc);
+    DCL_TRY(launch_norm_act_res(b, s2.mean, s2.rstd, ACT_LRELU, x, y, c, sp, st));
+    return 0;
+  }
+
+  // DeUp_Cat (cls_wise_former.py:716-729): conv1x1 -> convT k2s2 -> conv1x1(cat(skip, .))
+  int up_cat(const float* x, int c, int g, const float* skip, const std::string& name, float* u1, float* u2,
+             float* y) {
+    int64_t sp = (int64_t)g * g * g;
+    const ConvW& c2 = h->conv.at(name + ".conv2");
+    DCL_TRY(conv1(x, c, nullptr, 0, sp, h->conv.at(name + ".conv1"), u1));
+    DCL_TRY(launch_convt_k2s2(u1, u2, c2.w, c2.b, c / 2, c / 2, g, g, g, st));
+    DCL_TRY(conv1(skip, c / 2, u2, c / 2, sp * 8, h->conv.at(name + ".conv3"), y));
+    return 0;
+  }
+
+  // Residual(PreNormDrop(DualSelfAttention)) (ResidualNorm.py:4-32, SelfAttention.py:74-102)
+  int attn_block(const Transformer& t, const float* x, const float* x2, int mq, int mk, float* out) {
+    DCL_TRY(launch_layernorm(x, t.n1w, t.n1b, h->ln_a, mq, st));
+    DCL_TRY(launch_layernorm(x2, t.n2w, t.n2b, h->ln_b, mk, st));
+    DCL_TRY(launch_linear(h->ln_a, t.wqkv, nullptr, nullptr, h->qbuf, mq, 512, 512, false, st));
+    DCL_TRY(launch_linear(h->ln_b, t.wqkv + 512 * 512, nullptr, nullptr, h->kvbuf, mk, 1024, 512, false, st));
+    DCL_TRY(launch_attention(h->qbuf, h->kvbuf, h->obuf, mq, mk, st));
+    DCL_TRY(launch_linear(h->obuf, t.wout, t.bout, x, out, mq, 512, 512, false, st));
+    return 0;
+  }
+
+  // Residual(PreNorm(FeedForward)) (ResidualNorm.py:35-47)
+  int ffn_block(const Transformer& t, const float* x, int m, float* out) {
+    DCL_TRY(launch_layernorm(x, t.fnw, t.fnb, h->ffn_ln, m, st));
+    DCL_TRY(launch_linear(h->ffn_ln, t.w0, t.b0, nullptr, h->ffn_h, m, 512, 512, true, st));
+    DCL_TRY(launch_linear(h->ffn_h, t.w3, t.b3, x, out, m, 512, 512, false, st));
+    return 0;
+  }
+
+  int select_build(const float* score_tok, const float* class_tok, const float* feats, int n, const float* pe,
+                   int slot, float* seq) {
+    int* idx = h->topk + slot * TOP_NUM;
+    DCL_TRY(launch_select_topk(score_tok, feats, n, h->score, idx, st));
+    DCL_TRY(launch_build_sequence(class_tok, feats, idx, pe, seq, st));
+    return 0;
+  }
+
+  // one auxiliary head branch: conv k3 -> conv k3 (2 classes) -> trilinear upsample -> softmax
+  int aux_branch(const float* x, int c, int g, const std::string& first, const std::string& second, float* out) {
+    const ConvW& w1 = h->conv.at(first);
+    DCL_TRY(conv3(x, c, nullptr, 0, g, w1, 1, nullptr, ACT_NONE, nullptr, nullptr, h->aux_t1));
+    DCL_TRY(conv3(h->aux_t1, w1.cout, nullptr, 0, g, h->conv.at(second), 1, nullptr, ACT_NONE, nullptr, nullptr,
+                  h->aux_t2));
+    DCL_TRY(launch_upsample_softmax2(h->aux_t2, out, g, 128 / g, st));
+    return 0;
+  }
+
+  int run(const float* x, const int64_t xs[4], const float* keep_host, float* probs_out, float* const* aux) {
+    int rc = 0;
+    const bool want_aux = aux != nullptr;
+    const bool dense_feats = want_aux || h->cfg.keep_stages;
+    // ---- encoder ----
+    Floats16 keep;
+    for (int i = 0; i < 16; ++i) keep.v[i] = keep_host ? keep_host[i] : 1.f;
+    DCL_TRY(launch_fill16(h->keep_dev, keep, st));   // by-value kernel argument: no pageable-memory copy
+    {
+      ConvSrc s{x, nullptr, 4, 0, xs[0], xs[1], xs[2], nullptr, nullptr, ACT_NONE};
+      const ConvW& w = h->conv.at("Unet_list.InitConv.conv");
+      ConvDst d{h->l_t0[0], w.b, h->keep_dev, nullptr};
+      cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+      DCL_TRY(launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, 128, 128, 128, 1, st));
+      if (h->profiling) h->prof_end(ev, 0, 2.0 * 27.0 * 4 * 16 * (double)P3, st);
+    }
+    const char* blk[4][2] = {{"Unet_list.EnBlock1", "Unet_list.EnBlock1_1"}, {"Unet_list.EnBlock2_1", "Unet_list.EnBlock2_2"},
+                             {"Unet_list.EnBlock3_1", "Unet_list.EnBlock3_2"}, {"Unet_list.EnBlock4_1", "Unet_list.EnBlock4_2"}};
+    const char* down[4] = {"Unet_list.EnDown1.conv", "Unet_list.EnDown2.conv", "Unet_list.EnDown3.conv",
+                           "Unet_list.EnDown_4.conv"};
+    for (int l = 0; l < 4; ++l) {
+      int c = LVL_C[l], g = LVL_G[l];
+      DCL_TRY(en_block(h->l_t0[l], c, g, blk[l][0], h->l_a[l], h->l_t1[l]));
+      DCL_TRY(en_block(h->l_t1[l], c, g, blk[l][1], h->l_a[l], h->l_x[l]));
+      float* nxt = l < 3 ? h->l_t0[l + 1] : h->x4;
+      DCL_TRY(conv3(h->l_x[l], c, nullptr, 0, g, h->conv.at(down[l]), l < 3 ? 2 : 1, nullptr, ACT_NONE, nullptr,
+                    nullptr, nxt));
+    }
+    const float *x1 = h->l_x[0], *x2 = h->l_x[1], *x3 = h->l_x[2];
+    const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
+
+    // ---- Anatomy-induced Region Decoupler (cls_wise_former.py:284-328), the 3 sibling convs merged ----
+    DCL_TRY(conv3(x2, 32, nullptr, 0, 64, h->conv.at("conv_64_to_32"), 2, nullptr, ACT_NONE, nullptr, nullptr,
+                  h->e_down));
+    DCL_TRY(conv3(h->e_down, 32, x3, 64, 32, h->edge_merged, 1, nullptr, ACT_NONE, nullptr, nullptr, h->e_raw));
+    StatSlot se = stats(h->e_raw, 96, g32, &rc); DCL_TRY(rc);
+    DCL_TRY(conv3(h->x4, 256, nullptr, 0, 16, h->sem_merged, 1, nullptr, ACT_NONE, nullptr, nullptr, h->s_raw));
+    StatSlot ss = stats(h->s_raw, 384, g16, &rc); DCL_TRY(rc);
+    for (int r = 0; r < 3; ++r) {
+      DCL_TRY(launch_norm_act_tokenise(h->e_raw + r * 32 * g32, se.mean + 32 * r, se.rstd + 32 * r, ACT_LRELU, h->E[r],
+                                       dense_feats ? h->edge_dense[r] : nullptr, 32, 32, 4, 2, 2, st));
+      DCL_TRY(launch_norm_act_tokenise(h->s_raw + r * 128 * g16, ss.mean + 128 * r, ss.rstd + 128 * r, ACT_LRELU,
+                                       h->S[r], dense_feats ? h->sem_dense[r] : nullptr, 128, 16, 2, 2, 1, st));
+    }
+    if (want_aux) {   // mid heads (cls_wise_former.py:332-333)
+      for (int r = 0; r < 3; ++r) {
+        std::string n = REGION_NUM[r];
+        DCL_TRY(aux_branch(h->sem_dense[r], 128, 16, "mid_supervise_label.supervise_label_" + n,
+                           "mid_supervise_label.down_label_" + n, aux[6 + r]));
+        DCL_TRY(aux_branch(h->edge_dense[r], 32, 32, "mid_edge_supervise_label.edge_supervise_label_" + n,
+                           "mid_edge_supervise_label.edge_down_label_" + n, aux[9 + r]));
+      }
+    }
+
+    // ---- Edge-supported Intra-region Coupler per region (cls_wise_former.py:341-543) ----
+    for (int r = 0; r < 3; ++r) {
+      const Transformer& t = h->tr[r];
+      float *E = h->E[r], *S = h->S[r], *out = h->coupler_out[r];
+      DCL_TRY(select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, h->seq[0]));   // edge
+      DCL_TRY(select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, h->seq[1]));   // semantic supplement
+      DCL_TRY(select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, h->seq[2]));   // semantic
+      DCL_TRY(select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, h->seq[3]));   // edge supplement
+      DCL_TRY(attn_block(t, h->seq[0], h->seq[1], SEQ, SEQ, h->eqs));
+      DCL_TRY(attn_block(t, h->seq[2], h->seq[3], SEQ, SEQ, h->sqe));
+      DCL_TRY(attn_block(t, h->eqs, h->sqe, SEQ, SEQ, h->cross));
+      DCL_TRY(attn_block(t, h->sqe, h->eqs, SEQ, SEQ, h->cross + SEQ * 512));
+      DCL_TRY(ffn_block(t, h->cross, 2 * SEQ, out));
+      DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, st));
+      DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, st));
+      if (want_aux) {
+        DCL_TRY(launch_scale_untokenise(E, out, h->sup_edge[r], 32, 32, 4, 2, 2, st));
+        DCL_TRY(launch_scale_untokenise(S, out + SEQ * 512, h->sup_sem[r], 128, 16, 2, 2, 1, st));
+      }
+    }
+    if (want_aux) {   // final heads (cls_wise_former.py:545-546)
+      for (int r = 0; r < 3; ++r) {
+        std::string n = REGION_NUM[r];
+        DCL_TRY(aux_branch(h->sup_sem[r], 128, 16, "supervise_label.supervise_label_" + n,
+                           "supervise_label.down_label_" + n, aux[0 + r]));
+        DCL_TRY(aux_branch(h->sup_edge[r], 32, 32, "edge_supervise_label.edge_supervise_label_" + n,
+                           "edge_supervise_label.edge_down_label_" + n, aux[3 + r]));
+      }
+    }
+
+    // ---- Mutual Cross-region Coupler (cls_wise_former.py:549-582) ----
+    DCL_TRY(launch_add3(h->coupler_out[0] + SEQ * 512, h->coupler_out[1] + SEQ * 512, h->coupler_out[2] + SEQ * 512,
+                        h->f_tok, 512, st));
+    DCL_TRY(launch_add3(h->S[0], h->S[1], h->S[2], h->f_fea, 1024 * 512, st));
+    DCL_TRY(select_build(h->f_tok, h->f_tok, h->f_fea, 1024, h->pe[3], 12, h->seq[0]));
+    DCL_TRY(attn_block(h->tr[3], h->seq[0], h->seq[0], SEQ, SEQ, h->eqs));
+    DCL_TRY(ffn_block(h->tr[3], h->eqs, SEQ, h->coupler_out[3]));
+    DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
+    DCL_TRY(launch_scale_untokenise(h->f_fea, h->coupler_out[3], h->fused_dense, 128, 16, 2, 2, 1, st));
+    DCL_TRY(conv3(h->fused_dense, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, ACT_NONE, nullptr,
+                  nullptr, h->enc));
+
+    // ---- decoder (cls_wise_former.py:644-664) ----
+    DCL_TRY(conv1(h->enc, 256, nullptr, 0, g16, h->conv.at("decoder.down_channel"), h->d8_0));
+    DCL_TRY(post_block(h->d8_0, 128, 16, "decoder.Enblock8_1", h->d8_a, h->d8_b, h->d8_1));
+    DCL_TRY(post_block(h->d8_1, 128, 16, "decoder.Enblock8_2", h->d8_a, h->d8_b, h->d8_2));
+    const char* upn[3] = {"decoder.DeUp4", "decoder.DeUp3", "decoder.DeUp2"};
+    const char* dbn[3][2] = {{"decoder.DeBlock4", "decoder.DeBlock4_1"}, {"decoder.DeBlock3", "decoder.DeBlock3_1"},
+                             {"decoder.DeBlock2", "decoder.DeBlock2_1"}};
+    const float* skips[3] = {x3, x2, x1};
+    const float* cur = h->d8_2;
+    for (int l = 0; l < 3; ++l) {
+      int cin = 128 >> l, g_in = 16 << l, c = cin / 2, g = g_in * 2;
+      DCL_TRY(up_cat(cur, cin, g_in, skips[l], upn[l], h->up_u1[l], h->up_u2[l], h->dl_in[l]));
+      DCL_TRY(post_block(h->dl_in[l], c, g, dbn[l][0], h->dl_a[l], h->dl_b[l], h->dl_1[l]));
+      DCL_TRY(post_block(h->dl_1[l], c, g, dbn[l][1], h->dl_a[l], h->dl_b[l], h->dl_2[l]));
+      cur = h->dl_2[l];
+    }
+    DCL_TRY(conv1(cur, 16, nullptr, 0, P3, h->conv.at("decoder.endconv"), probs_out, true));
+    return 0;
+  }
+};
+
+static void register_stages(dcl_handle* h) {
+  const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
+  auto& s = h->stages;
+  s["init"] = {h->l_t0[0], 16 * P3};
+  s["x1_1"] = {h->l_x[0], 16 * P3};
+  s["x2_1"] = {h->l_x[1], 32 * P3 / 8};
+  s["x3_1"] = {h->l_x[2], 64 * g32};
+  s["x4"] = {h->x4, 256 * g16};
+  for (int r = 0; r < 3; ++r) {
+    s[std::string("edge_") + REGION_NUM[r]] = {h->edge_dense[r], 32 * g32};
+    s[std::string("sem_") + REGION_NUM[r]] = {h->sem_dense[r], 128 * g16};
+    s[std::string("coupler_") + REGION_KEY[r]] = {h->coupler_out[r], 258 * 512};
+  }
+  s["coupler_fusion"] = {h->coupler_out[3], SEQ * 512};
+  s["enc_out"] = {h->enc, 256 * g16};
+  s["dec8"] = {h->d8_2, 128 * g16};
+  s["dec4"] = {h->dl_2[0], 64 * g32};
+  s["dec3"] = {h->dl_2[1], 32 * P3 / 8};
+  s["dec2"] = {h->dl_2[2], 16 * P3};
+}
+
+static int check_handle(dcl_handle* h) {
+  if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
+  int dev = -1;
+  DCL_CUDA_OK(cudaGetDevice(&dev));
+  if (dev != h->device) { set_error("handle used on a different CUDA device than it was created on"); return DCL_ERR_STATE; }
+  if (!h->ready) DCL_TRY(prepare(h));
+  return 0;
+}
+
+static int grow(dcl_handle* h, void** p, int64_t* cap, int64_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  DCL_CUDA_OK(cudaMalloc(p, (size_t)bytes));
+  *cap = bytes;
+  return 0;
+}
+
+struct PlanItem { int start[3]; StitchBox box; };
+
+static int build_plan(int mode, const int32_t shape[3], int n_patches, const int32_t* starts,
+                      std::vector<PlanItem>* plan, int* zout) {
+  plan->clear();
+  if (mode == DCL_STITCH_REFERENCE || mode == DCL_STITCH_ALIGNED) {
+    if (shape[0] != 240 || shape[1] != 240 || shape[2] < 155) {
+      set_error("reference tiling needs a (4,240,240,>=155) volume (predict_overlap.py:34-41)");
+      return DCL_ERR_ARG;
+    }
+    *zout = 155;
+    const int zsrc = mode == DCL_STITCH_REFERENCE ? 96 : 101;   // predict_overlap.py:53: 96:123 (5-voxel shift)
+    for (int iz = 0; iz < 2; ++iz)
+      for (int ix = 0; ix < 2; ++ix)
+        for (int iy = 0; iy < 2; ++iy) {
+          PlanItem p;
+          p.start[0] = ix ? 112 : 0; p.start[1] = iy ? 112 : 0; p.start[2] = iz ? 27 : 0;
+          p.box.dst[0] = ix ? 128 : 0; p.box.ext[0] = ix ? 112 : 128; p.box.src[0] = ix ? 16 : 0;
+          p.box.dst[1] = iy ? 128 : 0; p.box.ext[1] = iy ? 112 : 128; p.box.src[1] = iy ? 16 : 0;
+          p.box.dst[2] = iz ? 128 : 0; p.box.ext[2] = iz ? 27 : 128; p.box.src[2] = iz ? zsrc : 0;
+          plan->push_back(p);
+        }
+    return 0;
+  }
+  if (mode != DCL_STITCH_UNIFORM && mode != DCL_STITCH_GAUSSIAN) { set_error("unknown stitch mode"); return DCL_ERR_ARG; }
+  if (n_patches <= 0 || !starts) { set_error("weighted modes need an explicit patch list"); return DCL_ERR_ARG; }
+  *zout = shape[2];
+  for (int i = 0; i < n_patches; ++i) {
+    PlanItem p{};
+    for (int a = 0; a < 3; ++a) {
+      p.start[a] = starts[3 * i + a];
+      if (p.start[a] < 0 || p.start[a] + 128 > shape[a]) { set_error("patch outside the volume"); return DCL_ERR_ARG; }
+    }
+    plan->push_back(p);
+  }
+  return 0;
+}
+
+static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], int mode,
+                       const std::vector<PlanItem>& plan, int first, int count, const float* keep_host, int zout,
+                       float* acc, float* wsum, cudaStream_t st) {
+  const int X = shape[0], Y = shape[1], Z = shape[2];
+  const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
+  const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
+  Fwd f{h, st};
+  for (int i = first; i < first + count; ++i) {
+    const PlanItem& p = plan[i];
+    const float* x = vol + (int64_t)p.start[0] * xs[1] + (int64_t)p.start[1] * xs[2] + p.start[2];
+    DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
+    cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+    double bytes;
+    if (weighted) {
+      DCL_TRY(launch_accumulate(h->probs, p.start, mode == DCL_STITCH_GAUSSIAN, acc, wsum, X, Y, zout, st));
+      bytes = (double)P3 * (4 * 4 + 2 * (4 * 4 + 4));     // read 4 probs; read+write 4 acc + wsum
+    } else {
+      DCL_TRY(launch_stitch_copy(h->probs, acc, p.box, X, Y, zout, st));
+      bytes = (double)p.box.ext[0] * p.box.ext[1] * p.box.ext[2] * 4 * 4 * 2;
+    }
+    if (h->profiling) h->prof_end(ev, 1, bytes, st);
+  }
+  return 0;
+}
+
+}  // namespace dcl
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" {
+
+DCL_API const char* dcl_last_error(void) { return g_error.c_str(); }
+DCL_API int dcl_abi_version(void) { return DCL_ABI_VERSION; }
+
+DCL_API int64_t dcl_workspace_bytes(const dcl_config* cfg) { return workspace_estimate(cfg); }
+
+DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
+  if (!cfg || !out) { set_error("dcl_create: null argument"); return DCL_ERR_ARG; }
+  if (cfg->abi_version != DCL_ABI_VERSION) { set_error("dcl_create: ABI version mismatch"); return DCL_ERR_ARG; }
+  if (cfg->precision < DCL_FP32 || cfg->precision > DCL_BF16) { set_error("dcl_create: bad precision"); return DCL_ERR_ARG; }
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    set_error("dcl_create: no CUDA device (this library has no CPU path)");
+    return DCL_ERR_CUDA;
+  }
+  dcl_handle* h = new dcl_handle();
+  h->cfg = *cfg;
+  if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; set_error("cudaGetDevice failed"); return DCL_ERR_CUDA; }
+  int rc = allocate_workspace(h);
+  if (rc != 0) { dcl_destroy(h); return rc; }
+  register_stages(h);
+  *out = h;
+  return DCL_OK;
+}
+
+DCL_API int dcl_destroy(dcl_handle* h) {
+  if (!h) return DCL_OK;
+  cudaDeviceSynchronize();
+  for (void* p : h->allocs) cudaFree(p);
+  if (h->vol_probs) cudaFree(h->vol_probs);
+  if (h->vol_wsum) cudaFree(h->vol_wsum);
+  if (h->stage_vol) cudaFree(h->stage_vol);
+  if (h->stage_probs) cudaFree(h->stage_probs);
+  if (h->stage_labels) cudaFree(h->stage_labels);
+  if (h->stage_target) cudaFree(h->stage_target);
+  delete h;
+  return DCL_OK;
+}
+
+DCL_API int dcl_weight_count(void) { return (int)catalogue().size(); }
+
+DCL_API int dcl_weight_spec(int index, char* name, int32_t cap, int64_t* numel, int32_t* aux_only) {
+  if (index < 0 || index >= (int)catalogue().size() || !name || cap <= 0) { set_error("dcl_weight_spec: bad argument"); return DCL_ERR_ARG; }
+  const WSpec& s = catalogue()[index];
+  strncpy(name, s.name.c_str(), cap - 1);
+  name[cap - 1] = 0;
+  if (numel) *numel = s.numel;
+  if (aux_only) *aux_only = s.aux ? 1 : 0;
+  return DCL_OK;
+}
+
+DCL_API int dcl_set_weight(dcl_handle* h, const char* name, const float* data, int64_t numel) {
+  if (!h || !name || !data) { set_error("dcl_set_weight: null argument"); return DCL_ERR_ARG; }
+  std::string n(name);
+  if (n.compare(0, 7, "module.") == 0) n = n.substr(7);
+  const WSpec* spec = nullptr;
+  for (const auto& s : catalogue())
+    if (s.name == n) { spec = &s; break; }
+  if (!spec) { set_error("dcl_set_weight: unknown state_dict key '" + n + "'"); return DCL_ERR_ARG; }
+  if (spec->numel != numel) {
+    set_error("dcl_set_weight: '" + n + "' expects " + std::to_string(spec->numel) + " elements, got " + std::to_string(numel));
+    return DCL_ERR_ARG;
+  }
+  std::vector<float>& v = h->host_w[n];
+  v.resize((size_t)numel);
+  DCL_CUDA_OK(cudaMemcpy(v.data(), data, (size_t)numel * 4, cudaMemcpyDefault));
+  h->ready = false;   // repacked lazily by the next compute call
+  return DCL_OK;
+}
+
+DCL_API int dcl_missing_weights(dcl_handle* h, char* first_missing, int32_t cap) {
+  if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
+  int missing = 0;
+  for (const auto& s : catalogue())
+    if (needed(h, s) && !h->host_w.count(s.name)) {
+      if (missing == 0 && first_missing && cap > 0) { strncpy(first_missing, s.name.c_str(), cap - 1); first_missing[cap - 1] = 0; }
+      ++missing;
+    }
+  return missing;
+}
+
+DCL_API int dcl_forward(dcl_handle* h, const float* x_dev, const int64_t x_strides[4], const float* keep_scale_host,
+                float* probs_dev, float* const* aux_dev, void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!x_dev || !x_strides || !probs_dev) { set_error("dcl_forward: null argument"); return DCL_ERR_ARG; }
+  if (x_strides[3] != 1) { set_error("dcl_forward: the Z stride of x must be 1"); return DCL_ERR_ARG; }
+  if (aux_dev && !h->cfg.want_aux) { set_error("dcl_forward: aux outputs need cfg.want_aux"); return DCL_ERR_ARG; }
+  int64_t before = g_launches;
+  Fwd f{h, (cudaStream_t)stream};
+  int rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
+  h->launches += g_launches - before;
+  return rc;
+}
+
+DCL_API int dcl_accumulate_patches(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                           int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host, int32_t first,
+                           int32_t count, float* acc_dev, float* wsum_dev, void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!vol_dev || !shape || !acc_dev) { set_error("dcl_accumulate_patches: null argument"); return DCL_ERR_ARG; }
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  DCL_TRY(build_plan(mode, shape, n_patches, starts_host, &plan, &zout));
+  if (first < 0 || count < 0 || first + count > (int)plan.size()) { set_error("patch range outside the plan"); return DCL_ERR_ARG; }
+  const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
+  if (weighted && !wsum_dev) { set_error("weighted modes need wsum"); return DCL_ERR_ARG; }
+  int64_t before = g_launches;
+  int rc = run_patches(h, vol_dev, shape, mode, plan, first, count, keep_scale_host, zout, acc_dev, wsum_dev,
+                       (cudaStream_t)stream);
+  h->launches += g_launches - before;
+  return rc;
+}
+
+DCL_API int dcl_finalize_labels(const float* acc_dev, const float* wsum_dev, int64_t voxels_total, int64_t v0, int64_t nvox,
+                        float* probs_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
+                        uint64_t* counts_out_dev, void* stream) {
+  if (!acc_dev || v0 < 0 || nvox < 0 || v0 + nvox > voxels_total) { set_error("dcl_finalize_labels: bad argument"); return DCL_ERR_ARG; }
+  return launch_finalize_labels(acc_dev, wsum_dev, voxels_total, v0, nvox, probs_out_dev, labels_out_dev, target_dev,
+                                (unsigned long long*)counts_out_dev, (cudaStream_t)stream);
+}
+
+DCL_API int dcl_predict_volume(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode, int32_t n_patches,
+                       const int32_t* starts_host, const float* keep_scale_host, float* probs_out_dev,
+                       uint8_t* labels_out_dev, const uint8_t* target_dev, uint64_t* counts_out_dev, void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!vol_dev || !shape) { set_error("dcl_predict_volume: null argument"); return DCL_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  DCL_TRY(build_plan(mode, shape, n_patches, starts_host, &plan, &zout));
+  const int64_t V = (int64_t)shape[0] * shape[1] * zout;
+  const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
+  DCL_TRY(grow(h, (void**)&h->vol_probs, &h->vol_probs_cap, 4 * V * 4));
+  float* acc = h->vol_probs;
+  float* wsum = nullptr;
+  if (weighted) {
+    DCL_TRY(grow(h, (void**)&h->vol_wsum, &h->vol_wsum_cap, V * 4));
+    wsum = h->vol_wsum;
+    DCL_CUDA_OK(cudaMemsetAsync(acc, 0, 4 * V * 4, st));
+    DCL_CUDA_OK(cudaMemsetAsync(wsum, 0, V * 4, st));
+  } else if (probs_out_dev) {
+    acc = probs_out_dev;   // the crop-overwrite plan covers every voxel exactly once
+  }
+  int64_t before = g_launches;
+  int rc = run_patches(h, vol_dev, shape, mode, plan, 0, (int)plan.size(), keep_scale_host, zout, acc, wsum, st);
+  if (rc == 0 && (labels_out_dev || counts_out_dev || (weighted && probs_out_dev))) {
+    if (counts_out_dev) DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, 13 * sizeof(uint64_t), st));
+    cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+    rc = launch_finalize_labels(acc, wsum, V, 0, V, weighted ? probs_out_dev : nullptr, labels_out_dev, target_dev,
+                                (unsigned long long*)counts_out_dev, st);
+    if (h->profiling)
+      h->prof_end(ev, 1, (double)V * (16 + (wsum ? 4 : 0) + (weighted && probs_out_dev ? 16 : 0) +
+                                      (labels_out_dev ? 1 : 0) + (target_dev ? 1 : 0)), st);
+  }
+  h->launches += g_launches - before;
+  return rc;
+}
+
+DCL_API int dcl_predict_volume_host(dcl_handle* h, const float* vol_host, const int32_t shape[3], int32_t mode,
+                            int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                            float* probs_out_host, uint8_t* labels_out_host, const uint8_t* target_host,
+                            uint64_t counts_out_host[13], void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!vol_host || !shape) { set_error("dcl_predict_volume_host: null argument"); return DCL_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool ref = mode == DCL_STITCH_REFERENCE || mode == DCL_STITCH_ALIGNED;
+  const int zout = ref ? 155 : shape[2];
+  const int64_t vin = (int64_t)shape[0] * shape[1] * shape[2], V = (int64_t)shape[0] * shape[1] * zout;
+  DCL_TRY(grow(h, (void**)&h->stage_vol, &h->stage_vol_cap, 4 * vin * 4));
+  if (h->stage_lab_cap < V) {
+    if (h->stage_labels) cudaFree(h->stage_labels);
+    if (h->stage_target) cudaFree(h->stage_target);
+    h->stage_labels = h->stage_target = nullptr; h->stage_lab_cap = 0;
+    DCL_CUDA_OK(cudaMalloc((void**)&h->stage_labels, (size_t)V));
+    DCL_CUDA_OK(cudaMalloc((void**)&h->stage_target, (size_t)V));
+    h->stage_lab_cap = V;
+  }
+  DCL_CUDA_OK(cudaMemcpyAsync(h->stage_vol, vol_host, 4 * vin * 4, cudaMemcpyHostToDevice, st));
+  if (target_host) DCL_CUDA_OK(cudaMemcpyAsync(h->stage_target, target_host, (size_t)V, cudaMemcpyHostToDevice, st));
+  if (probs_out_host) DCL_TRY(grow(h, (void**)&h->stage_probs, &h->stage_probs_cap, 4 * V * 4));
+  DCL_TRY(dcl_predict_volume(h, h->stage_vol, shape, mode, n_patches, starts_host, keep_scale_host,
+                             probs_out_host ? h->stage_probs : nullptr, h->stage_labels, target_host ? h->stage_target : nullptr,
+                             counts_out_host ? (uint64_t*)h->counts_dev : nullptr, stream));
+  if (labels_out_host) DCL_CUDA_OK(cudaMemcpyAsync(labels_out_host, h->stage_labels, (size_t)V, cudaMemcpyDeviceToHost, st));
+  if (counts_out_host) DCL_CUDA_OK(cudaMemcpyAsync(counts_out_host, h->counts_dev, 13 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  if (probs_out_host) DCL_CUDA_OK(cudaMemcpyAsync(probs_out_host, h->stage_probs, 4 * V * 4, cudaMemcpyDeviceToHost, st));
+  DCL_CUDA_OK(cudaStreamSynchronize(st));
+  return DCL_OK;
+}
+
+DCL_API int64_t dcl_read_stage(dcl_handle* h, const char* stage, float* out_dev, int64_t cap, void* stream) {
+  if (!h || !stage) { set_error("dcl_read_stage: null argument"); return DCL_ERR_ARG; }
+  if (!h->cfg.keep_stages) { set_error("dcl_read_stage: handle was created without keep_stages"); return DCL_ERR_STATE; }
+  auto it = h->stages.find(stage);
+  if (it == h->stages.end()) { set_error(std::string("dcl_read_stage: unknown stage '") + stage + "'"); return DCL_ERR_ARG; }
+  int64_t n = it->second.second;
+  if (out_dev) {
+    if (cap < n) { set_error("dcl_read_stage: output buffer too small"); return DCL_ERR_ARG; }
+    DCL_CUDA_OK(cudaMemcpyAsync(out_dev, it->second.first, n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  }
+  return n;
+}
+
+DCL_API int dcl_read_topk(dcl_handle* h, int32_t* out_host, void* stream) {
+  if (!h || !out_host) { set_error("dcl_read_topk: null argument"); return DCL_ERR_ARG; }
+  DCL_CUDA_OK(cudaMemcpyAsync(out_host, h->topk, 13 * 128 * sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  DCL_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  return DCL_OK;
+}
+
+DCL_API DCL_API int dcl_profile_enable(dcl_handle* h, int32_t on) {
+  if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
+  h->profiling = on != 0;
+  return DCL_OK;
+}
+
+DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64_t* launches, double* work_total) {
+  if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
+  double ms = 0, work = 0;
+  int64_t n = 0;
+  std::vector<dcl_handle::ProfRec> keep;
+  for (auto& r : h->prof) {
+    if (r.cls != cls) { keep.push_back(r); continue; }
+    DCL_CUDA_OK(cudaEventSynchronize(r.b));
+    float t = 0.f;
+    DCL_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; work += r.work; ++n;
+    h->event_pool.push_back(r.a);
+    h->event_pool.push_back(r.b);
+  }
+  h->prof.swap(keep);
+  if (ms_total) *ms_total = ms;
+  if (launches) *launches = n;
+  if (work_total) *work_total = work;
+  return DCL_OK;
+}
+
+int64_t dcl_launch_count(const dcl_handle* h) { return h ? h->launches : 0; }
+
+DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream) {
+  if (!x || !mean || !rstd || channels <= 0 || channels > 512) { set_error("dcl_op_instnorm_stats: bad argument"); return DCL_ERR_ARG; }
+  double* accum = nullptr;
+  DCL_CUDA_OK(cudaMalloc((void**)&accum, 2 * 512 * sizeof(double)));
+  cudaMemsetAsync(accum, 0, 2 * 512 * sizeof(double), (cudaStream_t)stream);
+  int rc = launch_instnorm_stats(x, channels, spatial, accum, mean, rstd, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  cudaFree(accum);
+  return rc;
+}
+
+DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32_t c1, const int32_t in_dhw[3], const float* w,
+                     const float* bias, int32_t cout, int32_t stride, const float* norm_mean, const float* norm_rstd,
+                     int32_t act, const float* residual, float* y, int32_t impl, void* stream) {
+  if (!x0 || !w || !y || !in_dhw || cout <= 0 || c0 <= 0) { set_error("dcl_op_conv3d_k3: bad argument"); return DCL_ERR_ARG; }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cin = c0 + c1;
+  std::vector<float> wh((size_t)cout * cin * 27);
+  DCL_CUDA_OK(cudaMemcpy(wh.data(), w, wh.size() * 4, cudaMemcpyDefault));
+  const int64_t sp = (int64_t)in_dhw[0] * in_dhw[1] * in_dhw[2];
+  ConvSrc s{x0, x1, c0, c1, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], norm_mean, norm_rstd, act};
+  ConvDst d{y, bias, nullptr, residual};
+  int rc;
+  if (impl == 0) {
+    const int cout_pad = (cout + 15) / 16 * 16;
+    std::vector<float> packed((size_t)cin * 27 * cout_pad, 0.f);
+    for (int co = 0; co < cout; ++co)
+      for (int ci = 0; ci < cin; ++ci)
+        for (int t = 0; t < 27; ++t) packed[((size_t)ci * 27 + t) * cout_pad + co] = wh[((size_t)co * cin + ci) * 27 + t];
+    float* wp = nullptr;
+    DCL_CUDA_OK(cudaMalloc((void**)&wp, packed.size() * 4));
+    DCL_CUDA_OK(cudaMemcpy(wp, packed.data(), packed.size() * 4, cudaMemcpyHostToDevice));
+    rc = launch_conv3d_k3(s, d, wp, cout, cout_pad, in_dhw[0], in_dhw[1], in_dhw[2], stride, st);
+    cudaStreamSynchronize(st);
+    cudaFree(wp);
+  } else {
+    if (in_dhw[0] != in_dhw[1] || in_dhw[1] != in_dhw[2] || x1 != nullptr ||
+        !tc_conv_supported(cin, cout, in_dhw[0], stride)) {
+      set_error("dcl_op_conv3d_k3: shape not supported by the tensor-core kernel");
+      return DCL_ERR_ARG;
+    }
+    TcWeights tw;
+    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, &tw));
+    rc = launch_conv3d_k3_tc(s, d, tw, cout, in_dhw[0], impl == 1, st);
+    cudaStreamSynchronize(st);
+    cudaFree(tw.dev);
+  }
+  return rc;
+}
+
+}  // extern "C"

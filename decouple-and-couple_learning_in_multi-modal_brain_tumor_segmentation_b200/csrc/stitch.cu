@@ -1,0 +1,183 @@
+// HBM-bound tail of the sliding window: crop-and-overwrite stitch (predict_overlap.py:49-56), weighted
+// overlap accumulate (extension modes), and the fused normalise + arg-max + label histogram + Dice
+// counters kernel (predict_overlap.py:141-153, utils/tools.py:89-109).
+#include "common.cuh"
+
+namespace dcl {
+
+constexpr int P = 128;
+constexpr int64_t P3 = (int64_t)P * P * P;
+
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+
+// out[c, dst+e] = probs[c, src+e] for e in the box.  Thread = one (x,y,z) of the box, all 4 classes;
+// z is contiguous in both tensors so warps read and write full sectors.
+__global__ void __launch_bounds__(256)
+stitch_copy_kernel(const float* __restrict__ probs, float* __restrict__ out, StitchBox box, int Y, int Zout,
+                   int64_t out_plane) {
+  const int64_t n = (int64_t)box.ext[0] * box.ext[1] * box.ext[2];
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= n) return;
+  const int z = e % box.ext[2];
+  const int y = (e / box.ext[2]) % box.ext[1];
+  const int x = e / ((int64_t)box.ext[2] * box.ext[1]);
+  const int64_t s = ((int64_t)(box.src[0] + x) * P + (box.src[1] + y)) * P + box.src[2] + z;
+  const int64_t d = ((int64_t)(box.dst[0] + x) * Y + (box.dst[1] + y)) * Zout + box.dst[2] + z;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) out[c * out_plane + d] = __ldg(probs + c * P3 + s);
+}
+
+int launch_stitch_copy(const float* probs, float* out, const StitchBox& box, int X, int Y, int Zout, cudaStream_t st) {
+  int64_t n = (int64_t)box.ext[0] * box.ext[1] * box.ext[2];
+  if (n <= 0) return 0;
+  stitch_copy_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(probs, out, box, Y, Zout, (int64_t)X * Y * Zout);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// acc[c, start+e] += w(e) * probs[c, e];  wsum[start+e] += w(e).  Patches of one volume are issued in
+// order on one stream, so the read-modify-write needs no atomics.
+__device__ __forceinline__ float blend_w1(int i, int gaussian) {
+  if (!gaussian) return 1.f;
+  float t = ((float)i - 63.5f) / 16.f;      // centre (P-1)/2, sigma P/8
+  return expf(-0.5f * (t * t));
+}
+
+__global__ void __launch_bounds__(256)
+accumulate_kernel(const float* __restrict__ probs, int sx, int sy, int sz, int gaussian, float* __restrict__ acc,
+                  float* __restrict__ wsum, int Y, int Z, int64_t plane) {
+  const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (e >= P3) return;
+  const int z = e % P;
+  const int y = (e / P) % P;
+  const int x = e / (P * P);
+  const float w = (blend_w1(x, gaussian) * blend_w1(y, gaussian)) * blend_w1(z, gaussian);
+  const int64_t d = ((int64_t)(sx + x) * Y + (sy + y)) * Z + sz + z;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c * plane + d] += w * __ldg(probs + c * P3 + e);
+  wsum[d] += w;
+}
+
+int launch_accumulate(const float* probs, const int start[3], int gaussian, float* acc, float* wsum, int X, int Y,
+                      int Z, cudaStream_t st) {
+  accumulate_kernel<<<(unsigned)((P3 + 255) / 256), 256, 0, st>>>(probs, start[0], start[1], start[2], gaussian, acc,
+                                                                 wsum, Y, Z, (int64_t)X * Y * Z);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// finalize: p_c = acc_c / wsum (or acc_c), label = argmax_c p_c (first maximum wins, as numpy),
+// 13 counters: histogram[4], then (|o|,|t|,|o&t|) for WT (>0), TC ({1,3}), ET (==3).
+// Persistent grid-stride kernel, 4 voxels per thread per step: four independent 128-bit streaming loads
+// (one per class plane) + one 32-bit label store = 17 B / voxel of algorithmic traffic.
+// ---------------------------------------------------------------------------------------------
+struct LabelCounts {
+  unsigned v[13];
+};
+
+__device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
+  int l = 0;
+  float m = a;
+  if (b > m) { m = b; l = 1; }
+  if (c > m) { m = c; l = 2; }
+  if (d > m) { l = 3; }
+  return l;
+}
+
+__device__ __forceinline__ void count_label(LabelCounts& k, int l, int t, bool has_target) {
+  k.v[l] += 1;
+  const bool owt = l > 0, otc = (l == 1) | (l == 3), oet = l == 3;
+  k.v[4] += owt; k.v[7] += otc; k.v[10] += oet;
+  if (has_target) {
+    const bool twt = t > 0, ttc = (t == 1) | (t == 3), tet = t == 3;
+    k.v[5] += twt; k.v[6] += owt & twt;
+    k.v[8] += ttc; k.v[9] += otc & ttc;
+    k.v[11] += tet; k.v[12] += oet & tet;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_labels_kernel(const float* __restrict__ acc, const float* __restrict__ wsum, int64_t total, int64_t v0,
+                       int64_t nvox, float* __restrict__ probs_out, uint8_t* __restrict__ labels,
+                       const uint8_t* __restrict__ target, unsigned long long* __restrict__ counts) {
+  LabelCounts k;
+#pragma unroll
+  for (int i = 0; i < 13; ++i) k.v[i] = 0;
+  const bool vec_ok = ((total | v0) & 3) == 0;
+  const int64_t nvec = vec_ok ? nvox / 4 : 0;
+  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nvec; g += (int64_t)gridDim.x * 256) {
+    const int64_t v = v0 + g * 4;
+    float4 a = ld_stream4(acc + v), b = ld_stream4(acc + total + v), c = ld_stream4(acc + 2 * total + v),
+           d = ld_stream4(acc + 3 * total + v);
+    if (wsum) {
+      float4 w = ld_stream4(wsum + v);
+      a.x /= w.x; b.x /= w.x; c.x /= w.x; d.x /= w.x;
+      a.y /= w.y; b.y /= w.y; c.y /= w.y; d.y /= w.y;
+      a.z /= w.z; b.z /= w.z; c.z /= w.z; d.z /= w.z;
+      a.w /= w.w; b.w /= w.w; c.w /= w.w; d.w /= w.w;
+    }
+    if (probs_out) {
+      *reinterpret_cast<float4*>(probs_out + v) = a;
+      *reinterpret_cast<float4*>(probs_out + total + v) = b;
+      *reinterpret_cast<float4*>(probs_out + 2 * total + v) = c;
+      *reinterpret_cast<float4*>(probs_out + 3 * total + v) = d;
+    }
+    const int l0 = argmax4(a.x, b.x, c.x, d.x), l1 = argmax4(a.y, b.y, c.y, d.y), l2 = argmax4(a.z, b.z, c.z, d.z),
+              l3 = argmax4(a.w, b.w, c.w, d.w);
+    if (labels) *reinterpret_cast<uchar4*>(labels + v) = make_uchar4(l0, l1, l2, l3);
+    if (counts) {
+      uchar4 t = target ? *reinterpret_cast<const uchar4*>(target + v) : make_uchar4(0, 0, 0, 0);
+      count_label(k, l0, t.x, target != nullptr);
+      count_label(k, l1, t.y, target != nullptr);
+      count_label(k, l2, t.z, target != nullptr);
+      count_label(k, l3, t.w, target != nullptr);
+    }
+  }
+  // scalar tail (and the whole range when the slab is not 4-aligned)
+  for (int64_t g = nvec * 4 + (int64_t)blockIdx.x * 256 + threadIdx.x; g < nvox; g += (int64_t)gridDim.x * 256) {
+    const int64_t v = v0 + g;
+    float a = acc[v], b = acc[total + v], c = acc[2 * total + v], d = acc[3 * total + v];
+    if (wsum) { float w = wsum[v]; a /= w; b /= w; c /= w; d /= w; }
+    if (probs_out) { probs_out[v] = a; probs_out[total + v] = b; probs_out[2 * total + v] = c; probs_out[3 * total + v] = d; }
+    const int l = argmax4(a, b, c, d);
+    if (labels) labels[v] = (uint8_t)l;
+    if (counts) count_label(k, l, target ? target[v] : 0, target != nullptr);
+  }
+  if (counts) {
+    __shared__ unsigned s_cnt[13];
+    if (threadIdx.x < 13) s_cnt[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      unsigned r = __reduce_add_sync(0xffffffffu, k.v[i]);
+      if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_cnt[i], r);
+    }
+    __syncthreads();
+    if (threadIdx.x < 13 && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+  }
+}
+
+int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, int64_t v0, int64_t nvox,
+                           float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                           cudaStream_t st) {
+  if (nvox <= 0) return 0;
+  int64_t work = (nvox + 3) / 4;
+  int64_t blocks = (work + 255) / 256;
+  const int64_t persistent = 148 * 8;   // one wave of 8 resident CTAs per SM
+  if (blocks > persistent) blocks = persistent;
+  finalize_labels_kernel<<<(unsigned)blocks, 256, 0, st>>>(acc, wsum, total, v0, nvox, probs_out, labels, target,
+                                                          counts);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dcl

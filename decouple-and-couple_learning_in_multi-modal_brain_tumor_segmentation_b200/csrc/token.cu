@@ -1,0 +1,308 @@
+// Token path of the region couplers: score + top-k selection, sequence assembly, LayerNorm, linear
+// layers, 8-head attention over 129-token sequences, row scatter.  All fp32 (the discrete
+// top-k makes low precision fragile here).
+#include <float.h>
+#include "common.cuh"
+
+namespace dcl {
+
+__device__ __forceinline__ float warp_sum_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_t(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// score[i] = <token, feats[i]>  (cls_wise_former.py:345: e_token @ feats^T).  One warp per row.
+__global__ void __launch_bounds__(256)
+score_kernel(const float* __restrict__ token, const float* __restrict__ feats, int n_tokens,
+             float* __restrict__ score) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n_tokens) return;
+  const float4* f = reinterpret_cast<const float4*>(feats + (int64_t)row * TOKEN_DIM);
+  const float4* t = reinterpret_cast<const float4*>(token);
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < TOKEN_DIM / 128; ++j) {
+    float4 a = __ldg(f + lane + 32 * j), b = __ldg(t + lane + 32 * j);
+    s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+  }
+  s = warp_sum_t(s);
+  if (lane == 0) score[row] = s;
+}
+
+// topk(128, largest, sorted) of up to 2048 scores (cls_wise_former.py:346): bitonic sort of
+// (score desc, index asc) pairs in shared memory by one 1024-thread block.
+__global__ void __launch_bounds__(1024)
+topk_kernel(const float* __restrict__ score, int n, int* __restrict__ idx_out) {
+  __shared__ float key[2048];
+  __shared__ int val[2048];
+  for (int i = threadIdx.x; i < 2048; i += 1024) {
+    key[i] = i < n ? score[i] : -FLT_MAX;
+    val[i] = i < n ? i : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 2; k <= 2048; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < 2048; i += 1024) {
+        int p = i ^ j;
+        if (p > i) {
+          float ka = key[i], kb = key[p];
+          int va = val[i], vb = val[p];
+          bool a_first = (ka > kb) || (ka == kb && va < vb);   // a precedes b in the final order
+          bool descending_block = ((i & k) == 0);
+          if (a_first != descending_block) { key[i] = kb; key[p] = ka; val[i] = vb; val[p] = va; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x < TOP_NUM) idx_out[threadIdx.x] = val[threadIdx.x];
+}
+
+int launch_select_topk(const float* token, const float* feats, int n_tokens, float* score_scratch, int* idx_out,
+                       cudaStream_t st) {
+  if (n_tokens > 2048 || n_tokens < TOP_NUM) { set_error("select_topk: 128 <= n_tokens <= 2048 required"); return -1; }
+  score_kernel<<<(n_tokens + 7) / 8, 256, 0, st>>>(token, feats, n_tokens, score_scratch);
+  topk_kernel<<<1, 1024, 0, st>>>(score_scratch, n_tokens, idx_out);
+  g_launches += 2;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// seq[0] = class token, seq[1+i] = feats[idx[i]] + pe_row  (index_select + positional encoding + cat,
+// cls_wise_former.py:347-350; PositionalEncoding.py:20-22 adds row 0 of `pe` to every token).
+__global__ void __launch_bounds__(128)
+build_sequence_kernel(const float* __restrict__ class_token, const float* __restrict__ feats,
+                      const int* __restrict__ idx, const float* __restrict__ pe_row, float* __restrict__ seq) {
+  const int r = blockIdx.x;
+  float4 v;
+  if (r == 0) {
+    v = __ldg(reinterpret_cast<const float4*>(class_token) + threadIdx.x);
+  } else {
+    v = __ldg(reinterpret_cast<const float4*>(feats + (int64_t)idx[r - 1] * TOKEN_DIM) + threadIdx.x);
+    float4 p = __ldg(reinterpret_cast<const float4*>(pe_row) + threadIdx.x);
+    v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w;
+  }
+  reinterpret_cast<float4*>(seq + (int64_t)r * TOKEN_DIM)[threadIdx.x] = v;
+}
+
+int launch_build_sequence(const float* class_token, const float* feats, const int* idx, const float* pe_row,
+                          float* seq, cudaStream_t st) {
+  build_sequence_kernel<<<SEQ, 128, 0, st>>>(class_token, feats, idx, pe_row, seq);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// nn.LayerNorm(512), eps 1e-5, one warp per row, two-pass variance in registers.
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 float* __restrict__ y, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * TOKEN_DIM);
+  float4 v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { v[j] = __ldg(xr + lane + 32 * j); s += (v[j].x + v[j].y) + (v[j].z + v[j].w); }
+  const float mean = warp_sum_t(s) * (1.f / TOKEN_DIM);
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum_t(q) * (1.f / TOKEN_DIM) + 1e-5f);
+  float4* yr = reinterpret_cast<float4*>(y + (int64_t)row * TOKEN_DIM);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * j);
+    float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * j);
+    float4 o;
+    o.x = (v[j].x - mean) * rstd * g.x + b.x;
+    o.y = (v[j].y - mean) * rstd * g.y + b.y;
+    o.z = (v[j].z - mean) * rstd * g.z + b.z;
+    o.w = (v[j].w - mean) * rstd * g.w + b.w;
+    yr[lane + 32 * j] = o;
+  }
+}
+
+int launch_layernorm(const float* x, const float* gamma, const float* beta, float* y, int rows, cudaStream_t st) {
+  layernorm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, y, rows);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// y = x W^T + b (+GELU erf) (+residual).  32x64 output tile, BK = 32, 256 threads x (2 x 4) outputs.
+constexpr int LBM = 32, LBN = 64, LBK = 32;
+
+__global__ void __launch_bounds__(256)
+linear_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+              const float* __restrict__ residual, float* __restrict__ y, int m, int n, int k, int gelu) {
+  __shared__ float xs[LBK][LBM + 1];
+  __shared__ __align__(16) float ws[LBK][LBN + 4];
+  const int m0 = blockIdx.y * LBM, n0 = blockIdx.x * LBN;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int k0 = 0; k0 < k; k0 += LBK) {
+    for (int e = threadIdx.x; e < LBM * LBK; e += 256) {
+      int c = e % LBK, r = e / LBK;
+      xs[c][r] = (m0 + r < m && k0 + c < k) ? __ldg(x + (int64_t)(m0 + r) * k + k0 + c) : 0.f;
+    }
+    for (int e = threadIdx.x; e < LBN * LBK; e += 256) {
+      int c = e % LBK, r = e / LBK;
+      ws[c][r] = (n0 + r < n && k0 + c < k) ? __ldg(w + (int64_t)(n0 + r) * k + k0 + c) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < LBK; ++kk) {
+      float a0 = xs[kk][ty * 2], a1 = xs[kk][ty * 2 + 1];
+      float4 b = *reinterpret_cast<const float4*>(&ws[kk][tx * 4]);
+      acc[0][0] = fmaf(a0, b.x, acc[0][0]); acc[0][1] = fmaf(a0, b.y, acc[0][1]);
+      acc[0][2] = fmaf(a0, b.z, acc[0][2]); acc[0][3] = fmaf(a0, b.w, acc[0][3]);
+      acc[1][0] = fmaf(a1, b.x, acc[1][0]); acc[1][1] = fmaf(a1, b.y, acc[1][1]);
+      acc[1][2] = fmaf(a1, b.z, acc[1][2]); acc[1][3] = fmaf(a1, b.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    int r = m0 + ty * 2 + i;
+    if (r >= m) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = n0 + tx * 4 + j;
+      if (c >= n) continue;
+      float v = acc[i][j] + (bias ? __ldg(bias + c) : 0.f);
+      if (gelu) v = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+      if (residual) v += __ldg(residual + (int64_t)r * n + c);
+      y[(int64_t)r * n + c] = v;
+    }
+  }
+}
+
+int launch_linear(const float* x, const float* w, const float* bias, const float* residual, float* y, int m, int n,
+                  int k, bool gelu, cudaStream_t st) {
+  dim3 grid((n + LBN - 1) / LBN, (m + LBM - 1) / LBM);
+  linear_kernel<<<grid, 256, 0, st>>>(x, w, bias, residual, y, m, n, k, gelu ? 1 : 0);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// DualSelfAttention core (SelfAttention.py:94-99): softmax(q k^T / 8) v per head.
+// Block = (16-query chunk, head), 4 warps x 4 query rows; K and V of the head live in shared memory.
+constexpr int ATT_HD = 64;
+constexpr int ATT_QCHUNK = 16;
+constexpr int ATT_MAXK = 160;
+
+__global__ void __launch_bounds__(128)
+attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int mq, int mk) {
+  extern __shared__ float sm[];
+  float* ks = sm;                          // [mk][65]
+  float* vs = ks + mk * (ATT_HD + 1);      // [mk][64]
+  float* qs = vs + mk * ATT_HD;            // [4 warps][64]
+  float* ps = qs + 4 * ATT_HD;             // [4 warps][ATT_MAXK]
+  const int head = blockIdx.y;
+  for (int e = threadIdx.x; e < mk * ATT_HD; e += 128) {
+    int d = e % ATT_HD, j = e / ATT_HD;
+    ks[j * (ATT_HD + 1) + d] = __ldg(kv + (int64_t)j * 1024 + head * ATT_HD + d);
+    vs[j * ATT_HD + d] = __ldg(kv + (int64_t)j * 1024 + 512 + head * ATT_HD + d);
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* qw = qs + warp * ATT_HD;
+  float* pw = ps + warp * ATT_MAXK;
+  for (int r = 0; r < ATT_QCHUNK / 4; ++r) {
+    const int row = blockIdx.x * ATT_QCHUNK + warp * (ATT_QCHUNK / 4) + r;
+    if (row >= mq) break;                       // warp-uniform
+    qw[lane] = __ldg(q + (int64_t)row * TOKEN_DIM + head * ATT_HD + lane);
+    qw[lane + 32] = __ldg(q + (int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32);
+    __syncwarp();
+    float mx = -FLT_MAX;
+    for (int j = lane; j < mk; j += 32) {
+      const float* kr = ks + j * (ATT_HD + 1);
+      float s = 0.f;
+#pragma unroll 16
+      for (int d = 0; d < ATT_HD; ++d) s = fmaf(qw[d], kr[d], s);
+      s *= 0.125f;                              // head_dim ** -0.5
+      pw[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = warp_max_t(mx);
+    float sum = 0.f;
+    for (int j = lane; j < mk; j += 32) { float e = expf(pw[j] - mx); pw[j] = e; sum += e; }
+    sum = warp_sum_t(sum);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < mk; ++j) {
+      float p = pw[j];
+      o0 = fmaf(p, vs[j * ATT_HD + lane], o0);
+      o1 = fmaf(p, vs[j * ATT_HD + lane + 32], o1);
+    }
+    out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o0 * inv;
+    out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32] = o1 * inv;
+    __syncwarp();
+  }
+}
+
+int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st) {
+  if (mk > ATT_MAXK) { set_error("attention: at most 160 keys"); return -1; }
+  size_t smem = (size_t)(mk * (ATT_HD + 1) + mk * ATT_HD + 4 * ATT_HD + 4 * ATT_MAXK) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    DCL_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  attention_kernel<<<dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8), 128, smem, st>>>(q, kv, out, mq, mk);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// feats[idx[i]] = rows[i]: the whole-row scatter_ of cls_wise_former.py:467 (fix_index.txt rows are [k]*512).
+__global__ void __launch_bounds__(128)
+scatter_rows_kernel(float* __restrict__ feats, const int* __restrict__ idx, const float* __restrict__ rows,
+                    int row_stride) {
+  const int i = blockIdx.x;
+  float4 v = __ldg(reinterpret_cast<const float4*>(rows + (int64_t)i * row_stride) + threadIdx.x);
+  reinterpret_cast<float4*>(feats + (int64_t)idx[i] * TOKEN_DIM)[threadIdx.x] = v;
+}
+
+int launch_scatter_rows(float* feats, const int* idx, const float* rows, int row_stride, cudaStream_t st) {
+  scatter_rows_kernel<<<TOP_NUM, 128, 0, st>>>(feats, idx, rows, row_stride);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+            float* __restrict__ y, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n4) return;
+  float4 u = __ldg(reinterpret_cast<const float4*>(a) + i);
+  float4 v = __ldg(reinterpret_cast<const float4*>(b) + i);
+  float4 w = __ldg(reinterpret_cast<const float4*>(c) + i);
+  reinterpret_cast<float4*>(y)[i] = make_float4((u.x + v.x) + w.x, (u.y + v.y) + w.y, (u.z + v.z) + w.z,
+                                                (u.w + v.w) + w.w);
+}
+
+int launch_add3(const float* a, const float* b, const float* c, float* y, int64_t n, cudaStream_t st) {
+  if (n % 4 != 0) { set_error("add3: n must be a multiple of 4"); return -1; }
+  add3_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(a, b, c, y, n / 4);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dcl

@@ -1,0 +1,174 @@
+/* dcl_b200.h -- C ABI of the B200-native sliding-window ClsWiseFormer inference path.
+ *
+ * The reference (mathwrx/Decouple-and-Couple_Learning_in_Multi-Modal_Brain_Tumor_Segmentation)
+ * has no FFI: its boundary is two Python call signatures and a checkpoint schema
+ * (SURVEY.md 8b).  Every entry point below names the reference call it replaces.  All
+ * functions return 0 on success and a negative dcl_status otherwise; the message of the last
+ * failure on the calling thread is returned by dcl_last_error().  No entry point falls back
+ * to a CPU implementation: without a CUDA device every compute call fails with
+ * DCL_ERR_CUDA.
+ *
+ * Conventions
+ *   - tensors are fp32, NCDHW with the reference's axis order (N, C, X=240, Y=240, Z=155);
+ *     Z is the contiguous axis (predict_overlap.py:34-41 slices it last)
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
+ *   - a handle is bound to the CUDA device that was current in dcl_create and is not
+ *     thread safe; use one handle per stream
+ *   - pointers named *_dev are device pointers, *_host host pointers; the caller owns all of them
+ */
+#ifndef DCL_B200_H
+#define DCL_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define DCL_API __attribute__((visibility("default")))
+#else
+#define DCL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCL_ABI_VERSION 1
+#define DCL_PATCH 128            /* crop_H/W/D of test_overlap.py:48-52, img_dim of cls_wise_former.py:759 */
+#define DCL_NUM_CLASSES 4        /* cls_wise_former.py:760 */
+#define DCL_NUM_MODALITIES 4     /* cls_wise_former.py:762 */
+#define DCL_KEEP_CHANNELS 16     /* InitConv out_channels, Unet_skipconnection.py:23 */
+#define DCL_NUM_AUX 12           /* 4 heads x 3 regions, cls_wise_former.py:226-230 */
+
+typedef enum dcl_status {
+  DCL_OK = 0,
+  DCL_ERR_ARG = -1,        /* bad argument (shape, NULL pointer, unknown name) */
+  DCL_ERR_CUDA = -2,       /* CUDA runtime / launch failure, or no device */
+  DCL_ERR_WEIGHTS = -3,    /* forward called before every required tensor was set */
+  DCL_ERR_STATE = -4       /* handle used on the wrong device / after destroy */
+} dcl_status;
+
+/* Arithmetic mode of the convolution / GEMM kernels. */
+typedef enum dcl_precision {
+  DCL_FP32 = 0,            /* fp32 FFMA kernels: the parity mode (1e-3 rel. to the reference) */
+  DCL_BF16X3 = 1,          /* tcgen05 bf16 MMA on split operands (hi+lo), fp32 accumulate: fp32-class accuracy */
+  DCL_BF16 = 2             /* tcgen05 bf16 MMA, fp32 accumulate (2e-2 rel.) */
+} dcl_precision;
+
+/* Stitch / blend rule applied to the per-patch class probabilities. */
+typedef enum dcl_stitch_mode {
+  DCL_STITCH_REFERENCE = 0, /* predict_overlap.py:49-56 crop-and-overwrite, bug compatible (z tail shifted by 5) */
+  DCL_STITCH_ALIGNED = 1,   /* same 8 corners, z tail taken from the aligned slice 101:128 */
+  DCL_STITCH_UNIFORM = 2,   /* extension: sum(w*p)/sum(w), w = 1 (any patch list) */
+  DCL_STITCH_GAUSSIAN = 3   /* extension: separable gaussian w, sigma = patch/8 */
+} dcl_stitch_mode;
+
+typedef struct dcl_config {
+  int32_t abi_version;      /* DCL_ABI_VERSION */
+  int32_t precision;        /* dcl_precision */
+  int32_t want_aux;         /* 1: also run the 4 auxiliary heads (SuperviseLabel.py, EdgeSuperviseLabel.py) */
+  int32_t keep_stages;      /* 1: keep named intermediate tensors readable through dcl_read_stage */
+  int32_t reserved[12];
+} dcl_config;
+
+typedef struct dcl_handle dcl_handle;
+
+DCL_API const char* dcl_last_error(void);
+DCL_API int dcl_abi_version(void);
+
+/* Replaces ClsWiseFormer.__init__ / get_cls_wise_former (cls_wise_former.py:43-278, :757-780):
+ * allocates device workspace for one 128^3 patch.  fix_index.txt (:275-278) is not needed. */
+DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out);
+DCL_API int dcl_destroy(dcl_handle* h);
+/* Bytes of device memory a handle allocates for `cfg` (dcl_workspace_bytes). */
+DCL_API int64_t dcl_workspace_bytes(const dcl_config* cfg);
+
+/* Replaces model.load_state_dict(checkpoint['state_dict']) (test_overlap.py:85-86).  `name` is
+ * the reference state_dict key (an optional leading "module." is ignored); `data` is fp32,
+ * host or device memory (detected), `numel` elements in the reference's layout.  Unknown names
+ * and wrong sizes are errors.  Weights are repacked into kernel layouts once. */
+DCL_API int dcl_set_weight(dcl_handle* h, const char* name, const float* data, int64_t numel);
+/* The weight catalogue (pure host code, needs no device): the reference state_dict keys this library
+ * accepts, their element counts, and whether they belong only to the auxiliary heads. */
+DCL_API int dcl_weight_count(void);
+DCL_API int dcl_weight_spec(int index, char* name, int32_t cap, int64_t* numel, int32_t* aux_only);
+/* Number of state_dict tensors still missing for the configured path (0 = ready). */
+DCL_API int dcl_missing_weights(dcl_handle* h, char* first_missing, int32_t cap);
+
+/* Replaces ClsWiseFormer.forward(x, missing_modal) (cls_wise_former.py:585-592) for N = 1.
+ *   x_dev        : first element of a (4,128,128,128) view; x_strides = element strides of
+ *                  (C, X, Y, Z); the Z stride must be 1 (views of a volume are accepted as is,
+ *                  predict_overlap.py:34-41)
+ *   keep_scale_host : 16 floats, the dropout3d channel scale (0 or 1/0.8) of
+ *                  Unet_skipconnection.py:31; NULL = deterministic (all ones)
+ *   probs_dev    : (4,128,128,128) dense softmax probabilities (forward()[0])
+ *   aux_dev      : NULL, or 12 dense (2,128,128,128) outputs ordered
+ *                  supervise{01,02,04}, edge{01,02,04}, mid_semantic{..}, mid_edge{..}
+ *                  (forward()[1..4]); requires cfg.want_aux */
+DCL_API int dcl_forward(dcl_handle* h, const float* x_dev, const int64_t x_strides[4],
+                const float* keep_scale_host, float* probs_dev, float* const* aux_dev, void* stream);
+
+/* Replaces tailor_and_concat (predict_overlap.py:31-58) plus the label tail of validate_softmax
+ * (:141-153) and utils/tools.py:89-109.
+ *   vol_dev      : (4, X, Y, Z) dense fp32 volume, Z >= 155 for the reference modes
+ *   starts_host  : n_patches x 3 patch origins (x,y,z); ignored (may be NULL) for
+ *                  REFERENCE/ALIGNED, which use the 8 fixed corners
+ *   keep_scale_host : n_patches x 16 or NULL
+ *   probs_out_dev: NULL or (4, X, Y, Zout) stitched probabilities (Zout = 155 in reference
+ *                  modes = y[..., :155], else Z)
+ *   labels_out_dev: NULL or (X, Y, Zout) uint8 arg-max labels
+ *   target_dev   : NULL or (X, Y, Zout) uint8 ground truth with label 4 already mapped to 3
+ *   counts_out_dev: NULL or 13 uint64: label histogram [0..3], then (|o|,|t|,|o&t|) for WT, TC, ET */
+DCL_API int dcl_predict_volume(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                       int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                       float* probs_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
+                       uint64_t* counts_out_dev, void* stream);
+
+/* Same call with HOST buffers (pinned or pageable): uploads the volume (and target), runs the
+ * path, downloads labels (+ probabilities if requested) and the 13 counters.  This is the call
+ * the reference's validate_softmax loop maps to (x.cuda() at :133 ... .cpu() at :141). */
+DCL_API int dcl_predict_volume_host(dcl_handle* h, const float* vol_host, const int32_t shape[3], int32_t mode,
+                            int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                            float* probs_out_host, uint8_t* labels_out_host, const uint8_t* target_host,
+                            uint64_t counts_out_host[13], void* stream);
+
+/* ---- multi-GPU: a rank runs only patches [first, first+count) of the plan into its
+ * private fp32 accumulator (acc: 4 x X x Y x Zout weighted sums, wsum: X x Y x Zout); the
+ * accumulators are then summed across ranks by the caller (NCCL reduce-scatter / all-reduce
+ * through torch.distributed) and finalised into labels. */
+DCL_API int dcl_accumulate_patches(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                           int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                           int32_t first, int32_t count, float* acc_dev, float* wsum_dev, void* stream);
+/* labels = argmax_c(acc_c / wsum) over voxels [v0, v0+nvox) of the flattened volume; counters as above. */
+DCL_API int dcl_finalize_labels(const float* acc_dev, const float* wsum_dev, int64_t voxels_total, int64_t v0,
+                        int64_t nvox, float* probs_out_dev, uint8_t* labels_out_dev,
+                        const uint8_t* target_dev, uint64_t* counts_out_dev, void* stream);
+
+/* ---- introspection used by the parity tests (tests/) and the bench ---- */
+/* Copies the named intermediate tensor of the last dcl_forward into out_dev (dense NCDHW / row
+ * major).  Returns its element count, or a negative status.  Requires cfg.keep_stages. */
+DCL_API int64_t dcl_read_stage(dcl_handle* h, const char* stage, float* out_dev, int64_t cap, void* stream);
+/* The 13 top-k index sets (128 int32 each, order: {01,02,04} x {ee,es,ss,se}, fusion). */
+DCL_API int dcl_read_topk(dcl_handle* h, int32_t* out_host /* 13*128 */, void* stream);
+/* Kernels launched by this handle since creation (the bench's gpu_launches claim). */
+DCL_API int64_t dcl_launch_count(const dcl_handle* h);
+
+/* Per-kernel-class device timing (CUDA events on the launching stream, recorded around every launch of
+ * the class while enabled).  Classes: 0 = 3x3x3 convolutions (work = 2*MAC flops),
+ * 1 = stitch / accumulate / label kernels (work = algorithmic bytes).  dcl_profile_read synchronises the
+ * events, returns the totals since the last read and clears them. */
+DCL_API int dcl_profile_enable(dcl_handle* h, int32_t on);
+DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64_t* launches, double* work_total);
+
+/* ---- single operators, exported for per-op parity tests against torch.nn.functional ---- */
+/* y = conv3d(act(norm(cat(x0,x1)))) * out_scale + residual; kernel 3, padding 1, stride 1|2.
+ * w is the PyTorch (Cout, C0+C1, 3,3,3) weight, device memory; norm_mean/rstd are per input channel
+ * (NULL = identity); act: 0 none, 1 relu, 2 leaky_relu(0.01).  impl: 0 fp32 FFMA, 1 bf16x3, 2 bf16 tcgen05. */
+DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32_t c1, const int32_t in_dhw[3],
+                     const float* w, const float* bias, int32_t cout, int32_t stride,
+                     const float* norm_mean, const float* norm_rstd, int32_t act,
+                     const float* residual, float* y, int32_t impl, void* stream);
+DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCL_B200_H */

@@ -1,0 +1,258 @@
+"""ORACLE (test infrastructure, not product code).
+
+CPU fp32 restatement of the reference ClsWiseFormer forward as one pure function over a
+``state_dict``.  Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
+``--impl reference`` legs of ``bench.py`` may import this file; the product path
+(``dcl_b200``) never does and fails loudly when its CUDA library is missing.
+
+Parity pin: ``tests/golden/make_golden.py`` imports the *real* reference from
+``/root/reference`` (in the build container) and stores stage digests, the 13 top-k index
+sets and sub-sampled outputs in ``tests/golden/*.npz``;  ``tests/test_oracle_golden.py``
+checks this restatement against them.  The reference ships no golden vectors of its own
+(SURVEY.md section 4), so that fixture is the pin.
+
+Each block cites the reference lines it restates (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+REGIONS = ("1", "2", "4")          # NCR/NET, ED, ET  (utils/tools.py:112-160)
+REGION_KEYS = ("01", "02", "04")
+TOP_NUM = 128                      # cls_wise_former.py:80
+SEM_GRID, SEM_PATCH = (16, 16, 16), (2, 2, 1)    # cls_wise_former.py:77-78
+EDGE_GRID, EDGE_PATCH = (32, 32, 32), (4, 2, 2)  # cls_wise_former.py:84-85
+
+
+def strip_module_prefix(sd):
+    """Checkpoints are saved from a DataParallel/DDP wrapper (test_overlap.py:78,86)."""
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
+def draw_keep_mask(n: int = 1) -> torch.Tensor:
+    """Replays the one RNG draw of an eval forward: F.dropout3d(y, 0.2) without
+    ``training=`` (Unet_skipconnection.py:31).  Returns the per-channel scale (0 or 1.25)."""
+    return torch.empty(n, 16, 1, 1, 1).bernoulli_(0.8).div_(0.8).reshape(n, 16)
+
+
+def tokenise(fea, grid, patch):
+    """convert_dim, cls_wise_former.py:15-23: tokens (d,h,w)-major, features (c,p0,p1,p2)."""
+    b, c = fea.shape[:2]
+    g = [grid[i] // patch[i] for i in range(3)]
+    t = fea.reshape(b, c, g[0], patch[0], g[1], patch[1], g[2], patch[2])
+    return t.permute(0, 2, 4, 6, 1, 3, 5, 7).reshape(b, g[0] * g[1] * g[2], -1).contiguous()
+
+
+def untokenise(tok, channels, grid, patch):
+    """split_dim, cls_wise_former.py:26-39 (inverse of tokenise)."""
+    b = tok.shape[0]
+    g = [grid[i] // patch[i] for i in range(3)]
+    t = tok.reshape(b, g[0], g[1], g[2], channels, patch[0], patch[1], patch[2])
+    return t.permute(0, 4, 1, 5, 2, 6, 3, 7).reshape(b, channels, *grid).contiguous()
+
+
+class _Net:
+    def __init__(self, sd, stages=None):
+        self.sd = sd
+        self.stages = stages
+
+    def tap(self, name, value):
+        if self.stages is not None:
+            self.stages[name] = value.detach().clone() if torch.is_tensor(value) else value
+        return value
+
+    def conv(self, x, name, stride=1, pad=1):
+        return F.conv3d(x, self.sd[name + ".weight"], self.sd[name + ".bias"], stride=stride, padding=pad)
+
+    def linear(self, x, name, bias=True):
+        return F.linear(x, self.sd[name + ".weight"], self.sd[name + ".bias"] if bias else None)
+
+    def ln(self, x, name):
+        return F.layer_norm(x, (x.shape[-1],), self.sd[name + ".weight"], self.sd[name + ".bias"], 1e-5)
+
+    # ---- U-Net encoder: Unet_skipconnection.py:36-57 (EnBlock), :114-144 (Unet.forward)
+    def en_block(self, x, p):
+        a = self.conv(F.relu(F.instance_norm(x)), p + ".conv1")
+        b = self.conv(F.relu(F.instance_norm(a)), p + ".conv2")
+        return b + x
+
+    def unet(self, x, keep_scale):
+        u = "Unet_list."
+        t = self.conv(x, u + "InitConv.conv") * keep_scale.reshape(x.shape[0], 16, 1, 1, 1)
+        self.tap("init", t)
+        t = self.en_block(self.en_block(t, u + "EnBlock1"), u + "EnBlock1_1")
+        x1 = self.tap("x1_1", t)
+        t = self.conv(x1, u + "EnDown1.conv", stride=2)
+        t = self.en_block(self.en_block(t, u + "EnBlock2_1"), u + "EnBlock2_2")
+        x2 = self.tap("x2_1", t)
+        t = self.conv(x2, u + "EnDown2.conv", stride=2)
+        t = self.en_block(self.en_block(t, u + "EnBlock3_1"), u + "EnBlock3_2")
+        x3 = self.tap("x3_1", t)
+        t = self.conv(x3, u + "EnDown3.conv", stride=2)
+        t = self.en_block(self.en_block(t, u + "EnBlock4_1"), u + "EnBlock4_2")
+        x4 = self.tap("x4", self.conv(t, u + "EnDown_4.conv", stride=1))
+        return x1, x2, x3, x4
+
+    # ---- DualSelfAttention, SelfAttention.py:74-102 (Q from x, K/V from x2; 8 heads of 64)
+    def dual_attention(self, x, x2, p, heads=8):
+        w = self.sd[p + ".qkv.weight"]
+        d = x.shape[-1]
+        q = F.linear(x, w[:d])
+        k = F.linear(x2, w[d:2 * d])
+        v = F.linear(x2, w[2 * d:])
+        hd = d // heads
+
+        def split(t):
+            return t.reshape(t.shape[0], t.shape[1], heads, hd).permute(0, 2, 1, 3)
+
+        att = (torch.einsum("bhxd,bhyd->bhxy", split(q), split(k)) * hd ** -0.5).softmax(dim=-1)
+        o = torch.einsum("bhxy,bhyd->bhxd", att, split(v)).permute(0, 2, 1, 3).reshape(x.shape)
+        return self.linear(o, p + ".out_proj")
+
+    # ---- Residual(PreNormDrop(DualSelfAttention)), ResidualNorm.py:4-32 (dropout = id in eval)
+    def attn_block(self, x, x2, t):
+        p = t + ".cross_attention_list.0.fn"
+        return self.dual_attention(self.ln(x, p + ".norm"), self.ln(x2, p + ".norm2"), p + ".fn") + x
+
+    # ---- Residual(PreNorm(FeedForward)), ResidualNorm.py:35-47 (GELU is the erf form)
+    def ffn_block(self, x, t):
+        p = t + ".cross_ffn_list.0.fn"
+        h = F.gelu(self.linear(self.ln(x, p + ".norm"), p + ".fn.net.0"))
+        return self.linear(h, p + ".fn.net.3") + x
+
+    # ---- TwoClsWiseTransformerModel.forward, ClsWiseTransformer.py:41-55
+    def intra_region_coupler(self, t, edge, sem_sup, sem, edge_sup):
+        eqs = self.attn_block(edge, sem_sup, t)
+        sqe = self.attn_block(sem, edge_sup, t)
+        re = self.attn_block(eqs, sqe, t)
+        rs = self.attn_block(sqe, eqs, t)
+        return self.ffn_block(torch.cat((re, rs), dim=1), t)
+
+    # ---- FusionClsWiseTransformerModel.forward, FusionClsWiseTransformer.py:42-54
+    def cross_region_coupler(self, t, x):
+        return self.ffn_block(self.attn_block(x, x, t), t)
+
+    # ---- token selection, cls_wise_former.py:345-350 (and 12 siblings)
+    def select(self, token, feats, pe_row, tag):
+        score = token @ feats.transpose(2, 1).contiguous()
+        idx = score.topk(TOP_NUM, dim=2, largest=True, sorted=True)[1][0, 0]
+        self.tap("topk_" + tag, idx)
+        picked = torch.index_select(feats, 1, idx) + pe_row      # PositionalEncoding.py:20-22: row 0 only
+        return torch.cat((token, picked), dim=1), idx
+
+    # ---- aux heads: SuperviseLabel.py:58-81, EdgeSuperviseLabel.py:55-76
+    def aux_head(self, feats, prefix, first, second, scale):
+        out = {}
+        for f, r, key in zip(feats, REGIONS, REGION_KEYS):
+            t = self.conv(self.conv(f, f"{prefix}.{first}_{r}"), f"{prefix}.{second}_{r}")
+            t = F.interpolate(t, scale_factor=scale, mode="trilinear", align_corners=False)
+            out[key] = t.softmax(dim=1)
+        return out
+
+    # ---- Decoder: cls_wise_former.py:644-664, blocks :691-754
+    def post_block(self, x, p):
+        a = F.leaky_relu(F.instance_norm(self.conv(x, p + ".conv1")), 0.01)
+        b = F.leaky_relu(F.instance_norm(self.conv(a, p + ".conv2")), 0.01)
+        return b + x
+
+    def up_cat(self, x, skip, p):
+        sd = self.sd
+        t = self.conv(x, p + ".conv1", pad=0)
+        t = F.conv_transpose3d(t, sd[p + ".conv2.weight"], sd[p + ".conv2.bias"], stride=2)
+        return self.conv(torch.cat((skip, t), dim=1), p + ".conv3", pad=0)
+
+    def decoder(self, x1, x2, x3, x):
+        d = "decoder."
+        t = self.conv(x, d + "down_channel", pad=0)
+        t = self.post_block(self.post_block(t, d + "Enblock8_1"), d + "Enblock8_2")
+        self.tap("dec8", t)
+        t = self.up_cat(t, x3, d + "DeUp4")
+        t = self.post_block(self.post_block(t, d + "DeBlock4"), d + "DeBlock4_1")
+        self.tap("dec4", t)
+        t = self.up_cat(t, x2, d + "DeUp3")
+        t = self.post_block(self.post_block(t, d + "DeBlock3"), d + "DeBlock3_1")
+        self.tap("dec3", t)
+        t = self.up_cat(t, x1, d + "DeUp2")
+        t = self.post_block(self.post_block(t, d + "DeBlock2"), d + "DeBlock2_1")
+        self.tap("dec2", t)
+        return self.conv(t, d + "endconv", pad=0).softmax(dim=1)
+
+
+@torch.no_grad()
+def forward(sd, x, keep_scale=None, want_aux=True, stages=None):
+    """ClsWiseFormer.forward(x, missing_modal) -> (probs, supervise, edge, mid_semantic, mid_edge)
+    (cls_wise_former.py:280-592).  ``x`` is (1,4,128,128,128) fp32; ``keep_scale`` is the
+    (1,16) dropout scale (see draw_keep_mask); None replays the reference RNG draw."""
+    assert x.shape[0] == 1, "the reference is only self-consistent for batch 1 (SURVEY H6)"
+    net = _Net(sd, stages)
+    x1, x2, x3, x4 = net.unet(x, keep_scale if keep_scale is not None else draw_keep_mask(1))
+
+    # Anatomy-induced Region Decoupler: edge (:284-300) and semantic (:314-328) branches
+    e_in = torch.cat((net.conv(x2, "conv_64_to_32", stride=2), x3), dim=1)
+    edge = [F.leaky_relu(F.instance_norm(net.conv(e_in, f"conv_mid_fea_{r}")), 0.01) for r in REGIONS]
+    sem = [F.leaky_relu(F.instance_norm(net.conv(x4, f"conv_semantic_{r}")), 0.01) for r in REGIONS]
+    for r, e, s in zip(REGIONS, edge, sem):
+        net.tap("edge_" + r, e)
+        net.tap("sem_" + r, s)
+
+    mid_sem = mid_edge = None
+    if want_aux:   # :332-333
+        mid_sem = net.aux_head(sem, "mid_supervise_label", "supervise_label", "down_label", 8)
+        mid_edge = net.aux_head(edge, "mid_edge_supervise_label", "edge_supervise_label", "edge_down_label", 4)
+
+    # Edge-supported Intra-region Coupler per region (:341-543)
+    sem_tok_out, sem_feats, sup_edge, sup_sem = [], [], [], []
+    for r, key, e, s in zip(REGIONS, REGION_KEYS, edge, sem):
+        E = tokenise(e, EDGE_GRID, EDGE_PATCH)        # (1,2048,512)
+        S = tokenise(s, SEM_GRID, SEM_PATCH)          # (1,1024,512)
+        et, st = sd[f"e_token_{key}"], sd[f"s_token_{key}"]
+        pe = sd[f"label_{key}_position_encoding.pe"][:1]
+        edge_seq, idx_e = net.select(et, E, pe, f"{key}_ee")
+        sem_sup, _ = net.select(et, S, pe, f"{key}_es")
+        sem_seq, idx_s = net.select(st, S, pe, f"{key}_ss")
+        edge_sup, _ = net.select(st, E, pe, f"{key}_se")
+        # note the concatenated class token for the supplements (:357, :376): s_token / e_token
+        sem_sup = torch.cat((st, sem_sup[:, 1:]), dim=1)
+        edge_sup = torch.cat((et, edge_sup[:, 1:]), dim=1)
+        out = net.intra_region_coupler(f"transformer_{key}", edge_seq, sem_sup, sem_seq, edge_sup)
+        net.tap("coupler_" + key, out)
+        n = TOP_NUM + 1
+        E[0, idx_e] = out[0, 1:n]                      # scatter_ of whole rows (:467)
+        S[0, idx_s] = out[0, n + 1:2 * n]              # (:477)
+        sup_edge.append(untokenise(out[:, 0:1] * E, 32, EDGE_GRID, EDGE_PATCH))
+        sup_sem.append(untokenise(out[:, n:n + 1] * S, 128, SEM_GRID, SEM_PATCH))
+        sem_tok_out.append(out[:, n:n + 1])
+        sem_feats.append(S)
+
+    sup = edge_out = None
+    if want_aux:   # :545-546
+        sup = net.aux_head(sup_sem, "supervise_label", "supervise_label", "down_label", 8)
+        edge_out = net.aux_head(sup_edge, "edge_supervise_label", "edge_supervise_label", "edge_down_label", 4)
+
+    # Mutual Cross-region Coupler (:549-579)
+    f_tok = sem_tok_out[0] + sem_tok_out[1] + sem_tok_out[2]
+    f_fea = sem_feats[0] + sem_feats[1] + sem_feats[2]
+    seq, idx_f = net.select(f_tok, f_fea, sd["fusion_label_pos.pe"][:1], "fusion")
+    out = net.cross_region_coupler("fusion_transformer_1_2_4", seq)
+    net.tap("coupler_fusion", out)
+    fused = f_fea.clone()
+    fused[0, idx_f] = out[0, 1:TOP_NUM + 1]
+    fused = out[:, 0:1] * fused
+    enc = net.tap("enc_out", net.conv(untokenise(fused, 128, SEM_GRID, SEM_PATCH), "sum_fusion"))  # :582
+
+    probs = net.decoder(x1, x2, x3, enc)
+    return probs, sup, edge_out, mid_sem, mid_edge
+
+
+class OracleModel:
+    """Callable with the reference's ``model(x, missing_modal)`` signature, for driving
+    the stitch oracle and the CPU baseline."""
+
+    def __init__(self, state_dict, keep_scale=None, want_aux=False):
+        self.sd = strip_module_prefix(state_dict)
+        self.keep_scale = keep_scale
+        self.want_aux = want_aux
+
+    def __call__(self, x, missing_modal=None):
+        return forward(self.sd, x, self.keep_scale, self.want_aux)

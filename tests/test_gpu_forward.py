@@ -1,0 +1,106 @@
+"""Parity of the CUDA forward (through the C ABI) with the oracle and the reference goldens."""
+import numpy as np
+import pytest
+import torch
+
+from tests.util import check_digest, config1_input, rel_err
+
+pytestmark = pytest.mark.gpu
+
+STAGES = ["init", "x1_1", "x2_1", "x3_1", "x4", "edge_1", "edge_2", "edge_4", "sem_1", "sem_2", "sem_4",
+          "coupler_01", "coupler_02", "coupler_04", "coupler_fusion", "enc_out", "dec8", "dec4", "dec3", "dec2"]
+STAGE_SHAPES = {"init": (1, 16, 128, 128, 128), "x1_1": (1, 16, 128, 128, 128), "x2_1": (1, 32, 64, 64, 64),
+                "x3_1": (1, 64, 32, 32, 32), "x4": (1, 256, 16, 16, 16), "enc_out": (1, 256, 16, 16, 16),
+                "dec8": (1, 128, 16, 16, 16), "dec4": (1, 64, 32, 32, 32), "dec3": (1, 32, 64, 64, 64),
+                "dec2": (1, 16, 128, 128, 128), "coupler_fusion": (1, 129, 512)}
+for _r in ("1", "2", "4"):
+    STAGE_SHAPES["edge_" + _r] = (1, 32, 32, 32, 32)
+    STAGE_SHAPES["sem_" + _r] = (1, 128, 16, 16, 16)
+for _k in ("01", "02", "04"):
+    STAGE_SHAPES["coupler_" + _k] = (1, 258, 512)
+FP32_TOL = 1e-3     # north_star: fp32 logits within 1e-3 relative of the reference forward
+
+
+@pytest.fixture(scope="module")
+def engine(seed0_state_dict):
+    import dcl_b200
+    eng = dcl_b200.Engine(dcl_b200.Precision.FP32, want_aux=True, keep_stages=True)
+    eng.load_state_dict(seed0_state_dict)
+    yield eng
+    eng.close()
+
+
+@pytest.fixture(scope="module")
+def run1(engine, golden_patch):
+    x = config1_input().cuda()
+    out = engine.forward(x, golden_patch["keep_scale"], want_aux=True)
+    torch.cuda.synchronize()
+    return out
+
+
+def test_forward_matches_reference_goldens(engine, run1, golden_patch):
+    g = golden_patch
+    probs, sup, edge, mid_sem, mid_edge = run1
+    topk = engine.read_topk()
+    for tag, idx in topk.items():          # only the selected SET matters (attention is permutation invariant)
+        assert set(idx.tolist()) == set(g["topk_" + tag].tolist()), f"top-k set {tag} differs"
+    errs = {}
+    for name in STAGES:
+        t = engine.read_stage(name).reshape(STAGE_SHAPES[name])
+        errs[name] = check_digest(name, t, g, FP32_TOL)
+    errs["probs"] = check_digest("probs", probs, g, FP32_TOL)
+    for nm, dct in (("sup", sup), ("edgeout", edge), ("mid_sem", mid_sem), ("mid_edge", mid_edge)):
+        for key, t in dct.items():
+            errs[f"{nm}_{key}"] = check_digest(f"{nm}_{key}", t, g, FP32_TOL)
+    print("stage rel errs:", {k: f"{v:.1e}" for k, v in errs.items()})
+    lab = probs[0].argmax(0).to(torch.uint8).cpu().numpy()
+    hist = np.bincount(lab.ravel(), minlength=4)
+    assert np.abs(hist - g["labels_hist"]).sum() <= 2e-4 * lab.size
+
+
+def test_forward_matches_oracle_full_tensor(run1, seed0_state_dict, golden_patch):
+    from oracle import clswiseformer_oracle as O
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = O.forward(seed0_state_dict, config1_input(), torch.from_numpy(golden_patch["keep_scale"]), want_aux=False)[0]
+    probs = run1[0].cpu()
+    assert rel_err(probs.numpy(), ref.numpy()) < FP32_TOL
+    # element-wise relative error as north_star words it (probabilities are bounded away from 0 here)
+    elem = ((probs - ref).abs() / ref.abs().clamp_min(1e-6)).max().item()
+    assert elem < FP32_TOL, elem
+    flips = (probs[0].argmax(0) != ref[0].argmax(0)).float().mean().item()
+    assert flips <= 1e-4, flips
+    sums = probs.sum(1)
+    assert (sums - 1).abs().max().item() < 1e-5
+
+
+def test_strided_view_and_determinism(engine, run1, golden_patch):
+    x = config1_input()
+    big = torch.zeros(1, 4, 160, 150, 140)
+    big[..., 7:135, 11:139, 5:133] = x
+    view = big.cuda()[..., 7:135, 11:139, 5:133]
+    assert not view.is_contiguous()
+    a = engine.forward(view, golden_patch["keep_scale"])
+    b = engine.forward(x.cuda(), golden_patch["keep_scale"])
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, run1[0])
+
+
+def test_deterministic_mask_is_all_ones(engine):
+    x = config1_input().cuda()
+    a = engine.forward(x, None)
+    b = engine.forward(x, np.ones(16, np.float32))
+    assert torch.equal(a, b)
+
+
+def test_dropin_module_forward(seed0_state_dict, golden_patch):
+    """The reference-facing API: get_cls_wise_former(...)(x, missing_modal) -> 5-tuple."""
+    from models.clswiseformer.cls_wise_former import get_cls_wise_former
+    model = torch.nn.DataParallel(get_cls_wise_former("brats", True, "fixed", 0), device_ids=[0])
+    model.load_state_dict({"module." + k: v for k, v in seed0_state_dict.items()})   # test_overlap.py:78,86
+    model.eval()
+    model.module.deterministic = True
+    with torch.no_grad():
+        out = model.module(config1_input().cuda(), None)
+    assert len(out) == 5 and out[0].shape == (1, 4, 128, 128, 128)
+    assert set(out[1]) == {"01", "02", "04"} and out[4]["04"].shape == (1, 2, 128, 128, 128)
+    assert (out[0].sum(1) - 1).abs().max().item() < 1e-5

@@ -1,0 +1,68 @@
+"""Per-operator parity on the GPU: the library's kernels against torch.nn.functional (CPU fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests.util import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _conv_case(c0, c1, cout, dims, stride, norm, act, residual, seed):
+    from dcl_b200.engine import op_conv3d_k3
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(c0, *dims, generator=g)
+    x1 = torch.randn(c1, *dims, generator=g) if c1 else None
+    cin = c0 + c1
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xin = torch.cat([x0, x1], 0) if c1 else x0
+    mean = rstd = None
+    ref_in = xin
+    if norm:
+        mean = torch.randn(cin, generator=g) * 0.3
+        rstd = torch.rand(cin, generator=g) + 0.5
+        ref_in = (xin - mean.view(-1, 1, 1, 1)) * rstd.view(-1, 1, 1, 1)
+    if act == 1:
+        ref_in = F.relu(ref_in)
+    elif act == 2:
+        ref_in = F.leaky_relu(ref_in, 0.01)
+    ref = F.conv3d(ref_in[None], w, b, stride=stride, padding=1)[0]
+    res = torch.randn(ref.shape, generator=g) if residual else None
+    if residual:
+        ref = ref + res
+    dev = "cuda"
+    y = op_conv3d_k3(x0.to(dev), w.to(dev), b.to(dev), x1.to(dev) if c1 else None, stride,
+                     (mean.to(dev), rstd.to(dev)) if norm else None, act, res.to(dev) if residual else None, impl=0)
+    torch.cuda.synchronize()
+    return y.cpu(), ref
+
+
+@pytest.mark.parametrize("case", [
+    dict(c0=4, c1=0, cout=16, dims=(32, 32, 32), stride=1, norm=False, act=0, residual=False),
+    dict(c0=16, c1=0, cout=16, dims=(32, 32, 64), stride=1, norm=True, act=1, residual=True),
+    dict(c0=16, c1=0, cout=32, dims=(32, 32, 32), stride=2, norm=False, act=0, residual=False),
+    dict(c0=32, c1=64, cout=96, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
+    dict(c0=32, c1=0, cout=8, dims=(16, 16, 16), stride=1, norm=True, act=2, residual=False),
+    dict(c0=8, c1=0, cout=2, dims=(20, 12, 36), stride=1, norm=False, act=0, residual=False),
+    dict(c0=5, c1=3, cout=19, dims=(9, 17, 18), stride=2, norm=True, act=2, residual=True),
+    dict(c0=128, c1=0, cout=128, dims=(16, 16, 16), stride=1, norm=True, act=1, residual=True),
+])
+def test_conv3d_k3_fp32(case):
+    y, ref = _conv_case(seed=7, **case)
+    assert y.shape == ref.shape
+    assert rel_err(y.numpy(), ref.numpy()) < 2e-5
+
+
+def test_instnorm_stats():
+    from dcl_b200.engine import op_instnorm_stats
+    g = torch.Generator().manual_seed(3)
+    for shape, shift in (((16, 64, 64, 64), 0.0), ((96, 32, 32, 32), 5.0), ((7, 9, 11, 13), -40.0)):
+        x = torch.randn(shape, generator=g) * 0.7 + shift
+        mean, rstd = op_instnorm_stats(x.cuda())
+        xd = x.double().flatten(1)
+        m = xd.mean(1)
+        r = 1.0 / torch.sqrt(xd.var(1, unbiased=False) + 1e-5)
+        assert rel_err(mean.cpu().numpy(), m.numpy()) < 1e-6
+        assert rel_err(rstd.cpu().numpy(), r.numpy()) < 1e-5

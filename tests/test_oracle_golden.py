@@ -1,0 +1,90 @@
+"""Pins the oracle (oracle/*.py, a CPU restatement) to the UNMODIFIED reference: the fixtures in
+tests/golden were produced by tests/golden/make_golden.py importing /root/reference."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import clswiseformer_oracle as O
+from oracle import stitch_oracle as S
+from tests.util import check_digest, config1_input, volume_input, volume_target
+
+STAGES = ["init", "x1_1", "x2_1", "x3_1", "x4", "edge_1", "edge_2", "edge_4", "sem_1", "sem_2", "sem_4",
+          "coupler_01", "coupler_02", "coupler_04", "coupler_fusion", "enc_out", "dec8", "dec4", "dec3", "dec2"]
+TOPK = [f"{k}_{s}" for k in ("01", "02", "04") for s in ("ee", "es", "ss", "se")] + ["fusion"]
+
+
+def test_oracle_forward_matches_reference(seed0_state_dict, golden_patch):
+    g = golden_patch
+    stages = {}
+    keep = torch.from_numpy(g["keep_scale"])
+    probs, sup, edge, mid_sem, mid_edge = O.forward(seed0_state_dict, config1_input(), keep, True, stages)
+    for tag in TOPK:   # the discrete selections must agree exactly (same ops, same order)
+        assert np.array_equal(stages["topk_" + tag].numpy(), g["topk_" + tag]), tag
+    for name in STAGES:
+        check_digest(name, stages[name], g, 1e-6)
+    check_digest("probs", probs, g, 1e-6)
+    for nm, dct in (("sup", sup), ("edgeout", edge), ("mid_sem", mid_sem), ("mid_edge", mid_edge)):
+        for key, t in dct.items():
+            check_digest(f"{nm}_{key}", t, g, 1e-6)
+    lab = probs[0].numpy().argmax(0).astype(np.uint8)
+    assert np.array_equal(np.bincount(lab.ravel(), minlength=4), g["labels_hist"])
+    assert hashlib.sha256(lab.tobytes()).digest() == g["labels_sha256"].tobytes()
+
+
+def test_stitch_oracle_matches_reference(seed0_state_dict, golden_volume):
+    g = golden_volume
+    keeps = iter(torch.from_numpy(g["keep_scale"]))
+
+    class Model:
+        def __call__(self, x, mm):
+            return O.forward(seed0_state_dict, x, next(keeps).reshape(1, 16), want_aux=False)
+
+    out = S.tailor_and_concat(volume_input(0), None, Model())
+    check_digest("stitched", out, g, 1e-6)
+    labels = S.labels_from_probs(out[0].numpy())
+    assert S.label_histogram(labels) == [int(v) for v in g["labels_hist"]]
+    assert hashlib.sha256(labels.astype(np.uint8).tobytes()).digest() == g["labels_sha256"].tobytes()
+    dice = S.softmax_output_dice(labels, volume_target(0))
+    assert np.allclose(dice, g["dice"], rtol=0, atol=1e-12)
+    # the integer counters give the same Dice
+    rc = S.region_counts(labels, volume_target(0))
+    assert np.allclose([(2 * c[2] + 1e-8) / (c[0] + c[1] + 1e-8) for c in rc], g["dice"], atol=1e-12)
+
+
+def test_reference_plan_reproduces_shift():
+    """predict_overlap.py:53-56 copies patch-local z 96:123 (global 123:150) into z 128:155."""
+    probs = [np.zeros((1, 128, 128, 128), np.float32) for _ in range(8)]
+    for p, (sx, sy, sz) in zip(probs, S.REFERENCE_STARTS):
+        p[0] = sz + np.arange(128, dtype=np.float32)[None, None, :]     # value = global z of the source voxel
+    out = S.stitch_reference_from_probs(probs)[0]
+    assert np.array_equal(out[0, 0, :128], np.arange(128))
+    assert np.array_equal(out[0, 0, 128:155], np.arange(123, 150))       # shifted by 5
+    assert np.array_equal(out[200, 200, 128:155], np.arange(123, 150))
+
+
+def test_weighted_accumulate_oracle_properties():
+    rng = np.random.RandomState(0)
+    starts = S.patch_starts((240, 240, 155), 64)
+    assert len(starts) == 18 and len(S.patch_starts((240, 240, 155), 32)) == 50
+    const = [np.full((4, 128, 128, 128), 0.25, np.float32) for _ in starts]
+    for mode in ("uniform", "gaussian"):
+        out = S.accumulate_from_probs(const, starts, mode)
+        assert np.allclose(out, 0.25, atol=1e-6)      # a partition of unity after normalisation
+    probs = [rng.rand(4, 128, 128, 128).astype(np.float32) for _ in range(2)]
+    two = S.accumulate_from_probs(probs, [(0, 0, 0), (112, 112, 27)], "uniform", (240, 240, 155))
+    assert np.allclose(two[:, 0, 0, 0], probs[0][:, 0, 0, 0])
+    assert np.allclose(two[:, 120, 120, 100], 0.5 * (probs[0][:, 120, 120, 100] + probs[1][:, 8, 8, 73]), atol=1e-6)
+
+
+def test_tokenise_roundtrip():
+    x = torch.randn(1, 32, 32, 32, 32)
+    t = O.tokenise(x, O.EDGE_GRID, O.EDGE_PATCH)
+    assert t.shape == (1, 2048, 512)
+    assert torch.equal(O.untokenise(t, 32, O.EDGE_GRID, O.EDGE_PATCH), x)
+    x = torch.randn(1, 128, 16, 16, 16)
+    t = O.tokenise(x, O.SEM_GRID, O.SEM_PATCH)
+    assert t.shape == (1, 1024, 512)
+    assert torch.equal(O.untokenise(t, 128, O.SEM_GRID, O.SEM_PATCH), x)
