@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the sliding-window ClsWiseFormer inference path (BASELINE.json metric: BraTS
+4x240x240x155 volumes/sec).
+
+    python bench.py [--gpus N --steps K --warmup W] [--precision fp32|bf16x3|bf16] [--workload overlap50|reference8|overlap75]
+    python bench.py --impl reference ...      # the CPU oracle port of the reference path on the host cores
+
+A step = one full volume: patch gather -> clswiseformer forward per 128^3 patch -> overlap
+accumulate / stitch -> normalise + arg-max + label histogram + Dice counters.  Default workload is
+BASELINE.json configs[1]: 50 % overlap (stride 64 -> 18 patches, uniform blend).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "decouple-and-couple_learning_in_multi-modal_brain_tumor_segmentation_b200")
+for p in (ROOT, os.path.join(PKG, "dropin")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+SHAPE = (240, 240, 155)
+VOXELS = SHAPE[0] * SHAPE[1] * SHAPE[2]
+FLOPS_PER_PATCH = 523.35e9 + 0.44e9      # conv+linear without aux heads + attention
+WORKLOADS = {"overlap50": ("UNIFORM", 64), "overlap75": ("UNIFORM", 32), "reference8": ("REFERENCE", None)}
+
+
+def seed0_weights():
+    from models.clswiseformer.cls_wise_former import get_cls_wise_former
+    torch.manual_seed(0)
+    return get_cls_wise_former("brats", True, "fixed", 0).state_dict()
+
+
+def synth_volume(i):
+    torch.manual_seed(1000 + i)
+    return torch.randn(1, 4, *SHAPE)
+
+
+def synth_target(i):
+    return torch.from_numpy(np.random.RandomState(i).randint(0, 4, SHAPE).astype(np.uint8))
+
+
+def keep_scales(i, n):
+    """Replay of the reference's always-on dropout3d draw, one per patch forward (seed 2000+i)."""
+    g = torch.Generator().manual_seed(2000 + i)
+    return torch.stack([torch.empty(1, 16, 1, 1, 1).bernoulli_(0.8, generator=g).div_(0.8).reshape(16)
+                        for _ in range(n)]).numpy()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"], "tensor": p["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [v.strip() for v in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_plan(name):
+    from dcl_b200 import StitchMode, patch_starts
+    mode_name, stride = WORKLOADS[name]
+    if stride is None:
+        return StitchMode.REFERENCE, None, 8
+    starts = patch_starts(SHAPE, stride)
+    return StitchMode[mode_name], starts, len(starts)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_volumes_per_s(workload, n_sample_patches, threads, steps=1, warmup=0):
+    """The oracle port of the reference path on the host cores: `n_sample_patches` real patch forwards
+    per step (extrapolated to the workload's patch count) + the full-size stitch / arg-max / Dice tail."""
+    from oracle import clswiseformer_oracle as O
+    from oracle import stitch_oracle as S
+    torch.set_num_threads(threads)
+    sd = seed0_weights()
+    mode_name, stride = WORKLOADS[workload]
+    starts = S.REFERENCE_STARTS if stride is None else S.patch_starts(SHAPE, stride)
+    x = synth_volume(0)
+    tgt = synth_target(0).numpy()
+    ks = keep_scales(0, len(starts))
+    per_step = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        probs = []
+        for j in range(n_sample_patches):
+            sx, sy, sz = starts[j]
+            probs.append(O.forward(sd, x[..., sx:sx + 128, sy:sy + 128, sz:sz + 128],
+                                   torch.from_numpy(ks[j:j + 1]), want_aux=False)[0][0].numpy())
+        t_patch = (time.perf_counter() - t0) / n_sample_patches
+        t1 = time.perf_counter()
+        full = [probs[j % n_sample_patches] for j in range(len(starts))]
+        if stride is None:
+            out = S.stitch_reference_from_probs(full)
+        else:
+            out = S.accumulate_from_probs(full, starts, "uniform")
+        labels = S.labels_from_probs(out)
+        S.label_histogram(labels)
+        S.softmax_output_dice(labels, tgt)
+        t_tail = time.perf_counter() - t1
+        if it >= warmup:
+            per_step.append(t_patch * len(starts) + t_tail)
+    sec = statistics.mean(per_step)
+    return 1.0 / sec, sec
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 2
+    t0 = time.perf_counter()
+    vps, sec = cpu_reference_volumes_per_s(args.workload, n_sample, threads, steps=args.steps, warmup=args.warmup)
+    _, _, n_patches = (None, None, 8) if WORKLOADS[args.workload][1] is None else (None, None, None)
+    from oracle import stitch_oracle as S
+    stride = WORKLOADS[args.workload][1]
+    n_patches = 8 if stride is None else len(S.patch_starts(SHAPE, stride))
+    sample = (f"{n_sample} of {n_patches} patch forwards per step on {threads} host threads (torch CPU fp32 oracle "
+              f"port of predict_overlap.py + clswiseformer), extrapolated x{n_patches / n_sample:g}, plus the "
+              f"full-volume stitch/argmax/Dice tail")
+    line = {
+        "impl": "reference", "metric": "BraTS 4x240x240x155 volumes/sec", "value": vps, "unit": "volumes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload), "patches_per_volume": n_patches,
+                   "weights": "random-init seed 0"},
+        "cpu_baseline": {"value": vps, "unit": "volumes/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": vps, "unit": "volumes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(w):
+    return {"overlap50": "predict_overlap sliding window, one 4x240x240x155 volume, 128^3 patches at 50% overlap "
+                         "(stride 64, 18 patches, uniform blend)",
+            "overlap75": "4x240x240x155 volume, 128^3 patches at 75% overlap (stride 32, 50 patches, uniform blend)",
+            "reference8": "predict_overlap.py 8-corner tiling + crop-overwrite stitch, one 4x240x240x155 volume"}[w]
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    import dcl_b200
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback "
+                         "(use --impl reference for the CPU oracle port)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    prec = {"fp32": dcl_b200.Precision.FP32, "bf16x3": dcl_b200.Precision.BF16X3, "bf16": dcl_b200.Precision.BF16}[
+        args.precision]
+    eng = dcl_b200.Engine(prec)
+    eng.load_state_dict(seed0_weights())
+    mode, starts, n_patches = workload_plan(args.workload)
+    n_rot = 3     # rotating inputs: 3 x 143 MB per rank, each larger than the 126 MB L2
+    vols_h = [synth_volume(rank * n_rot + i)[0].pin_memory() for i in range(n_rot)]
+    tgts_h = [synth_target(rank * n_rot + i).pin_memory() for i in range(n_rot)]
+    vols_d = [v.cuda() for v in vols_h]
+    tgts_d = [t.cuda() for t in tgts_h]
+    keeps = [keep_scales(rank * n_rot + i, n_patches) for i in range(n_rot)]
+
+    def step_dev(i):
+        j = i % n_rot
+        return eng.predict_volume(vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j],
+                                  want_probs=False, want_labels=True)
+
+    lab_h = torch.empty(SHAPE, dtype=torch.uint8).pin_memory()
+
+    def step_e2e(i):
+        j = i % n_rot
+        return eng.predict_volume_host(vols_h[j], mode, starts=starts, keep_scales=keeps[j], target_host=tgts_h[j],
+                                       labels_out=lab_h)
+
+    # ---- device-resident throughput ----
+    for i in range(args.warmup):
+        step_dev(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    eng.profile(True)
+    l0 = eng.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = step_dev(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count - l0
+    eng.profile(False)
+    conv_ms, conv_n, conv_flops = eng.profile_read(0)
+    tail_ms, tail_n, tail_bytes = eng.profile_read(1)
+    clocks = sampler.stop() if rank == 0 else None
+    counts = out["counts"].cpu().numpy()
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    for i in range(max(1, args.warmup // 2)):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res = step_e2e(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank == 0:
+        pk = peaks()
+        vps = world * args.steps / (ms / 1e3)
+        e2e_vps = world * args.steps / (e2e_ms / 1e3)
+        conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        tail_gbs = tail_bytes / (tail_ms * 1e-3) / 1e9 if tail_ms > 0 else 0.0
+        line = {
+            "metric": "BraTS 4x240x240x155 volumes/sec", "value": vps, "unit": "volumes/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "bf16": "bf16"}[
+                args.precision],
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.workload), "patches_per_volume": n_patches,
+                       "weights": "random-init seed 0", "sharding": "volumes across ranks, no collective",
+                       "l2": "inputs larger than L2: 3 rotating 143 MB volumes per rank, >1.8 GB of activations per patch"},
+            "e2e": {"value": e2e_vps, "unit": "volumes/s", "h2d_bytes_per_step": 4 * VOXELS * 4 + VOXELS,
+                    "d2h_bytes_per_step": VOXELS + 13 * 8},
+            "gpu_launches": launches,
+            "model_tflops": world * args.steps * n_patches * FLOPS_PER_PATCH / (ms / 1e3) / 1e12,
+            "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
+                         "frac": conv_tflops / pk["tensor"], "traffic": None,
+                         "kernel": "conv3d_k3 (3x3x3 convolutions, all launches of the timed region)",
+                         "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
+                         "share_of_step": conv_ms / ms, "peak_source": pk["source"] + " sustained bf16 dense"},
+            "roofline_accumulate": {"bound": "hbm", "achieved": tail_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                                    "frac": tail_gbs / pk["hbm"], "launches": tail_n,
+                                    "kernel": "accumulate / stitch_copy / finalize_labels",
+                                    "share_of_step": tail_ms / ms, "peak_source": pk["source"] + " copy"},
+            "clocks": clocks,
+            "label_hist": counts[:4].tolist(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, sec = cpu_reference_volumes_per_s(args.workload, 2, threads, steps=1, warmup=0)
+            line["cpu_baseline"] = {"value": v, "unit": "volumes/s", "cores": threads, "kind": "port",
+                                    "sample": f"2 of {n_patches} oracle patch forwards (torch CPU fp32) extrapolated to "
+                                              f"{n_patches} + full-volume stitch/argmax/Dice tail, one step"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--workload", default="overlap50", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
