@@ -80,7 +80,7 @@ _SIGNATURES = {
                                    C.POINTER(C.c_double)]),
     "dcl_op_conv3d_k3": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.POINTER(C.c_int32), C.c_void_p,
                                    C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p,
-                                   C.c_void_p, C.c_int32, C.c_void_p]),
+                                   C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dcl_op_instnorm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 

@@ -38,6 +38,10 @@ struct ConvSrc {
   const float* mean;       // per input channel (c0+c1) or nullptr
   const float* rstd;
   int act;
+  // alternative to mean/rstd: raw per-channel (sum, sum of squares) pairs accumulated by the producing
+  // kernel's epilogue (ConvDst::stats); the consumer derives mean / rstd itself (no finalize launch)
+  const double* sums;
+  float inv_n;             // 1 / (elements per channel)
 };
 
 struct ConvDst {
@@ -45,6 +49,7 @@ struct ConvDst {
   const float* bias;       // cout or nullptr
   const float* out_scale;  // per output channel multiplier applied after bias (dropout3d) or nullptr
   const float* residual;   // dense, same shape as y, added last; or nullptr
+  double* stats;           // nullptr, or 2*cout doubles: += (sum, sum of squares) of the stored values
 };
 
 // Packed k3 weights: [cin][27][cout_pad], cout_pad = round_up(cout, 16).

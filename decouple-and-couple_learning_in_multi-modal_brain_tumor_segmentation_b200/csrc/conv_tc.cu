@@ -1,14 +1,355 @@
-// Placeholder until the tcgen05 kernel lands: reports "unsupported" so the engine uses the fp32 kernels.
+// tcgen05 / TMEM implicit-GEMM 3x3x3 convolutions (precision mode DCL_BF16: bf16 operands, fp32
+// accumulate in tensor memory).  Replaces the cuDNN/oneDNN nn.Conv3d calls of
+// Unet_skipconnection.py:48-55 (EnBlock) and cls_wise_former.py:691-713,:732-754 (EnBlock2/DeBlock).
+//
+// Kernel "roll" (Cin = Cout = C in {16,32}, stride 1, cubic G^3 input, NCDHW fp32 in HBM):
+//   GEMM view      M = output voxels (128 per MMA), N = C, K = 27 taps x C.
+//   CTA            one strip of TH output rows x full W, walking along d ("rolling"): a ring of NSLOT
+//                  staged input planes lives in shared memory, each plane (TH+2) rows x (W+2) voxels
+//                  with channels split into 16-byte chunks: [chunk][row][w][8 x bf16].  Neighbouring
+//                  voxels are 16 bytes apart, so ANY (kd,kh,kw) tap of ANY 128-voxel run is a valid
+//                  K-major no-swizzle UMMA operand: the 27 taps are 27 descriptor start addresses
+//                  into the same staged data (no im2col copy, 1.25x halo re-read only).
+//   warps 0-3      epilogue: tcgen05.ld accumulator -> +bias (+residual) -> coalesced NCDHW stores,
+//                  per-channel sum / sum-of-squares of what was stored (the next layer's InstanceNorm)
+//   warp 4         TMEM allocation; one thread issues tcgen05.mma and tcgen05.commit
+//   warps 5-12     producers: coalesced global loads, fused InstanceNorm + activation of the input
+//                  tensor, bf16 conversion, zero padding, 16-byte shared stores
+//   barriers       full[slot] / empty[slot] (producers <-> MMA), acc_full[2] / acc_empty[2] (MMA <-> epilogue)
 #include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+#include <string.h>
+
+#include <vector>
 
 namespace dcl {
-int tc_pack_weights(const float*, int cout, int cin, TcWeights* out) {
+
+using namespace tc;
+
+template <int C_, int G_, int TH_, bool FLAT_>
+struct RollCfg {
+  static constexpr int C = C_, G = G_, TH = TH_;
+  static constexpr bool FLAT = FLAT_;
+  static constexpr int W = G;
+  static constexpr int P = W + 2;                 // staged positions per row (1 halo voxel each side)
+  static constexpr int ROWS = TH + 2;
+  static constexpr int NPOS = ROWS * P;           // positions per channel chunk of one plane
+  static constexpr int KC = C / 8;                // 16-byte channel chunks
+  static constexpr int KS = C / 16;               // K = 16 MMA steps per tap
+  static constexpr int SLOT_BYTES = KC * NPOS * 16;
+  static constexpr int NSLOT = 4;
+  static constexpr int RUN = (TH - 1) * P + W;    // flattened (row, w) positions holding real outputs
+  static constexpr int TSTRIDE = FLAT ? 128 : P;  // position of M tile t = t * TSTRIDE
+  static constexpr int NT = FLAT ? (RUN + 127) / 128 : TH;
+  static constexpr int ACC_COLS = NT * C;         // TMEM columns of one accumulator buffer
+  static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
+                                   : 2 * ACC_COLS <= 256 ? 256 : 512;
+  static constexpr int W_BYTES = 27 * C * C * 2;
+  static constexpr int ITEMS = KC * NPOS;         // 16-byte staging items per plane
+  static constexpr int OFF_W = NSLOT * SLOT_BYTES;
+  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // mean[C], rstd[C], bias[C] floats
+  static constexpr int OFF_BAR = OFF_SMALL + 3 * C * 4;      // 8-byte aligned (C multiple of 16)
+  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 4) * 8 + 16;
+  static_assert(FLAT || W == 128, "row-aligned M tiles need W == 128");
+  static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+};
+
+constexpr int EPI_WARPS = 4;
+constexpr int PROD_WARPS = 8;
+constexpr int ROLL_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
+constexpr int PROD_T0 = (EPI_WARPS + 1) * 32;
+constexpr int NPROD = PROD_WARPS * 32;
+
+template <class Cfg>
+__global__ void __launch_bounds__(ROLL_THREADS, 1)
+conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_packed, int dsplit) {
+  constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, P = Cfg::P, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
+  extern __shared__ __align__(128) uint8_t smem[];
+  float* s_mean = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);
+  float* s_rstd = s_mean + C;
+  float* s_bias = s_rstd + C;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* bar_empty = bar_full + NSLOT;
+  uint64_t* bar_acc_full = bar_empty + NSLOT;
+  uint64_t* bar_acc_empty = bar_acc_full + 2;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  const int ht = blockIdx.x / dsplit;
+  const int ds = blockIdx.x - ht * dsplit;
+  const int h0 = ht * TH;
+  const int d0 = (ds * G) / dsplit;
+  const int d1 = ((ds + 1) * G) / dsplit;
+  const int n_out = d1 - d0;
+  const int n_in = n_out + 2;
+
+  // ---- one-time setup ---------------------------------------------------------------------------
+  for (int i = tid; i < Cfg::W_BYTES / 16; i += ROLL_THREADS)
+    reinterpret_cast<uint4*>(smem + Cfg::OFF_W)[i] = __ldg(w_packed + i);
+  if (tid < C) {
+    float m = 0.f, r = 1.f;
+    if (src.sums != nullptr) {
+      double mu = src.sums[2 * tid] * (double)src.inv_n;
+      double var = src.sums[2 * tid + 1] * (double)src.inv_n - mu * mu;
+      m = (float)mu;
+      r = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
+    } else if (src.mean != nullptr) {
+      m = src.mean[tid];
+      r = src.rstd[tid];
+    }
+    s_mean[tid] = m;
+    s_rstd[tid] = r;
+    s_bias[tid] = dst.bias ? dst.bias[tid] : 0.f;
+  }
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_WARPS * 32); }
+    fence_barrier_init();
+  }
+  if (warp == EPI_WARPS) tmem_alloc(s_tmem, Cfg::TMEM_COLS);
+  fence_proxy_async();   // the weight tile was written through the generic proxy
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp >= EPI_WARPS + 1) {
+    // =============================== producers ===================================================
+    const int pt = tid - PROD_T0;
+    const int act = src.act;
+    constexpr int U = 4;
+    for (int j = 0; j < n_in; ++j) {
+      const int s = j % NSLOT;
+      mbar_wait(&bar_empty[s], ((uint32_t)(j / NSLOT) & 1u) ^ 1u);
+      const int d_in = d0 - 1 + j;
+      const bool d_ok = (unsigned)d_in < (unsigned)G;
+      uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
+      for (int e0 = pt; e0 < Cfg::ITEMS; e0 += NPROD * U) {
+        float v[U][8];
+        int kcs[U];
+        bool oks[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int e = e0 + u * NPROD;
+          const int kc = e / NPOS;
+          const int rem = e - kc * NPOS;
+          const int r = rem / P;
+          const int q = rem - r * P;
+          const int h_in = h0 - 1 + r, w_in = q - 1;
+          const bool ok = e < Cfg::ITEMS && d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G;
+          kcs[u] = kc;
+          oks[u] = ok;
+          if (ok) {
+            const float* p = src.x0 + (int64_t)(kc * 8) * src.s0c + (int64_t)d_in * src.s0d + (int64_t)h_in * src.s0h + w_in;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = __ldg(p + (int64_t)k * src.s0c);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int e = e0 + u * NPROD;
+          if (e < Cfg::ITEMS) {
+            if (oks[u]) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int c = kcs[u] * 8 + k;
+                v[u][k] = apply_act((v[u][k] - s_mean[c]) * s_rstd[c], act);
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16x2(v[u][0], v[u][1]);
+            o.y = pack_bf16x2(v[u][2], v[u][3]);
+            o.z = pack_bf16x2(v[u][4], v[u][5]);
+            o.w = pack_bf16x2(v[u][6], v[u][7]);
+            *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = o;
+          }
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&bar_full[s]);
+    }
+  } else if (warp == EPI_WARPS) {
+    // =============================== MMA issuer ==================================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, C);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t w_base = smem_base + Cfg::OFF_W;
+      for (int i = 0; i < n_out; ++i) {
+        const int b = i & 1;
+        if (i == 0) {
+          mbar_wait(&bar_full[0], 0);
+          mbar_wait(&bar_full[1], 0);
+        }
+        mbar_wait(&bar_full[(i + 2) % NSLOT], (uint32_t)((i + 2) / NSLOT) & 1u);
+        mbar_wait(&bar_acc_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
+        tc_fence_after();
+        for (int t = 0; t < Cfg::NT; ++t) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)(b * Cfg::ACC_COLS + t * C);
+          uint32_t accum = 0;
+#pragma unroll 1
+          for (int kd = 0; kd < 3; ++kd) {
+            const uint32_t slot_base = smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES);
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const int tap = (kd * 3 + kh) * 3 + kw;
+                const uint32_t a0 = slot_base + (uint32_t)((t * Cfg::TSTRIDE + kh * P + kw) * 16);
+                const uint32_t b0 = w_base + (uint32_t)(tap * C * C * 2);
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KS; ++ks) {
+                  const uint64_t ad = umma_desc(a0 + (uint32_t)(ks * 2 * NPOS * 16), NPOS * 16, 128);
+                  const uint64_t bd = umma_desc(b0 + (uint32_t)(ks * 2 * C * 16), C * 16, 128);
+                  umma_bf16(d_tmem, ad, bd, idesc, accum);
+                  accum = 1;
+                }
+              }
+            }
+          }
+        }
+        umma_commit(&bar_acc_full[b]);
+        umma_commit(&bar_empty[i % NSLOT]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ====================================================
+    const int64_t sp = (int64_t)G * G * G;
+    float st_s[C], st_q[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { st_s[c] = 0.f; st_q[c] = 0.f; }
+    const int m = warp * 32 + lane;   // accumulator row (TMEM lane) of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int i = 0; i < n_out; ++i) {
+      const int b = i & 1;
+      mbar_wait(&bar_acc_full[b], (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const int d = d0 + i;
+#pragma unroll 1
+      for (int t = 0; t < Cfg::NT; ++t) {
+        uint32_t acc[C / 16][16];
+#pragma unroll
+        for (int k = 0; k < C / 16; ++k) tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * C + 16 * k), acc[k]);
+        tmem_ld_wait();
+        if (t == Cfg::NT - 1) {   // all of this thread's TMEM reads of buffer b are done
+          tc_fence_before();
+          mbar_arrive(&bar_acc_empty[b]);
+        }
+        const int p = t * Cfg::TSTRIDE + m;
+        const int r = p / P;
+        const int w = p - r * P;
+        if (r < TH && w < G) {
+          const int64_t off = ((int64_t)d * G + (h0 + r)) * G + w;
+#pragma unroll
+          for (int c = 0; c < C; ++c) {
+            float val = __uint_as_float(acc[c / 16][c % 16]) + s_bias[c];
+            if (dst.residual) val += __ldg(dst.residual + c * sp + off);
+            dst.y[c * sp + off] = val;
+            st_s[c] += val;
+            st_q[c] += val * val;
+          }
+        }
+      }
+    }
+    if (dst.stats != nullptr) {
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        float a = st_s[c], q = st_q[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          a += __shfl_xor_sync(0xffffffffu, a, o);
+          q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane == 0) {
+          atomicAdd(dst.stats + 2 * c, (double)a);
+          atomicAdd(dst.stats + 2 * c + 1, (double)q);
+        }
+      }
+    }
+  }
+
+  // ---- teardown ---------------------------------------------------------------------------------
+  tc_fence_before();
+  __syncthreads();
+  if (warp == EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static uint16_t f32_to_bf16_rn(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// B operand tiles: [tap][cin/8][cout][8] bf16 = for every tap a K-major no-swizzle N x K matrix
+// (core matrix = 8 couts x 8 cins, 128 contiguous bytes; K chunks cout*16 bytes apart).
+int tc_pack_weights(const float* w_host, int cout, int cin, TcWeights* out) {
   out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0;
+  if (cin % 16 != 0 || cout % 16 != 0) return 0;   // no tensor-core kernel takes this shape
+  std::vector<uint16_t> packed((size_t)27 * cin * cout);
+  for (int tap = 0; tap < 27; ++tap)
+    for (int kc = 0; kc < cin / 8; ++kc)
+      for (int n = 0; n < cout; ++n)
+        for (int k = 0; k < 8; ++k)
+          packed[(((size_t)tap * (cin / 8) + kc) * cout + n) * 8 + k] =
+              f32_to_bf16_rn(w_host[((size_t)n * cin + kc * 8 + k) * 27 + tap]);
+  out->bytes = (int64_t)packed.size() * 2;
+  DCL_CUDA_OK(cudaMalloc(&out->dev, (size_t)out->bytes));
+  DCL_CUDA_OK(cudaMemcpy(out->dev, packed.data(), (size_t)out->bytes, cudaMemcpyHostToDevice));
   return 0;
 }
-bool tc_conv_supported(int, int, int, int) { return false; }
-int launch_conv3d_k3_tc(const ConvSrc&, const ConvDst&, const TcWeights&, int, int, bool, cudaStream_t) {
-  set_error("tensor-core convolution not built");
-  return -2;
+
+using RollC16 = RollCfg<16, 128, 8, false>;
+using RollC32 = RollCfg<32, 64, 8, true>;
+
+bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
+  if (split || stride != 1 || cin != cout) return false;
+  return (cin == 16 && g == 128) || (cin == 32 && g == 64);
 }
+
+template <class Cfg>
+static int launch_roll(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    DCL_CUDA_OK(cudaFuncSetAttribute(conv3d_k3_roll_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int htiles = Cfg::G / Cfg::TH;
+  int dsplit = 148 / htiles;
+  if (dsplit < 1) dsplit = 1;
+  if (dsplit > Cfg::G) dsplit = Cfg::G;
+  conv3d_k3_roll_kernel<Cfg><<<htiles * dsplit, ROLL_THREADS, Cfg::SMEM_BYTES, st>>>(
+      src, dst, reinterpret_cast<const uint4*>(w.dev), dsplit);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_conv3d_k3_tc(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, int cout, int g, bool split,
+                        cudaStream_t st) {
+  const int cin = src.c0 + src.c1;
+  if (!tc_conv_supported(cin, cout, g, 1, split) || src.x1 != nullptr || dst.out_scale != nullptr || w.dev == nullptr) {
+    set_error("conv3d_k3_tc: unsupported shape");
+    return -1;
+  }
+  if (cin == 16) return launch_roll<RollC16>(src, dst, w, st);
+  return launch_roll<RollC32>(src, dst, w, st);
+}
+
 }  // namespace dcl

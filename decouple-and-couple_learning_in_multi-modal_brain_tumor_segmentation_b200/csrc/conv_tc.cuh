@@ -14,7 +14,7 @@ struct TcWeights {
 // Packs a PyTorch (cout, cin, 3,3,3) fp32 weight (host) into the kernel's B-operand layout.
 int tc_pack_weights(const float* w_host, int cout, int cin, TcWeights* out);
 // True when launch_conv3d_k3_tc handles a cubic g^3 input with these channel counts.
-bool tc_conv_supported(int cin, int cout, int g, int stride);
+bool tc_conv_supported(int cin, int cout, int g, int stride, bool split);
 // Same contract as launch_conv3d_k3 (dense single-source input, fused input norm/activation, bias,
 // residual).  split = true: bf16x3 (hi*hi + hi*lo + lo*hi), false: plain bf16 operands.
 int launch_conv3d_k3_tc(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, int cout, int g, bool split,

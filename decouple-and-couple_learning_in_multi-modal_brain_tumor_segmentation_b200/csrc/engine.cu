@@ -413,7 +413,7 @@ struct Fwd {
     cudaEvent_t ev = nullptr;
     if (h->profiling) ev = h->prof_begin(st);
     int rc;
-    if (h->cfg.precision != DCL_FP32 && tc_conv_supported(c0 + c1, w.cout, g, stride) && x1 == nullptr)
+    if (h->cfg.precision != DCL_FP32 && tc_conv_supported(c0 + c1, w.cout, g, stride, h->cfg.precision == DCL_BF16X3) && x1 == nullptr)
       rc = launch_conv3d_k3_tc(s, d, w.tc, w.cout, g, h->cfg.precision == DCL_BF16X3, st);
     else
       rc = launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, g, g, g, stride, st);
@@ -978,7 +978,7 @@ DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spat
 
 DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32_t c1, const int32_t in_dhw[3], const float* w,
                      const float* bias, int32_t cout, int32_t stride, const float* norm_mean, const float* norm_rstd,
-                     int32_t act, const float* residual, float* y, int32_t impl, void* stream) {
+                     int32_t act, const float* residual, float* y, int32_t impl, double* stats_out, void* stream) {
   if (!x0 || !w || !y || !in_dhw || cout <= 0 || c0 <= 0) { set_error("dcl_op_conv3d_k3: bad argument"); return DCL_ERR_ARG; }
   cudaStream_t st = (cudaStream_t)stream;
   const int cin = c0 + c1;
@@ -986,7 +986,8 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
   DCL_CUDA_OK(cudaMemcpy(wh.data(), w, wh.size() * 4, cudaMemcpyDefault));
   const int64_t sp = (int64_t)in_dhw[0] * in_dhw[1] * in_dhw[2];
   ConvSrc s{x0, x1, c0, c1, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], norm_mean, norm_rstd, act};
-  ConvDst d{y, bias, nullptr, residual};
+  ConvDst d{y, bias, nullptr, residual, stats_out};
+  if (stats_out && impl == 0) { set_error("dcl_op_conv3d_k3: fused statistics need a tensor-core impl"); return DCL_ERR_ARG; }
   int rc;
   if (impl == 0) {
     const int cout_pad = (cout + 15) / 16 * 16;
@@ -1002,7 +1003,7 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
     cudaFree(wp);
   } else {
     if (in_dhw[0] != in_dhw[1] || in_dhw[1] != in_dhw[2] || x1 != nullptr ||
-        !tc_conv_supported(cin, cout, in_dhw[0], stride)) {
+        !tc_conv_supported(cin, cout, in_dhw[0], stride, impl == 1)) {
       set_error("dcl_op_conv3d_k3: shape not supported by the tensor-core kernel");
       return DCL_ERR_ARG;
     }

@@ -234,7 +234,7 @@ class Engine:
         return int(self._lib.dcl_launch_count(self._h))
 
 
-def op_conv3d_k3(x0, weight, bias=None, x1=None, stride=1, norm=None, act=0, residual=None, impl=0):
+def op_conv3d_k3(x0, weight, bias=None, x1=None, stride=1, norm=None, act=0, residual=None, impl=0, stats=None):
     """Single-operator entry (tests): y = conv3d(act(norm(cat(x0, x1))), k=3, p=1) + residual."""
     lib = N.load_library()
     c0, d, h, w = (int(v) for v in x0.shape)
@@ -246,7 +246,7 @@ def op_conv3d_k3(x0, weight, bias=None, x1=None, stride=1, norm=None, act=0, res
     mean, rstd = (norm if norm is not None else (None, None))
     N.check(lib.dcl_op_conv3d_k3(_ptr(x0.contiguous()), c0, _ptr(x1), c1, dims, _ptr(weight.contiguous()), _ptr(bias),
                                  cout, int(stride), _ptr(mean), _ptr(rstd), int(act), _ptr(residual), _ptr(y),
-                                 int(impl), _stream()))
+                                 int(impl), _ptr(stats), _stream()))
     return y
 
 

@@ -161,11 +161,13 @@ DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64
 /* ---- single operators, exported for per-op parity tests against torch.nn.functional ---- */
 /* y = conv3d(act(norm(cat(x0,x1)))) * out_scale + residual; kernel 3, padding 1, stride 1|2.
  * w is the PyTorch (Cout, C0+C1, 3,3,3) weight, device memory; norm_mean/rstd are per input channel
- * (NULL = identity); act: 0 none, 1 relu, 2 leaky_relu(0.01).  impl: 0 fp32 FFMA, 1 bf16x3, 2 bf16 tcgen05. */
+ * (NULL = identity); act: 0 none, 1 relu, 2 leaky_relu(0.01).  impl: 0 fp32 FFMA, 1 bf16x3, 2 bf16 tcgen05.
+ * stats_out: NULL, or 2*cout zero-initialised doubles that receive per-channel (sum, sum of squares) of y
+ * (tensor-core impls only: the fused InstanceNorm statistics of the epilogue). */
 DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32_t c1, const int32_t in_dhw[3],
                      const float* w, const float* bias, int32_t cout, int32_t stride,
                      const float* norm_mean, const float* norm_rstd, int32_t act,
-                     const float* residual, float* y, int32_t impl, void* stream);
+                     const float* residual, float* y, int32_t impl, double* stats_out, void* stream);
 DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,40 @@
+"""Runs N forwards of one 128^3 patch through dcl_forward (for ncu launch lists / quick timing).
+usage: python tools/one_patch.py [precision: fp32|bf16x3|bf16] [n_forwards]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "decouple-and-couple_learning_in_multi-modal_brain_tumor_segmentation_b200", "dropin"))
+
+import torch  # noqa: E402
+import dcl_b200  # noqa: E402
+from models.clswiseformer.cls_wise_former import get_cls_wise_former  # noqa: E402
+
+
+def main():
+    prec = {"fp32": dcl_b200.Precision.FP32, "bf16x3": dcl_b200.Precision.BF16X3, "bf16": dcl_b200.Precision.BF16}[
+        sys.argv[1] if len(sys.argv) > 1 else "fp32"]
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    torch.manual_seed(0)
+    sd = get_cls_wise_former("brats", True, "fixed", 0).state_dict()
+    torch.manual_seed(1)
+    x = torch.randn(1, 4, 128, 128, 128).cuda()
+    eng = dcl_b200.Engine(prec)
+    eng.load_state_dict(sd)
+    eng.forward(x, None)
+    torch.cuda.synchronize()
+    l0 = eng.launch_count
+    t0 = time.perf_counter()
+    for _ in range(n):
+        p = eng.forward(x, None)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / n
+    print(f"precision={prec.name} forwards={n} ms_per_patch={dt * 1e3:.3f} launches_per_patch={(eng.launch_count - l0) // n} "
+          f"checksum={float(p.double().sum()):.6f}")
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
