@@ -27,10 +27,11 @@ namespace dcl {
 
 using namespace tc;
 
-template <int C_, int G_, int TH_, bool FLAT_>
+template <int C_, int G_, int TH_, bool FLAT_, bool KHN_>
 struct RollCfg {
   static constexpr int C = C_, G = G_, TH = TH_;
   static constexpr bool FLAT = FLAT_;
+  static constexpr bool KHN = KHN_;                // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
   static constexpr int W = G;
   static constexpr int P = W + 2;                 // staged positions per row (1 halo voxel each side)
   static constexpr int ROWS = TH + 2;
@@ -52,6 +53,7 @@ struct RollCfg {
   static constexpr int OFF_BAR = OFF_SMALL + 3 * C * 4;      // 8-byte aligned (C multiple of 16)
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 4) * 8 + 16;
   static_assert(FLAT || W == 128, "row-aligned M tiles need W == 128");
+  static_assert(!KHN || !FLAT, "kh stacking needs row-aligned M tiles");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -191,6 +193,43 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
         mbar_wait(&bar_full[(i + 2) % NSLOT], (uint32_t)((i + 2) / NSLOT) & 1u);
         mbar_wait(&bar_acc_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        if constexpr (Cfg::KHN) {
+          // Staged row rho feeds output rows rho-2 (kh=2), rho-1 (kh=1), rho (kh=0) at once: their
+          // accumulators are adjacent TMEM column blocks and the weights of (kd,kw) are stored as one
+          // stacked N = 3C operand, so one MMA (one read of the 4 KB A tile) does the work of three.
+          constexpr uint32_t WB = 3 * C * C * 2;            // bytes of one (kd,kw) stacked weight matrix
+          constexpr uint32_t B_LBO = 3 * C * 16;
+#pragma unroll 1
+          for (int rho = 0; rho < TH + 2; ++rho) {
+            const int q_lo = rho >= 2 ? rho - 2 : 0;
+            const int q_hi = rho < TH ? rho : TH - 1;
+            const int blk0 = q_lo - (rho - 2);
+            const bool fresh = rho < TH;                    // output row rho gets its first contribution here
+#pragma unroll 1
+            for (int kd = 0; kd < 3; ++kd) {
+              const uint32_t slot_base = smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES);
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint32_t a0 = slot_base + (uint32_t)((rho * P + kw) * 16);
+                const uint32_t b0 = w_base + (uint32_t)(kd * 3 + kw) * WB + (uint32_t)(blk0 * C * 16);
+                const bool first = fresh && kd == 0 && kw == 0;
+                const int n_acc = (q_hi - q_lo + 1) - (first ? 1 : 0);   // blocks that accumulate
+#pragma unroll
+                for (int ks = 0; ks < Cfg::KS; ++ks) {
+                  const uint64_t ad = umma_desc(a0 + (uint32_t)(ks * 2 * NPOS * 16), NPOS * 16, 128);
+                  const uint32_t bk = b0 + (uint32_t)(ks * 2) * B_LBO;
+                  if (n_acc > 0)
+                    umma_bf16(tmem_base + (uint32_t)(b * Cfg::ACC_COLS + q_lo * C), ad, umma_desc(bk, B_LBO, 128),
+                              umma_idesc_bf16(128, n_acc * C), 1u);
+                  if (first)
+                    umma_bf16(tmem_base + (uint32_t)(b * Cfg::ACC_COLS + rho * C), ad,
+                              umma_desc(bk + (uint32_t)(n_acc * C * 16), B_LBO, 128), umma_idesc_bf16(128, C),
+                              ks == 0 ? 0u : 1u);
+                }
+              }
+            }
+          }
+        } else {
         for (int t = 0; t < Cfg::NT; ++t) {
           const uint32_t d_tmem = tmem_base + (uint32_t)(b * Cfg::ACC_COLS + t * C);
           uint32_t accum = 0;
@@ -214,6 +253,7 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
               }
             }
           }
+        }
         }
         umma_commit(&bar_acc_full[b]);
         umma_commit(&bar_empty[i % NSLOT]);
@@ -296,26 +336,39 @@ static uint16_t f32_to_bf16_rn(float f) {
   return (uint16_t)(u >> 16);
 }
 
-// B operand tiles: [tap][cin/8][cout][8] bf16 = for every tap a K-major no-swizzle N x K matrix
-// (core matrix = 8 couts x 8 cins, 128 contiguous bytes; K chunks cout*16 bytes apart).
+// B operand tiles, bf16, K-major no-swizzle (core matrix = 8 couts x 8 cins, 128 contiguous bytes):
+//   layout 0  [tap][cin/8][cout][8]                     one N = cout matrix per tap
+//   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]      one stacked N = 3*cout matrix per (kd,kw)
+static int tc_weight_layout(int cin, int cout) { return (cin == 16 && cout == 16) ? 1 : 0; }
+
 int tc_pack_weights(const float* w_host, int cout, int cin, TcWeights* out) {
   out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0;
   if (cin % 16 != 0 || cout % 16 != 0) return 0;   // no tensor-core kernel takes this shape
+  const int kcs = cin / 8;
   std::vector<uint16_t> packed((size_t)27 * cin * cout);
-  for (int tap = 0; tap < 27; ++tap)
-    for (int kc = 0; kc < cin / 8; ++kc)
-      for (int n = 0; n < cout; ++n)
-        for (int k = 0; k < 8; ++k)
-          packed[(((size_t)tap * (cin / 8) + kc) * cout + n) * 8 + k] =
-              f32_to_bf16_rn(w_host[((size_t)n * cin + kc * 8 + k) * 27 + tap]);
+  const int layout = tc_weight_layout(cin, cout);
+  for (int kd = 0; kd < 3; ++kd)
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw)
+        for (int kc = 0; kc < kcs; ++kc)
+          for (int n = 0; n < cout; ++n)
+            for (int k = 0; k < 8; ++k) {
+              const int tap = (kd * 3 + kh) * 3 + kw;
+              size_t dst;
+              if (layout == 0)
+                dst = (((size_t)tap * kcs + kc) * cout + n) * 8 + k;
+              else
+                dst = (((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * cout) + n) * 8 + k;
+              packed[dst] = f32_to_bf16_rn(w_host[((size_t)n * cin + kc * 8 + k) * 27 + tap]);
+            }
   out->bytes = (int64_t)packed.size() * 2;
   DCL_CUDA_OK(cudaMalloc(&out->dev, (size_t)out->bytes));
   DCL_CUDA_OK(cudaMemcpy(out->dev, packed.data(), (size_t)out->bytes, cudaMemcpyHostToDevice));
   return 0;
 }
 
-using RollC16 = RollCfg<16, 128, 8, false>;
-using RollC32 = RollCfg<32, 64, 8, true>;
+using RollC16 = RollCfg<16, 128, 8, false, true>;
+using RollC32 = RollCfg<32, 64, 8, true, false>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
   if (split || stride != 1 || cin != cout) return false;
