@@ -1,0 +1,284 @@
+// General tcgen05 implicit-GEMM convolution (precision mode DCL_BF16) for every conv the rolling kernel
+// (conv_tc.cu) does not take: any Cin / Cout, kernel 3 (27 taps) or 1, stride 1 or 2, any input size.
+// Replaces nn.Conv3d of Unet_skipconnection.py:60-78 (EnDown), cls_wise_former.py:284-328 (region
+// decoupler), :257-263 (sum_fusion), :691-713 / :732-754 at 16^3 and 32^3.
+//
+//   prep kernel   fp32 NCDHW (optionally two concatenated sources) -> InstanceNorm + activation ->
+//                 bf16, channel-blocked [Cin/8][D][H][W][8]: every (voxel, 8 channels) is one 16-byte
+//                 vector, so a shifted / strided tap of 128 output voxels is 128 x 16-byte gathers.
+//   GEMM kernel   M = 128 output voxels, N = n_tile output channels, K = taps x Cin.
+//     producers (4 warps)  cp.async 16 B with zero fill (padding + tail rows) straight into the K-major
+//                          no-swizzle UMMA operand layout, one (tap, <=64 channel) stage at a time;
+//                          weights come pre-packed in the same layout
+//     MMA (1 thread)       tcgen05.mma kind::f16 into one TMEM accumulator, tcgen05.commit frees stages
+//     epilogue (4 warps)   tcgen05.ld -> +bias, x channel scale, +residual -> fp32 NCDHW
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+namespace dcl {
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------------------------
+// prep: norm + act + bf16 + channel blocking (zero-pads channels up to a multiple of 16)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_blocked_kernel(ConvSrc src, int64_t spatial, int in_h, int in_w, uint4* __restrict__ out) {
+  const int kc = blockIdx.y;
+  const int cin = src.c0 + src.c1;
+  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (p >= spatial) return;
+  // x0 may be a strided view (s0c/s0d/s0h); x1 is dense
+  const int w = (int)(p % in_w);
+  const int64_t t = p / in_w;
+  const int h = (int)(t % in_h);
+  const int64_t d = t / in_h;
+  float v[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int c = kc * 8 + k;
+    float x = 0.f;
+    if (c < cin) {
+      if (c < src.c0)
+        x = __ldg(src.x0 + (int64_t)c * src.s0c + d * src.s0d + (int64_t)h * src.s0h + w);
+      else
+        x = __ldg(src.x1 + (int64_t)(c - src.c0) * spatial + p);
+      if (src.sums != nullptr) {
+        const double mu = src.sums[2 * c] * (double)src.inv_n;
+        const double var = src.sums[2 * c + 1] * (double)src.inv_n - mu * mu;
+        x = (x - (float)mu) * (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
+      } else if (src.mean != nullptr) {
+        x = (x - __ldg(src.mean + c)) * __ldg(src.rstd + c);
+      }
+      x = apply_act(x, src.act);
+    }
+    v[k] = x;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]);
+  o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]);
+  o.w = pack_bf16x2(v[6], v[7]);
+  out[(int64_t)kc * spatial + p] = o;
+}
+
+int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* out, cudaStream_t st) {
+  const int cin_pad = (src.c0 + src.c1 + 15) / 16 * 16;
+  const int64_t spatial = (int64_t)in_d * in_h * in_w;
+  dim3 grid((unsigned)((spatial + 255) / 256), cin_pad / 8);
+  prep_blocked_kernel<<<grid, 256, 0, st>>>(src, spatial, in_h, in_w, reinterpret_cast<uint4*>(out));
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM kernel
+// ---------------------------------------------------------------------------------------------
+struct GemmConvParams {
+  const uint4* a;          // blocked bf16 input [cin_pad/8][D][H][W]
+  const uint4* w;          // packed weights [taps][cin_pad/8][cout_pad][8 bf16]
+  const float* bias;       // cout or nullptr
+  const float* out_scale;  // cout or nullptr
+  const float* residual;   // fp32 NCDHW (cout, OD,OH,OW) or nullptr
+  float* y;                // fp32 NCDHW
+  int cin_pad, cout, cout_pad, n_tile;
+  int D, H, W, OD, OH, OW, stride, taps, kstage;
+};
+
+constexpr int G_EPI_WARPS = 4;
+constexpr int G_PROD_WARPS = 4;
+constexpr int G_THREADS = (G_EPI_WARPS + 1 + G_PROD_WARPS) * 32;
+constexpr int G_PROD_T0 = (G_EPI_WARPS + 1) * 32;
+constexpr int G_NPROD = G_PROD_WARPS * 32;
+constexpr int G_NS = 3;   // smem stages
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(G_THREADS, 2)
+conv_gemm_kernel(GemmConvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int a_bytes = 2 * p.kstage * 2048;               // [chunk][128 rows][16 B]
+  const int b_bytes = 2 * p.kstage * p.n_tile * 16;      // [chunk][n_tile rows][16 B]
+  const int stage_bytes = a_bytes + b_bytes;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + G_NS * stage_bytes);
+  uint64_t* bar_empty = bar_full + G_NS;
+  uint64_t* bar_acc = bar_empty + G_NS;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
+  const int64_t m0 = (int64_t)blockIdx.x * 128;
+  const int n0 = blockIdx.y * p.n_tile;
+  const int cpt = p.cin_pad / (16 * p.kstage);           // stages per tap
+  const int total = p.taps * cpt;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.n_tile) tmem_cols <<= 1;
+
+  if (tid == 0) {
+    for (int s = 0; s < G_NS; ++s) { mbar_init(&bar_full[s], G_NPROD); mbar_init(&bar_empty[s], 1); }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == G_EPI_WARPS) tmem_alloc(s_tmem, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp >= G_EPI_WARPS + 1) {
+    // =============================== producers ===================================================
+    const int pt = tid - G_PROD_T0;                       // 0..127 = A row of this thread
+    const int64_t m = m0 + pt;
+    const bool row_ok = m < m_total;
+    int ow = 0, oh = 0, od = 0;
+    if (row_ok) {
+      ow = (int)(m % p.OW);
+      const int64_t t = m / p.OW;
+      oh = (int)(t % p.OH);
+      od = (int)(t / p.OH);
+    }
+    const int64_t sp_in = (int64_t)p.D * p.H * p.W;
+    const int pad = p.taps == 27 ? 1 : 0;
+    const uint32_t smem_base = smem_u32(smem);
+    const int n_chunks = 2 * p.kstage;
+    const int b_items = n_chunks * p.n_tile;
+    for (int it = 0; it < total; ++it) {
+      const int s = it % G_NS;
+      mbar_wait(&bar_empty[s], ((uint32_t)(it / G_NS) & 1u) ^ 1u);
+      const int tap = it / cpt;
+      const int kc0 = (it - tap * cpt) * n_chunks;
+      int kd = 0, kh = 0, kw = 0;
+      if (p.taps == 27) { kd = tap / 9; kh = (tap / 3) % 3; kw = tap % 3; }
+      const int id = od * p.stride + kd - pad, ih = oh * p.stride + kh - pad, iw = ow * p.stride + kw - pad;
+      const bool ok = row_ok && (unsigned)id < (unsigned)p.D && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+      const int64_t lin = ok ? ((int64_t)id * p.H + ih) * p.W + iw : 0;
+      const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes) + (uint32_t)(pt * 16);
+      const uint4* a_src = p.a + (int64_t)kc0 * sp_in + lin;
+      for (int c = 0; c < n_chunks; ++c) cp_async16(a_dst + (uint32_t)(c * 2048), a_src + (int64_t)c * sp_in, ok ? 16u : 0u);
+      const uint32_t b_dst = smem_base + (uint32_t)(s * stage_bytes + a_bytes);
+      const uint4* b_src = p.w + ((int64_t)tap * (p.cin_pad / 8) + kc0) * p.cout_pad + n0;
+      for (int e = pt; e < b_items; e += G_NPROD) {
+        const int c = e / p.n_tile;
+        const int n = e - c * p.n_tile;
+        cp_async16(b_dst + (uint32_t)(e * 16), b_src + (int64_t)c * p.cout_pad + n, 16u);
+      }
+      cp_async_commit();
+      if (it >= 1) {
+        cp_async_wait<1>();
+        fence_proxy_async();
+        mbar_arrive(&bar_full[(it - 1) % G_NS]);
+      }
+    }
+    cp_async_wait<0>();
+    fence_proxy_async();
+    mbar_arrive(&bar_full[(total - 1) % G_NS]);
+  } else if (warp == G_EPI_WARPS) {
+    // =============================== MMA issuer ==================================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      const uint32_t smem_base = smem_u32(smem);
+      const uint32_t b_lbo = (uint32_t)p.n_tile * 16;
+      for (int it = 0; it < total; ++it) {
+        const int s = it % G_NS;
+        mbar_wait(&bar_full[s], (uint32_t)(it / G_NS) & 1u);
+        tc_fence_after();
+        const uint32_t a0 = smem_base + (uint32_t)(s * stage_bytes);
+        const uint32_t b0 = a0 + (uint32_t)a_bytes;
+        for (int ks = 0; ks < p.kstage; ++ks)
+          umma_bf16(tmem_base, umma_desc(a0 + (uint32_t)(ks * 2 * 2048), 2048, 128),
+                    umma_desc(b0 + (uint32_t)(ks * 2) * b_lbo, b_lbo, 128), idesc, (it | ks) != 0 ? 1u : 0u);
+        umma_commit(&bar_empty[s]);
+      }
+      umma_commit(bar_acc);
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue ====================================================
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int64_t m = m0 + warp * 32 + lane;
+    const bool row_ok = m < m_total;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+      uint32_t acc[16];
+      tmem_ld16(lane_addr + (uint32_t)c0, acc);
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int co = n0 + c0 + k;
+          if (co < p.cout) {
+            float val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
+            if (p.out_scale) val *= __ldg(p.out_scale + co);
+            const int64_t off = (int64_t)co * m_total + m;
+            if (p.residual) val += __ldg(p.residual + off);
+            p.y[off] = val;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == G_EPI_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// n_tile: a multiple of 16 that divides cout_pad, <= 256, chosen so the grid has enough CTAs
+static int pick_n_tile(int cout_pad, int64_t m_tiles) {
+  int best = 16;
+  for (int n = 16; n <= 256 && n <= cout_pad; n += 16) {
+    if (cout_pad % n != 0) continue;
+    const int64_t ctas = m_tiles * (cout_pad / n);
+    if (ctas >= 120 || n == 16) best = n;     // the largest tile that still fills the machine
+    else break;
+  }
+  return best;
+}
+
+int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
+                     int stride, int taps, cudaStream_t st) {
+  GemmConvParams p;
+  p.a = reinterpret_cast<const uint4*>(a_blocked);
+  p.w = reinterpret_cast<const uint4*>(w.dev);
+  p.bias = dst.bias; p.out_scale = dst.out_scale; p.residual = dst.residual; p.y = dst.y;
+  p.cin_pad = (w.cin + 15) / 16 * 16;
+  p.cout = w.cout;
+  p.cout_pad = (w.cout + 15) / 16 * 16;
+  p.D = in_d; p.H = in_h; p.W = in_w;
+  p.stride = stride; p.taps = taps;
+  if (taps == 27) {
+    p.OD = (in_d - 1) / stride + 1; p.OH = (in_h - 1) / stride + 1; p.OW = (in_w - 1) / stride + 1;
+  } else {
+    p.OD = (in_d - 1) / stride + 1; p.OH = (in_h - 1) / stride + 1; p.OW = (in_w - 1) / stride + 1;
+  }
+  const int k16 = p.cin_pad / 16;
+  p.kstage = k16 % 4 == 0 ? 4 : (k16 % 3 == 0 ? 3 : (k16 % 2 == 0 ? 2 : 1));
+  const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
+  const int64_t m_tiles = (m_total + 127) / 128;
+  p.n_tile = pick_n_tile(p.cout_pad, m_tiles);
+  const int stage_bytes = 2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16;
+  const int smem_bytes = G_NS * stage_bytes + (2 * G_NS + 1) * 8 + 16;
+  static int configured = 0;
+  if (smem_bytes > configured) {
+    DCL_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = 160 * 1024;
+  }
+  if (smem_bytes > 160 * 1024) { set_error("conv_gemm: stage does not fit shared memory"); return -1; }
+  dim3 grid((unsigned)m_tiles, p.cout_pad / p.n_tile);
+  conv_gemm_kernel<<<grid, G_THREADS, smem_bytes, st>>>(p);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dcl

@@ -341,26 +341,25 @@ static uint16_t f32_to_bf16_rn(float f) {
 //   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]      one stacked N = 3*cout matrix per (kd,kw)
 static int tc_weight_layout(int cin, int cout) { return (cin == 16 && cout == 16) ? 1 : 0; }
 
-int tc_pack_weights(const float* w_host, int cout, int cin, TcWeights* out) {
+int tc_pack_weights(const float* w_host, int cout, int cin, int taps, TcWeights* out) {
   out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0;
-  if (cin % 16 != 0 || cout % 16 != 0) return 0;   // no tensor-core kernel takes this shape
-  const int kcs = cin / 8;
-  std::vector<uint16_t> packed((size_t)27 * cin * cout);
-  const int layout = tc_weight_layout(cin, cout);
-  for (int kd = 0; kd < 3; ++kd)
-    for (int kh = 0; kh < 3; ++kh)
-      for (int kw = 0; kw < 3; ++kw)
-        for (int kc = 0; kc < kcs; ++kc)
-          for (int n = 0; n < cout; ++n)
-            for (int k = 0; k < 8; ++k) {
-              const int tap = (kd * 3 + kh) * 3 + kw;
-              size_t dst;
-              if (layout == 0)
-                dst = (((size_t)tap * kcs + kc) * cout + n) * 8 + k;
-              else
-                dst = (((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * cout) + n) * 8 + k;
-              packed[dst] = f32_to_bf16_rn(w_host[((size_t)n * cin + kc * 8 + k) * 27 + tap]);
-            }
+  const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;   // zero padded
+  const int kcs = cin_pad / 8;
+  std::vector<uint16_t> packed((size_t)taps * cin_pad * cout_pad, 0);
+  const int layout = taps == 27 ? tc_weight_layout(cin, cout) : 0;
+  for (int tap = 0; tap < taps; ++tap)
+    for (int ci = 0; ci < cin; ++ci)
+      for (int n = 0; n < cout; ++n) {
+        const int kc = ci / 8, k = ci % 8;
+        size_t dst;
+        if (layout == 0) {
+          dst = (((size_t)tap * kcs + kc) * cout_pad + n) * 8 + k;
+        } else {
+          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+          dst = (((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * cout_pad) + n) * 8 + k;
+        }
+        packed[dst] = f32_to_bf16_rn(w_host[((size_t)n * cin + ci) * taps + tap]);
+      }
   out->bytes = (int64_t)packed.size() * 2;
   DCL_CUDA_OK(cudaMalloc(&out->dev, (size_t)out->bytes));
   DCL_CUDA_OK(cudaMemcpy(out->dev, packed.data(), (size_t)out->bytes, cudaMemcpyHostToDevice));

@@ -11,8 +11,13 @@ struct TcWeights {
   int64_t bytes = 0;
 };
 
-// Packs a PyTorch (cout, cin, 3,3,3) fp32 weight (host) into the kernel's B-operand layout.
-int tc_pack_weights(const float* w_host, int cout, int cin, TcWeights* out);
+// Packs a PyTorch (cout, cin, taps) fp32 weight (host) into the kernel's B-operand layout (taps = 27 | 1).
+int tc_pack_weights(const float* w_host, int cout, int cin, int taps, TcWeights* out);
+// fp32 NCDHW (two-source concat, fused norm + activation) -> bf16 channel-blocked [cin_pad/8][D][H][W][8]
+int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* out, cudaStream_t st);
+// general implicit-GEMM convolution on a blocked bf16 input (taps = 27: kernel 3 pad 1, taps = 1: pointwise)
+int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
+                     int stride, int taps, cudaStream_t st);
 // True when launch_conv3d_k3_tc handles a cubic g^3 input with these channel counts.
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split);
 // Same contract as launch_conv3d_k3 (dense single-source input, fused input norm/activation, bias,

@@ -181,6 +181,7 @@ struct dcl_handle {
   float* probs;                                  // (4,128^3)
   float* keep_dev;                               // (16)
   double* stat_accum;                            // (2*512)
+  void* blk = nullptr;                           // bf16 channel-blocked conv input (DCL_BF16 only)
   std::vector<StatSlot> stat_slots;
   int stat_next = 0;
 
@@ -267,6 +268,7 @@ static int allocate_workspace(dcl_handle* h) {
     DCL_TRY(falloc(h, &h->dl_1[l], n)); DCL_TRY(falloc(h, &h->dl_2[l], n));
   }
   DCL_TRY(falloc(h, &h->probs, 4 * P3));
+  if (h->cfg.precision == DCL_BF16) DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * 2));
   DCL_TRY(falloc(h, &h->keep_dev, 16));
   DCL_TRY(dev_alloc(h, (void**)&h->stat_accum, 2 * 512 * sizeof(double)));
   if (!h->dry_run) DCL_CUDA_OK(cudaMemset(h->stat_accum, 0, 2 * 512 * sizeof(double)));
@@ -327,9 +329,9 @@ static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vec
   }
   DCL_TRY(upload(h, packed, &out->w));
   DCL_TRY(upload(h, bias, &out->b));
-  if (kind == W_CONV3 && h->cfg.precision != DCL_FP32) {
-    DCL_TRY(upload(h, raw, &out->raw));
-    DCL_TRY(tc_pack_weights(raw.data(), cout, cin, &out->tc));
+  if (h->cfg.precision == DCL_BF16 && (kind == W_CONV3 || kind == W_CONV1)) {
+    if (kind == W_CONV1) raw = *ws[0];   // (cout, cin)
+    DCL_TRY(tc_pack_weights(raw.data(), cout, cin, kind == W_CONV3 ? 27 : 1, &out->tc));
     h->allocs.push_back(out->tc.dev);
   }
   return 0;
@@ -413,10 +415,16 @@ struct Fwd {
     cudaEvent_t ev = nullptr;
     if (h->profiling) ev = h->prof_begin(st);
     int rc;
-    if (h->cfg.precision != DCL_FP32 && tc_conv_supported(c0 + c1, w.cout, g, stride, h->cfg.precision == DCL_BF16X3) && x1 == nullptr)
-      rc = launch_conv3d_k3_tc(s, d, w.tc, w.cout, g, h->cfg.precision == DCL_BF16X3, st);
-    else
+    if (h->cfg.precision == DCL_BF16) {
+      if (tc_conv_supported(c0 + c1, w.cout, g, stride, false) && x1 == nullptr && out_scale == nullptr) {
+        rc = launch_conv3d_k3_tc(s, d, w.tc, w.cout, g, false, st);
+      } else {
+        rc = launch_prep_blocked(s, g, g, g, h->blk, st);
+        if (rc == 0) rc = launch_conv_gemm(h->blk, w.tc, d, g, g, g, stride, 27, st);
+      }
+    } else {
       rc = launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, g, g, g, stride, st);
+    }
     if (h->profiling) {
       const double og = (double)((g - 1) / stride + 1);
       h->prof_end(ev, 0, 2.0 * 27.0 * (c0 + c1) * w.cout * og * og * og, st);
@@ -428,6 +436,10 @@ struct Fwd {
             bool softmax = false) {
     ConvSrc s{x0, x1, c0, c1, spatial, 0, 0, nullptr, nullptr, ACT_NONE};
     ConvDst d{y, w.b, nullptr, nullptr};
+    if (h->cfg.precision == DCL_BF16 && !softmax) {   // pointwise conv = 1-tap GEMM over a flat "row" of voxels
+      DCL_TRY(launch_prep_blocked(s, 1, 1, (int)spatial, h->blk, st));
+      return launch_conv_gemm(h->blk, w.tc, d, 1, 1, (int)spatial, 1, 1, st);
+    }
     return launch_conv1x1(s, d, w.w, w.cout, spatial, softmax, st);
   }
 
@@ -515,7 +527,12 @@ struct Fwd {
       const ConvW& w = h->conv.at("Unet_list.InitConv.conv");
       ConvDst d{h->l_t0[0], w.b, h->keep_dev, nullptr};
       cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
-      DCL_TRY(launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, 128, 128, 128, 1, st));
+      if (h->cfg.precision == DCL_BF16) {
+        DCL_TRY(launch_prep_blocked(s, 128, 128, 128, h->blk, st));
+        DCL_TRY(launch_conv_gemm(h->blk, w.tc, d, 128, 128, 128, 1, 27, st));
+      } else {
+        DCL_TRY(launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, 128, 128, 128, 1, st));
+      }
       if (h->profiling) h->prof_end(ev, 0, 2.0 * 27.0 * 4 * 16 * (double)P3, st);
     }
     const char* blk[4][2] = {{"Unet_list.EnBlock1", "Unet_list.EnBlock1_1"}, {"Unet_list.EnBlock2_1", "Unet_list.EnBlock2_2"},
@@ -1002,14 +1019,21 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
     cudaStreamSynchronize(st);
     cudaFree(wp);
   } else {
-    if (in_dhw[0] != in_dhw[1] || in_dhw[1] != in_dhw[2] || x1 != nullptr ||
-        !tc_conv_supported(cin, cout, in_dhw[0], stride, impl == 1)) {
-      set_error("dcl_op_conv3d_k3: shape not supported by the tensor-core kernel");
-      return DCL_ERR_ARG;
-    }
+    if (impl == 1) { set_error("dcl_op_conv3d_k3: bf16x3 has no tensor-core kernel yet"); return DCL_ERR_ARG; }
     TcWeights tw;
-    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, &tw));
-    rc = launch_conv3d_k3_tc(s, d, tw, cout, in_dhw[0], impl == 1, st);
+    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, 27, &tw));
+    const bool cubic = in_dhw[0] == in_dhw[1] && in_dhw[1] == in_dhw[2];
+    if (cubic && x1 == nullptr && tc_conv_supported(cin, cout, in_dhw[0], stride, false)) {
+      rc = launch_conv3d_k3_tc(s, d, tw, cout, in_dhw[0], false, st);
+    } else {
+      if (stats_out) { cudaFree(tw.dev); set_error("dcl_op_conv3d_k3: fused statistics need the rolling kernel"); return DCL_ERR_ARG; }
+      void* blk = nullptr;
+      DCL_CUDA_OK(cudaMalloc(&blk, (size_t)((cin + 15) / 16 * 16) * sp * 2));
+      rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
+      if (rc == 0) rc = launch_conv_gemm(blk, tw, d, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27, st);
+      cudaStreamSynchronize(st);
+      cudaFree(blk);
+    }
     cudaStreamSynchronize(st);
     cudaFree(tw.dev);
   }

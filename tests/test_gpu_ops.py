@@ -104,3 +104,46 @@ def test_conv3d_k3_tcgen05_bf16(c, g, act, residual):
     yd = y.double().flatten(1)
     assert rel_err(st[:, 0].numpy(), yd.sum(1).numpy()) < 1e-5
     assert rel_err(st[:, 1].numpy(), (yd * yd).sum(1).numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("case", [
+    dict(c0=4, c1=0, cout=16, dims=(32, 32, 32), stride=1, norm=False, act=0, residual=False),
+    dict(c0=16, c1=0, cout=32, dims=(32, 32, 32), stride=2, norm=False, act=0, residual=False),
+    dict(c0=32, c1=64, cout=96, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
+    dict(c0=32, c1=0, cout=8, dims=(16, 16, 16), stride=1, norm=True, act=2, residual=False),
+    dict(c0=8, c1=0, cout=2, dims=(20, 12, 36), stride=1, norm=False, act=0, residual=False),
+    dict(c0=5, c1=3, cout=19, dims=(9, 17, 18), stride=2, norm=True, act=2, residual=True),
+    dict(c0=128, c1=0, cout=128, dims=(16, 16, 16), stride=1, norm=True, act=1, residual=True),
+    dict(c0=64, c1=0, cout=64, dims=(32, 32, 32), stride=1, norm=True, act=2, residual=False),
+    dict(c0=256, c1=0, cout=384, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
+])
+def test_conv3d_k3_gemm_bf16(case):
+    """The general tcgen05 implicit-GEMM kernel (prep + cp.async im2col) against torch conv3d on
+    bf16-rounded operands."""
+    from dcl_b200.engine import op_conv3d_k3
+    g = torch.Generator().manual_seed(23)
+    c0, c1, cout, dims, stride = case["c0"], case["c1"], case["cout"], case["dims"], case["stride"]
+    cin = c0 + c1
+    x0 = torch.randn(c0, *dims, generator=g)
+    x1 = torch.randn(c1, *dims, generator=g) if c1 else None
+    w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
+    b = torch.randn(cout, generator=g)
+    xin = torch.cat([x0, x1], 0) if c1 else x0
+    mean = rstd = None
+    if case["norm"]:
+        mean = torch.randn(cin, generator=g) * 0.3
+        rstd = torch.rand(cin, generator=g) + 0.5
+        xin = (xin - mean.view(-1, 1, 1, 1)) * rstd.view(-1, 1, 1, 1)
+    xin = F.relu(xin) if case["act"] == 1 else (F.leaky_relu(xin, 0.01) if case["act"] == 2 else xin)
+    ref = F.conv3d(_bf16_round(xin)[None], _bf16_round(w), b, stride=stride, padding=1)[0]
+    res = torch.randn(ref.shape, generator=g) if case["residual"] else None
+    if res is not None:
+        ref = ref + res
+    y = op_conv3d_k3(x0.cuda(), w.cuda(), b.cuda(), x1.cuda() if c1 else None, stride,
+                     (mean.cuda(), rstd.cuda()) if case["norm"] else None, case["act"],
+                     res.cuda() if res is not None else None, impl=2)
+    torch.cuda.synchronize()
+    y = y.cpu()
+    assert y.shape == ref.shape
+    assert rel_err(y.numpy(), ref.numpy()) < 2e-3
+    assert float((y - ref).abs().mean() / ref.abs().mean()) < 1e-4
