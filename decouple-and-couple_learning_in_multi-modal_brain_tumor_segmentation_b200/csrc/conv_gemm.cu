@@ -84,6 +84,8 @@ struct GemmConvParams {
   float* y;                // fp32 NCDHW
   int cin_pad, cout, cout_pad, n_tile;
   int D, H, W, OD, OH, OW, stride, taps, kstage;
+  int row_major;           // 1: y / residual are fp32 [m][cout] (linear layers), 0: NCDHW [cout][m]
+  int gelu;                // exact (erf) GELU after the bias
 };
 
 constexpr int G_EPI_WARPS = 4;
@@ -91,7 +93,6 @@ constexpr int G_PROD_WARPS = 4;
 constexpr int G_THREADS = (G_EPI_WARPS + 1 + G_PROD_WARPS) * 32;
 constexpr int G_PROD_T0 = (G_EPI_WARPS + 1) * 32;
 constexpr int G_NPROD = G_PROD_WARPS * 32;
-constexpr int G_NS = 3;   // smem stages
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -100,8 +101,22 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// wait for the cp.async groups of the last K+1 stages one by one (oldest first) and publish them
+template <int K>
+__device__ __forceinline__ void drain_stages(uint64_t* bar_full, int total, int ns) {
+  if (K < total) {
+    cp_async_wait<K>();
+    fence_proxy_async();
+    mbar_arrive(&bar_full[(total - 1 - K) % ns]);
+  }
+  if constexpr (K > 0) drain_stages<K - 1>(bar_full, total, ns);
+}
+
+// G_NS shared-memory stages; producers keep LAG = G_NS - 2 cp.async groups in flight
+template <int G_NS>
 __global__ void __launch_bounds__(G_THREADS, 2)
 conv_gemm_kernel(GemmConvParams p) {
+  constexpr int LAG = G_NS - 2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int a_bytes = 2 * p.kstage * 2048;               // [chunk][128 rows][16 B]
   const int b_bytes = 2 * p.kstage * p.n_tile * 16;      // [chunk][n_tile rows][16 B]
@@ -169,15 +184,13 @@ conv_gemm_kernel(GemmConvParams p) {
         cp_async16(b_dst + (uint32_t)(e * 16), b_src + (int64_t)c * p.cout_pad + n, 16u);
       }
       cp_async_commit();
-      if (it >= 1) {
-        cp_async_wait<1>();
+      if (it >= LAG) {
+        cp_async_wait<LAG>();
         fence_proxy_async();
-        mbar_arrive(&bar_full[(it - 1) % G_NS]);
+        mbar_arrive(&bar_full[(it - LAG) % G_NS]);
       }
     }
-    cp_async_wait<0>();
-    fence_proxy_async();
-    mbar_arrive(&bar_full[(total - 1) % G_NS]);
+    drain_stages<LAG - 1>(bar_full, total, G_NS);
   } else if (warp == G_EPI_WARPS) {
     // =============================== MMA issuer ==================================================
     if (lane == 0) {
@@ -210,15 +223,36 @@ conv_gemm_kernel(GemmConvParams p) {
       tmem_ld16(lane_addr + (uint32_t)c0, acc);
       tmem_ld_wait();
       if (row_ok) {
+        if (p.row_major) {   // 16 consecutive outputs of one row: 4 x 16-byte stores
+          float v[16];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int co = n0 + c0 + k;
-          if (co < p.cout) {
+          for (int k = 0; k < 16; ++k) {
+            const int co = n0 + c0 + k;
             float val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
-            if (p.out_scale) val *= __ldg(p.out_scale + co);
-            const int64_t off = (int64_t)co * m_total + m;
-            if (p.residual) val += __ldg(p.residual + off);
-            p.y[off] = val;
+            if (p.gelu) val = 0.5f * val * (1.f + erff(val * 0.70710678118654752440f));
+            v[k] = val;
+          }
+          const int64_t off = m * p.cout + n0 + c0;
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+            if (p.residual) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off + k));
+              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            }
+            *reinterpret_cast<float4*>(p.y + off + k) = o;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int co = n0 + c0 + k;
+            if (co < p.cout) {
+              float val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
+              if (p.out_scale) val *= __ldg(p.out_scale + co);
+              const int64_t off = (int64_t)co * m_total + m;
+              if (p.residual) val += __ldg(p.residual + off);
+              p.y[off] = val;
+            }
           }
         }
       }
@@ -245,6 +279,8 @@ static int pick_n_tile(int cout_pad, int64_t m_tiles) {
   return best;
 }
 
+static int launch_gemm_params(GemmConvParams& p, cudaStream_t st);
+
 int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
                      int stride, int taps, cudaStream_t st) {
   GemmConvParams p;
@@ -256,29 +292,106 @@ int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& d
   p.cout_pad = (w.cout + 15) / 16 * 16;
   p.D = in_d; p.H = in_h; p.W = in_w;
   p.stride = stride; p.taps = taps;
+  p.row_major = 0; p.gelu = 0;
   if (taps == 27) {
     p.OD = (in_d - 1) / stride + 1; p.OH = (in_h - 1) / stride + 1; p.OW = (in_w - 1) / stride + 1;
   } else {
     p.OD = (in_d - 1) / stride + 1; p.OH = (in_h - 1) / stride + 1; p.OW = (in_w - 1) / stride + 1;
   }
+  return launch_gemm_params(p, st);
+}
+
+static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
   const int k16 = p.cin_pad / 16;
   p.kstage = k16 % 4 == 0 ? 4 : (k16 % 3 == 0 ? 3 : (k16 % 2 == 0 ? 2 : 1));
   const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
   const int64_t m_tiles = (m_total + 127) / 128;
   p.n_tile = pick_n_tile(p.cout_pad, m_tiles);
   const int stage_bytes = 2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16;
-  const int smem_bytes = G_NS * stage_bytes + (2 * G_NS + 1) * 8 + 16;
-  static int configured = 0;
-  if (smem_bytes > configured) {
-    DCL_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = 160 * 1024;
-  }
+  const int ns = stage_bytes <= 12 * 1024 ? 8 : stage_bytes <= 16 * 1024 ? 6 : stage_bytes <= 26 * 1024 ? 4 : 3;
+  const int smem_bytes = ns * stage_bytes + (2 * ns + 1) * 8 + 16;
   if (smem_bytes > 160 * 1024) { set_error("conv_gemm: stage does not fit shared memory"); return -1; }
+  static bool configured = false;
+  if (!configured) {
+    DCL_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DCL_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DCL_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    DCL_CUDA_OK(cudaFuncSetAttribute(conv_gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    configured = true;
+  }
   dim3 grid((unsigned)m_tiles, p.cout_pad / p.n_tile);
-  conv_gemm_kernel<<<grid, G_THREADS, smem_bytes, st>>>(p);
+  if (ns == 8) conv_gemm_kernel<8><<<grid, G_THREADS, smem_bytes, st>>>(p);
+  else if (ns == 6) conv_gemm_kernel<6><<<grid, G_THREADS, smem_bytes, st>>>(p);
+  else if (ns == 4) conv_gemm_kernel<4><<<grid, G_THREADS, smem_bytes, st>>>(p);
+  else conv_gemm_kernel<3><<<grid, G_THREADS, smem_bytes, st>>>(p);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Linear layers of the couplers (nn.Linear in SelfAttention.py:62-66, ResidualNorm.py:38-44) as the same
+// GEMM: rows = tokens.  prep_rows fuses the preceding nn.LayerNorm(512) (ResidualNorm.py:14-32).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+prep_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 int rows, uint4* __restrict__ out) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (int64_t)row * TOKEN_DIM) + lane * 4;   // 16 elements / lane
+  float v[16];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float4 t = __ldg(xr + j);
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+  if (gamma != nullptr) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s += v[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.f / TOKEN_DIM);
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { const float a = v[k] - mean; q += a * a; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.f / TOKEN_DIM) + 1e-5f);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = (v[k] - mean) * rstd * __ldg(gamma + lane * 16 + k) + __ldg(beta + lane * 16 + k);
+  }
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    uint4 o;
+    o.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+    o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+    o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+    o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    out[(int64_t)(lane * 2 + c) * rows + row] = o;
+  }
+}
+
+int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st) {
+  prep_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, rows, reinterpret_cast<uint4*>(out));
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
+                     int m, int n, int k, bool gelu, cudaStream_t st) {
+  if (n % 16 != 0 || k % 16 != 0) { set_error("linear_tc: n and k must be multiples of 16"); return -1; }
+  GemmConvParams p;
+  p.a = reinterpret_cast<const uint4*>(a_blocked);
+  p.w = reinterpret_cast<const uint4*>(w_packed);
+  p.bias = bias; p.out_scale = nullptr; p.residual = residual; p.y = y;
+  p.cin_pad = k; p.cout = n; p.cout_pad = n;
+  p.D = 1; p.H = 1; p.W = m; p.OD = 1; p.OH = 1; p.OW = m;
+  p.stride = 1; p.taps = 1;
+  p.row_major = 1; p.gelu = gelu ? 1 : 0;
+  return launch_gemm_params(p, st);
 }
 
 }  // namespace dcl

@@ -25,4 +25,10 @@ bool tc_conv_supported(int cin, int cout, int g, int stride, bool split);
 int launch_conv3d_k3_tc(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, int cout, int g, bool split,
                         cudaStream_t st);
 
+// fp32 [rows][512] (optionally LayerNorm'ed) -> bf16 blocked [64][rows][8]
+int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st);
+// y[m][n] = a[m][:] . w[n][:] + bias (+GELU) (+residual), a blocked bf16, w packed by tc_pack_weights(taps = 1)
+int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
+                     int m, int n, int k, bool gelu, cudaStream_t st);
+
 }  // namespace dcl

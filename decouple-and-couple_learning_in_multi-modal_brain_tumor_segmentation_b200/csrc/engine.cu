@@ -137,6 +137,7 @@ struct ConvW {          // packed conv weights on the device
 
 struct Transformer {
   float *n1w, *n1b, *n2w, *n2b, *wqkv, *wout, *bout, *fnw, *fnb, *w0, *b0, *w3, *b3;
+  void *pq = nullptr, *pkv = nullptr, *pout = nullptr, *p0 = nullptr, *p3 = nullptr;   // bf16 UMMA operand tiles (DCL_BF16)
 };
 
 struct StatSlot { float* mean; float* rstd; };
@@ -182,6 +183,7 @@ struct dcl_handle {
   float* keep_dev;                               // (16)
   double* stat_accum;                            // (2*512)
   void* blk = nullptr;                           // bf16 channel-blocked conv input (DCL_BF16 only)
+  void *tok_a = nullptr, *tok_b = nullptr;       // bf16 blocked token matrices feeding the linear GEMMs
   std::vector<StatSlot> stat_slots;
   int stat_next = 0;
 
@@ -268,7 +270,11 @@ static int allocate_workspace(dcl_handle* h) {
     DCL_TRY(falloc(h, &h->dl_1[l], n)); DCL_TRY(falloc(h, &h->dl_2[l], n));
   }
   DCL_TRY(falloc(h, &h->probs, 4 * P3));
-  if (h->cfg.precision == DCL_BF16) DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * 2));
+  if (h->cfg.precision == DCL_BF16) {
+    DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * 2));
+    DCL_TRY(dev_alloc(h, &h->tok_a, 258 * 512 * 2));
+    DCL_TRY(dev_alloc(h, &h->tok_b, 258 * 512 * 2));
+  }
   DCL_TRY(falloc(h, &h->keep_dev, 16));
   DCL_TRY(dev_alloc(h, (void**)&h->stat_accum, 2 * 512 * sizeof(double)));
   if (!h->dry_run) DCL_CUDA_OK(cudaMemset(h->stat_accum, 0, 2 * 512 * sizeof(double)));
@@ -384,6 +390,21 @@ static int prepare(dcl_handle* h) {
     t.fnw = R(f + "norm.weight"); t.fnb = R(f + "norm.bias");
     t.w0 = R(f + "fn.net.0.weight"); t.b0 = R(f + "fn.net.0.bias");
     t.w3 = R(f + "fn.net.3.weight"); t.b3 = R(f + "fn.net.3.bias");
+    if (h->cfg.precision == DCL_BF16) {
+      const std::vector<float>& qkv = h->host_w.at(a + "fn.qkv.weight");
+      auto pack = [&](const float* w, int n, void** out) -> int {
+        TcWeights tw;
+        DCL_TRY(tc_pack_weights(w, n, 512, 1, &tw));
+        h->allocs.push_back(tw.dev);
+        *out = tw.dev;
+        return 0;
+      };
+      DCL_TRY(pack(qkv.data(), 512, &t.pq));
+      DCL_TRY(pack(qkv.data() + 512 * 512, 1024, &t.pkv));
+      DCL_TRY(pack(h->host_w.at(a + "fn.out_proj.weight").data(), 512, &t.pout));
+      DCL_TRY(pack(h->host_w.at(f + "fn.net.0.weight").data(), 512, &t.p0));
+      DCL_TRY(pack(h->host_w.at(f + "fn.net.3.weight").data(), 512, &t.p3));
+    }
   }
   for (int r = 0; r < 3; ++r) {
     h->e_tok[r] = R(std::string("e_token_") + REGION_KEY[r]);
@@ -479,6 +500,16 @@ struct Fwd {
 
   // Residual(PreNormDrop(DualSelfAttention)) (ResidualNorm.py:4-32, SelfAttention.py:74-102)
   int attn_block(const Transformer& t, const float* x, const float* x2, int mq, int mk, float* out) {
+    if (h->cfg.precision == DCL_BF16) {   // LayerNorm fused into the bf16 operand prep, linears on tcgen05
+      DCL_TRY(launch_prep_rows(x, t.n1w, t.n1b, mq, h->tok_a, st));
+      DCL_TRY(launch_prep_rows(x2, t.n2w, t.n2b, mk, h->tok_b, st));
+      DCL_TRY(launch_linear_tc(h->tok_a, t.pq, nullptr, nullptr, h->qbuf, mq, 512, 512, false, st));
+      DCL_TRY(launch_linear_tc(h->tok_b, t.pkv, nullptr, nullptr, h->kvbuf, mk, 1024, 512, false, st));
+      DCL_TRY(launch_attention(h->qbuf, h->kvbuf, h->obuf, mq, mk, st));
+      DCL_TRY(launch_prep_rows(h->obuf, nullptr, nullptr, mq, h->tok_a, st));
+      DCL_TRY(launch_linear_tc(h->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st));
+      return 0;
+    }
     DCL_TRY(launch_layernorm(x, t.n1w, t.n1b, h->ln_a, mq, st));
     DCL_TRY(launch_layernorm(x2, t.n2w, t.n2b, h->ln_b, mk, st));
     DCL_TRY(launch_linear(h->ln_a, t.wqkv, nullptr, nullptr, h->qbuf, mq, 512, 512, false, st));
@@ -490,6 +521,13 @@ struct Fwd {
 
   // Residual(PreNorm(FeedForward)) (ResidualNorm.py:35-47)
   int ffn_block(const Transformer& t, const float* x, int m, float* out) {
+    if (h->cfg.precision == DCL_BF16) {
+      DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, h->tok_a, st));
+      DCL_TRY(launch_linear_tc(h->tok_a, t.p0, t.b0, nullptr, h->ffn_h, m, 512, 512, true, st));
+      DCL_TRY(launch_prep_rows(h->ffn_h, nullptr, nullptr, m, h->tok_b, st));
+      DCL_TRY(launch_linear_tc(h->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st));
+      return 0;
+    }
     DCL_TRY(launch_layernorm(x, t.fnw, t.fnb, h->ffn_ln, m, st));
     DCL_TRY(launch_linear(h->ffn_ln, t.w0, t.b0, nullptr, h->ffn_h, m, 512, 512, true, st));
     DCL_TRY(launch_linear(h->ffn_h, t.w3, t.b3, x, out, m, 512, 512, false, st));

@@ -36,40 +36,36 @@ score_kernel(const float* __restrict__ token, const float* __restrict__ feats, i
   if (lane == 0) score[row] = s;
 }
 
-// topk(128, largest, sorted) of up to 2048 scores (cls_wise_former.py:346): bitonic sort of
-// (score desc, index asc) pairs in shared memory by one 1024-thread block.
-__global__ void __launch_bounds__(1024)
+// topk(128, largest, sorted) of up to 2048 scores (cls_wise_former.py:346) by rank counting: element i
+// lands at position #{j : s_j > s_i or (s_j == s_i and j < i)}; positions < 128 are the sorted top-k
+// (ties broken by index, as a stable descending sort would).  128 elements per block, all scores in smem.
+__global__ void __launch_bounds__(128)
 topk_kernel(const float* __restrict__ score, int n, int* __restrict__ idx_out) {
-  __shared__ float key[2048];
-  __shared__ int val[2048];
-  for (int i = threadIdx.x; i < 2048; i += 1024) {
-    key[i] = i < n ? score[i] : -FLT_MAX;
-    val[i] = i < n ? i : 0x7fffffff;
-  }
+  __shared__ __align__(16) float key[2048];
+  for (int i = threadIdx.x; i < 2048; i += 128) key[i] = i < n ? score[i] : -FLT_MAX;
   __syncthreads();
-  for (int k = 2; k <= 2048; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < 2048; i += 1024) {
-        int p = i ^ j;
-        if (p > i) {
-          float ka = key[i], kb = key[p];
-          int va = val[i], vb = val[p];
-          bool a_first = (ka > kb) || (ka == kb && va < vb);   // a precedes b in the final order
-          bool descending_block = ((i & k) == 0);
-          if (a_first != descending_block) { key[i] = kb; key[p] = ka; val[i] = vb; val[p] = va; }
-        }
-      }
-      __syncthreads();
-    }
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (i >= n) return;
+  const float si = key[i];
+  int rank = 0;
+  const int n4 = (n + 3) / 4;
+#pragma unroll 4
+  for (int j4 = 0; j4 < n4; ++j4) {
+    const float4 v = *reinterpret_cast<const float4*>(key + 4 * j4);   // broadcast read
+    const int j = 4 * j4;
+    rank += (v.x > si || (v.x == si && j < i)) ? 1 : 0;
+    rank += (v.y > si || (v.y == si && j + 1 < i)) ? 1 : 0;
+    rank += (v.z > si || (v.z == si && j + 2 < i)) ? 1 : 0;
+    rank += (v.w > si || (v.w == si && j + 3 < i)) ? 1 : 0;
   }
-  if (threadIdx.x < TOP_NUM) idx_out[threadIdx.x] = val[threadIdx.x];
+  if (rank < TOP_NUM) idx_out[rank] = i;
 }
 
 int launch_select_topk(const float* token, const float* feats, int n_tokens, float* score_scratch, int* idx_out,
                        cudaStream_t st) {
   if (n_tokens > 2048 || n_tokens < TOP_NUM) { set_error("select_topk: 128 <= n_tokens <= 2048 required"); return -1; }
   score_kernel<<<(n_tokens + 7) / 8, 256, 0, st>>>(token, feats, n_tokens, score_scratch);
-  topk_kernel<<<1, 1024, 0, st>>>(score_scratch, n_tokens, idx_out);
+  topk_kernel<<<(n_tokens + 127) / 128, 128, 0, st>>>(score_scratch, n_tokens, idx_out);
   g_launches += 2;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -199,65 +195,107 @@ int launch_linear(const float* x, const float* w, const float* bias, const float
 }
 
 // DualSelfAttention core (SelfAttention.py:94-99): softmax(q k^T / 8) v per head.
-// Block = (16-query chunk, head), 4 warps x 4 query rows; K and V of the head live in shared memory.
+// Block = (16-query chunk, head), 4 warps x 4 query rows processed together; K (row pitch 68 floats so
+// 16-byte row reads of 8 consecutive keys hit 32 distinct banks) and V of the head live in shared memory,
+// filled with 16-byte loads.
 constexpr int ATT_HD = 64;
 constexpr int ATT_QCHUNK = 16;
 constexpr int ATT_MAXK = 160;
+constexpr int ATT_KP = ATT_HD + 4;
+constexpr int ATT_KG = ATT_MAXK / 32;     // key groups per lane
 
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int mq, int mk) {
-  extern __shared__ float sm[];
-  float* ks = sm;                          // [mk][65]
-  float* vs = ks + mk * (ATT_HD + 1);      // [mk][64]
-  float* qs = vs + mk * ATT_HD;            // [4 warps][64]
-  float* ps = qs + 4 * ATT_HD;             // [4 warps][ATT_MAXK]
+  extern __shared__ __align__(16) float sm[];
+  float* ks = sm;                              // [mk][68]
+  float* vs = ks + mk * ATT_KP;                // [mk][64]
+  float* qs = vs + mk * ATT_HD;                // [16][64]
+  float* ps = qs + ATT_QCHUNK * ATT_HD;        // [16][ATT_MAXK]
   const int head = blockIdx.y;
-  for (int e = threadIdx.x; e < mk * ATT_HD; e += 128) {
-    int d = e % ATT_HD, j = e / ATT_HD;
-    ks[j * (ATT_HD + 1) + d] = __ldg(kv + (int64_t)j * 1024 + head * ATT_HD + d);
-    vs[j * ATT_HD + d] = __ldg(kv + (int64_t)j * 1024 + 512 + head * ATT_HD + d);
+  const int row0 = blockIdx.x * ATT_QCHUNK;
+  for (int e = threadIdx.x; e < mk * (ATT_HD / 4); e += 128) {
+    const int d4 = e % (ATT_HD / 4), j = e / (ATT_HD / 4);
+    const float4 k4 = __ldg(reinterpret_cast<const float4*>(kv + (int64_t)j * 1024 + head * ATT_HD) + d4);
+    const float4 v4 = __ldg(reinterpret_cast<const float4*>(kv + (int64_t)j * 1024 + 512 + head * ATT_HD) + d4);
+    *reinterpret_cast<float4*>(ks + j * ATT_KP + 4 * d4) = k4;
+    *reinterpret_cast<float4*>(vs + j * ATT_HD + 4 * d4) = v4;
+  }
+  for (int e = threadIdx.x; e < ATT_QCHUNK * (ATT_HD / 4); e += 128) {
+    const int d4 = e % (ATT_HD / 4), r = e / (ATT_HD / 4);
+    float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < mq) q4 = __ldg(reinterpret_cast<const float4*>(q + (int64_t)(row0 + r) * TOKEN_DIM + head * ATT_HD) + d4);
+    *reinterpret_cast<float4*>(qs + r * ATT_HD + 4 * d4) = q4;
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* qw = qs + warp * ATT_HD;
-  float* pw = ps + warp * ATT_MAXK;
-  for (int r = 0; r < ATT_QCHUNK / 4; ++r) {
-    const int row = blockIdx.x * ATT_QCHUNK + warp * (ATT_QCHUNK / 4) + r;
-    if (row >= mq) break;                       // warp-uniform
-    qw[lane] = __ldg(q + (int64_t)row * TOKEN_DIM + head * ATT_HD + lane);
-    qw[lane + 32] = __ldg(q + (int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32);
-    __syncwarp();
-    float mx = -FLT_MAX;
-    for (int j = lane; j < mk; j += 32) {
-      const float* kr = ks + j * (ATT_HD + 1);
-      float s = 0.f;
-#pragma unroll 16
-      for (int d = 0; d < ATT_HD; ++d) s = fmaf(qw[d], kr[d], s);
-      s *= 0.125f;                              // head_dim ** -0.5
-      pw[j] = s;
-      mx = fmaxf(mx, s);
+  const float* qw = qs + warp * 4 * ATT_HD;     // this warp's 4 query rows
+  float* pw = ps + warp * 4 * ATT_MAXK;
+  float s[4][ATT_KG];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int g = 0; g < ATT_KG; ++g) s[r][g] = 0.f;
+#pragma unroll 4
+  for (int d4 = 0; d4 < ATT_HD / 4; ++d4) {
+    float4 qv[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) qv[r] = *reinterpret_cast<const float4*>(qw + r * ATT_HD + 4 * d4);
+#pragma unroll
+    for (int g = 0; g < ATT_KG; ++g) {
+      const int j = lane + 32 * g;
+      if (j < mk) {
+        const float4 kq = *reinterpret_cast<const float4*>(ks + j * ATT_KP + 4 * d4);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          s[r][g] = fmaf(qv[r].x, kq.x, s[r][g]);
+          s[r][g] = fmaf(qv[r].y, kq.y, s[r][g]);
+          s[r][g] = fmaf(qv[r].z, kq.z, s[r][g]);
+          s[r][g] = fmaf(qv[r].w, kq.w, s[r][g]);
+        }
+      }
     }
+  }
+  float inv[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int g = 0; g < ATT_KG; ++g)
+      if (lane + 32 * g < mk) { s[r][g] *= 0.125f; mx = fmaxf(mx, s[r][g]); }   // head_dim ** -0.5
     mx = warp_max_t(mx);
     float sum = 0.f;
-    for (int j = lane; j < mk; j += 32) { float e = expf(pw[j] - mx); pw[j] = e; sum += e; }
-    sum = warp_sum_t(sum);
-    __syncwarp();
-    const float inv = 1.f / sum;
-    float o0 = 0.f, o1 = 0.f;
-    for (int j = 0; j < mk; ++j) {
-      float p = pw[j];
-      o0 = fmaf(p, vs[j * ATT_HD + lane], o0);
-      o1 = fmaf(p, vs[j * ATT_HD + lane + 32], o1);
+#pragma unroll
+    for (int g = 0; g < ATT_KG; ++g)
+      if (lane + 32 * g < mk) { const float e = expf(s[r][g] - mx); pw[r * ATT_MAXK + lane + 32 * g] = e; sum += e; }
+    inv[r] = 1.f / warp_sum_t(sum);
+  }
+  __syncwarp();
+  float o[4][2];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) o[r][0] = o[r][1] = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < mk; ++j) {
+    const float v0 = vs[j * ATT_HD + lane], v1 = vs[j * ATT_HD + lane + 32];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float p = pw[r * ATT_MAXK + j];
+      o[r][0] = fmaf(p, v0, o[r][0]);
+      o[r][1] = fmaf(p, v1, o[r][1]);
     }
-    out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o0 * inv;
-    out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32] = o1 * inv;
-    __syncwarp();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int row = row0 + warp * 4 + r;
+    if (row < mq) {
+      out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o[r][0] * inv[r];
+      out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32] = o[r][1] * inv[r];
+    }
   }
 }
 
 int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st) {
   if (mk > ATT_MAXK) { set_error("attention: at most 160 keys"); return -1; }
-  size_t smem = (size_t)(mk * (ATT_HD + 1) + mk * ATT_HD + 4 * ATT_HD + 4 * ATT_MAXK) * sizeof(float);
+  size_t smem = (size_t)(mk * ATT_KP + mk * ATT_HD + ATT_QCHUNK * ATT_HD + ATT_QCHUNK * ATT_MAXK) * sizeof(float);
   static bool configured = false;
   if (!configured) {
     DCL_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
