@@ -19,6 +19,23 @@ void set_error(const std::string& msg);
 
 enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
 
+// Fused InstanceNorm statistics: per channel (sum, sum of squares) accumulated by conv epilogues as 64-bit
+// FIXED-POINT integers (integer atomics are associative, so the result does not depend on CTA order and the
+// forward stays bit-reproducible).  sum uses 24 fractional bits, sum of squares 16.
+typedef long long stat_t;
+constexpr double STAT_SCALE_S = 16777216.0, STAT_SCALE_Q = 65536.0;
+__device__ __forceinline__ void stat_add(stat_t* slot, int c, float sum, float sumsq) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(slot + 2 * c), (unsigned long long)__double2ll_rn((double)sum * STAT_SCALE_S));
+  atomicAdd(reinterpret_cast<unsigned long long*>(slot + 2 * c + 1), (unsigned long long)__double2ll_rn((double)sumsq * STAT_SCALE_Q));
+}
+// InstanceNorm3d(affine=False, eps=1e-5, biased variance) from the accumulated sums
+__device__ __forceinline__ void stat_mean_rstd(const stat_t* slot, int c, float inv_n, float* mean, float* rstd) {
+  const double mu = (double)slot[2 * c] * (1.0 / STAT_SCALE_S) * (double)inv_n;
+  const double var = (double)slot[2 * c + 1] * (1.0 / STAT_SCALE_Q) * (double)inv_n - mu * mu;
+  *mean = (float)mu;
+  *rstd = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
+}
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_RELU) return fmaxf(v, 0.f);
   if (act == ACT_LRELU) return v > 0.f ? v : 0.01f * v;
@@ -40,7 +57,7 @@ struct ConvSrc {
   int act;
   // alternative to mean/rstd: raw per-channel (sum, sum of squares) pairs accumulated by the producing
   // kernel's epilogue (ConvDst::stats); the consumer derives mean / rstd itself (no finalize launch)
-  const double* sums;
+  const stat_t* sums;
   float inv_n;             // 1 / (elements per channel)
 };
 
@@ -49,7 +66,7 @@ struct ConvDst {
   const float* bias;       // cout or nullptr
   const float* out_scale;  // per output channel multiplier applied after bias (dropout3d) or nullptr
   const float* residual;   // dense, same shape as y, added last; or nullptr
-  double* stats;           // nullptr, or 2*cout doubles: += (sum, sum of squares) of the stored values
+  stat_t* stats;           // nullptr, or 2*cout fixed-point sums: += (sum, sum of squares) of the stored values
 };
 
 // Packed k3 weights: [cin][27][cout_pad], cout_pad = round_up(cout, 16).

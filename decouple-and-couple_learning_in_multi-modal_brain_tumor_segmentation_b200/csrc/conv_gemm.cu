@@ -44,9 +44,9 @@ prep_blocked_kernel(ConvSrc src, int64_t spatial, int in_h, int in_w, uint4* __r
       else
         x = __ldg(src.x1 + (int64_t)(c - src.c0) * spatial + p);
       if (src.sums != nullptr) {
-        const double mu = src.sums[2 * c] * (double)src.inv_n;
-        const double var = src.sums[2 * c + 1] * (double)src.inv_n - mu * mu;
-        x = (x - (float)mu) * (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
+        float mu, rs;
+        stat_mean_rstd(src.sums, c, src.inv_n, &mu, &rs);
+        x = (x - mu) * rs;
       } else if (src.mean != nullptr) {
         x = (x - __ldg(src.mean + c)) * __ldg(src.rstd + c);
       }
@@ -76,15 +76,18 @@ int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* 
 // GEMM kernel
 // ---------------------------------------------------------------------------------------------
 struct GemmConvParams {
-  const uint4* a;          // blocked bf16 input [cin_pad/8][D][H][W]
+  const uint4* a;          // B-format input, channels [0, c0_chunks*8)
+  const uint4* a1;         // optional second source for the remaining channels (concat never materialised)
+  int c0_chunks;
   const uint4* w;          // packed weights [taps][cin_pad/8][cout_pad][8 bf16]
   const float* bias;       // cout or nullptr
   const float* out_scale;  // cout or nullptr
-  const float* residual;   // fp32 NCDHW (cout, OD,OH,OW) or nullptr
-  float* y;                // fp32 NCDHW
+  const void* residual;    // same format as y, or nullptr
+  void* y;
+  stat_t* stats;           // 2*cout fixed-point sums += per-channel (sum, sum of squares) of the outputs, or nullptr
   int cin_pad, cout, cout_pad, n_tile;
   int D, H, W, OD, OH, OW, stride, taps, kstage;
-  int row_major;           // 1: y / residual are fp32 [m][cout] (linear layers), 0: NCDHW [cout][m]
+  int out_mode;            // 0: fp32 NCDHW [cout][m]   1: fp32 row-major [m][cout]   2: B-format bf16
   int gelu;                // exact (erf) GELU after the bias
 };
 
@@ -125,6 +128,7 @@ conv_gemm_kernel(GemmConvParams p) {
   uint64_t* bar_empty = bar_full + G_NS;
   uint64_t* bar_acc = bar_empty + G_NS;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
+  float* s_stat = reinterpret_cast<float*>(s_tmem + 2);     // [4 warps][2][n_tile] partial sums
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
@@ -174,8 +178,11 @@ conv_gemm_kernel(GemmConvParams p) {
       const bool ok = row_ok && (unsigned)id < (unsigned)p.D && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
       const int64_t lin = ok ? ((int64_t)id * p.H + ih) * p.W + iw : 0;
       const uint32_t a_dst = smem_base + (uint32_t)(s * stage_bytes) + (uint32_t)(pt * 16);
-      const uint4* a_src = p.a + (int64_t)kc0 * sp_in + lin;
-      for (int c = 0; c < n_chunks; ++c) cp_async16(a_dst + (uint32_t)(c * 2048), a_src + (int64_t)c * sp_in, ok ? 16u : 0u);
+      for (int c = 0; c < n_chunks; ++c) {
+        const int kc = kc0 + c;
+        const uint4* a_src = kc < p.c0_chunks ? p.a + (int64_t)kc * sp_in : p.a1 + (int64_t)(kc - p.c0_chunks) * sp_in;
+        cp_async16(a_dst + (uint32_t)(c * 2048), a_src + lin, ok ? 16u : 0u);
+      }
       const uint32_t b_dst = smem_base + (uint32_t)(s * stage_bytes + a_bytes);
       const uint4* b_src = p.w + ((int64_t)tap * (p.cin_pad / 8) + kc0) * p.cout_pad + n0;
       for (int e = pt; e < b_items; e += G_NPROD) {
@@ -218,42 +225,104 @@ conv_gemm_kernel(GemmConvParams p) {
     const int64_t m = m0 + warp * 32 + lane;
     const bool row_ok = m < m_total;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    float* yf = reinterpret_cast<float*>(p.y);
+    const float* rf = reinterpret_cast<const float*>(p.residual);
     for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
       uint32_t acc[16];
       tmem_ld16(lane_addr + (uint32_t)c0, acc);
       tmem_ld_wait();
-      if (row_ok) {
-        if (p.row_major) {   // 16 consecutive outputs of one row: 4 x 16-byte stores
-          float v[16];
+      float v[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int co = n0 + c0 + k;
-            float val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
-            if (p.gelu) val = 0.5f * val * (1.f + erff(val * 0.70710678118654752440f));
-            v[k] = val;
-          }
+      for (int k = 0; k < 16; ++k) {
+        const int co = n0 + c0 + k;
+        float val = 0.f;
+        if (row_ok && co < p.cout) {
+          val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
+          if (p.out_scale) val *= __ldg(p.out_scale + co);
+          if (p.gelu) val = 0.5f * val * (1.f + erff(val * 0.70710678118654752440f));
+        }
+        v[k] = val;
+      }
+      if (row_ok) {
+        if (p.out_mode == 1) {          // 16 consecutive outputs of one row: 4 x 16-byte stores
           const int64_t off = m * p.cout + n0 + c0;
 #pragma unroll
           for (int k = 0; k < 16; k += 4) {
-            float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
-            if (p.residual) {
-              const float4 r = __ldg(reinterpret_cast<const float4*>(p.residual + off + k));
-              o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+            if (rf) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(rf + off + k));
+              v[k] += r.x; v[k + 1] += r.y; v[k + 2] += r.z; v[k + 3] += r.w;
             }
-            *reinterpret_cast<float4*>(p.y + off + k) = o;
+            *reinterpret_cast<float4*>(yf + off + k) = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
+          }
+        } else if (p.out_mode == 2) {   // B-format: two 16-byte vectors (8 channels each) per voxel
+          const uint4* rb = reinterpret_cast<const uint4*>(p.residual);
+          uint4* yb = reinterpret_cast<uint4*>(p.y);
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            const int kc = (n0 + c0) / 8 + hf;
+            if (kc * 8 < p.cout_pad) {
+              if (rb) {
+                const uint4 rv = __ldg(rb + (int64_t)kc * m_total + m);
+                const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  v[8 * hf + 2 * k] += __uint_as_float(pr[k] << 16);
+                  v[8 * hf + 2 * k + 1] += __uint_as_float(pr[k] & 0xffff0000u);
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16x2(v[8 * hf], v[8 * hf + 1]);
+              o.y = pack_bf16x2(v[8 * hf + 2], v[8 * hf + 3]);
+              o.z = pack_bf16x2(v[8 * hf + 4], v[8 * hf + 5]);
+              o.w = pack_bf16x2(v[8 * hf + 6], v[8 * hf + 7]);
+              yb[(int64_t)kc * m_total + m] = o;
+            }
           }
         } else {
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int co = n0 + c0 + k;
             if (co < p.cout) {
-              float val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
-              if (p.out_scale) val *= __ldg(p.out_scale + co);
               const int64_t off = (int64_t)co * m_total + m;
-              if (p.residual) val += __ldg(p.residual + off);
-              p.y[off] = val;
+              if (rf) v[k] += __ldg(rf + off);
+              yf[off] = v[k];
             }
           }
+        }
+      }
+      if (p.stats != nullptr) {
+        // per-channel sums over the 32 rows of this warp: transposed butterfly (16 shuffles per quantity),
+        // lane l ends up with channel ((l>>4)&1)*8 + ((l>>3)&1)*4 + ((l>>2)&1)*2 + ((l>>1)&1)
+        float q[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { if (!row_ok) v[k] = 0.f; q[k] = v[k] * v[k]; }
+#pragma unroll
+        for (int width = 8, bit = 16; width >= 1; width >>= 1, bit >>= 1) {
+          const bool up = (lane & bit) != 0;
+#pragma unroll
+          for (int k = 0; k < width; ++k) {
+            const float sv = up ? v[k] : v[k + width], kv = up ? v[k + width] : v[k];
+            const float sq = up ? q[k] : q[k + width], kq = up ? q[k + width] : q[k];
+            v[k] = kv + __shfl_xor_sync(0xffffffffu, sv, bit);
+            q[k] = kq + __shfl_xor_sync(0xffffffffu, sq, bit);
+          }
+        }
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+        q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+        if ((lane & 1) == 0) {
+          const int ch = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          s_stat[(warp * 2) * p.n_tile + ch] = v[0];
+          s_stat[(warp * 2 + 1) * p.n_tile + ch] = q[0];
+        }
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");   // the 4 epilogue warps only
+      for (int c = tid; c < p.n_tile; c += G_EPI_WARPS * 32) {
+        if (n0 + c < p.cout) {   // fixed summation order over the 4 epilogue warps
+          const float a = (s_stat[c] + s_stat[2 * p.n_tile + c]) + (s_stat[4 * p.n_tile + c] + s_stat[6 * p.n_tile + c]);
+          const float q = (s_stat[p.n_tile + c] + s_stat[3 * p.n_tile + c]) + (s_stat[5 * p.n_tile + c] + s_stat[7 * p.n_tile + c]);
+          stat_add(p.stats, n0 + c, a, q);
         }
       }
     }
@@ -281,24 +350,39 @@ static int pick_n_tile(int cout_pad, int64_t m_tiles) {
 
 static int launch_gemm_params(GemmConvParams& p, cudaStream_t st);
 
-int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
-                     int stride, int taps, cudaStream_t st) {
+int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st) {
   GemmConvParams p;
-  p.a = reinterpret_cast<const uint4*>(a_blocked);
+  const int cin_pad = (w.cin + 15) / 16 * 16;
+  if (w.dev == nullptr || g.a0 == nullptr || (g.c0 % 8) != 0 || (g.a1 == nullptr && g.c0 < w.cin) ||
+      (g.a1 != nullptr && g.c0 >= w.cin)) {
+    set_error("gemm_conv: bad source description");
+    return -1;
+  }
+  p.a = reinterpret_cast<const uint4*>(g.a0);
+  p.a1 = reinterpret_cast<const uint4*>(g.a1);
+  p.c0_chunks = g.a1 ? g.c0 / 8 : cin_pad / 8;
   p.w = reinterpret_cast<const uint4*>(w.dev);
-  p.bias = dst.bias; p.out_scale = dst.out_scale; p.residual = dst.residual; p.y = dst.y;
-  p.cin_pad = (w.cin + 15) / 16 * 16;
+  p.bias = g.bias; p.out_scale = g.out_scale; p.residual = g.residual; p.y = g.y; p.stats = g.stats;
+  p.cin_pad = cin_pad;
   p.cout = w.cout;
   p.cout_pad = (w.cout + 15) / 16 * 16;
-  p.D = in_d; p.H = in_h; p.W = in_w;
-  p.stride = stride; p.taps = taps;
-  p.row_major = 0; p.gelu = 0;
-  if (taps == 27) {
-    p.OD = (in_d - 1) / stride + 1; p.OH = (in_h - 1) / stride + 1; p.OW = (in_w - 1) / stride + 1;
-  } else {
-    p.OD = (in_d - 1) / stride + 1; p.OH = (in_h - 1) / stride + 1; p.OW = (in_w - 1) / stride + 1;
-  }
+  p.D = g.D; p.H = g.H; p.W = g.W;
+  p.stride = g.stride; p.taps = g.taps;
+  p.out_mode = g.out_mode; p.gelu = g.gelu;
+  p.OD = (g.D - 1) / g.stride + 1; p.OH = (g.H - 1) / g.stride + 1; p.OW = (g.W - 1) / g.stride + 1;
+  if (p.out_mode == 1 && (p.cout % 16) != 0) { set_error("gemm_conv: row-major output needs cout % 16 == 0"); return -1; }
   return launch_gemm_params(p, st);
+}
+
+// fp32-NCDHW-out convenience wrapper used by the mixed pipeline (prep kernel output as the only source)
+int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
+                     int stride, int taps, cudaStream_t st) {
+  GemmArgs g;
+  g.a0 = a_blocked; g.c0 = (w.cin + 15) / 16 * 16;
+  g.D = in_d; g.H = in_h; g.W = in_w; g.stride = stride; g.taps = taps;
+  g.bias = dst.bias; g.out_scale = dst.out_scale; g.residual = dst.residual; g.y = dst.y; g.stats = dst.stats;
+  g.out_mode = 0;
+  return launch_gemm_conv(g, w, st);
 }
 
 static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
@@ -309,7 +393,7 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
   p.n_tile = pick_n_tile(p.cout_pad, m_tiles);
   const int stage_bytes = 2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16;
   const int ns = stage_bytes <= 12 * 1024 ? 8 : stage_bytes <= 16 * 1024 ? 6 : stage_bytes <= 26 * 1024 ? 4 : 3;
-  const int smem_bytes = ns * stage_bytes + (2 * ns + 1) * 8 + 16;
+  const int smem_bytes = ns * stage_bytes + (2 * ns + 1) * 8 + 16 + 8 * p.n_tile * 4;
   if (smem_bytes > 160 * 1024) { set_error("conv_gemm: stage does not fit shared memory"); return -1; }
   static bool configured = false;
   if (!configured) {
@@ -383,15 +467,14 @@ int launch_prep_rows(const float* x, const float* gamma, const float* beta, int 
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
                      int m, int n, int k, bool gelu, cudaStream_t st) {
   if (n % 16 != 0 || k % 16 != 0) { set_error("linear_tc: n and k must be multiples of 16"); return -1; }
-  GemmConvParams p;
-  p.a = reinterpret_cast<const uint4*>(a_blocked);
-  p.w = reinterpret_cast<const uint4*>(w_packed);
-  p.bias = bias; p.out_scale = nullptr; p.residual = residual; p.y = y;
-  p.cin_pad = k; p.cout = n; p.cout_pad = n;
-  p.D = 1; p.H = 1; p.W = m; p.OD = 1; p.OH = 1; p.OW = m;
-  p.stride = 1; p.taps = 1;
-  p.row_major = 1; p.gelu = gelu ? 1 : 0;
-  return launch_gemm_params(p, st);
+  TcWeights w;
+  w.dev = const_cast<void*>(w_packed); w.cin = k; w.cout = n;
+  GemmArgs g;
+  g.a0 = a_blocked; g.c0 = k;
+  g.D = 1; g.H = 1; g.W = m; g.stride = 1; g.taps = 1;
+  g.bias = bias; g.residual = residual; g.y = y;
+  g.out_mode = 1; g.gelu = gelu ? 1 : 0;
+  return launch_gemm_conv(g, w, st);
 }
 
 }  // namespace dcl

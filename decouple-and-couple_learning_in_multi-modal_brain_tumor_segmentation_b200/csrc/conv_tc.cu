@@ -49,8 +49,8 @@ struct RollCfg {
   static constexpr int W_BYTES = 27 * C * C * 2;
   static constexpr int ITEMS = KC * NPOS;         // 16-byte staging items per plane
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
-  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // mean[C], rstd[C], bias[C] floats
-  static constexpr int OFF_BAR = OFF_SMALL + 3 * C * 4;      // 8-byte aligned (C multiple of 16)
+  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // mean[C], rstd[C], bias[C], scale[C] floats
+  static constexpr int OFF_BAR = OFF_SMALL + 4 * C * 4;      // 8-byte aligned (C multiple of 16)
   static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 4) * 8 + 16;
   static_assert(FLAT || W == 128, "row-aligned M tiles need W == 128");
   static_assert(!KHN || !FLAT, "kh stacking needs row-aligned M tiles");
@@ -64,14 +64,39 @@ constexpr int ROLL_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
 constexpr int PROD_T0 = (EPI_WARPS + 1) * 32;
 constexpr int NPROD = PROD_WARPS * 32;
 
+// Arguments of the rolling kernel.  All activation tensors are "B-format": bf16, channel-blocked
+// [C/8][G^3][8] (one 16-byte vector per voxel and 8-channel chunk).
+struct RollParams {
+  const uint4* xb;          // B-format input, or nullptr when x4 is used
+  const float* x4;          // fp32 NCDHW 4-channel (strided) source: InitConv reads the volume view directly
+  int64_t s4c, s4d, s4h;
+  const stat_t* sums;       // fused InstanceNorm of the input: per-channel (sum, sum of squares) ...
+  float inv_n;
+  const float* mean;        // ... or explicit mean / rstd
+  const float* rstd;
+  int act;
+  const uint4* w;           // packed weights
+  const float* bias;
+  const float* out_scale;   // per output channel multiplier after the bias (dropout3d), or nullptr
+  const uint4* resb;        // B-format residual or nullptr
+  uint4* yb;                // B-format output
+  stat_t* stats;            // 2*C fixed-point sums += (sum, sum of squares) of the fp32 outputs, or nullptr
+  int dsplit;
+};
+
+__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+  return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));
+}
+
 template <class Cfg>
 __global__ void __launch_bounds__(ROLL_THREADS, 1)
-conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_packed, int dsplit) {
+conv3d_k3_roll_kernel(RollParams prm) {
   constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, P = Cfg::P, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_mean = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);
   float* s_rstd = s_mean + C;
   float* s_bias = s_rstd + C;
+  float* s_scale = s_bias + C;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* bar_empty = bar_full + NSLOT;
   uint64_t* bar_acc_full = bar_empty + NSLOT;
@@ -82,6 +107,7 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
   const int warp = tid >> 5;
   const int lane = tid & 31;
 
+  const int dsplit = prm.dsplit;
   const int ht = blockIdx.x / dsplit;
   const int ds = blockIdx.x - ht * dsplit;
   const int h0 = ht * TH;
@@ -89,24 +115,24 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
   const int d1 = ((ds + 1) * G) / dsplit;
   const int n_out = d1 - d0;
   const int n_in = n_out + 2;
+  constexpr int64_t SP = (int64_t)G * G * G;
 
   // ---- one-time setup ---------------------------------------------------------------------------
   for (int i = tid; i < Cfg::W_BYTES / 16; i += ROLL_THREADS)
-    reinterpret_cast<uint4*>(smem + Cfg::OFF_W)[i] = __ldg(w_packed + i);
+    reinterpret_cast<uint4*>(smem + Cfg::OFF_W)[i] = __ldg(prm.w + i);
+  const bool has_norm = prm.sums != nullptr || prm.mean != nullptr;
   if (tid < C) {
     float m = 0.f, r = 1.f;
-    if (src.sums != nullptr) {
-      double mu = src.sums[2 * tid] * (double)src.inv_n;
-      double var = src.sums[2 * tid + 1] * (double)src.inv_n - mu * mu;
-      m = (float)mu;
-      r = (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + 1e-5));
-    } else if (src.mean != nullptr) {
-      m = src.mean[tid];
-      r = src.rstd[tid];
+    if (prm.sums != nullptr) {
+      stat_mean_rstd(prm.sums, tid, prm.inv_n, &m, &r);
+    } else if (prm.mean != nullptr) {
+      m = prm.mean[tid];
+      r = prm.rstd[tid];
     }
     s_mean[tid] = m;
     s_rstd[tid] = r;
-    s_bias[tid] = dst.bias ? dst.bias[tid] : 0.f;
+    s_bias[tid] = prm.bias ? prm.bias[tid] : 0.f;
+    s_scale[tid] = prm.out_scale ? prm.out_scale[tid] : 1.f;
   }
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); }
@@ -123,56 +149,67 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
   if (warp >= EPI_WARPS + 1) {
     // =============================== producers ===================================================
     const int pt = tid - PROD_T0;
-    const int act = src.act;
-    constexpr int U = 4;
+    const int act = prm.act;
+    const bool identity = !has_norm && act == ACT_NONE;
     for (int j = 0; j < n_in; ++j) {
       const int s = j % NSLOT;
       mbar_wait(&bar_empty[s], ((uint32_t)(j / NSLOT) & 1u) ^ 1u);
       const int d_in = d0 - 1 + j;
       const bool d_ok = (unsigned)d_in < (unsigned)G;
       uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
-      for (int e0 = pt; e0 < Cfg::ITEMS; e0 += NPROD * U) {
-        float v[U][8];
-        int kcs[U];
-        bool oks[U];
+      if (prm.xb != nullptr) {
+        // ---- B-format source: one 16-byte load per (chunk, voxel) item, all loads of a pass in flight
+        constexpr int U = 6;
+        for (int e0 = pt; e0 < Cfg::ITEMS; e0 += NPROD * U) {
+          uint4 v[U];
+          bool oks[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int e = e0 + u * NPROD;
-          const int kc = e / NPOS;
-          const int rem = e - kc * NPOS;
-          const int r = rem / P;
-          const int q = rem - r * P;
-          const int h_in = h0 - 1 + r, w_in = q - 1;
-          const bool ok = e < Cfg::ITEMS && d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G;
-          kcs[u] = kc;
-          oks[u] = ok;
-          if (ok) {
-            const float* p = src.x0 + (int64_t)(kc * 8) * src.s0c + (int64_t)d_in * src.s0d + (int64_t)h_in * src.s0h + w_in;
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NPROD;
+            const int kc = e / NPOS;
+            const int rem = e - kc * NPOS;
+            const int r = rem / P;
+            const int q = rem - r * P;
+            const int h_in = h0 - 1 + r, w_in = q - 1;
+            oks[u] = e < Cfg::ITEMS && d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (oks[u]) v[u] = __ldg(prm.xb + (int64_t)kc * SP + ((int64_t)d_in * G + h_in) * G + w_in);
+          }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[u][k] = __ldg(p + (int64_t)k * src.s0c);
-          } else {
+          for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NPROD;
+            if (e < Cfg::ITEMS) {
+              if (oks[u] && !identity) {
+                const int c0 = (e / NPOS) * 8;
+                uint32_t* pv = reinterpret_cast<uint32_t*>(&v[u]);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[u][k] = 0.f;
+                for (int k = 0; k < 4; ++k) {
+                  float2 f = unpack_bf16x2(pv[k]);
+                  f.x = apply_act((f.x - s_mean[c0 + 2 * k]) * s_rstd[c0 + 2 * k], act);
+                  f.y = apply_act((f.y - s_mean[c0 + 2 * k + 1]) * s_rstd[c0 + 2 * k + 1], act);
+                  pv[k] = pack_bf16x2(f.x, f.y);
+                }
+              }
+              *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = v[u];
+            }
           }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const int e = e0 + u * NPROD;
-          if (e < Cfg::ITEMS) {
-            if (oks[u]) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                const int c = kcs[u] * 8 + k;
-                v[u][k] = apply_act((v[u][k] - s_mean[c]) * s_rstd[c], act);
-              }
-            }
-            uint4 o;
-            o.x = pack_bf16x2(v[u][0], v[u][1]);
-            o.y = pack_bf16x2(v[u][2], v[u][3]);
-            o.z = pack_bf16x2(v[u][4], v[u][5]);
-            o.w = pack_bf16x2(v[u][6], v[u][7]);
-            *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = o;
+      } else {
+        // ---- fp32 NCDHW 4-channel source (InitConv): channels 4..C-1 are zero padding
+        for (int e = pt; e < NPOS; e += NPROD) {
+          const int r = e / P;
+          const int q = e - r * P;
+          const int h_in = h0 - 1 + r, w_in = q - 1;
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);
+          if (d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G) {
+            const float* p = prm.x4 + (int64_t)d_in * prm.s4d + (int64_t)h_in * prm.s4h + w_in;
+            o.x = pack_bf16x2(__ldg(p), __ldg(p + prm.s4c));
+            o.y = pack_bf16x2(__ldg(p + 2 * prm.s4c), __ldg(p + 3 * prm.s4c));
           }
+          *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = o;
+#pragma unroll
+          for (int kc = 1; kc < Cfg::KC; ++kc)
+            *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
       fence_proxy_async();
@@ -262,7 +299,6 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
     __syncwarp();
   } else {
     // =============================== epilogue ====================================================
-    const int64_t sp = (int64_t)G * G * G;
     float st_s[C], st_q[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) { st_s[c] = 0.f; st_q[c] = 0.f; }
@@ -289,17 +325,39 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
         if (r < TH && w < G) {
           const int64_t off = ((int64_t)d * G + (h0 + r)) * G + w;
 #pragma unroll
-          for (int c = 0; c < C; ++c) {
-            float val = __uint_as_float(acc[c / 16][c % 16]) + s_bias[c];
-            if (dst.residual) val += __ldg(dst.residual + c * sp + off);
-            dst.y[c * sp + off] = val;
-            st_s[c] += val;
-            st_q[c] += val * val;
+          for (int kc = 0; kc < C / 8; ++kc) {
+            float val[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int c = kc * 8 + k;
+              val[k] = (__uint_as_float(acc[c / 16][c % 16]) + s_bias[c]) * s_scale[c];
+            }
+            if (prm.resb != nullptr) {
+              const uint4 rv = __ldg(prm.resb + (int64_t)kc * SP + off);
+              const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float2 f = unpack_bf16x2(pr[k]);
+                val[2 * k] += f.x;
+                val[2 * k + 1] += f.y;
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              st_s[kc * 8 + k] += val[k];
+              st_q[kc * 8 + k] += val[k] * val[k];
+            }
+            uint4 o;
+            o.x = pack_bf16x2(val[0], val[1]);
+            o.y = pack_bf16x2(val[2], val[3]);
+            o.z = pack_bf16x2(val[4], val[5]);
+            o.w = pack_bf16x2(val[6], val[7]);
+            prm.yb[(int64_t)kc * SP + off] = o;
           }
         }
       }
     }
-    if (dst.stats != nullptr) {
+    if (prm.stats != nullptr) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
         float a = st_s[c], q = st_q[c];
@@ -308,10 +366,7 @@ conv3d_k3_roll_kernel(ConvSrc src, ConvDst dst, const uint4* __restrict__ w_pack
           a += __shfl_xor_sync(0xffffffffu, a, o);
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        if (lane == 0) {
-          atomicAdd(dst.stats + 2 * c, (double)a);
-          atomicAdd(dst.stats + 2 * c + 1, (double)q);
-        }
+        if (lane == 0) stat_add(prm.stats, c, a, q);
       }
     }
   }
@@ -339,14 +394,14 @@ static uint16_t f32_to_bf16_rn(float f) {
 // B operand tiles, bf16, K-major no-swizzle (core matrix = 8 couts x 8 cins, 128 contiguous bytes):
 //   layout 0  [tap][cin/8][cout][8]                     one N = cout matrix per tap
 //   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]      one stacked N = 3*cout matrix per (kd,kw)
-static int tc_weight_layout(int cin, int cout) { return (cin == 16 && cout == 16) ? 1 : 0; }
+static int tc_weight_layout(int cin, int cout) { return (cin <= 16 && cout == 16) ? 1 : 0; }
 
-int tc_pack_weights(const float* w_host, int cout, int cin, int taps, TcWeights* out) {
+int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_layout, TcWeights* out) {
   out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0;
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;   // zero padded
   const int kcs = cin_pad / 8;
   std::vector<uint16_t> packed((size_t)taps * cin_pad * cout_pad, 0);
-  const int layout = taps == 27 ? tc_weight_layout(cin, cout) : 0;
+  const int layout = (roll_layout && taps == 27) ? tc_weight_layout(cin, cout) : 0;
   for (int tap = 0; tap < taps; ++tap)
     for (int ci = 0; ci < cin; ++ci)
       for (int n = 0; n < cout; ++n) {
@@ -370,12 +425,12 @@ using RollC16 = RollCfg<16, 128, 8, false, true>;
 using RollC32 = RollCfg<32, 64, 8, true, false>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
-  if (split || stride != 1 || cin != cout) return false;
-  return (cin == 16 && g == 128) || (cin == 32 && g == 64);
+  if (split || stride != 1) return false;
+  return (cin == 16 && cout == 16 && g == 128) || (cin == 32 && cout == 32 && g == 64) || (cin == 4 && cout == 16 && g == 128);
 }
 
 template <class Cfg>
-static int launch_roll(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, cudaStream_t st) {
+static int launch_roll(RollParams& prm, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     DCL_CUDA_OK(cudaFuncSetAttribute(conv3d_k3_roll_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -386,22 +441,32 @@ static int launch_roll(const ConvSrc& src, const ConvDst& dst, const TcWeights& 
   int dsplit = 148 / htiles;
   if (dsplit < 1) dsplit = 1;
   if (dsplit > Cfg::G) dsplit = Cfg::G;
-  conv3d_k3_roll_kernel<Cfg><<<htiles * dsplit, ROLL_THREADS, Cfg::SMEM_BYTES, st>>>(
-      src, dst, reinterpret_cast<const uint4*>(w.dev), dsplit);
+  prm.dsplit = dsplit;
+  conv3d_k3_roll_kernel<Cfg><<<htiles * dsplit, ROLL_THREADS, Cfg::SMEM_BYTES, st>>>(prm);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int launch_conv3d_k3_tc(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, int cout, int g, bool split,
-                        cudaStream_t st) {
-  const int cin = src.c0 + src.c1;
-  if (!tc_conv_supported(cin, cout, g, 1, split) || src.x1 != nullptr || dst.out_scale != nullptr || w.dev == nullptr) {
-    set_error("conv3d_k3_tc: unsupported shape");
+int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cudaStream_t st) {
+  const int cin = w.cin;
+  if (!tc_conv_supported(cin, cout, g, 1, false) || w.dev == nullptr || (a.xb == nullptr) == (a.x4 == nullptr) ||
+      (cin == 4) != (a.x4 != nullptr)) {
+    set_error("roll_conv: unsupported shape / source");
     return -1;
   }
-  if (cin == 16) return launch_roll<RollC16>(src, dst, w, st);
-  return launch_roll<RollC32>(src, dst, w, st);
+  RollParams p;
+  p.xb = reinterpret_cast<const uint4*>(a.xb);
+  p.x4 = a.x4; p.s4c = a.s4c; p.s4d = a.s4d; p.s4h = a.s4h;
+  p.sums = a.norm.sums; p.inv_n = a.norm.inv_n; p.mean = a.norm.mean; p.rstd = a.norm.rstd; p.act = a.norm.act;
+  p.w = reinterpret_cast<const uint4*>(w.dev);
+  p.bias = a.bias; p.out_scale = a.out_scale;
+  p.resb = reinterpret_cast<const uint4*>(a.resb);
+  p.yb = reinterpret_cast<uint4*>(a.yb);
+  p.stats = a.stats;
+  p.dsplit = 1;
+  if (cout == 16) return launch_roll<RollC16>(p, st);
+  return launch_roll<RollC32>(p, st);
 }
 
 }  // namespace dcl

@@ -12,18 +12,70 @@ struct TcWeights {
 };
 
 // Packs a PyTorch (cout, cin, taps) fp32 weight (host) into the kernel's B-operand layout (taps = 27 | 1).
-int tc_pack_weights(const float* w_host, int cout, int cin, int taps, TcWeights* out);
+// roll_layout: the conv will run on the rolling kernel (stacked-kh weight order for 16-channel outputs)
+int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_layout, TcWeights* out);
 // fp32 NCDHW (two-source concat, fused norm + activation) -> bf16 channel-blocked [cin_pad/8][D][H][W][8]
 int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* out, cudaStream_t st);
 // general implicit-GEMM convolution on a blocked bf16 input (taps = 27: kernel 3 pad 1, taps = 1: pointwise)
 int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
                      int stride, int taps, cudaStream_t st);
-// True when launch_conv3d_k3_tc handles a cubic g^3 input with these channel counts.
+// ---- "B-format" activations of the bf16 pipeline: bf16, channel-blocked [C/8][spatial][8] ------------------
+// Fused transform of a conv input: InstanceNorm (from raw sums or explicit mean/rstd; all null = none) + activation.
+struct BNorm {
+  const stat_t* sums = nullptr;
+  float inv_n = 0.f;
+  const float* mean = nullptr;
+  const float* rstd = nullptr;
+  int act = ACT_NONE;
+};
+struct RollArgs {
+  const void* xb = nullptr;          // B-format input (cin = 16 | 32) ...
+  const float* x4 = nullptr;         // ... or the fp32 NCDHW 4-channel strided view InitConv reads
+  int64_t s4c = 0, s4d = 0, s4h = 0;
+  BNorm norm;
+  const float* bias = nullptr;
+  const float* out_scale = nullptr;
+  const void* resb = nullptr;        // B-format residual
+  void* yb = nullptr;                // B-format output
+  stat_t* stats = nullptr;           // 2*cout fixed-point sums += (sum, sum of squares) of the outputs
+};
+// General implicit-GEMM convolution / linear layer on B-format input (conv_gemm.cu).
+struct GemmArgs {
+  const void* a0 = nullptr; int c0 = 0;      // B-format source with c0 channels (multiple of 8)
+  const void* a1 = nullptr;                  // optional second source holding the remaining input channels
+  int D = 1, H = 1, W = 1, stride = 1, taps = 27;   // input dims; taps = 27 (k3 pad 1) | 1 (pointwise)
+  const float* bias = nullptr;
+  const float* out_scale = nullptr;
+  int out_mode = 2;                          // 0 fp32 NCDHW, 1 fp32 row-major [m][cout], 2 B-format
+  void* y = nullptr;
+  const void* residual = nullptr;            // same format as y
+  stat_t* stats = nullptr;                   // 2*cout fixed-point sums += (sum, sum of squares) of the outputs
+  int gelu = 0;
+};
+int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st);
+
+// True when the rolling kernel handles a cubic g^3 stride-1 conv with these channel counts.
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split);
-// Same contract as launch_conv3d_k3 (dense single-source input, fused input norm/activation, bias,
-// residual).  split = true: bf16x3 (hi*hi + hi*lo + lo*hi), false: plain bf16 operands.
-int launch_conv3d_k3_tc(const ConvSrc& src, const ConvDst& dst, const TcWeights& w, int cout, int g, bool split,
-                        cudaStream_t st);
+int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cudaStream_t st);
+
+// ---- HBM-bound B-format kernels (bf16_ops.cu) ---------------------------------------------------------------
+// y = act(norm(x)) (+ res), all B-format
+int launch_norm_act_b(const void* x, const BNorm& n, const void* res, void* y, int channels, int64_t spatial,
+                      cudaStream_t st);
+// B-format -> fp32 NCDHW
+int launch_unblock(const void* x, float* y, int channels, int64_t spatial, cudaStream_t st);
+// tokens = convert_dim(act(norm(x[chunk0*8 : chunk0*8 + channels]))) (+ dense fp32 NCDHW copy)
+int launch_tokenise_b(const void* x, const BNorm& n, int chunk0, float* tokens, float* dense_or_null, int channels,
+                      int grid, int p0, int p1, int p2, cudaStream_t st);
+// y (B-format) = split_dim(tokens * class_token)
+int launch_untokenise_b(const float* tokens, const float* class_token, void* y, int channels, int grid, int p0, int p1,
+                        int p2, cudaStream_t st);
+// DeUp_Cat as one kernel: mt [8][cin/2][cin], w3a [cin/2][cin/2], bt [8][cin/2] (composed on the host)
+int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const float* w3a, const float* bt, void* y,
+                        int cin, int gi, cudaStream_t st);
+// probs (fp32 NCDHW, 4 classes) = softmax(endconv(x)), x B-format 16 channels
+int launch_endconv_softmax_b(const void* x, const float* w, const float* b, float* probs, int64_t spatial,
+                             cudaStream_t st);
 
 // fp32 [rows][512] (optionally LayerNorm'ed) -> bf16 blocked [64][rows][8]
 int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st);

@@ -184,6 +184,17 @@ struct dcl_handle {
   double* stat_accum;                            // (2*512)
   void* blk = nullptr;                           // bf16 channel-blocked conv input (DCL_BF16 only)
   void *tok_a = nullptr, *tok_b = nullptr;       // bf16 blocked token matrices feeding the linear GEMMs
+  // ---- bf16 pipeline (DCL_BF16): B-format activations = bf16 [C/8][spatial][8] ----
+  void *b_t0[4], *b_a[4], *b_t1[4], *b_x[4];     // encoder levels (16@128, 32@64, 64@32, 128@16)
+  void *b_x4, *b_edown, *b_eraw, *b_sraw, *b_fused, *b_enc, *b_nrm;
+  void *b_d8[5];                                 // d8_0, a, b, 1, 2
+  void *b_dl[3][5];                              // decoder levels: in, a, b, 1, 2
+  stat_t* stat_arena = nullptr;                  // STAT_SLOTS x 1024 fixed-point sums, zeroed once per forward
+  int stat_used = 0;
+  struct DeUpW { float *mt, *w3a, *bt; } deup[3];
+  float *end_w = nullptr, *end_b = nullptr;
+  struct BStage { const void* p; int c; int64_t spatial; };
+  std::map<std::string, BStage> bstages;
   std::vector<StatSlot> stat_slots;
   int stat_next = 0;
 
@@ -230,6 +241,7 @@ static int falloc(dcl_handle* h, float** p, int64_t numel) { return dev_alloc(h,
 static const int64_t P3 = 128LL * 128 * 128;
 static const int LVL_C[4] = {16, 32, 64, 128};
 static const int LVL_G[4] = {128, 64, 32, 16};
+static const int STAT_SLOTS = 64;
 
 static int allocate_workspace(dcl_handle* h) {
   for (int l = 0; l < 4; ++l) {
@@ -274,6 +286,22 @@ static int allocate_workspace(dcl_handle* h) {
     DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * 2));
     DCL_TRY(dev_alloc(h, &h->tok_a, 258 * 512 * 2));
     DCL_TRY(dev_alloc(h, &h->tok_b, 258 * 512 * 2));
+    for (int l = 0; l < 4; ++l) {
+      int64_t bytes = (int64_t)LVL_C[l] * LVL_G[l] * LVL_G[l] * LVL_G[l] * 2;
+      DCL_TRY(dev_alloc(h, &h->b_t0[l], bytes)); DCL_TRY(dev_alloc(h, &h->b_a[l], bytes));
+      DCL_TRY(dev_alloc(h, &h->b_t1[l], bytes)); DCL_TRY(dev_alloc(h, &h->b_x[l], bytes));
+    }
+    const int64_t v16 = 16 * 16 * 16, v32 = 32 * 32 * 32;
+    DCL_TRY(dev_alloc(h, &h->b_x4, 256 * v16 * 2)); DCL_TRY(dev_alloc(h, &h->b_edown, 32 * v32 * 2));
+    DCL_TRY(dev_alloc(h, &h->b_eraw, 96 * v32 * 2)); DCL_TRY(dev_alloc(h, &h->b_sraw, 384 * v16 * 2));
+    DCL_TRY(dev_alloc(h, &h->b_fused, 128 * v16 * 2)); DCL_TRY(dev_alloc(h, &h->b_enc, 256 * v16 * 2));
+    DCL_TRY(dev_alloc(h, &h->b_nrm, 32 * (P3 / 8) * 2));
+    for (int i = 0; i < 5; ++i) DCL_TRY(dev_alloc(h, &h->b_d8[i], 128 * v16 * 2));
+    for (int l = 0; l < 3; ++l) {
+      int c = 64 >> l, g = 32 << l;
+      for (int i = 0; i < 5; ++i) DCL_TRY(dev_alloc(h, &h->b_dl[l][i], (int64_t)c * g * g * g * 2));
+    }
+    DCL_TRY(dev_alloc(h, (void**)&h->stat_arena, (int64_t)STAT_SLOTS * 1024 * sizeof(stat_t)));
   }
   DCL_TRY(falloc(h, &h->keep_dev, 16));
   DCL_TRY(dev_alloc(h, (void**)&h->stat_accum, 2 * 512 * sizeof(double)));
@@ -337,7 +365,8 @@ static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vec
   DCL_TRY(upload(h, bias, &out->b));
   if (h->cfg.precision == DCL_BF16 && (kind == W_CONV3 || kind == W_CONV1)) {
     if (kind == W_CONV1) raw = *ws[0];   // (cout, cin)
-    DCL_TRY(tc_pack_weights(raw.data(), cout, cin, kind == W_CONV3 ? 27 : 1, &out->tc));
+    DCL_TRY(tc_pack_weights(raw.data(), cout, cin, kind == W_CONV3 ? 27 : 1,
+                            kind == W_CONV3 && tc_conv_supported(cin, cout, cin == 32 ? 64 : 128, 1, false), &out->tc));
     h->allocs.push_back(out->tc.dev);
   }
   return 0;
@@ -394,7 +423,7 @@ static int prepare(dcl_handle* h) {
       const std::vector<float>& qkv = h->host_w.at(a + "fn.qkv.weight");
       auto pack = [&](const float* w, int n, void** out) -> int {
         TcWeights tw;
-        DCL_TRY(tc_pack_weights(w, n, 512, 1, &tw));
+        DCL_TRY(tc_pack_weights(w, n, 512, 1, false, &tw));
         h->allocs.push_back(tw.dev);
         *out = tw.dev;
         return 0;
@@ -412,6 +441,47 @@ static int prepare(dcl_handle* h) {
     h->pe[r] = R(std::string("label_") + REGION_KEY[r] + "_position_encoding.pe");
   }
   h->pe[3] = R("fusion_label_pos.pe");
+  if (h->cfg.precision == DCL_BF16) {
+    // DeUp_Cat composed into one linear map per transposed-conv tap (see bf16_ops.cu)
+    const char* upn[3] = {"decoder.DeUp4", "decoder.DeUp3", "decoder.DeUp2"};
+    for (int l = 0; l < 3; ++l) {
+      const int C = 128 >> l, CH = C / 2;
+      const std::string n = upn[l];
+      const std::vector<float>&w1 = h->host_w.at(n + ".conv1.weight"), &b1 = h->host_w.at(n + ".conv1.bias"),
+                               &wt = h->host_w.at(n + ".conv2.weight"), &bt = h->host_w.at(n + ".conv2.bias"),
+                               &w3 = h->host_w.at(n + ".conv3.weight"), &b3 = h->host_w.at(n + ".conv3.bias");
+      std::vector<float> mt((size_t)8 * CH * C), w3a((size_t)CH * CH), btc((size_t)8 * CH);
+      std::vector<double> tmp((size_t)CH * C), tb(CH);
+      for (int o = 0; o < CH; ++o)
+        for (int sidx = 0; sidx < CH; ++sidx) w3a[(size_t)o * CH + sidx] = w3[(size_t)o * C + sidx];   // skip comes first in the cat
+      for (int t = 0; t < 8; ++t) {
+        // tmp[j][c] = sum_i wt[i][j][t] * w1[i][c];  tb[j] = sum_i wt[i][j][t] * b1[i] + bt[j]
+        for (int j = 0; j < CH; ++j) {
+          double bj = bt[j];
+          for (int c = 0; c < C; ++c) tmp[(size_t)j * C + c] = 0.0;
+          for (int i = 0; i < CH; ++i) {
+            const double wv = wt[((size_t)i * CH + j) * 8 + t];
+            bj += wv * b1[i];
+            for (int c = 0; c < C; ++c) tmp[(size_t)j * C + c] += wv * w1[(size_t)i * C + c];
+          }
+          tb[j] = bj;
+        }
+        for (int o = 0; o < CH; ++o) {
+          double bo = b3[o];
+          for (int j = 0; j < CH; ++j) bo += (double)w3[(size_t)o * C + CH + j] * tb[j];
+          btc[(size_t)t * CH + o] = (float)bo;
+          for (int c = 0; c < C; ++c) {
+            double a = 0.0;
+            for (int j = 0; j < CH; ++j) a += (double)w3[(size_t)o * C + CH + j] * tmp[(size_t)j * C + c];
+            mt[((size_t)t * CH + o) * C + c] = (float)a;
+          }
+        }
+      }
+      DCL_TRY(upload(h, mt, &h->deup[l].mt)); DCL_TRY(upload(h, w3a, &h->deup[l].w3a)); DCL_TRY(upload(h, btc, &h->deup[l].bt));
+    }
+    DCL_TRY(upload(h, h->host_w.at("decoder.endconv.weight"), &h->end_w));
+    DCL_TRY(upload(h, h->host_w.at("decoder.endconv.bias"), &h->end_b));
+  }
   h->ready = true;
   return 0;
 }
@@ -437,12 +507,9 @@ struct Fwd {
     if (h->profiling) ev = h->prof_begin(st);
     int rc;
     if (h->cfg.precision == DCL_BF16) {
-      if (tc_conv_supported(c0 + c1, w.cout, g, stride, false) && x1 == nullptr && out_scale == nullptr) {
-        rc = launch_conv3d_k3_tc(s, d, w.tc, w.cout, g, false, st);
-      } else {
-        rc = launch_prep_blocked(s, g, g, g, h->blk, st);
-        if (rc == 0) rc = launch_conv_gemm(h->blk, w.tc, d, g, g, g, stride, 27, st);
-      }
+      // fp32 NCDHW tensors of the auxiliary heads: blocked-bf16 prep + the general GEMM kernel
+      rc = launch_prep_blocked(s, g, g, g, h->blk, st);
+      if (rc == 0) rc = launch_conv_gemm(h->blk, w.tc, d, g, g, g, stride, 27, st);
     } else {
       rc = launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, g, g, g, stride, st);
     }
@@ -674,6 +741,190 @@ struct Fwd {
   }
 };
 
+// ---- bf16 forward schedule (DCL_BF16): every activation is B-format, every conv runs on tcgen05 --------
+struct Fwd16 {
+  dcl_handle* h;
+  cudaStream_t st;
+
+  stat_t* new_stats() { return h->stat_arena + (size_t)(h->stat_used++ % STAT_SLOTS) * 1024; }
+  static BNorm norm_of(const stat_t* sums, int64_t spatial, int act) {
+    BNorm n;
+    n.sums = sums; n.inv_n = (float)(1.0 / (double)spatial); n.act = act;
+    return n;
+  }
+
+  // 3x3x3 conv, B-format in/out.  x1 (optional) = second concat source; norm = fused input transform.
+  int conv(const void* x0, int c0, const void* x1, int c1, int g, const ConvW& w, int stride, const BNorm* norm,
+           const float* out_scale, const void* resb, void* y, stat_t* stats, int taps = 27) {
+    cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+    int rc;
+    if (taps == 27 && x1 == nullptr && tc_conv_supported(c0, w.cout, g, stride, false)) {
+      RollArgs a;
+      a.xb = x0;
+      if (norm) a.norm = *norm;
+      a.bias = w.b; a.out_scale = out_scale; a.resb = resb; a.yb = y; a.stats = stats;
+      rc = launch_roll_conv(a, w.tc, w.cout, g, st);
+    } else {
+      const void* src = x0;
+      if (norm) {
+        if (x1 != nullptr) { set_error("bf16 conv: fused norm with two sources is not used by this network"); return -1; }
+        DCL_TRY(launch_norm_act_b(x0, *norm, nullptr, h->b_nrm, c0, (int64_t)g * g * g, st));
+        src = h->b_nrm;
+      }
+      GemmArgs ga;
+      ga.a0 = src; ga.c0 = c0; ga.a1 = x1;
+      ga.D = g; ga.H = g; ga.W = g; ga.stride = stride; ga.taps = taps;
+      ga.bias = w.b; ga.out_scale = out_scale; ga.out_mode = 2; ga.y = y; ga.residual = resb; ga.stats = stats;
+      rc = launch_gemm_conv(ga, w.tc, st);
+    }
+    if (h->profiling) {
+      const double og = (double)((g - 1) / stride + 1);
+      h->prof_end(ev, 0, 2.0 * taps * (c0 + c1) * w.cout * og * og * og, st);
+    }
+    return rc;
+  }
+
+  // EnBlock: y = conv2(relu(IN(conv1(relu(IN(x)))))) + x; sx = sums of x, *sy = sums of y (if wanted)
+  int en_block(const void* x, const stat_t* sx, int c, int g, const std::string& name, void* a, void* y, stat_t* sy) {
+    const int64_t sp = (int64_t)g * g * g;
+    stat_t* sa = new_stats();
+    BNorm n1 = norm_of(sx, sp, ACT_RELU), n2 = norm_of(sa, sp, ACT_RELU);
+    DCL_TRY(conv(x, c, nullptr, 0, g, h->conv.at(name + ".conv1"), 1, &n1, nullptr, nullptr, a, sa));
+    DCL_TRY(conv(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &n2, nullptr, x, y, sy));
+    return 0;
+  }
+
+  // EnBlock2 / DeBlock: y = lrelu(IN(conv2(lrelu(IN(conv1(x)))))) + x
+  int post_block(const void* x, int c, int g, const std::string& name, void* a, void* b, void* y) {
+    const int64_t sp = (int64_t)g * g * g;
+    stat_t *sa = new_stats(), *sb = new_stats();
+    DCL_TRY(conv(x, c, nullptr, 0, g, h->conv.at(name + ".conv1"), 1, nullptr, nullptr, nullptr, a, sa));
+    BNorm n1 = norm_of(sa, sp, ACT_LRELU);
+    DCL_TRY(conv(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &n1, nullptr, nullptr, b, sb));
+    DCL_TRY(launch_norm_act_b(b, norm_of(sb, sp, ACT_LRELU), x, y, c, sp, st));
+    return 0;
+  }
+
+  int run(const float* x, const int64_t xs[4], const float* keep_host, float* probs_out, float* const* aux) {
+    const bool want_aux = aux != nullptr;
+    const bool dense_feats = want_aux || h->cfg.keep_stages;
+    Fwd f{h, st};   // token-path and auxiliary-head helpers are shared with the fp32 schedule
+    h->stat_used = 0;
+    DCL_CUDA_OK(cudaMemsetAsync(h->stat_arena, 0, (size_t)STAT_SLOTS * 1024 * sizeof(stat_t), st));
+    Floats16 keep;
+    for (int i = 0; i < 16; ++i) keep.v[i] = keep_host ? keep_host[i] : 1.f;
+    DCL_TRY(launch_fill16(h->keep_dev, keep, st));
+    const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
+
+    // ---- encoder ----
+    stat_t* s_in = new_stats();
+    {
+      const ConvW& w = h->conv.at("Unet_list.InitConv.conv");
+      RollArgs a;
+      a.x4 = x; a.s4c = xs[0]; a.s4d = xs[1]; a.s4h = xs[2];
+      a.bias = w.b; a.out_scale = h->keep_dev; a.yb = h->b_t0[0]; a.stats = s_in;
+      cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+      DCL_TRY(launch_roll_conv(a, w.tc, 16, 128, st));
+      if (h->profiling) h->prof_end(ev, 0, 2.0 * 27.0 * 4 * 16 * (double)P3, st);
+    }
+    const char* blk[4][2] = {{"Unet_list.EnBlock1", "Unet_list.EnBlock1_1"}, {"Unet_list.EnBlock2_1", "Unet_list.EnBlock2_2"},
+                             {"Unet_list.EnBlock3_1", "Unet_list.EnBlock3_2"}, {"Unet_list.EnBlock4_1", "Unet_list.EnBlock4_2"}};
+    const char* down[4] = {"Unet_list.EnDown1.conv", "Unet_list.EnDown2.conv", "Unet_list.EnDown3.conv",
+                           "Unet_list.EnDown_4.conv"};
+    for (int l = 0; l < 4; ++l) {
+      const int c = LVL_C[l], g = LVL_G[l];
+      stat_t* s_mid = new_stats();
+      DCL_TRY(en_block(h->b_t0[l], s_in, c, g, blk[l][0], h->b_a[l], h->b_t1[l], s_mid));
+      DCL_TRY(en_block(h->b_t1[l], s_mid, c, g, blk[l][1], h->b_a[l], h->b_x[l], nullptr));
+      s_in = new_stats();
+      void* nxt = l < 3 ? h->b_t0[l + 1] : h->b_x4;
+      DCL_TRY(conv(h->b_x[l], c, nullptr, 0, g, h->conv.at(down[l]), l < 3 ? 2 : 1, nullptr, nullptr, nullptr, nxt,
+                   l < 3 ? s_in : nullptr));
+    }
+
+    // ---- Anatomy-induced Region Decoupler (the 3 sibling convs of each branch merged) ----
+    DCL_TRY(conv(h->b_x[1], 32, nullptr, 0, 64, h->conv.at("conv_64_to_32"), 2, nullptr, nullptr, nullptr, h->b_edown,
+                 nullptr));
+    stat_t *s_e = new_stats(), *s_s = new_stats();
+    DCL_TRY(conv(h->b_edown, 32, h->b_x[2], 64, 32, h->edge_merged, 1, nullptr, nullptr, nullptr, h->b_eraw, s_e));
+    DCL_TRY(conv(h->b_x4, 256, nullptr, 0, 16, h->sem_merged, 1, nullptr, nullptr, nullptr, h->b_sraw, s_s));
+    for (int r = 0; r < 3; ++r) {
+      BNorm ne = norm_of(s_e, g32, ACT_LRELU), ns = norm_of(s_s, g16, ACT_LRELU);
+      DCL_TRY(launch_tokenise_b(h->b_eraw, ne, 4 * r, h->E[r], dense_feats ? h->edge_dense[r] : nullptr, 32, 32, 4, 2, 2, st));
+      DCL_TRY(launch_tokenise_b(h->b_sraw, ns, 16 * r, h->S[r], dense_feats ? h->sem_dense[r] : nullptr, 128, 16, 2, 2, 1, st));
+    }
+    if (want_aux) {
+      for (int r = 0; r < 3; ++r) {
+        std::string n = REGION_NUM[r];
+        DCL_TRY(f.aux_branch(h->sem_dense[r], 128, 16, "mid_supervise_label.supervise_label_" + n,
+                             "mid_supervise_label.down_label_" + n, aux[6 + r]));
+        DCL_TRY(f.aux_branch(h->edge_dense[r], 32, 32, "mid_edge_supervise_label.edge_supervise_label_" + n,
+                             "mid_edge_supervise_label.edge_down_label_" + n, aux[9 + r]));
+      }
+    }
+
+    // ---- Edge-supported Intra-region Couplers ----
+    for (int r = 0; r < 3; ++r) {
+      const Transformer& t = h->tr[r];
+      float *E = h->E[r], *S = h->S[r], *out = h->coupler_out[r];
+      DCL_TRY(f.select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, h->seq[0]));
+      DCL_TRY(f.select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, h->seq[1]));
+      DCL_TRY(f.select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, h->seq[2]));
+      DCL_TRY(f.select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, h->seq[3]));
+      DCL_TRY(f.attn_block(t, h->seq[0], h->seq[1], SEQ, SEQ, h->eqs));
+      DCL_TRY(f.attn_block(t, h->seq[2], h->seq[3], SEQ, SEQ, h->sqe));
+      DCL_TRY(f.attn_block(t, h->eqs, h->sqe, SEQ, SEQ, h->cross));
+      DCL_TRY(f.attn_block(t, h->sqe, h->eqs, SEQ, SEQ, h->cross + SEQ * 512));
+      DCL_TRY(f.ffn_block(t, h->cross, 2 * SEQ, out));
+      DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, st));
+      DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, st));
+      if (want_aux) {
+        DCL_TRY(launch_scale_untokenise(E, out, h->sup_edge[r], 32, 32, 4, 2, 2, st));
+        DCL_TRY(launch_scale_untokenise(S, out + SEQ * 512, h->sup_sem[r], 128, 16, 2, 2, 1, st));
+      }
+    }
+    if (want_aux) {
+      for (int r = 0; r < 3; ++r) {
+        std::string n = REGION_NUM[r];
+        DCL_TRY(f.aux_branch(h->sup_sem[r], 128, 16, "supervise_label.supervise_label_" + n,
+                             "supervise_label.down_label_" + n, aux[0 + r]));
+        DCL_TRY(f.aux_branch(h->sup_edge[r], 32, 32, "edge_supervise_label.edge_supervise_label_" + n,
+                             "edge_supervise_label.edge_down_label_" + n, aux[3 + r]));
+      }
+    }
+
+    // ---- Mutual Cross-region Coupler ----
+    DCL_TRY(launch_add3(h->coupler_out[0] + SEQ * 512, h->coupler_out[1] + SEQ * 512, h->coupler_out[2] + SEQ * 512,
+                        h->f_tok, 512, st));
+    DCL_TRY(launch_add3(h->S[0], h->S[1], h->S[2], h->f_fea, 1024 * 512, st));
+    DCL_TRY(f.select_build(h->f_tok, h->f_tok, h->f_fea, 1024, h->pe[3], 12, h->seq[0]));
+    DCL_TRY(f.attn_block(h->tr[3], h->seq[0], h->seq[0], SEQ, SEQ, h->eqs));
+    DCL_TRY(f.ffn_block(h->tr[3], h->eqs, SEQ, h->coupler_out[3]));
+    DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
+    DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st));
+    DCL_TRY(conv(h->b_fused, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, nullptr, nullptr, h->b_enc, nullptr));
+
+    // ---- decoder ----
+    DCL_TRY(conv(h->b_enc, 256, nullptr, 0, 16, h->conv.at("decoder.down_channel"), 1, nullptr, nullptr, nullptr,
+                 h->b_d8[0], nullptr, 1));
+    DCL_TRY(post_block(h->b_d8[0], 128, 16, "decoder.Enblock8_1", h->b_d8[1], h->b_d8[2], h->b_d8[3]));
+    DCL_TRY(post_block(h->b_d8[3], 128, 16, "decoder.Enblock8_2", h->b_d8[1], h->b_d8[2], h->b_d8[4]));
+    const char* dbn[3][2] = {{"decoder.DeBlock4", "decoder.DeBlock4_1"}, {"decoder.DeBlock3", "decoder.DeBlock3_1"},
+                             {"decoder.DeBlock2", "decoder.DeBlock2_1"}};
+    const void* cur = h->b_d8[4];
+    for (int l = 0; l < 3; ++l) {
+      const int cin = 128 >> l, g_in = 16 << l, c = cin / 2, g = g_in * 2;
+      void** b = h->b_dl[l];
+      DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st));
+      DCL_TRY(post_block(b[0], c, g, dbn[l][0], b[1], b[2], b[3]));
+      DCL_TRY(post_block(b[3], c, g, dbn[l][1], b[1], b[2], b[4]));
+      cur = b[4];
+    }
+    DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
+    return 0;
+  }
+};
+
 static void register_stages(dcl_handle* h) {
   const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
   auto& s = h->stages;
@@ -693,6 +944,19 @@ static void register_stages(dcl_handle* h) {
   s["dec4"] = {h->dl_2[0], 64 * g32};
   s["dec3"] = {h->dl_2[1], 32 * P3 / 8};
   s["dec2"] = {h->dl_2[2], 16 * P3};
+  if (h->cfg.precision == DCL_BF16) {   // the conv-path stages live in B-format buffers in this mode
+    auto& b = h->bstages;
+    b["init"] = {h->b_t0[0], 16, P3};
+    b["x1_1"] = {h->b_x[0], 16, P3};
+    b["x2_1"] = {h->b_x[1], 32, P3 / 8};
+    b["x3_1"] = {h->b_x[2], 64, g32};
+    b["x4"] = {h->b_x4, 256, g16};
+    b["enc_out"] = {h->b_enc, 256, g16};
+    b["dec8"] = {h->b_d8[4], 128, g16};
+    b["dec4"] = {h->b_dl[0][4], 64, g32};
+    b["dec3"] = {h->b_dl[1][4], 32, P3 / 8};
+    b["dec2"] = {h->b_dl[2][4], 16, P3};
+  }
 }
 
 static int check_handle(dcl_handle* h) {
@@ -758,10 +1022,14 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
   const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
   Fwd f{h, st};
+  Fwd16 f16{h, st};
   for (int i = first; i < first + count; ++i) {
     const PlanItem& p = plan[i];
     const float* x = vol + (int64_t)p.start[0] * xs[1] + (int64_t)p.start[1] * xs[2] + p.start[2];
-    DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
+    if (h->cfg.precision == DCL_BF16)
+      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
+    else
+      DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
     cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
     double bytes;
     if (weighted) {
@@ -870,8 +1138,14 @@ DCL_API int dcl_forward(dcl_handle* h, const float* x_dev, const int64_t x_strid
   if (x_strides[3] != 1) { set_error("dcl_forward: the Z stride of x must be 1"); return DCL_ERR_ARG; }
   if (aux_dev && !h->cfg.want_aux) { set_error("dcl_forward: aux outputs need cfg.want_aux"); return DCL_ERR_ARG; }
   int64_t before = g_launches;
-  Fwd f{h, (cudaStream_t)stream};
-  int rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
+  int rc;
+  if (h->cfg.precision == DCL_BF16) {
+    Fwd16 f{h, (cudaStream_t)stream};
+    rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
+  } else {
+    Fwd f{h, (cudaStream_t)stream};
+    rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
+  }
   h->launches += g_launches - before;
   return rc;
 }
@@ -974,6 +1248,15 @@ DCL_API int dcl_predict_volume_host(dcl_handle* h, const float* vol_host, const 
 DCL_API int64_t dcl_read_stage(dcl_handle* h, const char* stage, float* out_dev, int64_t cap, void* stream) {
   if (!h || !stage) { set_error("dcl_read_stage: null argument"); return DCL_ERR_ARG; }
   if (!h->cfg.keep_stages) { set_error("dcl_read_stage: handle was created without keep_stages"); return DCL_ERR_STATE; }
+  auto bit = h->bstages.find(stage);
+  if (bit != h->bstages.end()) {
+    const int64_t n = (int64_t)bit->second.c * bit->second.spatial;
+    if (out_dev) {
+      if (cap < n) { set_error("dcl_read_stage: output buffer too small"); return DCL_ERR_ARG; }
+      DCL_TRY(launch_unblock(bit->second.p, out_dev, bit->second.c, bit->second.spatial, (cudaStream_t)stream));
+    }
+    return n;
+  }
   auto it = h->stages.find(stage);
   if (it == h->stages.end()) { set_error(std::string("dcl_read_stage: unknown stage '") + stage + "'"); return DCL_ERR_ARG; }
   int64_t n = it->second.second;
@@ -1041,7 +1324,7 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
   DCL_CUDA_OK(cudaMemcpy(wh.data(), w, wh.size() * 4, cudaMemcpyDefault));
   const int64_t sp = (int64_t)in_dhw[0] * in_dhw[1] * in_dhw[2];
   ConvSrc s{x0, x1, c0, c1, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], norm_mean, norm_rstd, act};
-  ConvDst d{y, bias, nullptr, residual, stats_out};
+  ConvDst d{y, bias, nullptr, residual, nullptr};
   if (stats_out && impl == 0) { set_error("dcl_op_conv3d_k3: fused statistics need a tensor-core impl"); return DCL_ERR_ARG; }
   int rc;
   if (impl == 0) {
@@ -1059,10 +1342,41 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
   } else {
     if (impl == 1) { set_error("dcl_op_conv3d_k3: bf16x3 has no tensor-core kernel yet"); return DCL_ERR_ARG; }
     TcWeights tw;
-    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, 27, &tw));
     const bool cubic = in_dhw[0] == in_dhw[1] && in_dhw[1] == in_dhw[2];
-    if (cubic && x1 == nullptr && tc_conv_supported(cin, cout, in_dhw[0], stride, false)) {
-      rc = launch_conv3d_k3_tc(s, d, tw, cout, in_dhw[0], false, st);
+    const bool roll = cubic && x1 == nullptr && tc_conv_supported(cin, cout, in_dhw[0], stride, false) && cin != 4;
+    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, 27, roll, &tw));
+    if (roll) {
+      // rolling kernel: B-format in / out, so convert around it (raw input; the norm is fused in the kernel)
+      void *xb = nullptr, *yb = nullptr, *rb = nullptr;
+      DCL_CUDA_OK(cudaMalloc(&xb, (size_t)cin * sp * 2));
+      DCL_CUDA_OK(cudaMalloc(&yb, (size_t)cout * sp * 2));
+      ConvSrc raw{x0, nullptr, c0, 0, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], nullptr, nullptr, ACT_NONE};
+      rc = launch_prep_blocked(raw, in_dhw[0], in_dhw[1], in_dhw[2], xb, st);
+      if (rc == 0 && residual) {
+        DCL_CUDA_OK(cudaMalloc(&rb, (size_t)cout * sp * 2));
+        ConvSrc rs{residual, nullptr, cout, 0, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], nullptr, nullptr, ACT_NONE};
+        rc = launch_prep_blocked(rs, in_dhw[0], in_dhw[1], in_dhw[2], rb, st);
+      }
+      RollArgs a;
+      a.xb = xb; a.norm.mean = norm_mean; a.norm.rstd = norm_rstd; a.norm.act = act;
+      stat_t* sfix = nullptr;
+      if (stats_out) {
+        DCL_CUDA_OK(cudaMalloc((void**)&sfix, 2 * cout * sizeof(stat_t)));
+        DCL_CUDA_OK(cudaMemsetAsync(sfix, 0, 2 * cout * sizeof(stat_t), st));
+      }
+      a.bias = bias; a.resb = rb; a.yb = yb; a.stats = sfix;
+      if (rc == 0) rc = launch_roll_conv(a, tw, cout, in_dhw[0], st);
+      if (rc == 0) rc = launch_unblock(yb, y, cout, sp, st);
+      cudaStreamSynchronize(st);
+      if (stats_out && rc == 0) {   // decode the fixed-point sums into the caller's doubles
+        std::vector<stat_t> hs(2 * cout);
+        std::vector<double> hd(2 * cout);
+        DCL_CUDA_OK(cudaMemcpy(hs.data(), sfix, hs.size() * sizeof(stat_t), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < cout; ++c) { hd[2 * c] = (double)hs[2 * c] / STAT_SCALE_S; hd[2 * c + 1] = (double)hs[2 * c + 1] / STAT_SCALE_Q; }
+        DCL_CUDA_OK(cudaMemcpy(stats_out, hd.data(), hd.size() * sizeof(double), cudaMemcpyDefault));
+      }
+      if (sfix) cudaFree(sfix);
+      cudaFree(xb); cudaFree(yb); if (rb) cudaFree(rb);
     } else {
       if (stats_out) { cudaFree(tw.dev); set_error("dcl_op_conv3d_k3: fused statistics need the rolling kernel"); return DCL_ERR_ARG; }
       void* blk = nullptr;

@@ -75,8 +75,10 @@ def _bf16_round(t):
 
 @pytest.mark.parametrize("c,g,act,residual", [(16, 128, 1, True), (16, 128, 2, False), (32, 64, 2, True), (32, 64, 0, False)])
 def test_conv3d_k3_tcgen05_bf16(c, g, act, residual):
-    """The tcgen05 rolling kernel against torch conv3d on bf16-rounded operands (fp32 accumulate on both
-    sides, so only the summation order differs), plus the fused per-channel statistics of its epilogue."""
+    """The tcgen05 rolling kernel against torch conv3d.  The kernel works on B-format (bf16) activations:
+    input and residual are rounded to bf16 on entry, the normalised input is rounded again before the MMA,
+    accumulation is fp32 and the output is stored as bf16 - the reference applies the same roundings, so what
+    is left is summation order plus one bf16 ulp (2^-9) of the output.  Also checks the fused statistics."""
     from dcl_b200.engine import op_conv3d_k3
     gen = torch.Generator().manual_seed(11 + c)
     x = torch.randn(c, g, g, g, generator=gen) * 1.7 + 0.4
@@ -84,26 +86,24 @@ def test_conv3d_k3_tcgen05_bf16(c, g, act, residual):
     b = torch.randn(c, generator=gen)
     mean = torch.randn(c, generator=gen) * 0.3
     rstd = torch.rand(c, generator=gen) + 0.5
-    xin = (x - mean.view(-1, 1, 1, 1)) * rstd.view(-1, 1, 1, 1)
+    xin = (_bf16_round(x) - mean.view(-1, 1, 1, 1)) * rstd.view(-1, 1, 1, 1)
     xin = F.relu(xin) if act == 1 else (F.leaky_relu(xin, 0.01) if act == 2 else xin)
     ref = F.conv3d(_bf16_round(xin)[None], _bf16_round(w), b, padding=1)[0]
     res = torch.randn(ref.shape, generator=gen) if residual else None
     if residual:
-        ref = ref + res
+        ref = ref + _bf16_round(res)
     stats = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
     y = op_conv3d_k3(x.cuda(), w.cuda(), b.cuda(), None, 1, (mean.cuda(), rstd.cuda()), act,
                      res.cuda() if residual else None, impl=2, stats=stats)
     torch.cuda.synchronize()
     y = y.cpu()
-    # elements whose normalised input sits on a bf16 rounding boundary may round differently on the two
-    # sides (fp32 (x-m)*r is fused differently): allow a bf16-ulp-sized slack on top of the tight bound
-    err = rel_err(y.numpy(), ref.numpy())
-    assert err < 2e-3, err
-    assert float((y - ref).abs().mean() / ref.abs().mean()) < 1e-4
+    assert rel_err(y.numpy(), ref.numpy()) < 4e-3
+    assert float((y - ref).abs().mean() / ref.abs().mean()) < 2e-3
+    assert float((y - _bf16_round(ref)).abs().mean() / ref.abs().mean()) < 2e-4     # identical up to rare ulp flips
     st = stats.cpu().view(c, 2)
-    yd = y.double().flatten(1)
-    assert rel_err(st[:, 0].numpy(), yd.sum(1).numpy()) < 1e-5
-    assert rel_err(st[:, 1].numpy(), (yd * yd).sum(1).numpy()) < 1e-5
+    rd = ref.double().flatten(1)
+    assert rel_err(st[:, 0].numpy(), rd.sum(1).numpy()) < 1e-4
+    assert rel_err(st[:, 1].numpy(), (rd * rd).sum(1).numpy()) < 1e-4
 
 
 @pytest.mark.parametrize("case", [
