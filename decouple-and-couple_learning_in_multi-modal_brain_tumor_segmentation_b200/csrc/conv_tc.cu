@@ -27,7 +27,9 @@ namespace dcl {
 
 using namespace tc;
 
-template <int C_, int G_, int TH_, bool FLAT_, bool KHN_>
+cudaError_t trace_set_conv_tc(long long* p) { return trace_set_local(p); }
+
+template <int C_, int G_, int TH_, bool FLAT_, bool KHN_, int NSLOT_>
 struct RollCfg {
   static constexpr int C = C_, G = G_, TH = TH_;
   static constexpr bool FLAT = FLAT_;
@@ -39,7 +41,7 @@ struct RollCfg {
   static constexpr int KC = C / 8;                // 16-byte channel chunks
   static constexpr int KS = C / 16;               // K = 16 MMA steps per tap
   static constexpr int SLOT_BYTES = KC * NPOS * 16;
-  static constexpr int NSLOT = 4;
+  static constexpr int NSLOT = NSLOT_;            // staged planes in flight: 3 feeding the MMAs + (NSLOT-3) being filled
   static constexpr int RUN = (TH - 1) * P + W;    // flattened (row, w) positions holding real outputs
   static constexpr int TSTRIDE = FLAT ? 128 : P;  // position of M tile t = t * TSTRIDE
   static constexpr int NT = FLAT ? (RUN + 127) / 128 : TH;
@@ -106,6 +108,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
+  if (tid == 0) trace_event(0, 0);     // kernel entry
 
   const int dsplit = prm.dsplit;
   const int ht = blockIdx.x / dsplit;
@@ -145,57 +148,86 @@ conv3d_k3_roll_kernel(RollParams prm) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
+  if (tid == 0) trace_event(1, 0);     // setup done
 
   if (warp >= EPI_WARPS + 1) {
     // =============================== producers ===================================================
     const int pt = tid - PROD_T0;
     const int act = prm.act;
     const bool identity = !has_norm && act == ACT_NONE;
-    for (int j = 0; j < n_in; ++j) {
-      const int s = j % NSLOT;
-      mbar_wait(&bar_empty[s], ((uint32_t)(j / NSLOT) & 1u) ^ 1u);
-      const int d_in = d0 - 1 + j;
-      const bool d_ok = (unsigned)d_in < (unsigned)G;
-      uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
-      if (prm.xb != nullptr) {
-        // ---- B-format source: one 16-byte load per (chunk, voxel) item, all loads of a pass in flight
-        constexpr int U = 6;
-        for (int e0 = pt; e0 < Cfg::ITEMS; e0 += NPROD * U) {
-          uint4 v[U];
-          bool oks[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * NPROD;
-            const int kc = e / NPOS;
-            const int rem = e - kc * NPOS;
-            const int r = rem / P;
-            const int q = rem - r * P;
-            const int h_in = h0 - 1 + r, w_in = q - 1;
-            oks[u] = e < Cfg::ITEMS && d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G;
-            v[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (oks[u]) v[u] = __ldg(prm.xb + (int64_t)kc * SP + ((int64_t)d_in * G + h_in) * G + w_in);
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int e = e0 + u * NPROD;
-            if (e < Cfg::ITEMS) {
-              if (oks[u] && !identity) {
-                const int c0 = (e / NPOS) * 8;
-                uint32_t* pv = reinterpret_cast<uint32_t*>(&v[u]);
+    if (prm.xb != nullptr) {
+      // ---- B-format source.  The staged layout IS the global layout (16-byte vectors), so a plane is
+      // fetched with zero-filling cp.async straight into its slot (no registers, AHEAD planes in flight) and
+      // the InstanceNorm + activation is then applied in place by the thread that copied the vector.
+      constexpr int AHEAD = NSLOT - 3;
+      const uint32_t smem_base = smem_u32(smem);
+      auto issue = [&](int j) {
+        const int d_in = d0 - 1 + j;
+        const bool d_ok = (unsigned)d_in < (unsigned)G;
+        const uint32_t slot_addr = smem_base + (uint32_t)((j % NSLOT) * Cfg::SLOT_BYTES);
+        for (int e = pt; e < Cfg::ITEMS; e += NPROD) {
+          const int kc = e / NPOS;
+          const int rem = e - kc * NPOS;
+          const int r = rem / P;
+          const int q = rem - r * P;
+          const int h_in = h0 - 1 + r, w_in = q - 1;
+          const bool ok = d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G;
+          const uint4* src = ok ? prm.xb + (int64_t)kc * SP + ((int64_t)d_in * G + h_in) * G + w_in : prm.xb;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_addr + (uint32_t)e * 16u), "l"(src),
+                       "r"(ok ? 16u : 0u)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      for (int j = 0; j < AHEAD && j < n_in; ++j) issue(j);
+      for (int j = 0; j < n_in; ++j) {
+        const int jn = j + AHEAD;
+        if (jn < n_in) {
+          mbar_wait(&bar_empty[jn % NSLOT], ((uint32_t)(jn / NSLOT) & 1u) ^ 1u);
+          if (pt == 0) trace_event(2, jn);  // producer: slot free, fetching plane jn
+          issue(jn);
+        }
+        const int pending = n_in - 1 - j < AHEAD ? n_in - 1 - j : AHEAD;   // groups committed after plane j
+        if (pending >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+        else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (!identity) {
+          const int d_in = d0 - 1 + j;
+          if ((unsigned)d_in < (unsigned)G) {
+            uint8_t* slot = smem + (j % NSLOT) * Cfg::SLOT_BYTES;
+            for (int e = pt; e < Cfg::ITEMS; e += NPROD) {
+              const int kc = e / NPOS;
+              const int rem = e - kc * NPOS;
+              const int r = rem / P;
+              const int q = rem - r * P;
+              const int h_in = h0 - 1 + r, w_in = q - 1;
+              if ((unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G) {   // padding stays zero
+                uint4 v = *reinterpret_cast<uint4*>(slot + (size_t)e * 16);
+                uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   float2 f = unpack_bf16x2(pv[k]);
-                  f.x = apply_act((f.x - s_mean[c0 + 2 * k]) * s_rstd[c0 + 2 * k], act);
-                  f.y = apply_act((f.y - s_mean[c0 + 2 * k + 1]) * s_rstd[c0 + 2 * k + 1], act);
+                  f.x = apply_act((f.x - s_mean[kc * 8 + 2 * k]) * s_rstd[kc * 8 + 2 * k], act);
+                  f.y = apply_act((f.y - s_mean[kc * 8 + 2 * k + 1]) * s_rstd[kc * 8 + 2 * k + 1], act);
                   pv[k] = pack_bf16x2(f.x, f.y);
                 }
+                *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = v;
               }
-              *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = v[u];
             }
           }
         }
-      } else {
-        // ---- fp32 NCDHW 4-channel source (InitConv): channels 4..C-1 are zero padding
+        fence_proxy_async();
+        mbar_arrive(&bar_full[j % NSLOT]);
+        if (pt == 0) trace_event(3, j);    // producer: plane j staged (this thread)
+      }
+    } else {
+      // ---- fp32 NCDHW 4-channel source (InitConv): channels 4..C-1 are zero padding
+      for (int j = 0; j < n_in; ++j) {
+        const int s = j % NSLOT;
+        mbar_wait(&bar_empty[s], ((uint32_t)(j / NSLOT) & 1u) ^ 1u);
+        const int d_in = d0 - 1 + j;
+        const bool d_ok = (unsigned)d_in < (unsigned)G;
+        uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
         for (int e = pt; e < NPOS; e += NPROD) {
           const int r = e / P;
           const int q = e - r * P;
@@ -211,13 +243,13 @@ conv3d_k3_roll_kernel(RollParams prm) {
           for (int kc = 1; kc < Cfg::KC; ++kc)
             *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
+        fence_proxy_async();
+        mbar_arrive(&bar_full[s]);
       }
-      fence_proxy_async();
-      mbar_arrive(&bar_full[s]);
     }
   } else if (warp == EPI_WARPS) {
     // =============================== MMA issuer ==================================================
-    if (lane == 0) {
+    {   // all 32 lanes run the loop; the elected lane issues (see umma_bf16_ws)
       constexpr uint32_t idesc = umma_idesc_bf16(128, C);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t w_base = smem_base + Cfg::OFF_W;
@@ -230,38 +262,41 @@ conv3d_k3_roll_kernel(RollParams prm) {
         mbar_wait(&bar_full[(i + 2) % NSLOT], (uint32_t)((i + 2) / NSLOT) & 1u);
         mbar_wait(&bar_acc_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
         tc_fence_after();
+        if (lane == 0) trace_event(4, i);               // MMA: inputs + accumulator ready, issuing step i
         if constexpr (Cfg::KHN) {
           // Staged row rho feeds output rows rho-2 (kh=2), rho-1 (kh=1), rho (kh=0) at once: their
           // accumulators are adjacent TMEM column blocks and the weights of (kd,kw) are stored as one
           // stacked N = 3C operand, so one MMA (one read of the 4 KB A tile) does the work of three.
+          // Fully unrolled: every descriptor is (one of 3 per-plane bases) + a compile-time constant, so
+          // the single issuing thread spends a handful of instructions per MMA.
           constexpr uint32_t WB = 3 * C * C * 2;            // bytes of one (kd,kw) stacked weight matrix
           constexpr uint32_t B_LBO = 3 * C * 16;
-#pragma unroll 1
+          uint64_t a_kd[3];
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd)
+            a_kd[kd] = umma_desc(smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES), NPOS * 16, 128);
+          const uint64_t b_base = umma_desc(w_base, B_LBO, 128);
+          const uint32_t acc0 = tmem_base + (uint32_t)(b * Cfg::ACC_COLS);
+#pragma unroll
           for (int rho = 0; rho < TH + 2; ++rho) {
             const int q_lo = rho >= 2 ? rho - 2 : 0;
             const int q_hi = rho < TH ? rho : TH - 1;
             const int blk0 = q_lo - (rho - 2);
             const bool fresh = rho < TH;                    // output row rho gets its first contribution here
-#pragma unroll 1
+#pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
-              const uint32_t slot_base = smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES);
 #pragma unroll
               for (int kw = 0; kw < 3; ++kw) {
-                const uint32_t a0 = slot_base + (uint32_t)((rho * P + kw) * 16);
-                const uint32_t b0 = w_base + (uint32_t)(kd * 3 + kw) * WB + (uint32_t)(blk0 * C * 16);
                 const bool first = fresh && kd == 0 && kw == 0;
                 const int n_acc = (q_hi - q_lo + 1) - (first ? 1 : 0);   // blocks that accumulate
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
-                  const uint64_t ad = umma_desc(a0 + (uint32_t)(ks * 2 * NPOS * 16), NPOS * 16, 128);
-                  const uint32_t bk = b0 + (uint32_t)(ks * 2) * B_LBO;
-                  if (n_acc > 0)
-                    umma_bf16(tmem_base + (uint32_t)(b * Cfg::ACC_COLS + q_lo * C), ad, umma_desc(bk, B_LBO, 128),
-                              umma_idesc_bf16(128, n_acc * C), 1u);
+                  const uint64_t ad = a_kd[kd] + (uint64_t)(((rho * P + kw) * 16 + ks * 2 * NPOS * 16) >> 4);
+                  const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * C * 16 + ks * 2 * B_LBO) >> 4);
+                  if (n_acc > 0) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
                   if (first)
-                    umma_bf16(tmem_base + (uint32_t)(b * Cfg::ACC_COLS + rho * C), ad,
-                              umma_desc(bk + (uint32_t)(n_acc * C * 16), B_LBO, 128), umma_idesc_bf16(128, C),
-                              ks == 0 ? 0u : 1u);
+                    umma_bf16_ws(acc0 + (uint32_t)(rho * C), ad, bd + (uint64_t)((n_acc * C * 16) >> 4),
+                              umma_idesc_bf16(128, C), ks == 0 ? 0u : 1u);
                 }
               }
             }
@@ -284,7 +319,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
                   const uint64_t ad = umma_desc(a0 + (uint32_t)(ks * 2 * NPOS * 16), NPOS * 16, 128);
                   const uint64_t bd = umma_desc(b0 + (uint32_t)(ks * 2 * C * 16), C * 16, 128);
-                  umma_bf16(d_tmem, ad, bd, idesc, accum);
+                  umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
                   accum = 1;
                 }
               }
@@ -292,8 +327,9 @@ conv3d_k3_roll_kernel(RollParams prm) {
           }
         }
         }
-        umma_commit(&bar_acc_full[b]);
-        umma_commit(&bar_empty[i % NSLOT]);
+        umma_commit_ws(&bar_acc_full[b]);
+        umma_commit_ws(&bar_empty[i % NSLOT]);
+        if (lane == 0) trace_event(5, i);               // MMA: step i issued
       }
     }
     __syncwarp();
@@ -308,6 +344,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
       const int b = i & 1;
       mbar_wait(&bar_acc_full[b], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
+      if (tid == 0) trace_event(6, i);   // epilogue: accumulator of step i complete
       const int d = d0 + i;
 #pragma unroll 1
       for (int t = 0; t < Cfg::NT; ++t) {
@@ -357,6 +394,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
         }
       }
     }
+    if (tid == 0) trace_event(7, n_out);   // epilogue: all planes stored
     if (prm.stats != nullptr) {
 #pragma unroll
       for (int c = 0; c < C; ++c) {
@@ -421,8 +459,8 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
   return 0;
 }
 
-using RollC16 = RollCfg<16, 128, 8, false, true>;
-using RollC32 = RollCfg<32, 64, 8, true, false>;
+using RollC16 = RollCfg<16, 128, 8, false, true, 5>;
+using RollC32 = RollCfg<32, 64, 8, true, false, 4>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
   if (split || stride != 1) return false;

@@ -53,6 +53,9 @@ struct GemmArgs {
   int gelu = 0;
 };
 int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st);
+// stride-1 3x3x3 conv with the input tile staged once ("slab" kernel, fused input norm); W in {16,32,64,128}
+bool slab_conv_supported(int cin, int cout, int d, int h, int w, int stride, int taps);
+int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, cudaStream_t st);
 
 // True when the rolling kernel handles a cubic g^3 stride-1 conv with these channel counts.
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split);

@@ -14,6 +14,11 @@
 
 namespace dcl {
 
+static long long* g_trace_host_ptr = nullptr;
+constexpr int TRACE_CAP_HOST = 4096;
+cudaError_t trace_set_conv_tc(long long* p);
+cudaError_t trace_set_conv_gemm(long long* p);
+
 thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_error = msg; }
@@ -764,6 +769,12 @@ struct Fwd16 {
       if (norm) a.norm = *norm;
       a.bias = w.b; a.out_scale = out_scale; a.resb = resb; a.yb = y; a.stats = stats;
       rc = launch_roll_conv(a, w.tc, w.cout, g, st);
+    } else if (taps == 27 && slab_conv_supported(c0 + c1, w.cout, g, g, g, stride, taps) && g <= 32) {
+      GemmArgs ga;
+      ga.a0 = x0; ga.c0 = c0; ga.a1 = x1;
+      ga.D = g; ga.H = g; ga.W = g; ga.stride = 1; ga.taps = 27;
+      ga.bias = w.b; ga.out_scale = out_scale; ga.out_mode = 2; ga.y = y; ga.residual = resb; ga.stats = stats;
+      rc = launch_slab_conv(ga, norm, w.tc, st);
     } else {
       const void* src = x0;
       if (norm) {
@@ -1303,6 +1314,29 @@ DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64
 
 int64_t dcl_launch_count(const dcl_handle* h) { return h ? h->launches : 0; }
 
+// debug: in-kernel timeline of CTA (0,0) of the tcgen05 kernels (tools/trace_kernel.py)
+DCL_API int dcl_trace_enable(int32_t on) {
+  const size_t bytes = (1 + 2 * TRACE_CAP_HOST) * sizeof(long long);
+  if (on && !g_trace_host_ptr) DCL_CUDA_OK(cudaMalloc((void**)&g_trace_host_ptr, bytes));
+  long long* p = on ? g_trace_host_ptr : nullptr;
+  if (p) DCL_CUDA_OK(cudaMemset(p, 0, bytes));
+  DCL_CUDA_OK(trace_set_conv_tc(p));
+  DCL_CUDA_OK(trace_set_conv_gemm(p));
+  return DCL_OK;
+}
+// copies the recorded (tag<<32|step, clock) pairs (slots with a non-zero clock) to out_host, returns the count
+// and clears the buffer
+DCL_API int64_t dcl_trace_read(int64_t* out_host, int64_t cap) {
+  if (!g_trace_host_ptr) return 0;
+  std::vector<long long> h(1 + 2 * TRACE_CAP_HOST);
+  DCL_CUDA_OK(cudaMemcpy(h.data(), g_trace_host_ptr, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+  int64_t n = 0;
+  for (int i = 0; i < TRACE_CAP_HOST && n < cap; ++i)
+    if (h[2 + 2 * i] != 0) { out_host[2 * n] = h[1 + 2 * i]; out_host[2 * n + 1] = h[2 + 2 * i]; ++n; }
+  DCL_CUDA_OK(cudaMemset(g_trace_host_ptr, 0, h.size() * sizeof(long long)));
+  return n;
+}
+
 DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream) {
   if (!x || !mean || !rstd || channels <= 0 || channels > 512) { set_error("dcl_op_instnorm_stats: bad argument"); return DCL_ERR_ARG; }
   double* accum = nullptr;
@@ -1381,8 +1415,22 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
       if (stats_out) { cudaFree(tw.dev); set_error("dcl_op_conv3d_k3: fused statistics need the rolling kernel"); return DCL_ERR_ARG; }
       void* blk = nullptr;
       DCL_CUDA_OK(cudaMalloc(&blk, (size_t)((cin + 15) / 16 * 16) * sp * 2));
-      rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
-      if (rc == 0) rc = launch_conv_gemm(blk, tw, d, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27, st);
+      if (slab_conv_supported(cin, cout, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27)) {
+        // slab kernel: raw blocked input, norm fused in the kernel, fp32 NCDHW output
+        ConvSrc raw = s;
+        raw.mean = nullptr; raw.rstd = nullptr; raw.act = ACT_NONE;
+        rc = launch_prep_blocked(raw, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
+        GemmArgs ga;
+        ga.a0 = blk; ga.c0 = (cin + 15) / 16 * 16;
+        ga.D = in_dhw[0]; ga.H = in_dhw[1]; ga.W = in_dhw[2]; ga.stride = 1; ga.taps = 27;
+        ga.bias = bias; ga.out_mode = 0; ga.y = y; ga.residual = residual;
+        BNorm bn;
+        bn.mean = norm_mean; bn.rstd = norm_rstd; bn.act = act;
+        if (rc == 0) rc = launch_slab_conv(ga, &bn, tw, st);
+      } else {
+        rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
+        if (rc == 0) rc = launch_conv_gemm(blk, tw, d, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27, st);
+      }
       cudaStreamSynchronize(st);
       cudaFree(blk);
     }

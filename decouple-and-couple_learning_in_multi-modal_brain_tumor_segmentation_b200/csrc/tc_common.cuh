@@ -6,6 +6,21 @@
 #include <stdint.h>
 
 namespace dcl {
+
+// ---- optional in-kernel timeline (debug): CTA (0,0) appends (tag, step, clock64) records -------------
+// Enabled by dcl_trace_enable(); every call site costs one predictable branch when disabled.
+static __device__ long long* g_trace_buf = nullptr;   // per translation unit; [0] = record count, then 2 words per record
+static inline cudaError_t trace_set_local(long long* p) { return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+constexpr int TRACE_CAP = 4096;                       // 32 tags x 128 steps
+__device__ __forceinline__ void trace_event(int tag, int step) {
+  long long* buf = g_trace_buf;
+  if (buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    const int i = (tag & 31) * 128 + (step & 127);      // fixed slot per (tag, step): a plain store, no atomics
+    buf[1 + 2 * i] = ((long long)tag << 32) | (unsigned)step;
+    buf[2 + 2 * i] = clock64();
+  }
+}
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -34,8 +49,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
+  int polls = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (++polls > 4) __nanosleep(polls > 64 ? 256 : 32);   // back off: idle roles must not hammer the smem port
+    if ((polls & 255) == 0 && clock64() - t0 > 4000000000LL) __trap();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -87,6 +104,43 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Warp-collective variants: executed by ALL 32 lanes of the (converged) MMA warp, one elected lane issues.
+// Keeping the issue loop free of C++-level divergence lets the compiler hold descriptors in uniform
+// registers and drop the per-instruction R2UR + BRA.U.ANY serialisation loop around UTCHMMA.
+__device__ __forceinline__ void umma_bf16_ws(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_masked_ws(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                    uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2,
+                                                    uint32_t m3) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_ws(uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar))
       : "memory");
 }
 // arrive on `bar` when every tcgen05.mma issued so far by this thread has completed

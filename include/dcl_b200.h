@@ -170,6 +170,11 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
                      const float* residual, float* y, int32_t impl, double* stats_out, void* stream);
 DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream);
 
+/* ---- debug: in-kernel timeline of CTA (0,0) of the tcgen05 kernels (tools/trace_kernel.py) ---- */
+DCL_API int dcl_trace_enable(int32_t on);
+/* Copies up to `cap` (tag<<32|step, SM clock) pairs recorded since the last read; returns the count. */
+DCL_API int64_t dcl_trace_read(int64_t* out_host, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,9 @@ def test_conv3d_k3_tcgen05_bf16(c, g, act, residual):
     dict(c0=128, c1=0, cout=128, dims=(16, 16, 16), stride=1, norm=True, act=1, residual=True),
     dict(c0=64, c1=0, cout=64, dims=(32, 32, 32), stride=1, norm=True, act=2, residual=False),
     dict(c0=256, c1=0, cout=384, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
+    dict(c0=32, c1=0, cout=32, dims=(6, 64, 64), stride=1, norm=True, act=1, residual=True),
+    dict(c0=16, c1=0, cout=16, dims=(5, 4, 128), stride=1, norm=True, act=2, residual=False),
+    dict(c0=128, c1=0, cout=256, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
 ])
 def test_conv3d_k3_gemm_bf16(case):
     """The general tcgen05 implicit-GEMM kernel (prep + cp.async im2col) against torch conv3d on
@@ -129,6 +132,12 @@ def test_conv3d_k3_gemm_bf16(case):
     w = torch.randn(cout, cin, 3, 3, 3, generator=g) / (cin * 27) ** 0.5
     b = torch.randn(cout, generator=g)
     xin = torch.cat([x0, x1], 0) if c1 else x0
+    # stride-1 convs on 16/32/64/128-wide rows run on the slab kernel, which stages the RAW input as bf16 and
+    # applies the norm in shared memory (one more bf16 rounding than the im2col GEMM path, whose prep kernel
+    # normalises in fp32 first)
+    slab = stride == 1 and dims[2] in (16, 32, 64, 128) and (dims[1] * dims[2]) % 128 == 0
+    if slab:
+        xin = _bf16_round(xin)
     mean = rstd = None
     if case["norm"]:
         mean = torch.randn(cin, generator=g) * 0.3

@@ -1,0 +1,62 @@
+"""In-kernel timelines (SM clocks of CTA 0) of the tcgen05 kernels for single-operator cases.
+usage: python tools/trace_kernel.py"""
+import ctypes as C
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import dcl_b200  # noqa: E402
+from dcl_b200 import _native as N  # noqa: E402
+from dcl_b200.engine import op_conv3d_k3  # noqa: E402
+
+lib = N.load_library()
+
+
+def read_trace():
+    buf = np.zeros(2 * 8192, dtype=np.int64)
+    n = lib.dcl_trace_read(buf.ctypes.data_as(C.c_void_p), 8192)
+    recs = [(int(buf[2 * i]) >> 32, int(buf[2 * i]) & 0xffffffff, int(buf[2 * i + 1])) for i in range(n)]
+    return recs
+
+
+def show(title, recs, names):
+    if not recs:
+        print(title, ": no records")
+        return
+    t0 = min(r[2] for r in recs)
+    print(f"== {title}: {len(recs)} records, span {max(r[2] for r in recs) - t0} clk")
+    for tag, step, t in sorted(recs, key=lambda r: r[2]):
+        print(f"  {t - t0:9d}  {names.get(tag, tag):28s} {step}")
+
+
+def conv_case(c, g, cout=None, stride=1, norm=True):
+    cout = cout or c
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(c, g, g, g, generator=gen).cuda()
+    w = (torch.randn(cout, c, 3, 3, 3, generator=gen) / (c * 27) ** 0.5).cuda()
+    b = torch.randn(cout, generator=gen).cuda()
+    mean = torch.zeros(c).cuda()
+    rstd = torch.ones(c).cuda()
+    for _ in range(2):
+        op_conv3d_k3(x, w, b, None, stride, (mean, rstd) if norm else None, 1 if norm else 0, None, impl=2)
+    torch.cuda.synchronize()
+    read_trace()
+    op_conv3d_k3(x, w, b, None, stride, (mean, rstd) if norm else None, 1 if norm else 0, None, impl=2)
+    torch.cuda.synchronize()
+    return read_trace()
+
+
+K1 = {0: "entry", 1: "setup done", 2: "prod: slot free, stage", 3: "prod: staged", 4: "mma: issue step", 5: "mma: issued",
+      6: "epi: acc complete", 7: "epi: all stored"}
+K2 = {0: "entry", 1: "setup done", 2: "prod: stage issued", 3: "mma: stage landed", 4: "epi: acc complete", 5: "epi: done",
+      10: "wgt: stage free, issue tap", 11: "slab: cp.async issued", 12: "slab: landed", 13: "slab: published",
+      14: "mma: tap weights landed", 15: "epi: acc complete", 16: "epi: done"}
+
+if __name__ == "__main__":
+    N.check(lib.dcl_trace_enable(1))
+    show("slab 64->64 32^3", conv_case(64, 32, norm=True), K2)
+    show("slab 128->128 16^3", conv_case(128, 16, norm=False), K2)
+    N.check(lib.dcl_trace_enable(0))
