@@ -287,7 +287,8 @@ def run_ours(args):
             "model_tflops": world * args.steps * n_patches * FLOPS_PER_PATCH / (ms / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
                          "frac": conv_tflops / pk["tensor"], "traffic": None,
-                         "kernel": "conv3d_k3 (3x3x3 convolutions, all launches of the timed region)",
+                         "kernel": "3x3x3 convolutions: tcgen05 rolling / slab / im2col-GEMM kernels in bf16 mode, FFMA kernel in fp32 mode "
+                                   "(all launches of the timed region)",
                          "launches": conv_n, "avg_launch_ms": conv_ms / max(conv_n, 1),
                          "share_of_step": conv_ms / ms, "peak_source": pk["source"] + " sustained bf16 dense"},
             "roofline_accumulate": {"bound": "hbm", "achieved": tail_gbs, "peak": pk["hbm"], "unit": "GB/s",
@@ -315,7 +316,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--workload", default="overlap50", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

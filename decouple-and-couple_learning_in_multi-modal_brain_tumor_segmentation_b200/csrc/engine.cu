@@ -147,6 +147,14 @@ struct Transformer {
 
 struct StatSlot { float* mean; float* rstd; };
 
+// scratch of one coupler (token path); three copies so the three regions can run on concurrent streams
+struct TokScratch {
+  float* score;
+  float* seq[4];
+  float *ln_a, *ln_b, *qbuf, *kvbuf, *obuf, *eqs, *sqe, *cross, *ffn_ln, *ffn_h;
+  void *tok_a, *tok_b;
+};
+
 }  // namespace dcl
 
 using namespace dcl;
@@ -189,6 +197,9 @@ struct dcl_handle {
   double* stat_accum;                            // (2*512)
   void* blk = nullptr;                           // bf16 channel-blocked conv input (DCL_BF16 only)
   void *tok_a = nullptr, *tok_b = nullptr;       // bf16 blocked token matrices feeding the linear GEMMs
+  TokScratch ts[3];                              // [0] aliases the buffers above
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // ---- bf16 pipeline (DCL_BF16): B-format activations = bf16 [C/8][spatial][8] ----
   void *b_t0[4], *b_a[4], *b_t1[4], *b_x[4];     // encoder levels (16@128, 32@64, 64@32, 128@16)
   void *b_x4, *b_edown, *b_eraw, *b_sraw, *b_fused, *b_enc, *b_nrm;
@@ -314,6 +325,24 @@ static int allocate_workspace(dcl_handle* h) {
   h->stat_slots.resize(48);
   for (auto& s : h->stat_slots) { DCL_TRY(falloc(h, &s.mean, 512)); DCL_TRY(falloc(h, &s.rstd, 512)); }
   DCL_TRY(dev_alloc(h, (void**)&h->counts_dev, 16 * sizeof(unsigned long long)));
+  h->ts[0] = TokScratch{h->score, {h->seq[0], h->seq[1], h->seq[2], h->seq[3]}, h->ln_a, h->ln_b, h->qbuf, h->kvbuf, h->obuf,
+                        h->eqs, h->sqe, h->cross, h->ffn_ln, h->ffn_h, h->tok_a, h->tok_b};
+  for (int i = 1; i < 3; ++i) {
+    TokScratch& t = h->ts[i];
+    DCL_TRY(falloc(h, &t.score, 2048));
+    for (int k = 0; k < 4; ++k) DCL_TRY(falloc(h, &t.seq[k], SEQ * 512));
+    DCL_TRY(falloc(h, &t.ln_a, 258 * 512)); DCL_TRY(falloc(h, &t.ln_b, 258 * 512));
+    DCL_TRY(falloc(h, &t.qbuf, 258 * 512)); DCL_TRY(falloc(h, &t.kvbuf, 258 * 1024));
+    DCL_TRY(falloc(h, &t.obuf, 258 * 512));
+    DCL_TRY(falloc(h, &t.eqs, SEQ * 512)); DCL_TRY(falloc(h, &t.sqe, SEQ * 512));
+    DCL_TRY(falloc(h, &t.cross, 258 * 512)); DCL_TRY(falloc(h, &t.ffn_ln, 258 * 512));
+    DCL_TRY(falloc(h, &t.ffn_h, 258 * 512));
+    t.tok_a = t.tok_b = nullptr;
+    if (h->cfg.precision == DCL_BF16) {
+      DCL_TRY(dev_alloc(h, &t.tok_a, 258 * 512 * 2));
+      DCL_TRY(dev_alloc(h, &t.tok_b, 258 * 512 * 2));
+    }
+  }
   return 0;
 }
 
@@ -495,6 +524,7 @@ static int prepare(dcl_handle* h) {
 struct Fwd {
   dcl_handle* h;
   cudaStream_t st;
+  TokScratch* ts;      // token-path scratch this schedule instance works in
 
   StatSlot stats(const float* x, int c, int64_t spatial, int* rc) {
     StatSlot s = h->stat_slots[h->stat_next++ % h->stat_slots.size()];
@@ -573,43 +603,43 @@ struct Fwd {
   // Residual(PreNormDrop(DualSelfAttention)) (ResidualNorm.py:4-32, SelfAttention.py:74-102)
   int attn_block(const Transformer& t, const float* x, const float* x2, int mq, int mk, float* out) {
     if (h->cfg.precision == DCL_BF16) {   // LayerNorm fused into the bf16 operand prep, linears on tcgen05
-      DCL_TRY(launch_prep_rows(x, t.n1w, t.n1b, mq, h->tok_a, st));
-      DCL_TRY(launch_prep_rows(x2, t.n2w, t.n2b, mk, h->tok_b, st));
-      DCL_TRY(launch_linear_tc(h->tok_a, t.pq, nullptr, nullptr, h->qbuf, mq, 512, 512, false, st));
-      DCL_TRY(launch_linear_tc(h->tok_b, t.pkv, nullptr, nullptr, h->kvbuf, mk, 1024, 512, false, st));
-      DCL_TRY(launch_attention(h->qbuf, h->kvbuf, h->obuf, mq, mk, st));
-      DCL_TRY(launch_prep_rows(h->obuf, nullptr, nullptr, mq, h->tok_a, st));
-      DCL_TRY(launch_linear_tc(h->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st));
+      DCL_TRY(launch_prep_rows(x, t.n1w, t.n1b, mq, ts->tok_a, st));
+      DCL_TRY(launch_prep_rows(x2, t.n2w, t.n2b, mk, ts->tok_b, st));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.pq, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st));
+      DCL_TRY(launch_linear_tc(ts->tok_b, t.pkv, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st));
+      DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, ts->obuf, mq, mk, st));
+      DCL_TRY(launch_prep_rows(ts->obuf, nullptr, nullptr, mq, ts->tok_a, st));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st));
       return 0;
     }
-    DCL_TRY(launch_layernorm(x, t.n1w, t.n1b, h->ln_a, mq, st));
-    DCL_TRY(launch_layernorm(x2, t.n2w, t.n2b, h->ln_b, mk, st));
-    DCL_TRY(launch_linear(h->ln_a, t.wqkv, nullptr, nullptr, h->qbuf, mq, 512, 512, false, st));
-    DCL_TRY(launch_linear(h->ln_b, t.wqkv + 512 * 512, nullptr, nullptr, h->kvbuf, mk, 1024, 512, false, st));
-    DCL_TRY(launch_attention(h->qbuf, h->kvbuf, h->obuf, mq, mk, st));
-    DCL_TRY(launch_linear(h->obuf, t.wout, t.bout, x, out, mq, 512, 512, false, st));
+    DCL_TRY(launch_layernorm(x, t.n1w, t.n1b, ts->ln_a, mq, st));
+    DCL_TRY(launch_layernorm(x2, t.n2w, t.n2b, ts->ln_b, mk, st));
+    DCL_TRY(launch_linear(ts->ln_a, t.wqkv, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st));
+    DCL_TRY(launch_linear(ts->ln_b, t.wqkv + 512 * 512, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st));
+    DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, ts->obuf, mq, mk, st));
+    DCL_TRY(launch_linear(ts->obuf, t.wout, t.bout, x, out, mq, 512, 512, false, st));
     return 0;
   }
 
   // Residual(PreNorm(FeedForward)) (ResidualNorm.py:35-47)
   int ffn_block(const Transformer& t, const float* x, int m, float* out) {
     if (h->cfg.precision == DCL_BF16) {
-      DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, h->tok_a, st));
-      DCL_TRY(launch_linear_tc(h->tok_a, t.p0, t.b0, nullptr, h->ffn_h, m, 512, 512, true, st));
-      DCL_TRY(launch_prep_rows(h->ffn_h, nullptr, nullptr, m, h->tok_b, st));
-      DCL_TRY(launch_linear_tc(h->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st));
+      DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, ts->tok_a, st));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, ts->ffn_h, m, 512, 512, true, st));
+      DCL_TRY(launch_prep_rows(ts->ffn_h, nullptr, nullptr, m, ts->tok_b, st));
+      DCL_TRY(launch_linear_tc(ts->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st));
       return 0;
     }
-    DCL_TRY(launch_layernorm(x, t.fnw, t.fnb, h->ffn_ln, m, st));
-    DCL_TRY(launch_linear(h->ffn_ln, t.w0, t.b0, nullptr, h->ffn_h, m, 512, 512, true, st));
-    DCL_TRY(launch_linear(h->ffn_h, t.w3, t.b3, x, out, m, 512, 512, false, st));
+    DCL_TRY(launch_layernorm(x, t.fnw, t.fnb, ts->ffn_ln, m, st));
+    DCL_TRY(launch_linear(ts->ffn_ln, t.w0, t.b0, nullptr, ts->ffn_h, m, 512, 512, true, st));
+    DCL_TRY(launch_linear(ts->ffn_h, t.w3, t.b3, x, out, m, 512, 512, false, st));
     return 0;
   }
 
   int select_build(const float* score_tok, const float* class_tok, const float* feats, int n, const float* pe,
                    int slot, float* seq) {
     int* idx = h->topk + slot * TOP_NUM;
-    DCL_TRY(launch_select_topk(score_tok, feats, n, h->score, idx, st));
+    DCL_TRY(launch_select_topk(score_tok, feats, n, ts->score, idx, st));
     DCL_TRY(launch_build_sequence(class_tok, feats, idx, pe, seq, st));
     return 0;
   }
@@ -687,15 +717,15 @@ struct Fwd {
     for (int r = 0; r < 3; ++r) {
       const Transformer& t = h->tr[r];
       float *E = h->E[r], *S = h->S[r], *out = h->coupler_out[r];
-      DCL_TRY(select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, h->seq[0]));   // edge
-      DCL_TRY(select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, h->seq[1]));   // semantic supplement
-      DCL_TRY(select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, h->seq[2]));   // semantic
-      DCL_TRY(select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, h->seq[3]));   // edge supplement
-      DCL_TRY(attn_block(t, h->seq[0], h->seq[1], SEQ, SEQ, h->eqs));
-      DCL_TRY(attn_block(t, h->seq[2], h->seq[3], SEQ, SEQ, h->sqe));
-      DCL_TRY(attn_block(t, h->eqs, h->sqe, SEQ, SEQ, h->cross));
-      DCL_TRY(attn_block(t, h->sqe, h->eqs, SEQ, SEQ, h->cross + SEQ * 512));
-      DCL_TRY(ffn_block(t, h->cross, 2 * SEQ, out));
+      DCL_TRY(select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, ts->seq[0]));   // edge
+      DCL_TRY(select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, ts->seq[1]));   // semantic supplement
+      DCL_TRY(select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, ts->seq[2]));   // semantic
+      DCL_TRY(select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, ts->seq[3]));   // edge supplement
+      DCL_TRY(attn_block(t, ts->seq[0], ts->seq[1], SEQ, SEQ, ts->eqs));
+      DCL_TRY(attn_block(t, ts->seq[2], ts->seq[3], SEQ, SEQ, ts->sqe));
+      DCL_TRY(attn_block(t, ts->eqs, ts->sqe, SEQ, SEQ, ts->cross));
+      DCL_TRY(attn_block(t, ts->sqe, ts->eqs, SEQ, SEQ, ts->cross + SEQ * 512));
+      DCL_TRY(ffn_block(t, ts->cross, 2 * SEQ, out));
       DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, st));
       DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, st));
       if (want_aux) {
@@ -717,9 +747,9 @@ struct Fwd {
     DCL_TRY(launch_add3(h->coupler_out[0] + SEQ * 512, h->coupler_out[1] + SEQ * 512, h->coupler_out[2] + SEQ * 512,
                         h->f_tok, 512, st));
     DCL_TRY(launch_add3(h->S[0], h->S[1], h->S[2], h->f_fea, 1024 * 512, st));
-    DCL_TRY(select_build(h->f_tok, h->f_tok, h->f_fea, 1024, h->pe[3], 12, h->seq[0]));
-    DCL_TRY(attn_block(h->tr[3], h->seq[0], h->seq[0], SEQ, SEQ, h->eqs));
-    DCL_TRY(ffn_block(h->tr[3], h->eqs, SEQ, h->coupler_out[3]));
+    DCL_TRY(select_build(h->f_tok, h->f_tok, h->f_fea, 1024, h->pe[3], 12, ts->seq[0]));
+    DCL_TRY(attn_block(h->tr[3], ts->seq[0], ts->seq[0], SEQ, SEQ, ts->eqs));
+    DCL_TRY(ffn_block(h->tr[3], ts->eqs, SEQ, h->coupler_out[3]));
     DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
     DCL_TRY(launch_scale_untokenise(h->f_fea, h->coupler_out[3], h->fused_dense, 128, 16, 2, 2, 1, st));
     DCL_TRY(conv3(h->fused_dense, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, ACT_NONE, nullptr,
@@ -819,7 +849,7 @@ struct Fwd16 {
   int run(const float* x, const int64_t xs[4], const float* keep_host, float* probs_out, float* const* aux) {
     const bool want_aux = aux != nullptr;
     const bool dense_feats = want_aux || h->cfg.keep_stages;
-    Fwd f{h, st};   // token-path and auxiliary-head helpers are shared with the fp32 schedule
+    Fwd f{h, st, &h->ts[0]};   // token-path and auxiliary-head helpers are shared with the fp32 schedule
     h->stat_used = 0;
     DCL_CUDA_OK(cudaMemsetAsync(h->stat_arena, 0, (size_t)STAT_SLOTS * 1024 * sizeof(stat_t), st));
     Floats16 keep;
@@ -874,26 +904,36 @@ struct Fwd16 {
       }
     }
 
-    // ---- Edge-supported Intra-region Couplers ----
+    // ---- Edge-supported Intra-region Couplers: the three regions are independent until the cross-region
+    // coupler, and each is a chain of small latency-bound kernels, so they run on three concurrent streams
+    // (region 0 on the caller's stream, regions 1-2 on the handle's auxiliary streams, own scratch each)
+    DCL_CUDA_OK(cudaEventRecord(h->ev_fork, st));
     for (int r = 0; r < 3; ++r) {
+      cudaStream_t sr = r == 0 ? st : h->aux_stream[r - 1];
+      if (r > 0) DCL_CUDA_OK(cudaStreamWaitEvent(sr, h->ev_fork, 0));
+      Fwd fr{h, sr, &h->ts[r]};
+      TokScratch* ts = &h->ts[r];
       const Transformer& t = h->tr[r];
       float *E = h->E[r], *S = h->S[r], *out = h->coupler_out[r];
-      DCL_TRY(f.select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, h->seq[0]));
-      DCL_TRY(f.select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, h->seq[1]));
-      DCL_TRY(f.select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, h->seq[2]));
-      DCL_TRY(f.select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, h->seq[3]));
-      DCL_TRY(f.attn_block(t, h->seq[0], h->seq[1], SEQ, SEQ, h->eqs));
-      DCL_TRY(f.attn_block(t, h->seq[2], h->seq[3], SEQ, SEQ, h->sqe));
-      DCL_TRY(f.attn_block(t, h->eqs, h->sqe, SEQ, SEQ, h->cross));
-      DCL_TRY(f.attn_block(t, h->sqe, h->eqs, SEQ, SEQ, h->cross + SEQ * 512));
-      DCL_TRY(f.ffn_block(t, h->cross, 2 * SEQ, out));
-      DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, st));
-      DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, st));
+      DCL_TRY(fr.select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, ts->seq[0]));
+      DCL_TRY(fr.select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, ts->seq[1]));
+      DCL_TRY(fr.select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, ts->seq[2]));
+      DCL_TRY(fr.select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, ts->seq[3]));
+      DCL_TRY(fr.attn_block(t, ts->seq[0], ts->seq[1], SEQ, SEQ, ts->eqs));
+      DCL_TRY(fr.attn_block(t, ts->seq[2], ts->seq[3], SEQ, SEQ, ts->sqe));
+      DCL_TRY(fr.attn_block(t, ts->eqs, ts->sqe, SEQ, SEQ, ts->cross));
+      DCL_TRY(fr.attn_block(t, ts->sqe, ts->eqs, SEQ, SEQ, ts->cross + SEQ * 512));
+      DCL_TRY(fr.ffn_block(t, ts->cross, 2 * SEQ, out));
+      DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, sr));
+      DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, sr));
       if (want_aux) {
-        DCL_TRY(launch_scale_untokenise(E, out, h->sup_edge[r], 32, 32, 4, 2, 2, st));
-        DCL_TRY(launch_scale_untokenise(S, out + SEQ * 512, h->sup_sem[r], 128, 16, 2, 2, 1, st));
+        DCL_TRY(launch_scale_untokenise(E, out, h->sup_edge[r], 32, 32, 4, 2, 2, sr));
+        DCL_TRY(launch_scale_untokenise(S, out + SEQ * 512, h->sup_sem[r], 128, 16, 2, 2, 1, sr));
       }
+      if (r > 0) DCL_CUDA_OK(cudaEventRecord(h->ev_join[r - 1], sr));
     }
+    DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join[0], 0));
+    DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     if (want_aux) {
       for (int r = 0; r < 3; ++r) {
         std::string n = REGION_NUM[r];
@@ -908,9 +948,9 @@ struct Fwd16 {
     DCL_TRY(launch_add3(h->coupler_out[0] + SEQ * 512, h->coupler_out[1] + SEQ * 512, h->coupler_out[2] + SEQ * 512,
                         h->f_tok, 512, st));
     DCL_TRY(launch_add3(h->S[0], h->S[1], h->S[2], h->f_fea, 1024 * 512, st));
-    DCL_TRY(f.select_build(h->f_tok, h->f_tok, h->f_fea, 1024, h->pe[3], 12, h->seq[0]));
-    DCL_TRY(f.attn_block(h->tr[3], h->seq[0], h->seq[0], SEQ, SEQ, h->eqs));
-    DCL_TRY(f.ffn_block(h->tr[3], h->eqs, SEQ, h->coupler_out[3]));
+    DCL_TRY(f.select_build(h->f_tok, h->f_tok, h->f_fea, 1024, h->pe[3], 12, h->ts[0].seq[0]));
+    DCL_TRY(f.attn_block(h->tr[3], h->ts[0].seq[0], h->ts[0].seq[0], SEQ, SEQ, h->ts[0].eqs));
+    DCL_TRY(f.ffn_block(h->tr[3], h->ts[0].eqs, SEQ, h->coupler_out[3]));
     DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
     DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st));
     DCL_TRY(conv(h->b_fused, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, nullptr, nullptr, h->b_enc, nullptr));
@@ -1032,7 +1072,7 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
   const int X = shape[0], Y = shape[1], Z = shape[2];
   const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
-  Fwd f{h, st};
+  Fwd f{h, st, &h->ts[0]};
   Fwd16 f16{h, st};
   for (int i = first; i < first + count; ++i) {
     const PlanItem& p = plan[i];
@@ -1081,6 +1121,13 @@ DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
   if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; set_error("cudaGetDevice failed"); return DCL_ERR_CUDA; }
   int rc = allocate_workspace(h);
   if (rc != 0) { dcl_destroy(h); return rc; }
+  for (int i = 0; i < 2; ++i) {
+    if (cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      dcl_destroy(h); set_error("dcl_create: stream / event creation failed"); return DCL_ERR_CUDA;
+    }
+  }
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { dcl_destroy(h); set_error("dcl_create: event creation failed"); return DCL_ERR_CUDA; }
   register_stages(h);
   *out = h;
   return DCL_OK;
@@ -1090,6 +1137,11 @@ DCL_API int dcl_destroy(dcl_handle* h) {
   if (!h) return DCL_OK;
   cudaDeviceSynchronize();
   for (void* p : h->allocs) cudaFree(p);
+  for (int i = 0; i < 2; ++i) {
+    if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);
   if (h->stage_vol) cudaFree(h->stage_vol);
@@ -1154,7 +1206,7 @@ DCL_API int dcl_forward(dcl_handle* h, const float* x_dev, const int64_t x_strid
     Fwd16 f{h, (cudaStream_t)stream};
     rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
   } else {
-    Fwd f{h, (cudaStream_t)stream};
+    Fwd f{h, (cudaStream_t)stream, &h->ts[0]};
     rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
   }
   h->launches += g_launches - before;
