@@ -29,35 +29,34 @@ using namespace tc;
 
 cudaError_t trace_set_conv_tc(long long* p) { return trace_set_local(p); }
 
-template <int C_, int G_, int TH_, bool FLAT_, bool KHN_, int NSLOT_>
+template <int C_, int G_, int TH_, bool KHN_, int NSLOT_>
 struct RollCfg {
   static constexpr int C = C_, G = G_, TH = TH_;
-  static constexpr bool FLAT = FLAT_;
-  static constexpr bool KHN = KHN_;                // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
-  static constexpr int W = G;
-  static constexpr int P = W + 2;                 // staged positions per row (1 halo voxel each side)
+  static constexpr bool KHN = KHN_;               // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
+  static constexpr int W = G;                     // staged rows have NO halo columns (kw = 0/2 use lane masks)
   static constexpr int ROWS = TH + 2;
-  static constexpr int NPOS = ROWS * P;           // positions per channel chunk of one plane
+  static constexpr int NPOS = ROWS * W + 2;       // positions per channel chunk of one plane (+1 pad front/back)
   static constexpr int KC = C / 8;                // 16-byte channel chunks
   static constexpr int KS = C / 16;               // K = 16 MMA steps per tap
   static constexpr int SLOT_BYTES = KC * NPOS * 16;
-  static constexpr int NSLOT = NSLOT_;            // staged planes in flight: 3 feeding the MMAs + (NSLOT-3) being filled
-  static constexpr int RUN = (TH - 1) * P + W;    // flattened (row, w) positions holding real outputs
-  static constexpr int TSTRIDE = FLAT ? 128 : P;  // position of M tile t = t * TSTRIDE
-  static constexpr int NT = FLAT ? (RUN + 127) / 128 : TH;
+  static constexpr int NSLOT = NSLOT_;            // staged planes: 3 feeding the MMAs + (NSLOT-3) in flight
+  static constexpr int TROWS = 128 / W;           // output rows per 128-voxel M tile (1 for W=128, 2 for W=64)
+  static constexpr int NT = TH / TROWS;           // M tiles per plane
   static constexpr int ACC_COLS = NT * C;         // TMEM columns of one accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
                                    : 2 * ACC_COLS <= 256 ? 256 : 512;
   static constexpr int W_BYTES = 27 * C * C * 2;
-  static constexpr int ITEMS = KC * NPOS;         // 16-byte staging items per plane
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
-  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // mean[C], rstd[C], bias[C], scale[C] floats
-  static constexpr int OFF_BAR = OFF_SMALL + 4 * C * 4;      // 8-byte aligned (C multiple of 16)
-  static constexpr int SMEM_BYTES = OFF_BAR + (2 * NSLOT + 4) * 8 + 16;
-  static_assert(FLAT || W == 128, "row-aligned M tiles need W == 128");
-  static_assert(!KHN || !FLAT, "kh stacking needs row-aligned M tiles");
+  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // scale[C], shift[C], bias[C], out_scale[C] floats
+  static constexpr int OFF_BAR = OFF_SMALL + 4 * C * 4;      // 16-byte aligned (C multiple of 16)
+  static constexpr int SMEM_BYTES = OFF_BAR + (3 * NSLOT + 4) * 8 + 16;
+  static_assert(W == 64 || W == 128, "rows must tile 128-voxel M tiles");
+  static_assert(!KHN || TROWS == 1, "kh stacking needs one-row M tiles");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+  // output lanes switched off for kw = 0 (their w == 0) and kw = 2 (w == W-1): exactly zero padding
+  static constexpr uint32_t mask0(int j) { return W == 128 ? (j == 0 ? 1u : 0u) : ((j & 1) == 0 ? 1u : 0u); }
+  static constexpr uint32_t mask2(int j) { return W == 128 ? (j == 3 ? 0x80000000u : 0u) : ((j & 1) == 1 ? 0x80000000u : 0u); }
 };
 
 constexpr int EPI_WARPS = 4;
@@ -93,15 +92,17 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 template <class Cfg>
 __global__ void __launch_bounds__(ROLL_THREADS, 1)
 conv3d_k3_roll_kernel(RollParams prm) {
-  constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, P = Cfg::P, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
+  constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, W = Cfg::W, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
+  constexpr int ROWS = Cfg::ROWS, KC = Cfg::KC;
   extern __shared__ __align__(128) uint8_t smem[];
-  float* s_mean = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);
-  float* s_rstd = s_mean + C;
-  float* s_bias = s_rstd + C;
-  float* s_scale = s_bias + C;
-  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
-  uint64_t* bar_empty = bar_full + NSLOT;
-  uint64_t* bar_acc_full = bar_empty + NSLOT;
+  float* s_scale = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);   // rstd
+  float* s_shift = s_scale + C;                                        // -mean * rstd
+  float* s_bias = s_shift + C;
+  float* s_oscale = s_bias + C;
+  uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);   // plane staged + transformed
+  uint64_t* bar_empty = bar_full + NSLOT;                                  // MMAs reading the slot are done
+  uint64_t* bar_land = bar_empty + NSLOT;                                  // bulk copies of the plane landed
+  uint64_t* bar_acc_full = bar_land + NSLOT;
   uint64_t* bar_acc_empty = bar_acc_full + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
@@ -123,6 +124,11 @@ conv3d_k3_roll_kernel(RollParams prm) {
   // ---- one-time setup ---------------------------------------------------------------------------
   for (int i = tid; i < Cfg::W_BYTES / 16; i += ROLL_THREADS)
     reinterpret_cast<uint4*>(smem + Cfg::OFF_W)[i] = __ldg(prm.w + i);
+  for (int i = tid; i < NSLOT * KC * 2; i += ROLL_THREADS) {   // the pad positions of every slot chunk stay zero
+    const int sc = i >> 1;
+    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KC) * Cfg::SLOT_BYTES + (size_t)((sc % KC) * NPOS + ((i & 1) ? NPOS - 1 : 0)) * 16) =
+        make_uint4(0u, 0u, 0u, 0u);
+  }
   const bool has_norm = prm.sums != nullptr || prm.mean != nullptr;
   if (tid < C) {
     float m = 0.f, r = 1.f;
@@ -132,18 +138,18 @@ conv3d_k3_roll_kernel(RollParams prm) {
       m = prm.mean[tid];
       r = prm.rstd[tid];
     }
-    s_mean[tid] = m;
-    s_rstd[tid] = r;
+    s_scale[tid] = r;
+    s_shift[tid] = -m * r;
     s_bias[tid] = prm.bias ? prm.bias[tid] : 0.f;
-    s_scale[tid] = prm.out_scale ? prm.out_scale[tid] : 1.f;
+    s_oscale[tid] = prm.out_scale ? prm.out_scale[tid] : 1.f;
   }
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); }
+    for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); mbar_init(&bar_land[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_WARPS * 32); }
     fence_barrier_init();
   }
   if (warp == EPI_WARPS) tmem_alloc(s_tmem, Cfg::TMEM_COLS);
-  fence_proxy_async();   // the weight tile was written through the generic proxy
+  fence_proxy_async();   // weights / pads were written through the generic proxy
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -153,72 +159,86 @@ conv3d_k3_roll_kernel(RollParams prm) {
   if (warp >= EPI_WARPS + 1) {
     // =============================== producers ===================================================
     const int pt = tid - PROD_T0;
+    const int pw = warp - (EPI_WARPS + 1);
     const int act = prm.act;
     const bool identity = !has_norm && act == ACT_NONE;
+    const uint32_t smem_base = smem_u32(smem);
     if (prm.xb != nullptr) {
-      // ---- B-format source.  The staged layout IS the global layout (16-byte vectors), so a plane is
-      // fetched with zero-filling cp.async straight into its slot (no registers, AHEAD planes in flight) and
-      // the InstanceNorm + activation is then applied in place by the thread that copied the vector.
+      // ---- B-format source.  A staged (chunk, row) is W contiguous 16-byte vectors in global memory AND in the
+      // slot, so a plane is KC*ROWS bulk async copies issued by one warp (AHEAD planes in flight); the
+      // InstanceNorm + activation is then applied in place, warp-per-row (conflict-free 16-byte accesses).
       constexpr int AHEAD = NSLOT - 3;
-      const uint32_t smem_base = smem_u32(smem);
-      auto issue = [&](int j) {
+      constexpr uint32_t ROW_BYTES = (uint32_t)W * 16u;
+      auto issue = [&](int j) {     // producer warp 0 only
         const int d_in = d0 - 1 + j;
         const bool d_ok = (unsigned)d_in < (unsigned)G;
-        const uint32_t slot_addr = smem_base + (uint32_t)((j % NSLOT) * Cfg::SLOT_BYTES);
-        for (int e = pt; e < Cfg::ITEMS; e += NPROD) {
-          const int kc = e / NPOS;
-          const int rem = e - kc * NPOS;
-          const int r = rem / P;
-          const int q = rem - r * P;
-          const int h_in = h0 - 1 + r, w_in = q - 1;
-          const bool ok = d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G;
-          const uint4* src = ok ? prm.xb + (int64_t)kc * SP + ((int64_t)d_in * G + h_in) * G + w_in : prm.xb;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(slot_addr + (uint32_t)e * 16u), "l"(src),
-                       "r"(ok ? 16u : 0u)
+        const int s = j % NSLOT;
+        const uint32_t bar = smem_u32(&bar_land[s]);
+        int vh = 0;
+        for (int r = 0; r < ROWS; ++r) vh += (unsigned)(h0 - 1 + r) < (unsigned)G ? 1 : 0;
+        if (lane == 0)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(d_ok ? vh * KC : 0) * ROW_BYTES), "r"(bar)
                        : "memory");
+        __syncwarp();
+        for (int e = lane; e < KC * ROWS; e += 32) {
+          const int kc = e / ROWS, r = e - kc * ROWS;
+          const int h_in = h0 - 1 + r;
+          const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (kc * NPOS + 1 + r * W) * 16);
+          if (d_ok && (unsigned)h_in < (unsigned)G) {
+            const uint4* src = prm.xb + (int64_t)kc * SP + ((int64_t)d_in * G + h_in) * G;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                         "l"(src), "r"(ROW_BYTES), "r"(bar)
+                         : "memory");
+          } else {
+            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + 1 + r * W) * 16);
+            for (int i = 0; i < W; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
       };
-      for (int j = 0; j < AHEAD && j < n_in; ++j) issue(j);
+      if (pw == 0)
+        for (int j = 0; j < AHEAD && j < n_in; ++j) issue(j);
       for (int j = 0; j < n_in; ++j) {
-        const int jn = j + AHEAD;
-        if (jn < n_in) {
-          mbar_wait(&bar_empty[jn % NSLOT], ((uint32_t)(jn / NSLOT) & 1u) ^ 1u);
-          if (pt == 0) trace_event(2, jn);  // producer: slot free, fetching plane jn
-          issue(jn);
-        }
-        const int pending = n_in - 1 - j < AHEAD ? n_in - 1 - j : AHEAD;   // groups committed after plane j
-        if (pending >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-        else if (pending == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const int s = j % NSLOT;
+        mbar_wait(&bar_land[s], (uint32_t)(j / NSLOT) & 1u);
         if (!identity) {
           const int d_in = d0 - 1 + j;
           if ((unsigned)d_in < (unsigned)G) {
-            uint8_t* slot = smem + (j % NSLOT) * Cfg::SLOT_BYTES;
-            for (int e = pt; e < Cfg::ITEMS; e += NPROD) {
-              const int kc = e / NPOS;
-              const int rem = e - kc * NPOS;
-              const int r = rem / P;
-              const int q = rem - r * P;
-              const int h_in = h0 - 1 + r, w_in = q - 1;
-              if ((unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G) {   // padding stays zero
-                uint4 v = *reinterpret_cast<uint4*>(slot + (size_t)e * 16);
-                uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+            for (int e = pw; e < KC * ROWS; e += PROD_WARPS) {       // one (chunk, row) per warp pass
+              const int kc = e / ROWS, r = e - kc * ROWS;
+              if ((unsigned)(h0 - 1 + r) >= (unsigned)G) continue;   // zero padding stays zero
+              const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + kc * 8), sc1 = *reinterpret_cast<const float4*>(s_scale + kc * 8 + 4);
+              const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + kc * 8), sh1 = *reinterpret_cast<const float4*>(s_shift + kc * 8 + 4);
+              const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+              const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+              uint4* q = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + 1 + r * W) * 16);
+              uint4 v[W / 32];
+#pragma unroll
+              for (int i = 0; i < W / 32; ++i) v[i] = q[lane + 32 * i];
+#pragma unroll
+              for (int i = 0; i < W / 32; ++i) {
+                uint32_t* pv = reinterpret_cast<uint32_t*>(&v[i]);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  float2 f = unpack_bf16x2(pv[k]);
-                  f.x = apply_act((f.x - s_mean[kc * 8 + 2 * k]) * s_rstd[kc * 8 + 2 * k], act);
-                  f.y = apply_act((f.y - s_mean[kc * 8 + 2 * k + 1]) * s_rstd[kc * 8 + 2 * k + 1], act);
-                  pv[k] = pack_bf16x2(f.x, f.y);
+                  float fx = fmaf(__uint_as_float(pv[k] << 16), sc[2 * k], sh[2 * k]);
+                  float fy = fmaf(__uint_as_float(pv[k] & 0xffff0000u), sc[2 * k + 1], sh[2 * k + 1]);
+                  if (act == ACT_RELU) { fx = fmaxf(fx, 0.f); fy = fmaxf(fy, 0.f); }
+                  else if (act == ACT_LRELU) { fx = fmaxf(fx, 0.01f * fx); fy = fmaxf(fy, 0.01f * fy); }
+                  pv[k] = pack_bf16x2(fx, fy);
                 }
-                *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = v;
+                q[lane + 32 * i] = v[i];
               }
             }
           }
         }
         fence_proxy_async();
-        mbar_arrive(&bar_full[j % NSLOT]);
+        mbar_arrive(&bar_full[s]);
         if (pt == 0) trace_event(3, j);    // producer: plane j staged (this thread)
+        const int jn = j + AHEAD;
+        if (pw == 0 && jn < n_in) {
+          mbar_wait(&bar_empty[jn % NSLOT], ((uint32_t)(jn / NSLOT) & 1u) ^ 1u);
+          if (pt == 0) trace_event(2, jn);  // producer: slot free, fetching plane jn
+          issue(jn);
+        }
       }
     } else {
       // ---- fp32 NCDHW 4-channel source (InitConv): channels 4..C-1 are zero padding
@@ -228,20 +248,20 @@ conv3d_k3_roll_kernel(RollParams prm) {
         const int d_in = d0 - 1 + j;
         const bool d_ok = (unsigned)d_in < (unsigned)G;
         uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
-        for (int e = pt; e < NPOS; e += NPROD) {
-          const int r = e / P;
-          const int q = e - r * P;
-          const int h_in = h0 - 1 + r, w_in = q - 1;
+        for (int e = pt; e < ROWS * W; e += NPROD) {
+          const int r = e / W;
+          const int w_in = e - r * W;
+          const int h_in = h0 - 1 + r;
           uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (d_ok && (unsigned)h_in < (unsigned)G && (unsigned)w_in < (unsigned)G) {
+          if (d_ok && (unsigned)h_in < (unsigned)G) {
             const float* p = prm.x4 + (int64_t)d_in * prm.s4d + (int64_t)h_in * prm.s4h + w_in;
             o.x = pack_bf16x2(__ldg(p), __ldg(p + prm.s4c));
             o.y = pack_bf16x2(__ldg(p + 2 * prm.s4c), __ldg(p + 3 * prm.s4c));
           }
-          *reinterpret_cast<uint4*>(slot + (size_t)e * 16) = o;
+          *reinterpret_cast<uint4*>(slot + (size_t)(1 + e) * 16) = o;
 #pragma unroll
-          for (int kc = 1; kc < Cfg::KC; ++kc)
-            *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
+          for (int kc = 1; kc < KC; ++kc)
+            *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + 1 + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         fence_proxy_async();
         mbar_arrive(&bar_full[s]);
@@ -263,20 +283,20 @@ conv3d_k3_roll_kernel(RollParams prm) {
         mbar_wait(&bar_acc_empty[b], ((uint32_t)(i >> 1) & 1u) ^ 1u);
         tc_fence_after();
         if (lane == 0) trace_event(4, i);               // MMA: inputs + accumulator ready, issuing step i
+        uint64_t a_kd[3];
+#pragma unroll
+        for (int kd = 0; kd < 3; ++kd)
+          a_kd[kd] = umma_desc(smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES), NPOS * 16, 128);
+        const uint32_t acc0 = tmem_base + (uint32_t)(b * Cfg::ACC_COLS);
         if constexpr (Cfg::KHN) {
           // Staged row rho feeds output rows rho-2 (kh=2), rho-1 (kh=1), rho (kh=0) at once: their
           // accumulators are adjacent TMEM column blocks and the weights of (kd,kw) are stored as one
           // stacked N = 3C operand, so one MMA (one read of the 4 KB A tile) does the work of three.
-          // Fully unrolled: every descriptor is (one of 3 per-plane bases) + a compile-time constant, so
-          // the single issuing thread spends a handful of instructions per MMA.
+          // Fully unrolled: every descriptor is (one of 3 per-plane bases) + a compile-time constant.
+          // kw runs 1,0,2 so that the MMA that initialises an accumulator (accumulate = 0) is unmasked.
           constexpr uint32_t WB = 3 * C * C * 2;            // bytes of one (kd,kw) stacked weight matrix
           constexpr uint32_t B_LBO = 3 * C * 16;
-          uint64_t a_kd[3];
-#pragma unroll
-          for (int kd = 0; kd < 3; ++kd)
-            a_kd[kd] = umma_desc(smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES), NPOS * 16, 128);
           const uint64_t b_base = umma_desc(w_base, B_LBO, 128);
-          const uint32_t acc0 = tmem_base + (uint32_t)(b * Cfg::ACC_COLS);
 #pragma unroll
           for (int rho = 0; rho < TH + 2; ++rho) {
             const int q_lo = rho >= 2 ? rho - 2 : 0;
@@ -286,46 +306,58 @@ conv3d_k3_roll_kernel(RollParams prm) {
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const bool first = fresh && kd == 0 && kw == 0;
+              for (int kwi = 0; kwi < 3; ++kwi) {
+                const int kw = kwi == 0 ? 1 : (kwi == 1 ? 0 : 2);
+                const bool first = fresh && kd == 0 && kwi == 0;
                 const int n_acc = (q_hi - q_lo + 1) - (first ? 1 : 0);   // blocks that accumulate
+                const uint32_t m0 = kw == 0 ? Cfg::mask0(0) : (kw == 2 ? Cfg::mask2(0) : 0u);
+                const uint32_t m1 = kw == 0 ? Cfg::mask0(1) : (kw == 2 ? Cfg::mask2(1) : 0u);
+                const uint32_t m2 = kw == 0 ? Cfg::mask0(2) : (kw == 2 ? Cfg::mask2(2) : 0u);
+                const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
-                  const uint64_t ad = a_kd[kd] + (uint64_t)(((rho * P + kw) * 16 + ks * 2 * NPOS * 16) >> 4);
+                  const uint64_t ad = a_kd[kd] + (uint64_t)(1 + rho * W + (kw - 1) + ks * 2 * NPOS);
                   const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * C * 16 + ks * 2 * B_LBO) >> 4);
-                  if (n_acc > 0) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
+                  if (n_acc > 0) {
+                    if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
+                    else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u, m0, m1, m2, m3);
+                  }
                   if (first)
                     umma_bf16_ws(acc0 + (uint32_t)(rho * C), ad, bd + (uint64_t)((n_acc * C * 16) >> 4),
-                              umma_idesc_bf16(128, C), ks == 0 ? 0u : 1u);
+                                 umma_idesc_bf16(128, C), ks == 0 ? 0u : 1u);
                 }
               }
             }
           }
         } else {
-        for (int t = 0; t < Cfg::NT; ++t) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)(b * Cfg::ACC_COLS + t * C);
-          uint32_t accum = 0;
+          const uint64_t b_base = umma_desc(w_base, C * 16, 128);
 #pragma unroll 1
-          for (int kd = 0; kd < 3; ++kd) {
-            const uint32_t slot_base = smem_base + (uint32_t)(((i + kd) % NSLOT) * Cfg::SLOT_BYTES);
+          for (int t = 0; t < Cfg::NT; ++t) {
+            const uint32_t d_tmem = acc0 + (uint32_t)(t * C);
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
+            for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
-              for (int kw = 0; kw < 3; ++kw) {
-                const int tap = (kd * 3 + kh) * 3 + kw;
-                const uint32_t a0 = slot_base + (uint32_t)((t * Cfg::TSTRIDE + kh * P + kw) * 16);
-                const uint32_t b0 = w_base + (uint32_t)(tap * C * C * 2);
+              for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
-                for (int ks = 0; ks < Cfg::KS; ++ks) {
-                  const uint64_t ad = umma_desc(a0 + (uint32_t)(ks * 2 * NPOS * 16), NPOS * 16, 128);
-                  const uint64_t bd = umma_desc(b0 + (uint32_t)(ks * 2 * C * 16), C * 16, 128);
-                  umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
-                  accum = 1;
+                for (int kwi = 0; kwi < 3; ++kwi) {
+                  const int kw = kwi == 0 ? 1 : (kwi == 1 ? 0 : 2);
+                  const int tap = (kd * 3 + kh) * 3 + kw;
+                  const uint32_t m0 = kw == 0 ? Cfg::mask0(0) : (kw == 2 ? Cfg::mask2(0) : 0u);
+                  const uint32_t m1 = kw == 0 ? Cfg::mask0(1) : (kw == 2 ? Cfg::mask2(1) : 0u);
+                  const uint32_t m2 = kw == 0 ? Cfg::mask0(2) : (kw == 2 ? Cfg::mask2(2) : 0u);
+                  const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
+#pragma unroll
+                  for (int ks = 0; ks < Cfg::KS; ++ks) {
+                    const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(1 + (t * Cfg::TROWS + kh) * W + (kw - 1) + ks * 2 * NPOS);
+                    const uint64_t bd = b_base + (uint64_t)((tap * C * C * 2 + ks * 2 * C * 16) >> 4);
+                    const uint32_t accum = (kd | kh | kwi | ks) != 0 ? 1u : 0u;
+                    if (kw == 1) umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
+                    else umma_bf16_masked_ws(d_tmem, ad, bd, idesc, accum, m0, m1, m2, m3);
+                  }
                 }
               }
             }
           }
-        }
         }
         umma_commit_ws(&bar_acc_full[b]);
         umma_commit_ws(&bar_empty[i % NSLOT]);
@@ -342,10 +374,23 @@ conv3d_k3_roll_kernel(RollParams prm) {
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     for (int i = 0; i < n_out; ++i) {
       const int b = i & 1;
+      const int d = d0 + i;
+      // the residual of the NEXT plane is pulled into L2 now (no registers held), so that its loads in the tile
+      // loop below cost an L2 hit instead of an HBM round trip per tile
+      if (prm.resb != nullptr) {
+        for (int dd = (i == 0 ? d : d + 1); dd <= d + 1 && dd < d1; ++dd) {
+#pragma unroll
+          for (int t = 0; t < Cfg::NT; ++t) {
+            const int64_t off = ((int64_t)dd * G + (h0 + t * Cfg::TROWS + m / W)) * G + (m % W);
+#pragma unroll
+            for (int kc = 0; kc < C / 8; ++kc)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.resb + (int64_t)kc * SP + off));
+          }
+        }
+      }
       mbar_wait(&bar_acc_full[b], (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       if (tid == 0) trace_event(6, i);   // epilogue: accumulator of step i complete
-      const int d = d0 + i;
 #pragma unroll 1
       for (int t = 0; t < Cfg::NT; ++t) {
         uint32_t acc[C / 16][16];
@@ -356,41 +401,38 @@ conv3d_k3_roll_kernel(RollParams prm) {
           tc_fence_before();
           mbar_arrive(&bar_acc_empty[b]);
         }
-        const int p = t * Cfg::TSTRIDE + m;
-        const int r = p / P;
-        const int w = p - r * P;
-        if (r < TH && w < G) {
-          const int64_t off = ((int64_t)d * G + (h0 + r)) * G + w;
+        const int r = t * Cfg::TROWS + m / W;
+        const int w = m % W;
+        const int64_t off = ((int64_t)d * G + (h0 + r)) * G + w;
 #pragma unroll
-          for (int kc = 0; kc < C / 8; ++kc) {
-            float val[8];
+        for (int kc = 0; kc < C / 8; ++kc) {
+          float val[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const int c = kc * 8 + k;
-              val[k] = (__uint_as_float(acc[c / 16][c % 16]) + s_bias[c]) * s_scale[c];
-            }
-            if (prm.resb != nullptr) {
-              const uint4 rv = __ldg(prm.resb + (int64_t)kc * SP + off);
-              const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float2 f = unpack_bf16x2(pr[k]);
-                val[2 * k] += f.x;
-                val[2 * k + 1] += f.y;
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              st_s[kc * 8 + k] += val[k];
-              st_q[kc * 8 + k] += val[k] * val[k];
-            }
-            uint4 o;
-            o.x = pack_bf16x2(val[0], val[1]);
-            o.y = pack_bf16x2(val[2], val[3]);
-            o.z = pack_bf16x2(val[4], val[5]);
-            o.w = pack_bf16x2(val[6], val[7]);
-            prm.yb[(int64_t)kc * SP + off] = o;
+          for (int k = 0; k < 8; ++k) {
+            const int c = kc * 8 + k;
+            val[k] = (__uint_as_float(acc[c / 16][c % 16]) + s_bias[c]) * s_oscale[c];
           }
+          if (prm.resb != nullptr) {
+            const uint4 rv = __ldg(prm.resb + (int64_t)kc * SP + off);
+            const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = unpack_bf16x2(pr[k]);
+              val[2 * k] += f.x;
+              val[2 * k + 1] += f.y;
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            st_s[kc * 8 + k] += val[k];
+            st_q[kc * 8 + k] += val[k] * val[k];
+          }
+          uint4 o;
+          o.x = pack_bf16x2(val[0], val[1]);
+          o.y = pack_bf16x2(val[2], val[3]);
+          o.z = pack_bf16x2(val[4], val[5]);
+          o.w = pack_bf16x2(val[6], val[7]);
+          prm.yb[(int64_t)kc * SP + off] = o;
         }
       }
     }
@@ -459,8 +501,8 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
   return 0;
 }
 
-using RollC16 = RollCfg<16, 128, 8, false, true, 5>;
-using RollC32 = RollCfg<32, 64, 8, true, false, 4>;
+using RollC16 = RollCfg<16, 128, 8, true, 5>;
+using RollC32 = RollCfg<32, 64, 8, false, 4>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
   if (split || stride != 1) return false;
