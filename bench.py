@@ -210,23 +210,45 @@ def run_ours(args):
     eng.load_state_dict(seed0_weights())
     mode, starts, n_patches = workload_plan(args.workload)
     n_rot = 3     # rotating inputs: 3 x 143 MB per rank, each larger than the 126 MB L2
-    vols_h = [synth_volume(rank * n_rot + i)[0].pin_memory() for i in range(n_rot)]
-    tgts_h = [synth_target(rank * n_rot + i).pin_memory() for i in range(n_rot)]
+    by_patch = args.sharding == "patch" and world > 1     # one volume per step, its patches split over the ranks
+    base = 0 if by_patch else rank * n_rot
+    vols_h = [synth_volume(base + i)[0].pin_memory() for i in range(n_rot)]
+    tgts_h = [synth_target(base + i).pin_memory() for i in range(n_rot)]
     vols_d = [v.cuda() for v in vols_h]
     tgts_d = [t.cuda() for t in tgts_h]
-    keeps = [keep_scales(rank * n_rot + i, n_patches) for i in range(n_rot)]
-
-    def step_dev(i):
-        j = i % n_rot
-        return eng.predict_volume(vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j],
-                                  want_probs=False, want_labels=True)
-
+    keeps = [keep_scales(base + i, n_patches) for i in range(n_rot)]
     lab_h = torch.empty(SHAPE, dtype=torch.uint8).pin_memory()
 
-    def step_e2e(i):
-        j = i % n_rot
-        return eng.predict_volume_host(vols_h[j], mode, starts=starts, keep_scales=keeps[j], target_host=tgts_h[j],
-                                       labels_out=lab_h)
+    if by_patch:
+        from dcl_b200 import sharded
+        if starts is None:
+            raise SystemExit("--sharding patch needs a weighted workload (overlap50 / overlap75)")
+        stage = torch.empty_like(vols_d[0])
+
+        def step_dev(i):
+            j = i % n_rot
+            return sharded.predict_volume_sharded(eng, vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j])
+
+        def step_e2e(i):     # every rank uploads the volume over its own PCIe link; rank 0 downloads the label map
+            j = i % n_rot
+            stage.copy_(vols_h[j], non_blocking=True)
+            tgt = tgts_h[j].cuda(non_blocking=True)
+            out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j], target=tgt)
+            if rank == 0:
+                lab_h.copy_(out["labels"], non_blocking=True)
+                out["counts"].cpu()
+            torch.cuda.synchronize()
+            return out
+    else:
+        def step_dev(i):
+            j = i % n_rot
+            return eng.predict_volume(vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j],
+                                      want_probs=False, want_labels=True)
+
+        def step_e2e(i):
+            j = i % n_rot
+            return eng.predict_volume_host(vols_h[j], mode, starts=starts, keep_scales=keeps[j], target_host=tgts_h[j],
+                                           labels_out=lab_h)
 
     # ---- device-resident throughput (no per-kernel events inside this region) ----
     for i in range(args.warmup):
@@ -278,24 +300,27 @@ def run_ours(args):
     ms, e2e_ms = t.tolist()
     if rank == 0:
         pk = peaks()
-        vps = world * args.steps / (ms / 1e3)
-        e2e_vps = world * args.steps / (e2e_ms / 1e3)
+        vols_per_step = 1 if by_patch else world
+        vps = vols_per_step * args.steps / (ms / 1e3)
+        e2e_vps = vols_per_step * args.steps / (e2e_ms / 1e3)
         conv_tflops = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         tail_gbs = tail_bytes / (tail_ms * 1e-3) / 1e9 if tail_ms > 0 else 0.0
         line = {
             "metric": "BraTS 4x240x240x155 volumes/sec", "value": vps, "unit": "volumes/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": "strong" if by_patch else "weak", "vs_baseline": None,
             "dtype": {"fp32": "fp32", "bf16x3": "bf16x3 (split bf16 operands, fp32 accumulate)", "bf16": "bf16"}[
                 args.precision],
             "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "patches_per_volume": n_patches,
-                       "weights": "random-init seed 0", "sharding": "volumes across ranks, no collective",
+                       "weights": "random-init seed 0",
+                       "sharding": ("one volume per step, patch slabs across ranks, NCCL reduce-scatter of the accumulators"
+                                    if by_patch else "volumes across ranks, no collective"),
                        "l2": "inputs larger than L2: 3 rotating 143 MB volumes per rank, >1.8 GB of activations per patch"},
             "e2e": {"value": e2e_vps, "unit": "volumes/s", "h2d_bytes_per_step": 4 * VOXELS * 4 + VOXELS,
                     "d2h_bytes_per_step": VOXELS + 13 * 8},
             "gpu_launches": launches,
-            "model_tflops": world * args.steps * n_patches * FLOPS_PER_PATCH / (ms / 1e3) / 1e12,
+            "model_tflops": vols_per_step * args.steps * n_patches * FLOPS_PER_PATCH / (ms / 1e3) / 1e12,
             "roofline": {"bound": "tensor", "achieved": conv_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
                          "frac": conv_tflops / pk["tensor"], "traffic": None,
                          "kernel": "3x3x3 convolutions: tcgen05 rolling / slab / im2col-GEMM kernels in bf16 mode, FFMA kernel in fp32 mode "
@@ -329,6 +354,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16x3", "bf16"])
     ap.add_argument("--workload", default="overlap50", choices=sorted(WORKLOADS))
+    ap.add_argument("--sharding", default="volume", choices=["volume", "patch"],
+                    help="N > 1: 'volume' = one volume per rank per step (no collective, weak scaling); "
+                         "'patch' = one volume per step split by patch slab with an NCCL exchange (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

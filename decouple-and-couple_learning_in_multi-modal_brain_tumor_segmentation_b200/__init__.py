@@ -11,6 +11,7 @@ package as ``dcl_b200`` (alias module at the repository root) or through ``impor
 from ._native import (DclError, Precision, StitchMode, abi_version, build_library, library_path, load_library,
                       weight_catalogue, workspace_bytes)
 from .engine import Engine, patch_starts, reference_starts
+from . import sharded
 
 __all__ = ["DclError", "Precision", "StitchMode", "Engine", "abi_version", "build_library", "library_path",
-           "load_library", "weight_catalogue", "workspace_bytes", "patch_starts", "reference_starts"]
+           "load_library", "weight_catalogue", "workspace_bytes", "patch_starts", "reference_starts", "sharded"]

@@ -138,3 +138,65 @@ def test_dropin_tailor_and_concat(seed0_state_dict, vol, golden_volume):
     with torch.no_grad():
         y = predict_overlap.tailor_and_concat(vol, None, model)
     check_digest("stitched", y, golden_volume, 1e-3)
+
+
+def test_sharded_path_world1_equals_predict_volume(engine, vol):
+    """dcl_accumulate_patches + dcl_finalize_labels (the building blocks of the multi-GPU path) reproduce
+    dcl_predict_volume bit for bit when a single rank owns every patch."""
+    from dcl_b200 import StitchMode, patch_starts, sharded
+    starts = patch_starts((240, 240, 155), 96)
+    keeps = np.ones((len(starts), 16), np.float32)
+    tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
+    want = engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt, want_probs=False)
+    got = sharded.predict_volume_sharded(engine, vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
+    torch.cuda.synchronize()
+    assert torch.equal(got["labels"], want["labels"])
+    assert torch.equal(got["counts"], want["counts"])
+
+
+def _sharded_rank(rank, world, port, out_dir, sd):
+    import os
+    import torch.distributed as dist
+    import dcl_b200
+    from dcl_b200 import StitchMode, patch_starts, sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        eng = dcl_b200.Engine(dcl_b200.Precision.FP32)
+        eng.load_state_dict(sd)
+        starts = patch_starts((240, 240, 155), 96)
+        keeps = np.ones((len(starts), 16), np.float32)
+        v = volume_input(0).cuda()
+        tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
+        out = sharded.predict_volume_sharded(eng, v, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
+        torch.cuda.synchronize()
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), labels=out["labels"].cpu().numpy(),
+                 counts=out["counts"].cpu().numpy())
+        eng.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_sharded_two_gpus_nccl_equals_one_gpu(engine, vol, seed0_state_dict, tmp_path):
+    """One volume, patches split over 2 ranks, NCCL reduce-scatter of the accumulators: the label map may differ from
+    the single-GPU result only where fp32 re-association of the overlap sums flips a near-tie (<= 1e-4 of voxels)."""
+    import socket
+    import torch.multiprocessing as mp
+    from dcl_b200 import StitchMode, patch_starts
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    sd = {k: v.cpu() for k, v in seed0_state_dict.items()}
+    mp.spawn(_sharded_rank, args=(2, port, str(tmp_path), sd), nprocs=2, join=True)
+    starts = patch_starts((240, 240, 155), 96)
+    keeps = np.ones((len(starts), 16), np.float32)
+    tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
+    want = engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt, want_probs=False)
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert np.array_equal(r0["labels"], r1["labels"]) and np.array_equal(r0["counts"], r1["counts"])
+    wl = want["labels"].cpu().numpy()
+    assert (r0["labels"] != wl).mean() <= 1e-4
+    assert np.abs(r0["counts"][:4] - want["counts"].cpu().numpy()[:4]).sum() <= 2e-4 * wl.size

@@ -1,0 +1,111 @@
+"""Host logic of the single-volume multi-GPU path (dcl_b200/sharded.py) under the `gloo` backend with
+world_size 2 on CPU: patch partition, accumulator exchange, owned-range finalise, label gather, counter reduce.
+The CUDA kernels are replaced by oracle stand-ins (tests may use the oracle); the result must equal the
+single-process oracle bit for bit and must not depend on the number of ranks."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dcl_b200 import StitchMode, sharded
+from oracle import stitch_oracle as S
+
+SHAPE = (144, 144, 136)
+
+
+def _patch_probs(i):
+    """Deterministic per-patch 'probabilities' on a 1/64 grid, so that fp32 sums are exact in any order."""
+    return (np.random.RandomState(100 + i).randint(0, 64, (4, 128, 128, 128)) / 64.0).astype(np.float32)
+
+
+def _cpu_accumulate(vol, mode, starts, keep_scales, first, count, acc, wsum):
+    X, Y, Z = SHAPE
+    a = acc.view(4, X, Y, Z).numpy()
+    w = wsum.view(X, Y, Z).numpy()
+    for i in range(first, first + count):
+        sx, sy, sz = starts[i]
+        a[:, sx:sx + 128, sy:sy + 128, sz:sz + 128] += _patch_probs(i)
+        w[sx:sx + 128, sy:sy + 128, sz:sz + 128] += 1.0
+
+
+def _cpu_finalize(acc_l, wsum_l, labels_l, tgt_l, counts):
+    probs = acc_l.numpy() / wsum_l.numpy()[None]
+    lab = probs.argmax(0)
+    labels_l.copy_(torch.from_numpy(lab.astype(np.uint8)))
+    c = [int((lab == k).sum()) for k in range(4)]
+    if tgt_l is not None:
+        c += [v for trip in S.region_counts(lab, tgt_l.numpy()) for v in trip]
+    else:
+        c += [0] * 9
+    counts += torch.tensor(c, dtype=torch.int64)
+
+
+def _expected(starts, target):
+    want = S.accumulate_from_probs([_patch_probs(i) for i in range(len(starts))], starts, "uniform", shape=SHAPE)
+    lab = S.labels_from_probs(want)
+    counts = S.label_histogram(lab) + [v for trip in S.region_counts(lab, target) for v in trip]
+    return lab.astype(np.uint8), counts
+
+
+def _worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        starts = S.patch_starts(SHAPE, 16)
+        target = np.random.RandomState(7).randint(0, 4, SHAPE)
+        vol = torch.zeros((4,) + SHAPE)
+        out = sharded.predict_volume_sharded(None, vol, StitchMode.UNIFORM, starts=starts,
+                                             target=torch.from_numpy(target), accumulate=_cpu_accumulate,
+                                             finalize=_cpu_finalize)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), labels=out["labels"].numpy(), counts=out["counts"].numpy(),
+                 patches=np.array(out["patches"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_partition_and_ranges():
+    assert sharded.partition_patches(18, 8) == [(0, 3), (3, 3), (6, 2), (8, 2), (10, 2), (12, 2), (14, 2), (16, 2)]
+    assert sharded.partition_patches(8, 8) == [(i, 1) for i in range(8)]
+    assert sharded.partition_patches(3, 4) == [(0, 1), (1, 1), (2, 1), (3, 0)]
+    for world in (1, 2, 3, 8):
+        for total in (8928000, 1001):
+            ranges = [sharded.owned_range(total, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and sum(n for _, n in ranges) == total
+            for (a, n), (b, _) in zip(ranges, ranges[1:]):
+                assert a + n == b
+    with pytest.raises(Exception):
+        sharded.partition_patches(4, 0)
+
+
+def test_two_rank_gloo_equals_single_process_oracle(tmp_path):
+    world = 2
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    starts = S.patch_starts(SHAPE, 16)
+    assert len(starts) == 8
+    target = np.random.RandomState(7).randint(0, 4, SHAPE)
+    want_labels, want_counts = _expected(starts, target)
+    got = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    assert got[0]["patches"].tolist() == [0, 4] and got[1]["patches"].tolist() == [4, 4]
+    for g in got:                                   # every rank ends with the full, identical result
+        assert np.array_equal(g["labels"], want_labels)
+        assert g["counts"].tolist() == want_counts
+
+
+def test_single_process_path_needs_no_process_group():
+    starts = S.patch_starts(SHAPE, 16)[:2]
+    vol = torch.zeros((4,) + SHAPE)
+    out = sharded.predict_volume_sharded(None, vol, StitchMode.UNIFORM, starts=starts, accumulate=_cpu_accumulate,
+                                         finalize=lambda a, w, l, t, c: l.zero_())
+    assert out["patches"] == (0, 2) and out["labels"].shape == SHAPE
