@@ -115,6 +115,15 @@ int launch_scatter_rows(float* feats, const int* idx, const float* rows, int row
 int launch_add3(const float* a, const float* b, const float* c, float* y, int64_t n, cudaStream_t st);
 
 struct Floats16 { float v[16]; };
+// Per-patch arguments of a forward, kept in device memory so that the captured CUDA graph of the forward is the same
+// for every patch: the first convolution reads its source view from here, the dropout scale sits in keep[16].
+struct PatchDesc {
+  const float* x;           // first element of the (4,128,128,128) view
+  long long sc, sd, sh;     // element strides of (C, X, Y); the Z stride is 1
+  float keep[16];
+};
+// *dst = v, passed by value (one tiny launch per patch, outside the graph)
+int launch_patch_desc(PatchDesc* dst, const PatchDesc& v, cudaStream_t st);
 // dst[0..16) = v, passed by value (keeps the per-patch dropout scale off the memcpy path)
 int launch_fill16(float* dst, const Floats16& v, cudaStream_t st);
 

@@ -22,7 +22,7 @@ namespace dcl {
 
 using namespace tc;
 
-cudaError_t trace_set_conv_gemm(long long* p) { return trace_set_local(p); }
+cudaError_t trace_set_conv_gemm(long long* p, int cta) { return trace_set_local(p, cta); }
 
 // ---------------------------------------------------------------------------------------------
 // prep: norm + act + bf16 + channel blocking (zero-pads channels up to a multiple of 16)
@@ -111,26 +111,90 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // Epilogue of one 128-row accumulator tile (TMEM columns [0, n_tile) at lane_addr): bias, channel scale,
 // GELU, residual, store in the requested format, per-channel statistics into s_stat[warp][2][n_tile].
+// STACK: the accumulator holds the three kw partial products P_0 | P_1 | P_2 (n_tile columns each, see the slab
+// kernel); out[m] = P_0[m-1] + P_1[m] + P_2[m+1] without the terms that cross a row end (rows are `roww` voxels,
+// a tile is whole rows).  Neighbouring lanes come from shuffles, neighbouring warps through `xchg`.
+template <bool STACK = false>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint32_t lane_addr, int64_t m, int64_t m_total,
-                                                   int n0, float* s_stat, int warp, int lane) {
+                                                   int n0, float* s_stat, const float* s_bo, int warp, int lane,
+                                                   int roww = 0, float* xchg = nullptr, int grp0 = 0) {
   const bool row_ok = m < m_total;
   float* yf = reinterpret_cast<float*>(p.y);
   const float* rf = reinterpret_cast<const float*>(p.residual);
-  for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+  int grp = grp0;   // running 16-column group index: the exchange buffer alternates with it
+  for (int c0 = 0; c0 < p.n_tile; c0 += 16, ++grp) {
     uint32_t acc[16];
-    tmem_ld16(lane_addr + (uint32_t)c0, acc);
-    tmem_ld_wait();
+    if (!STACK) {
+      tmem_ld16(lane_addr + (uint32_t)c0, acc);
+      tmem_ld_wait();
+    } else {
+      uint32_t a0[16], a2[16];
+      tmem_ld16(lane_addr + (uint32_t)c0, a0);
+      tmem_ld16(lane_addr + (uint32_t)(p.n_tile + c0), acc);
+      tmem_ld16(lane_addr + (uint32_t)(2 * p.n_tile + c0), a2);
+      tmem_ld_wait();
+      const int wpos = (warp * 32 + lane) % roww;
+      const bool wide = roww > 32;                       // a row spans several warps: exchange the edge lanes
+      float* xs = xchg + (grp & 1) * (G_EPI_WARPS * 32);
+      if (wide) {
+        if (lane == 31) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 4)
+            *reinterpret_cast<float4*>(xs + (warp * 2) * 16 + k) =
+                make_float4(__uint_as_float(a0[k]), __uint_as_float(a0[k + 1]), __uint_as_float(a0[k + 2]), __uint_as_float(a0[k + 3]));
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int k = 0; k < 16; k += 4)
+            *reinterpret_cast<float4*>(xs + (warp * 2 + 1) * 16 + k) =
+                make_float4(__uint_as_float(a2[k]), __uint_as_float(a2[k + 1]), __uint_as_float(a2[k + 2]), __uint_as_float(a2[k + 3]));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+      }
+      const bool has_l = wpos > 0, has_r = wpos < roww - 1;
+      // branch-free edge lanes: every lane reads the (valid) neighbour-warp slots as broadcasts and selects
+      float el[16], er[16];
+      if (wide) {
+        const float* xl = xs + ((warp > 0 ? warp - 1 : 0) * 2) * 16;
+        const float* xr = xs + ((warp < G_EPI_WARPS - 1 ? warp + 1 : warp) * 2 + 1) * 16;
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(xl + k), r4 = *reinterpret_cast<const float4*>(xr + k);
+          el[k] = l4.x; el[k + 1] = l4.y; el[k + 2] = l4.z; el[k + 3] = l4.w;
+          er[k] = r4.x; er[k + 1] = r4.y; er[k + 2] = r4.z; er[k + 3] = r4.w;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { el[k] = 0.f; er[k] = 0.f; }   // rows end at warp edges: the edge terms are masked
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        float up = __shfl_up_sync(0xffffffffu, __uint_as_float(a0[k]), 1);
+        float dn = __shfl_down_sync(0xffffffffu, __uint_as_float(a2[k]), 1);
+        up = lane == 0 ? el[k] : up;
+        dn = lane == 31 ? er[k] : dn;
+        acc[k] = __float_as_uint((__uint_as_float(acc[k]) + (has_l ? up : 0.f)) + (has_r ? dn : 0.f));
+      }
+    }
+    // bias / channel scale of these 16 columns come from shared memory (staged once per CTA, zero / one beyond cout):
+    // vector loads up front instead of one dependent global load per element
+    float bs[16], os[16];
+#pragma unroll
+    for (int k = 0; k < 16; k += 4) {
+      const float4 b4 = *reinterpret_cast<const float4*>(s_bo + c0 + k);
+      const float4 o4 = *reinterpret_cast<const float4*>(s_bo + p.n_tile + c0 + k);
+      bs[k] = b4.x; bs[k + 1] = b4.y; bs[k + 2] = b4.z; bs[k + 3] = b4.w;
+      os[k] = o4.x; os[k + 1] = o4.y; os[k + 2] = o4.z; os[k + 3] = o4.w;
+    }
     float v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const int co = n0 + c0 + k;
-      float val = 0.f;
-      if (row_ok && co < p.cout) {
-        val = __uint_as_float(acc[k]) + (p.bias ? __ldg(p.bias + co) : 0.f);
-        if (p.out_scale) val *= __ldg(p.out_scale + co);
-        if (p.gelu) val = 0.5f * val * (1.f + erff(val * 0.70710678118654752440f));
-      }
-      v[k] = val;
+      const float val = (__uint_as_float(acc[k]) + bs[k]) * os[k];
+      v[k] = (row_ok && n0 + c0 + k < p.cout) ? val : 0.f;
+    }
+    if (p.gelu) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = 0.5f * v[k] * (1.f + erff(v[k] * 0.70710678118654752440f));   // gelu(0) = 0
     }
     if (row_ok) {
       if (p.out_mode == 1) {          // 16 consecutive outputs of one row: 4 x 16-byte stores
@@ -232,9 +296,11 @@ conv_gemm_kernel(GemmConvParams p) {
   uint64_t* bar_acc = bar_empty + G_NS;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
   float* s_stat = reinterpret_cast<float*>(s_tmem + 2);     // [4 warps][2][n_tile] partial sums
+  float* s_bo = s_stat + 8 * p.n_tile;                      // [n_tile] bias, [n_tile] channel scale
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) trace_event(0, 0);     // kernel entry
+  long long* const tbuf = trace_begin();
+  if (tid == 0) trace_event(tbuf, 0, 0);     // kernel entry
   const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
   const int64_t m0 = (int64_t)blockIdx.x * 128;
   const int n0 = blockIdx.y * p.n_tile;
@@ -250,11 +316,16 @@ conv_gemm_kernel(GemmConvParams p) {
   }
   if (warp == G_EPI_WARPS) tmem_alloc(s_tmem, tmem_cols);
   for (int i = tid; i < 8 * p.n_tile; i += G_THREADS) s_stat[i] = 0.f;
+  for (int i = tid; i < p.n_tile; i += G_THREADS) {
+    const bool in = n0 + i < p.cout;
+    s_bo[i] = in && p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+    s_bo[p.n_tile + i] = in && p.out_scale ? __ldg(p.out_scale + n0 + i) : 1.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
-  if (tid == 0) trace_event(1, 0);   // setup done
+  if (tid == 0) trace_event(tbuf, 1, 0);   // setup done
 
   if (warp >= G_EPI_WARPS + 1) {
     // =============================== producers ===================================================
@@ -309,7 +380,7 @@ conv_gemm_kernel(GemmConvParams p) {
           a_src += step;
         }
         cp_async_commit();
-        if (pt == 0) trace_event(2, it);   // stage issued
+        if (pt == 0) trace_event(tbuf, 2, it);   // stage issued
         if (it >= LAG) {
           cp_async_wait<LAG>();
           fence_proxy_async();
@@ -330,7 +401,7 @@ conv_gemm_kernel(GemmConvParams p) {
         const int s = it % G_NS;
         mbar_wait(&bar_full[s], (uint32_t)(it / G_NS) & 1u);
         tc_fence_after();
-        if (lane == 0) trace_event(3, it);              // stage landed, MMAs issued next
+        if (lane == 0) trace_event(tbuf, 3, it);              // stage landed, MMAs issued next
         uint64_t ad = a_desc0 + (uint64_t)((uint32_t)(s * stage_bytes) >> 4);
         uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(s * stage_bytes) >> 4);
         for (int ks = 0; ks < p.kstage; ++ks) {
@@ -347,8 +418,8 @@ conv_gemm_kernel(GemmConvParams p) {
     // =============================== epilogue ====================================================
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    if (tid == 0) trace_event(4, 0);   // accumulator complete
-    gemm_epilogue_tile(p, tmem_base + ((uint32_t)(warp * 32) << 16), m0 + warp * 32 + lane, m_total, n0, s_stat, warp, lane);
+    if (tid == 0) trace_event(tbuf, 4, 0);   // accumulator complete
+    gemm_epilogue_tile(p, tmem_base + ((uint32_t)(warp * 32) << 16), m0 + warp * 32 + lane, m_total, n0, s_stat, s_bo, warp, lane);
     if (p.stats != nullptr) {
       asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");   // the 4 epilogue warps only
       for (int c = tid; c < p.n_tile; c += G_EPI_WARPS * 32) {
@@ -361,7 +432,7 @@ conv_gemm_kernel(GemmConvParams p) {
     }
   }
 
-  if (tid == 0) trace_event(5, 0);     // epilogue done
+  if (tid == 0) trace_event(tbuf, 5, 0);     // epilogue done
   tc_fence_before();
   __syncthreads();
   if (warp == G_EPI_WARPS) {
@@ -373,17 +444,23 @@ conv_gemm_kernel(GemmConvParams p) {
 // ---------------------------------------------------------------------------------------------
 // "Slab" kernel: stride-1 3x3x3 convolution whose input tile is staged ONCE.
 //   CTA        MT consecutive 128-voxel output tiles of one plane (R = MT*128/W full-width rows) x n_tile
-//              output channels.  The input slab = 3 planes x (R+2) rows x W voxels x Cin is fetched once with
-//              zero-filling cp.async (B-format is already the UMMA operand layout), InstanceNorm + activation
-//              applied in place; the 27 taps are 27 start addresses into it.  Rows have NO halo columns: a
-//              kw = 0 / 2 tap simply reads the neighbouring position and the output lanes whose neighbour would
-//              wrap to another row (w = 0 / w = W-1) are switched off with the MMA's disable-output-lane mask,
-//              which is exactly zero padding.  Versus the im2col GEMM above this cuts L2->SM traffic for the
-//              activations 27x; weights stream through a small ring with bulk async copies (one tap per stage).
-//   warps      0-3 epilogue, 4 MMA issuer, 5-12 slab producers, 13 weight streamer.
+//              output channels.  The input slab = 3 planes x (R+2) rows x W voxels x Cin is fetched with one bulk
+//              async copy per (8-channel chunk, plane) - B-format rows are contiguous and already the UMMA operand
+//              layout - and InstanceNorm + activation are applied in place by 12 warps.
+//   kw taps    are NOT shifted operand reads (a 16-byte shift breaks the 128-byte alignment of the core matrices
+//              and costs ~80 instead of ~48 clk per MMA, tools/ubench).  Instead the three kw weight matrices are
+//              stacked along N: one MMA with N = 3*n_tile reads the aligned A tile once and fills three
+//              accumulators P_kw[m] = sum_{kd,kh,cin} X[d+kd-1][h+kh-1][w(m)] W[kd][kh][kw]; the epilogue forms
+//              out[m] = P_0[m-1] + P_1[m] + P_2[m+1] with warp shuffles (and a 2-float-per-channel exchange
+//              between neighbouring warps when a row spans more than one warp), dropping the terms that would
+//              cross a row end - which is exactly the zero padding along w.
+//   weights    repacked once per layer as [n tile][kd,kh][cin/8][kw][n_tile][8]: a ring stage (one (kd,kh),
+//              all resident channels, 3 kw) is ONE bulk async copy.
+//   warps      0-3 epilogue (+ transform), 4 MMA issuer, 5-12 transform, 13 loader (slab + weight ring).
 // ---------------------------------------------------------------------------------------------
 struct SlabParams {
-  GemmConvParams g;         // a / a1 / c0_chunks / w / bias / residual / y / stats / cout / n_tile / D,H,W / out_mode
+  GemmConvParams g;         // a / a1 / c0_chunks / bias / residual / y / stats / cout / n_tile / D,H,W / out_mode
+  const uint4* wslab;       // repacked weights
   const stat_t* sums;       // fused input InstanceNorm (+ activation), as in the rolling kernel
   float inv_n;
   const float* mean;
@@ -393,34 +470,39 @@ struct SlabParams {
   int rows;                 // R = mt * 128 / W
   int kc_pass;              // 8-channel chunks resident per pass (Cin is processed in npass passes)
   int npass;
-  int nb;                   // weight ring depth (taps)
-  uint32_t mk0[4], mk2[4];  // output lanes switched off for kw = 0 (w == 0) and kw = 2 (w == W-1)
-  uint32_t idesc;
+  int nb;                   // weight ring depth (stages)
+  uint32_t idesc;           // M = 128, N = 3 * n_tile
 };
 
-constexpr int S_PROD_WARPS = 8;
-constexpr int S_THREADS = (G_EPI_WARPS + 1 + S_PROD_WARPS + 1) * 32;
-constexpr int S_WEIGHT_WARP = G_EPI_WARPS + 1 + S_PROD_WARPS;
-// taps are processed with kw in the order 1,0,2: the first MMA of a tile must write every lane (accumulate = 0),
-// so it has to be an unmasked (kw = 1) tap
-__device__ __forceinline__ int slab_tap(int j, int* kd, int* kh, int* kw) {
-  const int kdh = j / 3, i = j - kdh * 3;
-  *kd = kdh / 3; *kh = kdh - *kd * 3; *kw = i == 0 ? 1 : (i == 1 ? 0 : 2);
-  return kdh * 3 + *kw;
-}
-constexpr int S_PROD_T0 = (G_EPI_WARPS + 1) * 32;
-constexpr int S_NPROD = S_PROD_WARPS * 32;
+constexpr int S_XF_WARPS = 12;                       // warps 0-3 and 5-12 transform the slab
+constexpr int S_LOAD_WARP = G_EPI_WARPS + 1 + 8;     // 13
+constexpr int S_THREADS = (S_LOAD_WARP + 1) * 32;
 
-__device__ __forceinline__ void umma_bf16_masked(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                                 uint32_t accumulate, uint32_t m0, uint32_t m1, uint32_t m2, uint32_t m3) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n\t"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(m0), "r"(m1), "r"(m2), "r"(m3)
-      : "memory");
+template <int ACT>
+__device__ __forceinline__ uint4 slab_xf(uint4 v, const float (&sc)[8], const float (&sh)[8]) {
+  uint32_t* pv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float fx = fmaf(__uint_as_float(pv[k] << 16), sc[2 * k], sh[2 * k]);
+    float fy = fmaf(__uint_as_float(pv[k] & 0xffff0000u), sc[2 * k + 1], sh[2 * k + 1]);
+    if (ACT == ACT_RELU) { fx = fmaxf(fx, 0.f); fy = fmaxf(fy, 0.f); }
+    else if (ACT == ACT_LRELU) { fx = fmaxf(fx, 0.01f * fx); fy = fmaxf(fy, 0.01f * fy); }
+    pv[k] = pack_bf16x2(fx, fy);
+  }
+  return v;
+}
+
+template <int ACT>
+__device__ __forceinline__ void slab_xf_run(uint4* base, int n_vec, int lane, const float (&sc)[8], const float (&sh)[8]) {
+  int i = lane;
+  for (; i + 96 < n_vec; i += 128) {     // 4 independent vectors in flight per lane
+    uint4 v0 = base[i], v1 = base[i + 32], v2 = base[i + 64], v3 = base[i + 96];
+    base[i] = slab_xf<ACT>(v0, sc, sh);
+    base[i + 32] = slab_xf<ACT>(v1, sc, sh);
+    base[i + 64] = slab_xf<ACT>(v2, sc, sh);
+    base[i + 96] = slab_xf<ACT>(v3, sc, sh);
+  }
+  for (; i < n_vec; i += 32) base[i] = slab_xf<ACT>(base[i], sc, sh);
 }
 
 __global__ void __launch_bounds__(S_THREADS, 1)
@@ -429,35 +511,41 @@ conv_slab_kernel(SlabParams sp) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = p.W, H = p.H, D = p.D;
   const int R = sp.rows;
-  const int npos = 3 * (R + 2) * W + 2;                  // +1 pad position in front and behind
+  const int npos = 3 * (R + 2) * W;                      // 16-byte positions per channel chunk
   const int slab_bytes = sp.kc_pass * npos * 16;
-  const int b_tap_bytes = sp.kc_pass * p.n_tile * 16;    // one tap, all resident channels
-  const int b_stage = 3 * b_tap_bytes;                   // ring stage = the 3 kw taps of one (kd,kh)
+  const int nst = 3 * p.n_tile;                          // stacked N
+  const int b_stage = sp.kc_pass * nst * 16;             // ring stage = one (kd,kh): [chunk][kw][n_tile] x 16 B
   uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(smem + slab_bytes + sp.nb * b_stage);
   uint64_t* bar_bempty = bar_bfull + sp.nb;
-  uint64_t* bar_slab_full = bar_bempty + sp.nb;
-  uint64_t* bar_slab_empty = bar_slab_full + 1;
+  uint64_t* bar_slab_full = bar_bempty + sp.nb;          // slab transformed (one arrive per transform warp)
+  uint64_t* bar_slab_empty = bar_slab_full + 1;          // MMAs of the pass are done with the slab
   uint64_t* bar_slab_land = bar_slab_empty + 1;          // bulk copies of the slab have landed (byte count)
   uint64_t* bar_acc = bar_slab_land + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
   float* s_stat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tmem + 2) + 15) & ~(uintptr_t)15);  // [4 warps][2][n_tile]
   float* s_scale = s_stat + 8 * p.n_tile;                // [cin_pad]  rstd
   float* s_shift = s_scale + p.cin_pad;                  // [cin_pad]  -mean * rstd
+  float* s_xchg = s_shift + p.cin_pad;                   // [2 buffers][4 warps][2][16]
+  float* s_bo = s_xchg + 2 * G_EPI_WARPS * 32;           // [n_tile] bias, [n_tile] channel scale
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) trace_event(0, 0);
+  long long* const tbuf = trace_begin();
+  if (tid == 0) trace_event(tbuf, 0, 0);
   const int64_t m_total = (int64_t)D * H * W;
   const int64_t m0 = (int64_t)blockIdx.x * (sp.mt * 128);
   const int n0 = blockIdx.y * p.n_tile;
   const int d_out = (int)(m0 / ((int64_t)H * W));
   const int h0 = (int)((m0 - (int64_t)d_out * H * W) / W);
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < sp.mt * p.n_tile) tmem_cols <<= 1;
+  while ((int)tmem_cols < sp.mt * nst) tmem_cols <<= 1;
   const bool has_norm = sp.sums != nullptr || sp.mean != nullptr;
+  // staged rows r = 0..R+1 hold input rows h0-1+r; [r_lo, r_hi] are inside the volume
+  const int r_lo = h0 == 0 ? 1 : 0;
+  const int r_hi = h0 + R >= H ? R : R + 1;
 
   if (tid == 0) {
     for (int s = 0; s < sp.nb; ++s) { mbar_init(&bar_bfull[s], 1); mbar_init(&bar_bempty[s], 1); }
-    mbar_init(bar_slab_full, S_NPROD);
+    mbar_init(bar_slab_full, S_XF_WARPS);
     mbar_init(bar_slab_empty, 1);
     mbar_init(bar_slab_land, 1);
     mbar_init(bar_acc, 1);
@@ -465,165 +553,78 @@ conv_slab_kernel(SlabParams sp) {
   }
   if (warp == G_EPI_WARPS) tmem_alloc(s_tmem, tmem_cols);
   for (int i = tid; i < 8 * p.n_tile; i += S_THREADS) s_stat[i] = 0.f;
-  if (has_norm)
-    for (int c = tid; c < p.cin_pad; c += S_THREADS) {
-      float m = 0.f, r = 1.f;
-      if (sp.sums != nullptr) stat_mean_rstd(sp.sums, c, sp.inv_n, &m, &r);
-      else { m = sp.mean[c]; r = sp.rstd[c]; }
-      s_scale[c] = r;
-      s_shift[c] = -m * r;
-    }
+  for (int i = tid; i < p.n_tile; i += S_THREADS) {
+    const bool in = n0 + i < p.cout;
+    s_bo[i] = in && p.bias ? __ldg(p.bias + n0 + i) : 0.f;
+    s_bo[p.n_tile + i] = in && p.out_scale ? __ldg(p.out_scale + n0 + i) : 1.f;
+  }
+  for (int c = tid; c < p.cin_pad; c += S_THREADS) {
+    float m = 0.f, r = 1.f;
+    if (sp.sums != nullptr) stat_mean_rstd(sp.sums, c, sp.inv_n, &m, &r);
+    else if (sp.mean != nullptr) { m = sp.mean[c]; r = sp.rstd[c]; }
+    s_scale[c] = r;
+    s_shift[c] = -m * r;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *s_tmem;
   const uint32_t smem_base = smem_u32(smem);
   const int kcs_total = p.cin_pad / 8;
-  if (tid == 0) trace_event(1, 0);
+  if (tid == 0) trace_event(tbuf, 1, 0);
 
-  if (warp == S_WEIGHT_WARP) {
-    // =============================== weight streamer =============================================
-    // one ring stage = one tap (all resident channels); lane c issues the bulk async copy of chunk c
-    {
-      const uint32_t b_seg = (uint32_t)p.n_tile * 16;
-      int bit = 0;
-      for (int pass = 0; pass < sp.npass; ++pass) {
-        const int kc_base = pass * sp.kc_pass;
-        for (int kdh = 0; kdh < 9; ++kdh, ++bit) {
-          const int s = bit % sp.nb;
-          const uint32_t bar = smem_u32(&bar_bfull[s]);
-          if (lane == 0) {
-            mbar_wait(&bar_bempty[s], ((uint32_t)(bit / sp.nb) & 1u) ^ 1u);
-            trace_event(10, bit);   // weight stage free, issuing 3 taps
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(3 * sp.kc_pass) * b_seg), "r"(bar)
-                         : "memory");
-          }
-          __syncwarp();
-          const uint32_t b_dst = smem_base + (uint32_t)(slab_bytes + s * b_stage);
-          for (int e = lane; e < 3 * sp.kc_pass; e += 32) {
-            const int i = e / sp.kc_pass, c = e - i * sp.kc_pass;
-            const int kw = i == 0 ? 1 : (i == 1 ? 0 : 2);            // kw order 1,0,2 (see slab_tap)
-            const uint4* b_src = p.w + ((int64_t)(kdh * 3 + kw) * kcs_total + kc_base + c) * p.cout_pad + n0;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             b_dst + (uint32_t)(i * b_tap_bytes) + (uint32_t)c * b_seg),
-                         "l"(b_src), "r"(b_seg), "r"(bar)
-                         : "memory");
-          }
-        }
-      }
-    }
-  } else if (warp >= G_EPI_WARPS + 1) {
-    // =============================== slab producers ==============================================
-    const int pt = tid - S_PROD_T0;
+  if (warp == S_LOAD_WARP) {
+    // =============================== loader: slab + weight ring ==================================
     const int64_t sp_in = m_total;
     const int64_t delta1 = p.a1 ? (p.a1 - p.a) - (int64_t)p.c0_chunks * sp_in : 0;
-    const bool identity = !has_norm && sp.act == ACT_NONE;
-    const int items_per_chunk = 3 * (R + 2) * W;
+    const uint32_t run_bytes = (uint32_t)((r_hi - r_lo + 1) * W) * 16u;
+    int vd = 0;
+    for (int pl = 0; pl < 3; ++pl) vd += (unsigned)(d_out - 1 + pl) < (unsigned)D ? 1 : 0;
+    const uint4* wsrc = sp.wslab + (int64_t)blockIdx.y * 9 * kcs_total * nst;
+    int bit = 0;
     for (int pass = 0; pass < sp.npass; ++pass) {
       const int kc_base = pass * sp.kc_pass;
       if (pass > 0) mbar_wait(bar_slab_empty, (uint32_t)(pass - 1) & 1u);   // MMAs of the previous pass are done
-      // ---- the slab: every (chunk, plane, row) is W contiguous 16-byte vectors in global memory AND in the
-      // slab, so it is one bulk async copy; rows outside the volume are zero-filled by the thread instead
-      const int n_rows = 3 * (R + 2);
-      const uint32_t row_bytes = (uint32_t)W * 16u;
-      if (pt == 0) {
-        int vd = 0, vh = 0;
-        for (int pl = 0; pl < 3; ++pl) vd += (unsigned)(d_out - 1 + pl) < (unsigned)D ? 1 : 0;
-        for (int r = 0; r < R + 2; ++r) vh += (unsigned)(h0 - 1 + r) < (unsigned)H ? 1 : 0;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(vd * vh * sp.kc_pass) * row_bytes),
+      if (lane == 0)
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(vd * sp.kc_pass) * run_bytes),
                      "r"(smem_u32(bar_slab_land))
                      : "memory");
-      }
-      asm volatile("bar.sync 2, %0;" ::"n"(S_NPROD) : "memory");   // expect_tx is registered before any copy lands
-      for (int e = pt; e < sp.kc_pass * n_rows; e += S_NPROD) {
-        const int c = e / n_rows;
-        const int rr = e - c * n_rows;
-        const int pl = rr / (R + 2);
-        const int r = rr - pl * (R + 2);
-        const int d_in = d_out - 1 + pl, h_in = h0 - 1 + r;
+      __syncwarp();
+      for (int e = lane; e < sp.kc_pass * 3; e += 32) {
+        const int c = e / 3, pl = e - c * 3;
+        const int d_in = d_out - 1 + pl;
+        if ((unsigned)d_in >= (unsigned)D) continue;
         const int kc = kc_base + c;
-        const uint32_t dst = smem_base + (uint32_t)((c * npos + 1 + rr * W) * 16);
-        if ((unsigned)d_in < (unsigned)D && (unsigned)h_in < (unsigned)H) {
-          const uint4* src = p.a + (int64_t)kc * sp_in + (kc >= p.c0_chunks ? delta1 : 0) + ((int64_t)d_in * H + h_in) * W;
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                       "l"(src), "r"(row_bytes), "r"(smem_u32(bar_slab_land))
+        const uint4* src = p.a + (int64_t)kc * sp_in + (kc >= p.c0_chunks ? delta1 : 0) + ((int64_t)d_in * H + (h0 - 1 + r_lo)) * W;
+        const uint32_t dst = smem_base + (uint32_t)((c * npos + (pl * (R + 2) + r_lo) * W) * 16);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(src), "r"(run_bytes), "r"(smem_u32(bar_slab_land))
+                     : "memory");
+      }
+      if (lane == 0) trace_event(tbuf, 11, pass);   // slab copies issued
+      for (int kdh = 0; kdh < 9; ++kdh, ++bit) {
+        const int s = bit % sp.nb;
+        if (lane == 0) {
+          mbar_wait(&bar_bempty[s], ((uint32_t)(bit / sp.nb) & 1u) ^ 1u);
+          trace_event(tbuf, 10, bit);   // weight stage free, issuing (kd,kh)
+          const uint32_t bar = smem_u32(&bar_bfull[s]);
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)b_stage), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                           smem_base + (uint32_t)(slab_bytes + s * b_stage)),
+                       "l"(wsrc + ((int64_t)kdh * kcs_total + kc_base) * nst), "r"((uint32_t)b_stage), "r"(bar)
                        : "memory");
-        } else {
-          uint4* z = reinterpret_cast<uint4*>(smem + (size_t)(c * npos + 1 + rr * W) * 16);
-          for (int i = 0; i < W; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
+        __syncwarp();
       }
-      if (pt < 2 * sp.kc_pass)   // the two pad positions of each chunk (only read by masked-off lanes; keep them finite)
-        *reinterpret_cast<uint4*>(smem + (size_t)((pt >> 1) * npos + ((pt & 1) ? npos - 1 : 0)) * 16) = make_uint4(0u, 0u, 0u, 0u);
-      if (pt == 0) trace_event(11, pass);   // slab copies issued
-      mbar_wait(bar_slab_land, (uint32_t)pass & 1u);
-      if (pt == 0) trace_event(12, pass);   // slab landed
-      if (!identity) {
-        // in-place InstanceNorm + activation.  A warp walks whole rows (all index math once per row, lanes on
-        // consecutive 16-byte vectors = conflict free); W = 16 packs two rows per warp pass.
-        const int lanes_per_row = W < 32 ? W : 32;
-        const int rows_per_iter = 32 / lanes_per_row;
-        const int sub = lane / lanes_per_row, li = lane - sub * lanes_per_row;
-        const int total_rows = sp.kc_pass * n_rows;
-        constexpr int UR = 4;                               // independent rows in flight per lane (latency hiding)
-        const int pw = warp - (G_EPI_WARPS + 1);
-        for (int row0 = pw * rows_per_iter * UR; row0 < total_rows; row0 += S_PROD_WARPS * rows_per_iter * UR) {
-          uint4* qp[UR];
-          uint4 v[UR];
-          int kcs[UR];
-          bool ok[UR];
-#pragma unroll
-          for (int u = 0; u < UR; ++u) {
-            const int row = row0 + u * rows_per_iter + sub;
-            const int c = row / n_rows;
-            const int rr = row - c * n_rows;
-            const int pl = rr / (R + 2);
-            const int r = rr - pl * (R + 2);
-            const int d_in = d_out - 1 + pl, h_in = h0 - 1 + r;
-            ok[u] = row < total_rows && li < W && (unsigned)d_in < (unsigned)D && (unsigned)h_in < (unsigned)H;
-            kcs[u] = kc_base + c;
-            qp[u] = reinterpret_cast<uint4*>(smem + (size_t)(c * npos + 1 + rr * W + li) * 16);
-            if (ok[u]) v[u] = *qp[u];
-          }
-          for (int i = 0; i < W; i += 32) {                 // W = 64 / 128: further 32-vector segments of the rows
-#pragma unroll
-            for (int u = 0; u < UR; ++u) {
-              if (!ok[u]) continue;
-              if (i > 0) v[u] = qp[u][i];
-              const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + kcs[u] * 8), sc1 = *reinterpret_cast<const float4*>(s_scale + kcs[u] * 8 + 4);
-              const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + kcs[u] * 8), sh1 = *reinterpret_cast<const float4*>(s_shift + kcs[u] * 8 + 4);
-              const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-              const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-              uint32_t* pv = reinterpret_cast<uint32_t*>(&v[u]);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                float fx = fmaf(__uint_as_float(pv[k] << 16), sc[2 * k], sh[2 * k]);
-                float fy = fmaf(__uint_as_float(pv[k] & 0xffff0000u), sc[2 * k + 1], sh[2 * k + 1]);
-                if (sp.act == ACT_RELU) { fx = fmaxf(fx, 0.f); fy = fmaxf(fy, 0.f); }
-                else if (sp.act == ACT_LRELU) { fx = fmaxf(fx, 0.01f * fx); fy = fmaxf(fy, 0.01f * fy); }
-                pv[k] = pack_bf16x2(fx, fy);
-              }
-              qp[u][i] = v[u];
-            }
-          }
-        }
-      }
-      fence_proxy_async();
-      mbar_arrive(bar_slab_full);
-      if (pt == 0) trace_event(13, pass);   // slab transformed + published
     }
   } else if (warp == G_EPI_WARPS) {
     // =============================== MMA issuer ==================================================
     {   // all 32 lanes run the loop; the elected lane issues (see umma_bf16_ws)
       const uint32_t idesc = sp.idesc;
-      const uint32_t b_lbo = (uint32_t)p.n_tile * 16;
-      const uint32_t a_lbo = (uint32_t)npos * 16;
-      const int rows_per_tile = 128 / W;
-      // descriptors = base + (byte offset >> 4): the single issuing thread only adds small integers per MMA
-      const uint64_t a_desc0 = umma_desc(smem_base, a_lbo, 128);
-      const uint64_t b_desc0 = umma_desc(smem_base + (uint32_t)slab_bytes, b_lbo, 128);
-      const uint32_t a_ks = 2u * (uint32_t)npos, b_ks = 2u * (uint32_t)p.n_tile;    // K-step strides in 16-byte units
-      const uint32_t a_tile = (uint32_t)(rows_per_tile * W);
+      // descriptors = base + (byte offset >> 4): every A start address is a multiple of W*16 >= 256 bytes
+      const uint64_t a_desc0 = umma_desc(smem_base, (uint32_t)npos * 16, 128);
+      const uint64_t b_desc0 = umma_desc(smem_base + (uint32_t)slab_bytes, (uint32_t)nst * 16, 128);
+      const uint32_t a_ks = 2u * (uint32_t)npos, b_ks = 2u * (uint32_t)nst;    // K-step strides in 16-byte units
       const int nks = sp.kc_pass / 2;
       int bit = 0;
       for (int pass = 0; pass < sp.npass; ++pass) {
@@ -631,28 +632,20 @@ conv_slab_kernel(SlabParams sp) {
         tc_fence_after();
         for (int kdh = 0; kdh < 9; ++kdh, ++bit) {
           const int kd = kdh / 3, kh = kdh - kd * 3;
-          const uint32_t pos_row = (uint32_t)(1 + (kd * (R + 2) + kh) * W);
+          const uint32_t pos_row = (uint32_t)((kd * (R + 2) + kh) * W);
           const int s = bit % sp.nb;
           mbar_wait(&bar_bfull[s], (uint32_t)(bit / sp.nb) & 1u);
           tc_fence_after();
-          if (lane == 0) trace_event(14, bit);   // weights of this (kd,kh) landed, issuing MMAs
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int kw = i == 0 ? 1 : (i == 1 ? 0 : 2);             // same order as the weight streamer
-            const uint64_t b_tap = b_desc0 + (uint64_t)((uint32_t)(s * b_stage + i * b_tap_bytes) >> 4);
-            const uint64_t a_tap = a_desc0 + (uint64_t)(pos_row + (uint32_t)(kw - 1));
-            const uint32_t q0 = kw == 0 ? sp.mk0[0] : sp.mk2[0], q1 = kw == 0 ? sp.mk0[1] : sp.mk2[1];
-            const uint32_t q2 = kw == 0 ? sp.mk0[2] : sp.mk2[2], q3 = kw == 0 ? sp.mk0[3] : sp.mk2[3];
-            const uint32_t accum = (pass | kdh | i) != 0 ? 1u : 0u;
-            for (int t = 0; t < sp.mt; ++t) {
-              const uint32_t d_tmem = tmem_base + (uint32_t)(t * p.n_tile);
-              uint64_t ad = a_tap + (uint64_t)((uint32_t)t * a_tile), bd = b_tap;
-              uint32_t acc_t = accum;
-              for (int ks = 0; ks < nks; ++ks) {
-                if (kw == 1) umma_bf16_ws(d_tmem, ad, bd, idesc, acc_t);
-                else umma_bf16_masked_ws(d_tmem, ad, bd, idesc, acc_t, q0, q1, q2, q3);
-                ad += a_ks; bd += b_ks; acc_t = 1u;
-              }
+          if (lane == 0) trace_event(tbuf, 14, bit);   // weights of this (kd,kh) landed, issuing MMAs
+          const uint64_t b_st = b_desc0 + (uint64_t)((uint32_t)(s * b_stage) >> 4);
+          const uint32_t accum = (pass | kdh) != 0 ? 1u : 0u;
+          for (int t = 0; t < sp.mt; ++t) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * nst);
+            uint64_t ad = a_desc0 + (uint64_t)(pos_row + (uint32_t)t * 128u), bd = b_st;
+            uint32_t acc_t = accum;
+            for (int ks = 0; ks < nks; ++ks) {
+              umma_bf16_ws(d_tmem, ad, bd, idesc, acc_t);
+              ad += a_ks; bd += b_ks; acc_t = 1u;
             }
           }
           umma_commit_ws(&bar_bempty[s]);
@@ -663,20 +656,61 @@ conv_slab_kernel(SlabParams sp) {
     }
     __syncwarp();
   } else {
-    // =============================== epilogue ====================================================
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    if (tid == 0) trace_event(15, 0);     // accumulators complete
-    for (int t = 0; t < sp.mt; ++t)
-      gemm_epilogue_tile(p, tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * p.n_tile),
-                         m0 + t * 128 + warp * 32 + lane, m_total, n0, s_stat, warp, lane);
-    if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
-      for (int c = tid; c < p.n_tile; c += G_EPI_WARPS * 32) {
-        if (n0 + c < p.cout) {
-          const float a = (s_stat[c] + s_stat[2 * p.n_tile + c]) + (s_stat[4 * p.n_tile + c] + s_stat[6 * p.n_tile + c]);
-          const float q = (s_stat[p.n_tile + c] + s_stat[3 * p.n_tile + c]) + (s_stat[5 * p.n_tile + c] + s_stat[7 * p.n_tile + c]);
-          stat_add(p.stats, n0 + c, a, q);
+    // =============================== transform (12 warps), then epilogue (warps 0-3) ==============
+    const int xw = warp < G_EPI_WARPS ? warp : warp - 1;    // 0..11
+    const bool identity = !has_norm && sp.act == ACT_NONE;
+    // rows / planes outside the volume are zero padding: written once, never touched by the bulk copies
+    for (int q = xw; q < sp.kc_pass * 3; q += S_XF_WARPS) {
+      const int c = q / 3, pl = q - c * 3;
+      uint4* chunk = reinterpret_cast<uint4*>(smem + (size_t)(c * npos + pl * (R + 2) * W) * 16);
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      if ((unsigned)(d_out - 1 + pl) >= (unsigned)D) {
+        for (int i = lane; i < (R + 2) * W; i += 32) chunk[i] = z;
+      } else {
+        if (r_lo == 1) for (int i = lane; i < W; i += 32) chunk[i] = z;
+        if (r_hi == R) for (int i = lane; i < W; i += 32) chunk[(R + 1) * W + i] = z;
+      }
+    }
+    for (int pass = 0; pass < sp.npass; ++pass) {
+      const int kc_base = pass * sp.kc_pass;
+      mbar_wait(bar_slab_land, (uint32_t)pass & 1u);
+      if (tid == 0) trace_event(tbuf, 12, pass);   // slab landed
+      if (!identity) {
+        const int n_vec = (r_hi - r_lo + 1) * W;
+        for (int q = xw; q < sp.kc_pass * 3; q += S_XF_WARPS) {
+          const int c = q / 3, pl = q - c * 3;
+          if ((unsigned)(d_out - 1 + pl) >= (unsigned)D) continue;
+          const int kc = kc_base + c;
+          const float4 sc0 = *reinterpret_cast<const float4*>(s_scale + kc * 8), sc1 = *reinterpret_cast<const float4*>(s_scale + kc * 8 + 4);
+          const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + kc * 8), sh1 = *reinterpret_cast<const float4*>(s_shift + kc * 8 + 4);
+          const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+          const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+          uint4* base = reinterpret_cast<uint4*>(smem + (size_t)(c * npos + (pl * (R + 2) + r_lo) * W) * 16);
+          if (sp.act == ACT_RELU) slab_xf_run<ACT_RELU>(base, n_vec, lane, sc, sh);
+          else if (sp.act == ACT_LRELU) slab_xf_run<ACT_LRELU>(base, n_vec, lane, sc, sh);
+          else slab_xf_run<ACT_NONE>(base, n_vec, lane, sc, sh);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_slab_full);
+      if (tid == 0) trace_event(tbuf, 13, pass);   // slab transformed + published
+    }
+    if (warp < G_EPI_WARPS) {
+      mbar_wait(bar_acc, 0);
+      tc_fence_after();
+      if (tid == 0) trace_event(tbuf, 15, 0);     // accumulators complete
+      for (int t = 0; t < sp.mt; ++t)
+        gemm_epilogue_tile<true>(p, tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * nst),
+                                 m0 + t * 128 + warp * 32 + lane, m_total, n0, s_stat, s_bo, warp, lane, W, s_xchg, t * (p.n_tile / 16));
+      if (p.stats != nullptr) {
+        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+        for (int c = tid; c < p.n_tile; c += G_EPI_WARPS * 32) {
+          if (n0 + c < p.cout) {
+            const float a = (s_stat[c] + s_stat[2 * p.n_tile + c]) + (s_stat[4 * p.n_tile + c] + s_stat[6 * p.n_tile + c]);
+            const float q = (s_stat[p.n_tile + c] + s_stat[3 * p.n_tile + c]) + (s_stat[5 * p.n_tile + c] + s_stat[7 * p.n_tile + c]);
+            stat_add(p.stats, n0 + c, a, q);
+          }
         }
       }
     }
@@ -684,6 +718,7 @@ conv_slab_kernel(SlabParams sp) {
 
   tc_fence_before();
   __syncthreads();
+  if (tid == 0) trace_event(tbuf, 16, 0);   // all roles done
   if (warp == G_EPI_WARPS) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -738,6 +773,26 @@ bool slab_conv_supported(int cin, int cout, int d, int h, int w, int stride, int
   return cin_pad <= 256;
 }
 
+// canonical [tap][cin/8][cout_pad] -> slab order [n tile][kd,kh][cin/8][kw][n_tile] (16-byte elements)
+__global__ void __launch_bounds__(256)
+slab_repack_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int kcs, int cout_pad, int n_tile) {
+  const int64_t total = (int64_t)27 * kcs * cout_pad;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total) return;
+  const int n = (int)(i % cout_pad);
+  const int kc = (int)((i / cout_pad) % kcs);
+  const int tap = (int)(i / ((int64_t)cout_pad * kcs));
+  const int kdh = tap / 3, kw = tap - kdh * 3;
+  const int j = n / n_tile, nn = n - j * n_tile;
+  dst[((((int64_t)j * 9 + kdh) * kcs + kc) * 3 + kw) * n_tile + nn] = src[i];
+}
+
+void tc_free_weights(TcWeights* w) {
+  if (w->dev) cudaFree(w->dev);
+  if (w->slab_dev) cudaFree(w->slab_dev);
+  w->dev = nullptr; w->slab_dev = nullptr; w->slab_ntile = 0;
+}
+
 int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, cudaStream_t st) {
   if (!slab_conv_supported(w.cin, w.cout, g.D, g.H, g.W, g.stride, g.taps) || w.dev == nullptr || g.a0 == nullptr) {
     set_error("slab_conv: unsupported shape");
@@ -763,53 +818,55 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   const int64_t m_total = (int64_t)g.D * g.H * g.W;
   const int64_t plane = (int64_t)g.H * g.W;
   const int smem_cap = 227 * 1024;
-  // configuration search: tiles per CTA (mt), output channels per CTA (nt), input-channel passes; cost model =
-  // waves x (fixed + max(MMA issue time, L2->SM fill time)) in SM clocks
+  // configuration search: tiles per CTA (mt), output channels per CTA (nt; the MMA runs N = 3*nt <= 256),
+  // input-channel passes; cost model in SM clocks = waves x (fixed + slab fetch + transform + max(MMA, weight stream))
   int best_mt = 0, best_nt = 0, best_pass = 0, best_nb = 0;
   double best_cost = 1e30;
   for (int mt = 1; mt <= 4; mt <<= 1) {
     if (plane % (mt * 128) != 0) continue;
     const int64_t m_ctas = m_total / (mt * 128);
     const int rows = mt * 128 / g.W;
-    const int npos = 3 * (rows + 2) * g.W + 2;
-    for (int nt = 16; nt <= 256 && nt <= p.cout_pad; nt += 16) {
-      if (p.cout_pad % nt != 0 || mt * nt > 512) continue;
+    const int npos = 3 * (rows + 2) * g.W;
+    for (int nt = 16; 3 * nt <= 256 && nt <= p.cout_pad; nt += 16) {
+      if (p.cout_pad % nt != 0 || mt * 3 * nt > 512) continue;
       for (int npass = 1; npass <= 2; ++npass) {
         if ((cin_pad / 16) % npass != 0) continue;
         const int kc_pass = cin_pad / 8 / npass;
         const int slab = kc_pass * npos * 16;
-        const int b_stage = 3 * kc_pass * nt * 16;
-        const int fixed = (2 * 8 + 4) * 8 + 16 + 8 * nt * 4 + 2 * cin_pad * 4 + 64;
+        const int b_stage = kc_pass * 3 * nt * 16;
+        const int fixed = (2 * 6 + 4) * 8 + 16 + 10 * nt * 4 + 2 * cin_pad * 4 + 1024 + 64;
         int nb = (smem_cap - slab - fixed) / b_stage;
         if (nb > 6) nb = 6;
         if (nb < 2) continue;
         const double ctas = (double)m_ctas * (p.cout_pad / nt);
         const double waves = ceil(ctas / 148.0);
-        const double per_mma = nt <= 64 ? 60.0 : nt / 2.0 + 12.0;
-        const double mma = (double)npass * 27 * mt * (kc_pass / 2) * per_mma;
-        const double fill = ((double)slab * npass + 27.0 * cin_pad * nt * 2) / 28.0;
-        const double cost = waves * (8000.0 + (mma > fill ? mma : fill) + (nb < 3 ? 4000.0 : 0.0) + 1500.0 * (npass - 1));
+        const double per_mma = 3 * nt <= 96 ? 50.0 : 3 * nt / 2.0 + 4.0;
+        const double mma = (double)npass * 9 * mt * (kc_pass / 2) * per_mma;
+        const double wstream = 27.0 * cin_pad * nt * 2 / 40.0;
+        const double cost = waves * (6000.0 + (double)npass * (slab / 40.0 + slab / 60.0) + (mma > wstream ? mma : wstream) +
+                                     (nb < 3 ? 3000.0 : 0.0) + mt * nt * 6.0);
         if (cost < best_cost) { best_cost = cost; best_mt = mt; best_nt = nt; best_pass = npass; best_nb = nb; }
       }
     }
   }
   if (best_mt == 0) { set_error("slab_conv: tile does not fit shared memory"); return -1; }
   sp.mt = best_mt; p.n_tile = best_nt; sp.npass = best_pass; sp.nb = best_nb;
-  sp.idesc = umma_idesc_bf16(128, best_nt);
-  for (int j = 0; j < 4; ++j) {
-    uint32_t a = 0, b = 0;
-    for (int i = 0; i < 32; ++i) {
-      const int wpos = (32 * j + i) % g.W;
-      if (wpos == 0) a |= 1u << i;
-      if (wpos == g.W - 1) b |= 1u << i;
-    }
-    sp.mk0[j] = a; sp.mk2[j] = b;
-  }
+  sp.idesc = umma_idesc_bf16(128, 3 * best_nt);
   sp.rows = best_mt * 128 / g.W;
   sp.kc_pass = cin_pad / 8 / best_pass;
-  const int npos = 3 * (sp.rows + 2) * g.W + 2;
-  const int smem_bytes = sp.kc_pass * npos * 16 + sp.nb * 3 * sp.kc_pass * p.n_tile * 16 + (2 * sp.nb + 4) * 8 + 16 +
-                         8 * p.n_tile * 4 + 2 * cin_pad * 4 + 64;
+  if (w.slab_dev == nullptr || w.slab_ntile != best_nt) {   // one-time repack for this tile width (cached in w)
+    if (w.slab_dev) { cudaStreamSynchronize(st); cudaFree(w.slab_dev); w.slab_dev = nullptr; }
+    const int64_t n16 = (int64_t)27 * (cin_pad / 8) * p.cout_pad;
+    DCL_CUDA_OK(cudaMalloc(&w.slab_dev, (size_t)n16 * 16));
+    slab_repack_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(p.w, reinterpret_cast<uint4*>(w.slab_dev), cin_pad / 8,
+                                                                   p.cout_pad, best_nt);
+    DCL_CUDA_OK(cudaGetLastError());
+    w.slab_ntile = best_nt;
+  }
+  sp.wslab = reinterpret_cast<const uint4*>(w.slab_dev);
+  const int npos = 3 * (sp.rows + 2) * g.W;
+  const int smem_bytes = sp.kc_pass * npos * 16 + sp.nb * sp.kc_pass * 3 * p.n_tile * 16 + (2 * sp.nb + 4) * 8 + 16 + 16 +
+                         10 * p.n_tile * 4 + 2 * cin_pad * 4 + 1024 + 64;
   static bool configured = false;
   if (!configured) {
     DCL_CUDA_OK(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));
@@ -844,7 +901,7 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
   const int total_stages = p.taps * (p.cin_pad / (16 * p.kstage));
   int ns = stage_bytes <= 12 * 1024 ? 8 : stage_bytes <= 16 * 1024 ? 6 : stage_bytes <= 26 * 1024 ? 4 : 3;
   if (total_stages <= 8 && 8 * stage_bytes <= 150 * 1024) ns = 8;
-  const int smem_bytes = ns * stage_bytes + (2 * ns + 1) * 8 + 16 + 8 * p.n_tile * 4;
+  const int smem_bytes = ns * stage_bytes + (2 * ns + 1) * 8 + 16 + 10 * p.n_tile * 4;
   if (smem_bytes > 160 * 1024) { set_error("conv_gemm: stage does not fit shared memory"); return -1; }
   static bool configured = false;
   if (!configured) {

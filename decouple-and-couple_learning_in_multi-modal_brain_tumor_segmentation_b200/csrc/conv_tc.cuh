@@ -9,7 +9,11 @@ struct TcWeights {
   void* dev = nullptr;
   int cout = 0, cin = 0;
   int64_t bytes = 0;
+  // lazily built copy in the slab kernel's streaming order for one tile width (launch_slab_conv)
+  mutable void* slab_dev = nullptr;
+  mutable int slab_ntile = 0;
 };
+void tc_free_weights(TcWeights* w);   // frees dev and slab_dev
 
 // Packs a PyTorch (cout, cin, taps) fp32 weight (host) into the kernel's B-operand layout (taps = 27 | 1).
 // roll_layout: the conv will run on the rolling kernel (stacked-kh weight order for 16-channel outputs)
@@ -32,6 +36,7 @@ struct RollArgs {
   const void* xb = nullptr;          // B-format input (cin = 16 | 32) ...
   const float* x4 = nullptr;         // ... or the fp32 NCDHW 4-channel strided view InitConv reads
   int64_t s4c = 0, s4d = 0, s4h = 0;
+  const PatchDesc* desc = nullptr;   // ... or the same view described in device memory (graph-replayable forward)
   BNorm norm;
   const float* bias = nullptr;
   const float* out_scale = nullptr;

@@ -2,6 +2,8 @@
 // schedule and the sliding-window driver.  Every arithmetic step is a kernel from this library;
 // there is no CPU compute path.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -16,8 +18,8 @@ namespace dcl {
 
 static long long* g_trace_host_ptr = nullptr;
 constexpr int TRACE_CAP_HOST = 4096;
-cudaError_t trace_set_conv_tc(long long* p);
-cudaError_t trace_set_conv_gemm(long long* p);
+cudaError_t trace_set_conv_tc(long long* p, int cta);
+cudaError_t trace_set_conv_gemm(long long* p, int cta);
 
 thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
@@ -193,12 +195,17 @@ struct dcl_handle {
   float *d8_0, *d8_a, *d8_b, *d8_1, *d8_2;
   float *up_u1[3], *up_u2[3], *dl_in[3], *dl_a[3], *dl_b[3], *dl_1[3], *dl_2[3];   // decoder levels (32^3, 64^3, 128^3)
   float* probs;                                  // (4,128^3)
-  float* keep_dev;                               // (16)
+  float* keep_dev;                               // (16)  (bf16 mode: aliases patch_desc->keep)
+  PatchDesc* patch_desc = nullptr;               // per-patch arguments of the graph-replayed bf16 forward
+  cudaGraphExec_t fwd_graph = nullptr;           // the captured bf16 forward (no aux outputs)
+  int64_t fwd_graph_launches = 0;
+  int fwd_eager_runs = 0;
+  bool fwd_graph_off = false;
   double* stat_accum;                            // (2*512)
   void* blk = nullptr;                           // bf16 channel-blocked conv input (DCL_BF16 only)
   void *tok_a = nullptr, *tok_b = nullptr;       // bf16 blocked token matrices feeding the linear GEMMs
   TokScratch ts[3];                              // [0] aliases the buffers above
-  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // [2] = capture stream of the forward graph
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   // ---- bf16 pipeline (DCL_BF16): B-format activations = bf16 [C/8][spatial][8] ----
   void *b_t0[4], *b_a[4], *b_t1[4], *b_x[4];     // encoder levels (16@128, 32@64, 64@32, 128@16)
@@ -225,7 +232,7 @@ struct dcl_handle {
   std::map<std::string, std::pair<const float*, int64_t>> stages;
 
   // ---- per-class event timing (dcl_profile_*) ----
-  struct ProfRec { cudaEvent_t a, b; int cls; double work; };
+  struct ProfRec { cudaEvent_t a, b; int cls, cls2; double work; };
   bool profiling = false;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> event_pool;
@@ -235,12 +242,18 @@ struct dcl_handle {
     cudaEventRecord(e, st);
     return e;
   }
-  void prof_end(cudaEvent_t a, int cls, double work, cudaStream_t st) {
+  void prof_end(cudaEvent_t a, int cls, double work, cudaStream_t st, int cls2 = -1) {
     cudaEvent_t b;
     if (!event_pool.empty()) { b = event_pool.back(); event_pool.pop_back(); } else cudaEventCreate(&b);
     cudaEventRecord(b, st);
-    prof.push_back({a, b, cls, work});
+    prof.push_back({a, b, cls, cls2, work});
   }
+  // scoped helper for the kernel classes that are only timed (no work figure)
+  struct ProfScope {
+    dcl_handle* h; cudaStream_t st; int cls; cudaEvent_t ev;
+    ProfScope(dcl_handle* h_, cudaStream_t st_, int cls_) : h(h_), st(st_), cls(cls_), ev(h_->profiling ? h_->prof_begin(st_) : nullptr) {}
+    ~ProfScope() { if (ev) h->prof_end(ev, cls, 0.0, st); }
+  };
 };
 
 namespace dcl {
@@ -319,7 +332,12 @@ static int allocate_workspace(dcl_handle* h) {
     }
     DCL_TRY(dev_alloc(h, (void**)&h->stat_arena, (int64_t)STAT_SLOTS * 1024 * sizeof(stat_t)));
   }
-  DCL_TRY(falloc(h, &h->keep_dev, 16));
+  if (h->cfg.precision == DCL_BF16) {
+    DCL_TRY(dev_alloc(h, (void**)&h->patch_desc, sizeof(PatchDesc)));
+    h->keep_dev = h->dry_run ? nullptr : h->patch_desc->keep;
+  } else {
+    DCL_TRY(falloc(h, &h->keep_dev, 16));
+  }
   DCL_TRY(dev_alloc(h, (void**)&h->stat_accum, 2 * 512 * sizeof(double)));
   if (!h->dry_run) DCL_CUDA_OK(cudaMemset(h->stat_accum, 0, 2 * 512 * sizeof(double)));
   h->stat_slots.resize(48);
@@ -363,10 +381,12 @@ static int upload(dcl_handle* h, const std::vector<float>& v, float** out) {
 
 // srcs: list of (weight, bias) host tensors concatenated along cout.
 static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vector<float>*>& ws,
-                     const std::vector<const std::vector<float>*>& bs, int cout_each, int cin, ConvW* out) {
+                     const std::vector<const std::vector<float>*>& bs, int cout_each, int cin, ConvW* out,
+                     bool stride1 = true) {
   const int parts = (int)ws.size();
   const int cout = cout_each * parts;
   out->cout = cout; out->cin = cin;
+  if (out->tc.slab_dev) { cudaFree(out->tc.slab_dev); out->tc.slab_dev = nullptr; out->tc.slab_ntile = 0; }   // stale repack
   std::vector<float> bias((size_t)cout);
   for (int p = 0; p < parts; ++p)
     for (int c = 0; c < cout_each; ++c) bias[p * cout_each + c] = (*bs[p])[c];
@@ -400,7 +420,7 @@ static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vec
   if (h->cfg.precision == DCL_BF16 && (kind == W_CONV3 || kind == W_CONV1)) {
     if (kind == W_CONV1) raw = *ws[0];   // (cout, cin)
     DCL_TRY(tc_pack_weights(raw.data(), cout, cin, kind == W_CONV3 ? 27 : 1,
-                            kind == W_CONV3 && tc_conv_supported(cin, cout, cin == 32 ? 64 : 128, 1, false), &out->tc));
+                            kind == W_CONV3 && stride1 && tc_conv_supported(cin, cout, cin == 32 ? 64 : 128, 1, false), &out->tc));
     h->allocs.push_back(out->tc.dev);
   }
   return 0;
@@ -409,6 +429,8 @@ static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vec
 static bool needed(const dcl_handle* h, const WSpec& s) { return !s.aux || h->cfg.want_aux; }
 
 static int prepare(dcl_handle* h) {
+  if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; }   // weights are about to move
+  h->fwd_eager_runs = 0;
   for (const auto& s : catalogue())
     if (needed(h, s) && !h->host_w.count(s.name)) {
       set_error("weight not set: " + s.name);
@@ -432,7 +454,8 @@ static int prepare(dcl_handle* h) {
       }
     } else {
       std::string mod = s.name.substr(0, s.name.size() - 7);
-      DCL_TRY(pack_conv(h, s.kind, {W(s.name)}, {W(mod + ".bias")}, s.cout, s.cin, &h->conv[mod]));
+      // conv_64_to_32 is the one 32->32 convolution with stride 2: it runs on the GEMM kernel, not the rolling one
+      DCL_TRY(pack_conv(h, s.kind, {W(s.name)}, {W(mod + ".bias")}, s.cout, s.cin, &h->conv[mod], mod != "conv_64_to_32"));
     }
   }
   DCL_TRY(pack_conv(h, W_CONV3, {W("conv_mid_fea_1.weight"), W("conv_mid_fea_2.weight"), W("conv_mid_fea_4.weight")},
@@ -792,20 +815,23 @@ struct Fwd16 {
   int conv(const void* x0, int c0, const void* x1, int c1, int g, const ConvW& w, int stride, const BNorm* norm,
            const float* out_scale, const void* resb, void* y, stat_t* stats, int taps = 27) {
     cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
-    int rc;
+    int rc, kind;
     if (taps == 27 && x1 == nullptr && tc_conv_supported(c0, w.cout, g, stride, false)) {
+      kind = c0 == 32 ? 3 : 2;
       RollArgs a;
       a.xb = x0;
       if (norm) a.norm = *norm;
       a.bias = w.b; a.out_scale = out_scale; a.resb = resb; a.yb = y; a.stats = stats;
       rc = launch_roll_conv(a, w.tc, w.cout, g, st);
     } else if (taps == 27 && slab_conv_supported(c0 + c1, w.cout, g, g, g, stride, taps) && g <= 32) {
+      kind = 4;
       GemmArgs ga;
       ga.a0 = x0; ga.c0 = c0; ga.a1 = x1;
       ga.D = g; ga.H = g; ga.W = g; ga.stride = 1; ga.taps = 27;
       ga.bias = w.b; ga.out_scale = out_scale; ga.out_mode = 2; ga.y = y; ga.residual = resb; ga.stats = stats;
       rc = launch_slab_conv(ga, norm, w.tc, st);
     } else {
+      kind = 5;
       const void* src = x0;
       if (norm) {
         if (x1 != nullptr) { set_error("bf16 conv: fused norm with two sources is not used by this network"); return -1; }
@@ -820,7 +846,7 @@ struct Fwd16 {
     }
     if (h->profiling) {
       const double og = (double)((g - 1) / stride + 1);
-      h->prof_end(ev, 0, 2.0 * taps * (c0 + c1) * w.cout * og * og * og, st);
+      h->prof_end(ev, taps == 27 ? 0 : 11, 2.0 * taps * (c0 + c1) * w.cout * og * og * og, st, kind);
     }
     return rc;
   }
@@ -842,19 +868,67 @@ struct Fwd16 {
     DCL_TRY(conv(x, c, nullptr, 0, g, h->conv.at(name + ".conv1"), 1, nullptr, nullptr, nullptr, a, sa));
     BNorm n1 = norm_of(sa, sp, ACT_LRELU);
     DCL_TRY(conv(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &n1, nullptr, nullptr, b, sb));
+    dcl_handle::ProfScope ps(h, st, 7);
     DCL_TRY(launch_norm_act_b(b, norm_of(sb, sp, ACT_LRELU), x, y, c, sp, st));
     return 0;
   }
 
+  // The forward proper.  Its per-patch arguments (source view, dropout scale) live in h->patch_desc, so the
+  // sequence of launches is identical for every patch and can be replayed as a CUDA graph.
   int run(const float* x, const int64_t xs[4], const float* keep_host, float* probs_out, float* const* aux) {
+    PatchDesc d;
+    d.x = x; d.sc = xs[0]; d.sd = xs[1]; d.sh = xs[2];
+    for (int i = 0; i < 16; ++i) d.keep[i] = keep_host ? keep_host[i] : 1.f;
+    DCL_TRY(launch_patch_desc(h->patch_desc, d, st));
+    const bool graphable = aux == nullptr && !h->profiling && !h->fwd_graph_off;
+    if (!graphable) return body(probs_out, aux);
+    if (h->fwd_graph == nullptr) {
+      if (h->fwd_eager_runs < 1) {     // the first forward runs eagerly: one-time attribute calls and weight repacks
+        ++h->fwd_eager_runs;
+        return body(probs_out, nullptr);
+      }
+      // capture the whole forward (including the three concurrent coupler streams) into a graph writing h->probs
+      // (captured on a private stream: the caller's stream may be the legacy default stream, which cannot capture)
+      const int64_t before = g_launches;
+      cudaGraph_t graph = nullptr;
+      cudaStream_t cs = h->aux_stream[2];
+      if (cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        h->fwd_graph_off = true;
+        if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: stream capture unavailable\n");
+        return body(probs_out, nullptr);
+      }
+      Fwd16 cap{h, cs};
+      const int rc = cap.body(h->probs, nullptr);
+      const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+      if (rc != 0 || e != cudaSuccess || graph == nullptr ||
+          cudaGraphInstantiate(&h->fwd_graph, graph, 0) != cudaSuccess) {
+        cudaGetLastError();
+        if (graph) cudaGraphDestroy(graph);
+        h->fwd_graph = nullptr;
+        h->fwd_graph_off = true;       // stay on the eager launches (same kernels)
+        if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: graph capture failed rc=%d e=%d (%s)\n", rc, (int)e, g_error.c_str());
+        g_launches = before;
+        return body(probs_out, nullptr);
+      }
+      cudaGraphDestroy(graph);
+      if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: forward captured, %lld launches\n", (long long)(g_launches - before));
+      h->fwd_graph_launches = g_launches - before;
+      g_launches = before;
+    }
+    DCL_CUDA_OK(cudaGraphLaunch(h->fwd_graph, st));
+    g_launches += h->fwd_graph_launches;
+    if (probs_out != h->probs)
+      DCL_CUDA_OK(cudaMemcpyAsync(probs_out, h->probs, 4 * P3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return 0;
+  }
+
+  int body(float* probs_out, float* const* aux) {
     const bool want_aux = aux != nullptr;
     const bool dense_feats = want_aux || h->cfg.keep_stages;
     Fwd f{h, st, &h->ts[0]};   // token-path and auxiliary-head helpers are shared with the fp32 schedule
     h->stat_used = 0;
     DCL_CUDA_OK(cudaMemsetAsync(h->stat_arena, 0, (size_t)STAT_SLOTS * 1024 * sizeof(stat_t), st));
-    Floats16 keep;
-    for (int i = 0; i < 16; ++i) keep.v[i] = keep_host ? keep_host[i] : 1.f;
-    DCL_TRY(launch_fill16(h->keep_dev, keep, st));
     const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
 
     // ---- encoder ----
@@ -862,11 +936,11 @@ struct Fwd16 {
     {
       const ConvW& w = h->conv.at("Unet_list.InitConv.conv");
       RollArgs a;
-      a.x4 = x; a.s4c = xs[0]; a.s4d = xs[1]; a.s4h = xs[2];
+      a.desc = h->patch_desc;
       a.bias = w.b; a.out_scale = h->keep_dev; a.yb = h->b_t0[0]; a.stats = s_in;
       cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
       DCL_TRY(launch_roll_conv(a, w.tc, 16, 128, st));
-      if (h->profiling) h->prof_end(ev, 0, 2.0 * 27.0 * 4 * 16 * (double)P3, st);
+      if (h->profiling) h->prof_end(ev, 0, 2.0 * 27.0 * 4 * 16 * (double)P3, st, 2);
     }
     const char* blk[4][2] = {{"Unet_list.EnBlock1", "Unet_list.EnBlock1_1"}, {"Unet_list.EnBlock2_1", "Unet_list.EnBlock2_2"},
                              {"Unet_list.EnBlock3_1", "Unet_list.EnBlock3_2"}, {"Unet_list.EnBlock4_1", "Unet_list.EnBlock4_2"}};
@@ -890,6 +964,7 @@ struct Fwd16 {
     DCL_TRY(conv(h->b_edown, 32, h->b_x[2], 64, 32, h->edge_merged, 1, nullptr, nullptr, nullptr, h->b_eraw, s_e));
     DCL_TRY(conv(h->b_x4, 256, nullptr, 0, 16, h->sem_merged, 1, nullptr, nullptr, nullptr, h->b_sraw, s_s));
     for (int r = 0; r < 3; ++r) {
+      dcl_handle::ProfScope ps(h, st, 10);
       BNorm ne = norm_of(s_e, g32, ACT_LRELU), ns = norm_of(s_s, g16, ACT_LRELU);
       DCL_TRY(launch_tokenise_b(h->b_eraw, ne, 4 * r, h->E[r], dense_feats ? h->edge_dense[r] : nullptr, 32, 32, 4, 2, 2, st));
       DCL_TRY(launch_tokenise_b(h->b_sraw, ns, 16 * r, h->S[r], dense_feats ? h->sem_dense[r] : nullptr, 128, 16, 2, 2, 1, st));
@@ -907,6 +982,7 @@ struct Fwd16 {
     // ---- Edge-supported Intra-region Couplers: the three regions are independent until the cross-region
     // coupler, and each is a chain of small latency-bound kernels, so they run on three concurrent streams
     // (region 0 on the caller's stream, regions 1-2 on the handle's auxiliary streams, own scratch each)
+    cudaEvent_t ev_tok = h->profiling ? h->prof_begin(st) : nullptr;
     DCL_CUDA_OK(cudaEventRecord(h->ev_fork, st));
     for (int r = 0; r < 3; ++r) {
       cudaStream_t sr = r == 0 ? st : h->aux_stream[r - 1];
@@ -953,6 +1029,7 @@ struct Fwd16 {
     DCL_TRY(f.ffn_block(h->tr[3], h->ts[0].eqs, SEQ, h->coupler_out[3]));
     DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
     DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st));
+    if (ev_tok) h->prof_end(ev_tok, 8, 0.0, st);
     DCL_TRY(conv(h->b_fused, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, nullptr, nullptr, h->b_enc, nullptr));
 
     // ---- decoder ----
@@ -966,11 +1043,15 @@ struct Fwd16 {
     for (int l = 0; l < 3; ++l) {
       const int cin = 128 >> l, g_in = 16 << l, c = cin / 2, g = g_in * 2;
       void** b = h->b_dl[l];
-      DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st));
+      {
+        dcl_handle::ProfScope ps(h, st, 6);
+        DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st));
+      }
       DCL_TRY(post_block(b[0], c, g, dbn[l][0], b[1], b[2], b[3]));
       DCL_TRY(post_block(b[3], c, g, dbn[l][1], b[1], b[2], b[4]));
       cur = b[4];
     }
+    dcl_handle::ProfScope ps(h, st, 9);
     DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
     return 0;
   }
@@ -1121,6 +1202,9 @@ DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
   if (cudaGetDevice(&h->device) != cudaSuccess) { delete h; set_error("cudaGetDevice failed"); return DCL_ERR_CUDA; }
   int rc = allocate_workspace(h);
   if (rc != 0) { dcl_destroy(h); return rc; }
+  if (cudaStreamCreateWithFlags(&h->aux_stream[2], cudaStreamNonBlocking) != cudaSuccess) {
+    dcl_destroy(h); set_error("dcl_create: stream creation failed"); return DCL_ERR_CUDA;
+  }
   for (int i = 0; i < 2; ++i) {
     if (cudaStreamCreateWithFlags(&h->aux_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
@@ -1136,11 +1220,17 @@ DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
 DCL_API int dcl_destroy(dcl_handle* h) {
   if (!h) return DCL_OK;
   cudaDeviceSynchronize();
+  if (h->fwd_graph) cudaGraphExecDestroy(h->fwd_graph);
   for (void* p : h->allocs) cudaFree(p);
+  for (auto& kv : h->conv)
+    if (kv.second.tc.slab_dev) cudaFree(kv.second.tc.slab_dev);
+  if (h->edge_merged.tc.slab_dev) cudaFree(h->edge_merged.tc.slab_dev);
+  if (h->sem_merged.tc.slab_dev) cudaFree(h->sem_merged.tc.slab_dev);
   for (int i = 0; i < 2; ++i) {
     if (h->aux_stream[i]) cudaStreamDestroy(h->aux_stream[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
+  if (h->aux_stream[2]) cudaStreamDestroy(h->aux_stream[2]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);
@@ -1339,6 +1429,11 @@ DCL_API int dcl_read_topk(dcl_handle* h, int32_t* out_host, void* stream) {
 
 DCL_API DCL_API int dcl_profile_enable(dcl_handle* h, int32_t on) {
   if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
+  if (on) {   // a new measurement window: recycle the recorded events
+    cudaDeviceSynchronize();
+    for (auto& r : h->prof) { h->event_pool.push_back(r.a); h->event_pool.push_back(r.b); }
+    h->prof.clear();
+  }
   h->profiling = on != 0;
   return DCL_OK;
 }
@@ -1347,17 +1442,13 @@ DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64
   if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
   double ms = 0, work = 0;
   int64_t n = 0;
-  std::vector<dcl_handle::ProfRec> keep;
   for (auto& r : h->prof) {
-    if (r.cls != cls) { keep.push_back(r); continue; }
+    if (r.cls != cls && r.cls2 != cls) continue;
     DCL_CUDA_OK(cudaEventSynchronize(r.b));
     float t = 0.f;
     DCL_CUDA_OK(cudaEventElapsedTime(&t, r.a, r.b));
     ms += t; work += r.work; ++n;
-    h->event_pool.push_back(r.a);
-    h->event_pool.push_back(r.b);
   }
-  h->prof.swap(keep);
   if (ms_total) *ms_total = ms;
   if (launches) *launches = n;
   if (work_total) *work_total = work;
@@ -1372,8 +1463,8 @@ DCL_API int dcl_trace_enable(int32_t on) {
   if (on && !g_trace_host_ptr) DCL_CUDA_OK(cudaMalloc((void**)&g_trace_host_ptr, bytes));
   long long* p = on ? g_trace_host_ptr : nullptr;
   if (p) DCL_CUDA_OK(cudaMemset(p, 0, bytes));
-  DCL_CUDA_OK(trace_set_conv_tc(p));
-  DCL_CUDA_OK(trace_set_conv_gemm(p));
+  DCL_CUDA_OK(trace_set_conv_tc(p, on > 0 ? on - 1 : 0));      // on = 1 + blockIdx.x of the traced CTA
+  DCL_CUDA_OK(trace_set_conv_gemm(p, on > 0 ? on - 1 : 0));
   return DCL_OK;
 }
 // copies the recorded (tag<<32|step, clock) pairs (slots with a non-zero clock) to out_host, returns the count
@@ -1387,6 +1478,52 @@ DCL_API int64_t dcl_trace_read(int64_t* out_host, int64_t cap) {
     if (h[2 + 2 * i] != 0) { out_host[2 * n] = h[1 + 2 * i]; out_host[2 * n + 1] = h[2 + 2 * i]; ++n; }
   DCL_CUDA_OK(cudaMemset(g_trace_host_ptr, 0, h.size() * sizeof(long long)));
   return n;
+}
+
+
+// bench helper (tools/op_time.py): average device time in us of `reps` back-to-back launches of the bf16 kernel
+// that the forward would pick for a cubic g^3 convolution.  mode 1 = fused input norm + residual + statistics.
+DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stride, int32_t mode, int32_t reps) {
+  const int64_t sp = (int64_t)g * g * g;
+  const int og = (g - 1) / stride + 1;
+  const int64_t osp = (int64_t)og * og * og;
+  const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
+  std::vector<float> w((size_t)cout * cin * 27);
+  for (size_t i = 0; i < w.size(); ++i) w[i] = (float)((i * 2654435761u >> 8) & 0xffff) / 65536.f - 0.5f;
+  const bool roll = stride == 1 && tc_conv_supported(cin, cout, g, 1, false) && cin != 4;
+  TcWeights tw;
+  if (tc_pack_weights(w.data(), cout, cin, 27, roll, &tw) != 0) return -1.0;
+  void *x = nullptr, *y = nullptr, *r = nullptr;
+  float* bias = nullptr;
+  stat_t *sin = nullptr, *sout = nullptr;
+  cudaMalloc(&x, (size_t)cin_pad * sp * 2); cudaMalloc(&y, (size_t)cout_pad * osp * 2); cudaMalloc(&r, (size_t)cout_pad * osp * 2);
+  cudaMalloc((void**)&bias, cout_pad * 4); cudaMalloc((void**)&sin, 2 * cin_pad * sizeof(stat_t)); cudaMalloc((void**)&sout, 2 * cout_pad * sizeof(stat_t));
+  cudaMemset(x, 0x3c, (size_t)cin_pad * sp * 2); cudaMemset(r, 0x3c, (size_t)cout_pad * osp * 2); cudaMemset(bias, 0, cout_pad * 4);
+  cudaMemset(sin, 0, 2 * cin_pad * sizeof(stat_t)); cudaMemset(sout, 0, 2 * cout_pad * sizeof(stat_t));
+  BNorm bn; bn.sums = sin; bn.inv_n = 1.f / (float)sp; bn.act = ACT_RELU;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  for (int it = 0; it < reps + 3 && rc == 0; ++it) {
+    if (it == 3) cudaEventRecord(e0, 0);
+    if (roll) {
+      RollArgs a; a.xb = x; if (mode) { a.norm = bn; a.resb = r; a.stats = sout; }
+      a.bias = bias; a.yb = y;
+      rc = launch_roll_conv(a, tw, cout, g, 0);
+    } else {
+      GemmArgs ga; ga.a0 = x; ga.c0 = cin_pad; ga.D = g; ga.H = g; ga.W = g; ga.stride = stride; ga.taps = 27;
+      ga.bias = bias; ga.out_mode = 2; ga.y = y;
+      if (mode) { ga.residual = r; ga.stats = sout; }
+      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && g <= 32) rc = launch_slab_conv(ga, mode ? &bn : nullptr, tw, 0);
+      else rc = launch_gemm_conv(ga, tw, 0);
+    }
+  }
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(x); cudaFree(y); cudaFree(r); cudaFree(bias); cudaFree(sin); cudaFree(sout);
+  tc_free_weights(&tw);
+  return rc == 0 ? (double)ms * 1e3 / reps : -1.0;
 }
 
 DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream) {
@@ -1487,7 +1624,7 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
       cudaFree(blk);
     }
     cudaStreamSynchronize(st);
-    cudaFree(tw.dev);
+    tc_free_weights(&tw);
   }
   return rc;
 }

@@ -177,6 +177,18 @@ int launch_scale_untokenise(const float* tokens, const float* class_token, float
 
 __global__ void fill16_kernel(float* __restrict__ dst, Floats16 v) { dst[threadIdx.x] = v.v[threadIdx.x]; }
 
+__global__ void patch_desc_kernel(PatchDesc* __restrict__ dst, PatchDesc v) {
+  if (threadIdx.x == 0) { dst->x = v.x; dst->sc = v.sc; dst->sd = v.sd; dst->sh = v.sh; }
+  if (threadIdx.x < 16) dst->keep[threadIdx.x] = v.keep[threadIdx.x];
+}
+
+int launch_patch_desc(PatchDesc* dst, const PatchDesc& v, cudaStream_t st) {
+  patch_desc_kernel<<<1, 32, 0, st>>>(dst, v);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int launch_fill16(float* dst, const Floats16& v, cudaStream_t st) {
   fill16_kernel<<<1, 16, 0, st>>>(dst, v);
   ++g_launches;

@@ -10,11 +10,19 @@ namespace dcl {
 // ---- optional in-kernel timeline (debug): CTA (0,0) appends (tag, step, clock64) records -------------
 // Enabled by dcl_trace_enable(); every call site costs one predictable branch when disabled.
 static __device__ long long* g_trace_buf = nullptr;   // per translation unit; [0] = record count, then 2 words per record
-static inline cudaError_t trace_set_local(long long* p) { return cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p)); }
+static __device__ int g_trace_cta = 0;                 // blockIdx.x of the traced CTA (blockIdx.y = z = 0)
+static inline cudaError_t trace_set_local(long long* p, int cta = 0) {
+  cudaError_t e = cudaMemcpyToSymbol(g_trace_cta, &cta, sizeof(cta));
+  return e != cudaSuccess ? e : cudaMemcpyToSymbol(g_trace_buf, &p, sizeof(p));
+}
 constexpr int TRACE_CAP = 4096;                       // 32 tags x 128 steps
-__device__ __forceinline__ void trace_event(int tag, int step) {
-  long long* buf = g_trace_buf;
-  if (buf != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+// The buffer pointer is read ONCE per thread at kernel entry (trace_begin) and kept in a register: a call site in a
+// hot loop must not pay a global load of the pointer.
+__device__ __forceinline__ long long* trace_begin() {
+  return (blockIdx.x == (unsigned)g_trace_cta && blockIdx.y == 0 && blockIdx.z == 0) ? g_trace_buf : nullptr;
+}
+__device__ __forceinline__ void trace_event(long long* buf, int tag, int step) {
+  if (buf != nullptr) {
     const int i = (tag & 31) * 128 + (step & 127);      // fixed slot per (tag, step): a plain store, no atomics
     buf[1 + 2 * i] = ((long long)tag << 32) | (unsigned)step;
     buf[2 + 2 * i] = clock64();

@@ -152,9 +152,12 @@ DCL_API int dcl_read_topk(dcl_handle* h, int32_t* out_host /* 13*128 */, void* s
 DCL_API int64_t dcl_launch_count(const dcl_handle* h);
 
 /* Per-kernel-class device timing (CUDA events on the launching stream, recorded around every launch of
- * the class while enabled).  Classes: 0 = 3x3x3 convolutions (work = 2*MAC flops),
- * 1 = stitch / accumulate / label kernels (work = algorithmic bytes).  dcl_profile_read synchronises the
- * events, returns the totals since the last read and clears them. */
+ * the class while enabled).  Classes: 0 = all 3x3x3 convolutions (work = 2*MAC flops), 1 = stitch / accumulate /
+ * label kernels (work = algorithmic bytes); bf16 mode also: 2 = rolling conv 16ch@128^3, 3 = rolling conv
+ * 32ch@64^3, 4 = slab conv, 5 = im2col GEMM conv (stride 2), 6 = DeUp_Cat, 7 = norm+act+residual, 8 = the token
+ * path (select .. couplers .. untokenise, fork to join), 9 = endconv+softmax, 10 = tokenise, 11 = 1x1 convs.
+ * dcl_profile_enable(h, 1) starts a new window (clears earlier records); dcl_profile_read synchronises the
+ * events and returns the totals of one class over the window. */
 DCL_API int dcl_profile_enable(dcl_handle* h, int32_t on);
 DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64_t* launches, double* work_total);
 
@@ -169,6 +172,10 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
                      const float* norm_mean, const float* norm_rstd, int32_t act,
                      const float* residual, float* y, int32_t impl, double* stats_out, void* stream);
 DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spatial, float* mean, float* rstd, void* stream);
+
+/* bench helper (tools/op_time.py): average device time in us of `reps` back-to-back launches of the bf16 kernel the
+ * forward picks for a cubic g^3 3x3x3 convolution (mode 1 = fused input norm + residual + statistics) */
+DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stride, int32_t mode, int32_t reps);
 
 /* ---- debug: in-kernel timeline of CTA (0,0) of the tcgen05 kernels (tools/trace_kernel.py) ---- */
 DCL_API int dcl_trace_enable(int32_t on);

@@ -33,6 +33,23 @@ def main():
     dt = (time.perf_counter() - t0) / n
     print(f"precision={prec.name} forwards={n} ms_per_patch={dt * 1e3:.3f} launches_per_patch={(eng.launch_count - l0) // n} "
           f"checksum={float(p.double().sum()):.6f}")
+    if len(sys.argv) > 3 and sys.argv[3] == "prof":
+        names = {0: "all k3 convs", 2: "roll16@128", 3: "roll32@64", 4: "slab", 5: "gemm conv", 6: "deup", 7: "norm_act_b",
+                 8: "token path", 9: "endconv", 10: "tokenise", 11: "1x1 conv"}
+        eng.profile(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n):
+            eng.forward(x, None)
+        ev1.record()
+        torch.cuda.synchronize()
+        eng.profile(False)
+        print(f"profiled pass: {ev0.elapsed_time(ev1) / n * 1e3:.0f} us per patch")
+        for cls, name in names.items():
+            ms, cnt, work = eng.profile_read(cls)
+            if cnt:
+                extra = f"  {work / (ms * 1e-3) / 1e12:7.1f} TFLOP/s" if work > 0 else ""
+                print(f"  {name:14s} {ms / n * 1e3:8.1f} us per patch  {cnt // n:3d} launches  {ms / cnt * 1e3:7.1f} us each{extra}")
     eng.close()
 
 

@@ -50,13 +50,21 @@ def conv_case(c, g, cout=None, stride=1, norm=True):
 
 
 K1 = {0: "entry", 1: "setup done", 2: "prod: slot free, stage", 3: "prod: staged", 4: "mma: issue step", 5: "mma: issued",
-      6: "epi: acc complete", 7: "epi: all stored"}
+      6: "epi: acc complete", 7: "epi: all stored", 8: "epi: item ld issued", 9: "epi: item acc in regs",
+      10: "epi: item exchanged", 11: "epi: item stored"}
 K2 = {0: "entry", 1: "setup done", 2: "prod: stage issued", 3: "mma: stage landed", 4: "epi: acc complete", 5: "epi: done",
       10: "wgt: stage free, issue tap", 11: "slab: cp.async issued", 12: "slab: landed", 13: "slab: published",
-      14: "mma: tap weights landed", 15: "epi: acc complete", 16: "epi: done"}
+      14: "mma: tap weights landed", 15: "epi: acc complete", 16: "all roles done"}
 
 if __name__ == "__main__":
-    N.check(lib.dcl_trace_enable(1))
+    cta = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+    N.check(lib.dcl_trace_enable(1 + cta))
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "roll"):
+        show("roll 16->16 128^3", conv_case(16, 128, norm=True), K1)
+        show("roll 32->32 64^3", conv_case(32, 64, norm=True), K1)
+    if which == "roll":
+        sys.exit(0)
     show("slab 64->64 32^3", conv_case(64, 32, norm=True), K2)
     show("slab 128->128 16^3", conv_case(128, 16, norm=False), K2)
     N.check(lib.dcl_trace_enable(0))
