@@ -117,12 +117,15 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 template <bool STACK = false>
 __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint32_t lane_addr, int64_t m, int64_t m_total,
                                                    int n0, float* s_stat, const float* s_bo, int warp, int lane,
-                                                   int roww = 0, float* xchg = nullptr, int grp0 = 0) {
+                                                   int roww = 0, float* xchg = nullptr, int grp0 = 0, int c0_begin = 0,
+                                                   int c0_step = 16, int stat_slot = -1, int bar_id = 1) {
+  // warp = TMEM lane quarter (0..3); stat_slot = row pair of s_stat this warp owns (default: warp)
+  if (stat_slot < 0) stat_slot = warp;
   const bool row_ok = m < m_total;
   float* yf = reinterpret_cast<float*>(p.y);
   const float* rf = reinterpret_cast<const float*>(p.residual);
   int grp = grp0;   // running 16-column group index: the exchange buffer alternates with it
-  for (int c0 = 0; c0 < p.n_tile; c0 += 16, ++grp) {
+  for (int c0 = c0_begin; c0 < p.n_tile; c0 += c0_step, ++grp) {
     uint32_t acc[16];
     if (!STACK) {
       tmem_ld16(lane_addr + (uint32_t)c0, acc);
@@ -149,7 +152,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint
             *reinterpret_cast<float4*>(xs + (warp * 2 + 1) * 16 + k) =
                 make_float4(__uint_as_float(a2[k]), __uint_as_float(a2[k + 1]), __uint_as_float(a2[k + 2]), __uint_as_float(a2[k + 3]));
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
+        asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "n"(G_EPI_WARPS * 32) : "memory");
       }
       const bool has_l = wpos > 0, has_r = wpos < roww - 1;
       // branch-free edge lanes: every lane reads the (valid) neighbour-warp slots as broadcasts and selects
@@ -264,8 +267,8 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint
       q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
       if ((lane & 1) == 0) {
         const int ch = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        s_stat[(warp * 2) * p.n_tile + ch] += v[0];       // slot owned by this lane: no race
-        s_stat[(warp * 2 + 1) * p.n_tile + ch] += q[0];
+        s_stat[(stat_slot * 2) * p.n_tile + ch] += v[0];       // slot owned by this lane: no race
+        s_stat[(stat_slot * 2 + 1) * p.n_tile + ch] += q[0];
       }
     }
   }
@@ -523,10 +526,10 @@ conv_slab_kernel(SlabParams sp) {
   uint64_t* bar_acc = bar_slab_land + 1;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc + 1);
   float* s_stat = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tmem + 2) + 15) & ~(uintptr_t)15);  // [4 warps][2][n_tile]
-  float* s_scale = s_stat + 8 * p.n_tile;                // [cin_pad]  rstd
+  float* s_scale = s_stat + 16 * p.n_tile;               // [cin_pad]  rstd      (s_stat: [2 groups][4 warps][2][n_tile])
   float* s_shift = s_scale + p.cin_pad;                  // [cin_pad]  -mean * rstd
-  float* s_xchg = s_shift + p.cin_pad;                   // [2 buffers][4 warps][2][16]
-  float* s_bo = s_xchg + 2 * G_EPI_WARPS * 32;           // [n_tile] bias, [n_tile] channel scale
+  float* s_xchg = s_shift + p.cin_pad;                   // [2 groups][2 buffers][4 warps][2][16]
+  float* s_bo = s_xchg + 4 * G_EPI_WARPS * 32;           // [n_tile] bias, [n_tile] channel scale
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   long long* const tbuf = trace_begin();
@@ -552,7 +555,7 @@ conv_slab_kernel(SlabParams sp) {
     fence_barrier_init();
   }
   if (warp == G_EPI_WARPS) tmem_alloc(s_tmem, tmem_cols);
-  for (int i = tid; i < 8 * p.n_tile; i += S_THREADS) s_stat[i] = 0.f;
+  for (int i = tid; i < 16 * p.n_tile; i += S_THREADS) s_stat[i] = 0.f;
   for (int i = tid; i < p.n_tile; i += S_THREADS) {
     const bool in = n0 + i < p.cout;
     s_bo[i] = in && p.bias ? __ldg(p.bias + n0 + i) : 0.f;
@@ -696,20 +699,32 @@ conv_slab_kernel(SlabParams sp) {
       if (lane == 0) mbar_arrive(bar_slab_full);
       if (tid == 0) trace_event(tbuf, 13, pass);   // slab transformed + published
     }
-    if (warp < G_EPI_WARPS) {
+    // ---- epilogue: two groups of four warps (0-3 and 8-11; a warp reads the TMEM lane quarter warp % 4) take
+    // alternate (tile, 16-column group) items
+    if (warp < G_EPI_WARPS || (warp >= 8 && warp < 12)) {
+      const int eg = warp >> 3, ew = warp & 3;
+      const int ng = p.n_tile / 16;
       mbar_wait(bar_acc, 0);
       tc_fence_after();
       if (tid == 0) trace_event(tbuf, 15, 0);     // accumulators complete
-      for (int t = 0; t < sp.mt; ++t)
-        gemm_epilogue_tile<true>(p, tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(t * nst),
-                                 m0 + t * 128 + warp * 32 + lane, m_total, n0, s_stat, s_bo, warp, lane, W, s_xchg, t * (p.n_tile / 16));
+      int done = 0;
+      for (int t = 0; t < sp.mt; ++t) {
+        const int c0b = ((eg + t * ng) & 1) * 16;
+        gemm_epilogue_tile<true>(p, tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(t * nst),
+                                 m0 + t * 128 + ew * 32 + lane, m_total, n0, s_stat, s_bo, ew, lane, W,
+                                 s_xchg + eg * (2 * G_EPI_WARPS * 32), done, c0b, 32, eg * 4 + ew, 1 + eg);
+        done += (p.n_tile - c0b + 31) / 32;
+      }
       if (p.stats != nullptr) {
-        asm volatile("bar.sync 1, %0;" ::"n"(G_EPI_WARPS * 32) : "memory");
-        for (int c = tid; c < p.n_tile; c += G_EPI_WARPS * 32) {
-          if (n0 + c < p.cout) {
-            const float a = (s_stat[c] + s_stat[2 * p.n_tile + c]) + (s_stat[4 * p.n_tile + c] + s_stat[6 * p.n_tile + c]);
-            const float q = (s_stat[p.n_tile + c] + s_stat[3 * p.n_tile + c]) + (s_stat[5 * p.n_tile + c] + s_stat[7 * p.n_tile + c]);
-            stat_add(p.stats, n0 + c, a, q);
+        asm volatile("bar.sync 3, %0;" ::"n"(2 * G_EPI_WARPS * 32) : "memory");   // both groups
+        if (warp < G_EPI_WARPS) {
+          for (int c = tid; c < p.n_tile; c += G_EPI_WARPS * 32) {
+            if (n0 + c < p.cout) {   // fixed summation order over the 8 partials
+              float a = 0.f, q = 0.f;
+#pragma unroll
+              for (int sl = 0; sl < 8; ++sl) { a += s_stat[(2 * sl) * p.n_tile + c]; q += s_stat[(2 * sl + 1) * p.n_tile + c]; }
+              stat_add(p.stats, n0 + c, a, q);
+            }
           }
         }
       }
@@ -834,7 +849,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
         const int kc_pass = cin_pad / 8 / npass;
         const int slab = kc_pass * npos * 16;
         const int b_stage = kc_pass * 3 * nt * 16;
-        const int fixed = (2 * 6 + 4) * 8 + 16 + 10 * nt * 4 + 2 * cin_pad * 4 + 1024 + 64;
+        const int fixed = (2 * 6 + 4) * 8 + 16 + 18 * nt * 4 + 2 * cin_pad * 4 + 2048 + 64;
         int nb = (smem_cap - slab - fixed) / b_stage;
         if (nb > 6) nb = 6;
         if (nb < 2) continue;
@@ -866,7 +881,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   sp.wslab = reinterpret_cast<const uint4*>(w.slab_dev);
   const int npos = 3 * (sp.rows + 2) * g.W;
   const int smem_bytes = sp.kc_pass * npos * 16 + sp.nb * sp.kc_pass * 3 * p.n_tile * 16 + (2 * sp.nb + 4) * 8 + 16 + 16 +
-                         10 * p.n_tile * 4 + 2 * cin_pad * 4 + 1024 + 64;
+                         18 * p.n_tile * 4 + 2 * cin_pad * 4 + 2048 + 64;
   static bool configured = false;
   if (!configured) {
     DCL_CUDA_OK(cudaFuncSetAttribute(conv_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));

@@ -66,6 +66,10 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split);
 int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cudaStream_t st);
 
+// Rolling stride-2 kernel for EnDown1 (16 -> 32 channels, 128^3 -> 64^3), B-format in / out (conv_s2.cu)
+bool s2_roll_supported(int cin, int cout, int g);
+int launch_s2_roll_conv(const void* xb, const TcWeights& w, const float* bias, void* yb, stat_t* stats, cudaStream_t st);
+
 // ---- HBM-bound B-format kernels (bf16_ops.cu) ---------------------------------------------------------------
 // y = act(norm(x)) (+ res), all B-format
 int launch_norm_act_b(const void* x, const BNorm& n, const void* res, void* y, int channels, int64_t spatial,

@@ -830,6 +830,10 @@ struct Fwd16 {
       ga.D = g; ga.H = g; ga.W = g; ga.stride = 1; ga.taps = 27;
       ga.bias = w.b; ga.out_scale = out_scale; ga.out_mode = 2; ga.y = y; ga.residual = resb; ga.stats = stats;
       rc = launch_slab_conv(ga, norm, w.tc, st);
+    } else if (taps == 27 && stride == 2 && x1 == nullptr && norm == nullptr && out_scale == nullptr && resb == nullptr &&
+               s2_roll_supported(c0, w.cout, g)) {
+      kind = 12;
+      rc = launch_s2_roll_conv(x0, w.tc, w.b, y, stats, st);
     } else {
       kind = 5;
       const void* src = x0;
@@ -1514,6 +1518,7 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
       ga.bias = bias; ga.out_mode = 2; ga.y = y;
       if (mode) { ga.residual = r; ga.stats = sout; }
       if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && g <= 32) rc = launch_slab_conv(ga, mode ? &bn : nullptr, tw, 0);
+      else if (stride == 2 && s2_roll_supported(cin, cout, g)) rc = launch_s2_roll_conv(x, tw, bias, y, mode ? sout : nullptr, 0);
       else rc = launch_gemm_conv(ga, tw, 0);
     }
   }
@@ -1604,7 +1609,18 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
       if (stats_out) { cudaFree(tw.dev); set_error("dcl_op_conv3d_k3: fused statistics need the rolling kernel"); return DCL_ERR_ARG; }
       void* blk = nullptr;
       DCL_CUDA_OK(cudaMalloc(&blk, (size_t)((cin + 15) / 16 * 16) * sp * 2));
-      if (slab_conv_supported(cin, cout, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27)) {
+      if (stride == 2 && cubic && x1 == nullptr && norm_mean == nullptr && act == ACT_NONE && residual == nullptr &&
+          s2_roll_supported(cin, cout, in_dhw[0])) {
+        // rolling stride-2 kernel (EnDown1): B-format in / out
+        const int64_t osp = sp / 8;
+        void* yb = nullptr;
+        DCL_CUDA_OK(cudaMalloc(&yb, (size_t)cout * osp * 2));
+        rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
+        if (rc == 0) rc = launch_s2_roll_conv(blk, tw, bias, yb, nullptr, st);
+        if (rc == 0) rc = launch_unblock(yb, y, cout, osp, st);
+        cudaStreamSynchronize(st);
+        cudaFree(yb);
+      } else if (slab_conv_supported(cin, cout, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27)) {
         // slab kernel: raw blocked input, norm fused in the kernel, fp32 NCDHW output
         ConvSrc raw = s;
         raw.mean = nullptr; raw.rstd = nullptr; raw.act = ACT_NONE;

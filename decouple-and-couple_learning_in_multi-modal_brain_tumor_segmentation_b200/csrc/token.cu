@@ -39,33 +39,44 @@ score_kernel(const float* __restrict__ token, const float* __restrict__ feats, i
 // topk(128, largest, sorted) of up to 2048 scores (cls_wise_former.py:346) by rank counting: element i
 // lands at position #{j : s_j > s_i or (s_j == s_i and j < i)}; positions < 128 are the sorted top-k
 // (ties broken by index, as a stable descending sort would).  128 elements per block, all scores in smem.
-__global__ void __launch_bounds__(128)
+// Block = 8 warps x 4 elements; the 32 lanes of a warp split the scan over all scores (each lane keeps its
+// n/32 scores in registers), so an element's rank is 64 compares per lane plus one warp reduction.
+constexpr int TOPK_EPW = 4;                         // elements per warp
+constexpr int TOPK_EPB = 8 * TOPK_EPW;              // elements per block
+__global__ void __launch_bounds__(256)
 topk_kernel(const float* __restrict__ score, int n, int* __restrict__ idx_out) {
-  __shared__ __align__(16) float key[2048];
-  for (int i = threadIdx.x; i < 2048; i += 128) key[i] = i < n ? score[i] : -FLT_MAX;
-  __syncthreads();
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (i >= n) return;
-  const float si = key[i];
-  int rank = 0;
-  const int n4 = (n + 3) / 4;
-#pragma unroll 4
-  for (int j4 = 0; j4 < n4; ++j4) {
-    const float4 v = *reinterpret_cast<const float4*>(key + 4 * j4);   // broadcast read
-    const int j = 4 * j4;
-    rank += (v.x > si || (v.x == si && j < i)) ? 1 : 0;
-    rank += (v.y > si || (v.y == si && j + 1 < i)) ? 1 : 0;
-    rank += (v.z > si || (v.z == si && j + 2 < i)) ? 1 : 0;
-    rank += (v.w > si || (v.w == si && j + 3 < i)) ? 1 : 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float key[64];                                    // key[t] = score[lane + 32 t]
+#pragma unroll
+  for (int t = 0; t < 64; ++t) {
+    const int j = lane + 32 * t;
+    key[t] = j < n ? __ldg(score + j) : -FLT_MAX;
   }
-  if (rank < TOP_NUM) idx_out[rank] = i;
+  const int nt = (n + 31) / 32;
+#pragma unroll
+  for (int e = 0; e < TOPK_EPW; ++e) {
+    const int i = blockIdx.x * TOPK_EPB + warp * TOPK_EPW + e;
+    if (i >= n) break;                              // uniform per warp
+    const float si = __ldg(score + i);
+    int rank = 0;
+#pragma unroll
+    for (int t = 0; t < 64; ++t) {
+      if (t < nt) {
+        const int j = lane + 32 * t;
+        rank += (key[t] > si || (key[t] == si && j < i)) ? 1 : 0;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rank += __shfl_xor_sync(0xffffffffu, rank, o);
+    if (lane == 0 && rank < TOP_NUM) idx_out[rank] = i;
+  }
 }
 
 int launch_select_topk(const float* token, const float* feats, int n_tokens, float* score_scratch, int* idx_out,
                        cudaStream_t st) {
   if (n_tokens > 2048 || n_tokens < TOP_NUM) { set_error("select_topk: 128 <= n_tokens <= 2048 required"); return -1; }
   score_kernel<<<(n_tokens + 7) / 8, 256, 0, st>>>(token, feats, n_tokens, score_scratch);
-  topk_kernel<<<(n_tokens + 127) / 128, 128, 0, st>>>(score_scratch, n_tokens, idx_out);
+  topk_kernel<<<(n_tokens + TOPK_EPB - 1) / TOPK_EPB, 256, 0, st>>>(score_scratch, n_tokens, idx_out);
   g_launches += 2;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

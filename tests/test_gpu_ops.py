@@ -119,6 +119,8 @@ def test_conv3d_k3_tcgen05_bf16(c, g, act, residual):
     dict(c0=32, c1=0, cout=32, dims=(6, 64, 64), stride=1, norm=True, act=1, residual=True),
     dict(c0=16, c1=0, cout=16, dims=(5, 4, 128), stride=1, norm=True, act=2, residual=False),
     dict(c0=128, c1=0, cout=256, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
+    dict(c0=16, c1=0, cout=32, dims=(128, 128, 128), stride=2, norm=False, act=0, residual=False),   # rolling stride-2 kernel
+    dict(c0=32, c1=0, cout=64, dims=(64, 64, 64), stride=2, norm=False, act=0, residual=False),
 ])
 def test_conv3d_k3_gemm_bf16(case):
     """The general tcgen05 implicit-GEMM kernel (prep + cp.async im2col) against torch conv3d on
@@ -154,5 +156,9 @@ def test_conv3d_k3_gemm_bf16(case):
     torch.cuda.synchronize()
     y = y.cpu()
     assert y.shape == ref.shape
-    assert rel_err(y.numpy(), ref.numpy()) < 2e-3
-    assert float((y - ref).abs().mean() / ref.abs().mean()) < 1e-4
+    # the rolling stride-2 kernel stores its output as bf16 (B-format): one more rounding of 2^-9
+    bf16_out = stride == 2 and (c0, cout, dims[0]) == (16, 32, 128)
+    assert rel_err(y.numpy(), ref.numpy()) < (4e-3 if bf16_out else 2e-3)
+    assert float((y - ref).abs().mean() / ref.abs().mean()) < (2e-3 if bf16_out else 1e-4)
+    if bf16_out:
+        assert float((y - _bf16_round(ref)).abs().mean() / ref.abs().mean()) < 2e-4     # identical up to rare ulp flips
