@@ -179,107 +179,130 @@ int launch_untokenise_b(const float* tokens, const float* class_token, void* y, 
 // conv1 (1x1) -> ConvTranspose3d k2 s2 -> conv3 (1x1) on cat(skip, .) is linear, and every output voxel has
 // exactly one parent input voxel and one of 8 taps t = (kd,kh,kw):
 //     y[v] = W3a . skip[v] + M_t . x[parent(v)] + b_t,   M_t = W3b . Wt_t^T . W1,  b_t = W3b.(Wt_t^T b1 + bt) + b3
-// (M_t, b_t composed on the host in fp64).  Thread = one input voxel, one (kd,kh), both kw, 16 outputs.
-// Weights (fp32) in shared memory: wm[kw][c][16], ws[s][16], bt[kw][16].
+// (M_t, b_t composed on the host in fp64).  The op is HBM bound (reads x once per tap pair from L2, skip once,
+// writes y once) with ~5 GFLOP of tiny-K GEMM work, so it runs on warp-level bf16 MMAs (mma.sync m16n8k16, fp32
+// accumulate) fed straight from the B-format tensors: a quad of lanes covers one 16-byte voxel vector, so every
+// fragment load / store of a warp is one contiguous 128-byte (x) or 256-byte-span (skip / y, both kw) access and
+// no shared-memory staging of activations is needed.  A CTA serves one (kd,kh); a warp walks tiles of 16 parent
+// voxels along w and produces their 2 x 16 outputs (kw = 0, 1).  Weights: bf16 in shared memory, rows padded by
+// 8 elements (conflict-free fragment reads).
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 template <int CIN>
-__global__ void __launch_bounds__(128)
-deup_fused_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, const float* __restrict__ mt,
-                    const float* __restrict__ w3a, const float* __restrict__ bt, uint4* __restrict__ y, int gi) {
+__global__ void __launch_bounds__(256)
+deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, const float* __restrict__ mt,
+                  const float* __restrict__ w3a, const float* __restrict__ bt, uint4* __restrict__ y, int gi) {
   constexpr int CH = CIN / 2;                       // skip / output channels
-  __shared__ __align__(16) float s_wm[2][CIN][16];
-  __shared__ __align__(16) float s_ws[CH][16];
-  __shared__ float s_b[2][16];
+  constexpr int NT = CH / 8, KX = CIN / 16, KS = CH / 16;
+  constexpr int LDM = CIN + 8, LDS_ = CH + 8;       // padded row lengths (elements)
+  extern __shared__ __align__(16) uint8_t deup_smem[];
+  __nv_bfloat16* s_wm = reinterpret_cast<__nv_bfloat16*>(deup_smem);          // [2 kw][CH][LDM]
+  __nv_bfloat16* s_ws = s_wm + 2 * CH * LDM;                                   // [CH][LDS_]
+  float* s_b = reinterpret_cast<float*>(s_ws + CH * LDS_);                     // [2 kw][CH]
   const int kdh = blockIdx.y;                       // kd*2 + kh
-  const int og = blockIdx.z;                        // 16-output group
-  for (int e = threadIdx.x; e < 2 * CIN * 16; e += 128) {
-    const int o = e % 16, c = (e / 16) % CIN, kw = e / (16 * CIN);
-    s_wm[kw][c][o] = __ldg(mt + ((int64_t)(kdh * 2 + kw) * CH + og * 16 + o) * CIN + c);   // mt[t][o][c]
+  for (int e = threadIdx.x; e < 2 * CH * CIN; e += 256) {
+    const int c = e % CIN, o = (e / CIN) % CH, kw = e / (CIN * CH);
+    s_wm[(kw * CH + o) * LDM + c] = __float2bfloat16_rn(__ldg(mt + ((int64_t)(kdh * 2 + kw) * CH + o) * CIN + c));   // mt[t][o][c]
   }
-  for (int e = threadIdx.x; e < CH * 16; e += 128) {
-    const int o = e % 16, s = e / 16;
-    s_ws[s][o] = __ldg(w3a + (int64_t)(og * 16 + o) * CH + s);                            // w3a[o][s]
+  for (int e = threadIdx.x; e < CH * CH; e += 256) {
+    const int sc = e % CH, o = e / CH;
+    s_ws[o * LDS_ + sc] = __float2bfloat16_rn(__ldg(w3a + (int64_t)o * CH + sc));                                     // w3a[o][s]
   }
-  if (threadIdx.x < 32) s_b[threadIdx.x / 16][threadIdx.x % 16] = __ldg(bt + (kdh * 2 + threadIdx.x / 16) * CH + og * 16 + threadIdx.x % 16);
+  for (int e = threadIdx.x; e < 2 * CH; e += 256) s_b[e] = __ldg(bt + (int64_t)(kdh * 2) * CH + e);                   // bt[t][o]
   __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, c = lane & 3;            // fragment row / column-pair of this lane
   const int64_t sp_in = (int64_t)gi * gi * gi;
-  const int64_t p = (int64_t)blockIdx.x * 128 + threadIdx.x;
-  if (p >= sp_in) return;
-  const int w = (int)(p % gi);
-  const int h = (int)((p / gi) % gi);
-  const int d = (int)(p / ((int64_t)gi * gi));
   const int go = 2 * gi;
-  const int64_t sp_out = (int64_t)go * go * go;
-  const int64_t q0 = ((int64_t)(2 * d + (kdh >> 1)) * go + (2 * h + (kdh & 1))) * go + 2 * w;   // kw = 0; kw = 1 is q0 + 1
-  float acc[2][16];
+  const int64_t sp_out = 8 * sp_in;
+  const int tiles_per_row = gi / 16;
+  const int64_t n_tiles = sp_in / 16;
+  const uint32_t* xw = reinterpret_cast<const uint32_t*>(x);
+  const uint32_t* sw = reinterpret_cast<const uint32_t*>(skip);
+  uint32_t* yw = reinterpret_cast<uint32_t*>(y);
+  for (int64_t tile = (int64_t)blockIdx.x * 8 + warp; tile < n_tiles; tile += (int64_t)gridDim.x * 8) {
+    const int w0 = (int)(tile % tiles_per_row) * 16;
+    const int64_t dh = tile / tiles_per_row;
+    const int h = (int)(dh % gi), d = (int)(dh / gi);
+    const int64_t p0 = (dh * gi) + w0;
+    const int64_t q0 = ((int64_t)(2 * d + (kdh >> 1)) * go + (2 * h + (kdh & 1))) * go + 2 * w0;
+    // A fragments of the 16 parent voxels (shared by both kw): chunk 2ks holds k 0-7, chunk 2ks+1 holds k 8-15
+    uint32_t ax[KX][4];
 #pragma unroll
-  for (int o = 0; o < 16; ++o) { acc[0][o] = s_b[0][o]; acc[1][o] = s_b[1][o]; }
-#pragma unroll 1
-  for (int kc = 0; kc < CIN / 8; ++kc) {
-    float f[8];
-    unpack8(__ldg(x + (int64_t)kc * sp_in + p), f);
+    for (int ks = 0; ks < KX; ++ks) {
+      const int64_t b0 = ((int64_t)(2 * ks) * sp_in + p0) * 4 + c, b1 = ((int64_t)(2 * ks + 1) * sp_in + p0) * 4 + c;
+      ax[ks][0] = __ldg(xw + b0 + g * 4);
+      ax[ks][1] = __ldg(xw + b0 + (g + 8) * 4);
+      ax[ks][2] = __ldg(xw + b1 + g * 4);
+      ax[ks][3] = __ldg(xw + b1 + (g + 8) * 4);
+    }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int kw = 0; kw < 2; ++kw) {
+      const int64_t qa = q0 + 2 * g + kw, qb = q0 + 2 * (g + 8) + kw;     // output voxels of fragment rows g, g+8
+      uint32_t as[KS][4];
 #pragma unroll
-      for (int kw = 0; kw < 2; ++kw) {
-        const float4* wr = reinterpret_cast<const float4*>(&s_wm[kw][kc * 8 + k][0]);
+      for (int ks = 0; ks < KS; ++ks) {
+        as[ks][0] = __ldg(sw + ((int64_t)(2 * ks) * sp_out + qa) * 4 + c);
+        as[ks][1] = __ldg(sw + ((int64_t)(2 * ks) * sp_out + qb) * 4 + c);
+        as[ks][2] = __ldg(sw + ((int64_t)(2 * ks + 1) * sp_out + qa) * 4 + c);
+        as[ks][3] = __ldg(sw + ((int64_t)(2 * ks + 1) * sp_out + qb) * 4 + c);
+      }
 #pragma unroll
-        for (int o4 = 0; o4 < 4; ++o4) {
-          const float4 wv = wr[o4];
-          acc[kw][4 * o4] = fmaf(f[k], wv.x, acc[kw][4 * o4]);
-          acc[kw][4 * o4 + 1] = fmaf(f[k], wv.y, acc[kw][4 * o4 + 1]);
-          acc[kw][4 * o4 + 2] = fmaf(f[k], wv.z, acc[kw][4 * o4 + 2]);
-          acc[kw][4 * o4 + 3] = fmaf(f[k], wv.w, acc[kw][4 * o4 + 3]);
-        }
+      for (int nt = 0; nt < NT; ++nt) {
+        float acc[4];
+        acc[0] = acc[2] = s_b[kw * CH + nt * 8 + 2 * c];
+        acc[1] = acc[3] = s_b[kw * CH + nt * 8 + 2 * c + 1];
+        const __nv_bfloat16* wr = s_wm + (kw * CH + nt * 8 + g) * LDM + 2 * c;   // B fragment: n = g, k = 2c (+8)
+#pragma unroll
+        for (int ks = 0; ks < KX; ++ks)
+          mma_bf16_16816(acc, ax[ks], *reinterpret_cast<const uint32_t*>(wr + ks * 16), *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8));
+        const __nv_bfloat16* wsr = s_ws + (nt * 8 + g) * LDS_ + 2 * c;
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks)
+          mma_bf16_16816(acc, as[ks], *reinterpret_cast<const uint32_t*>(wsr + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + ks * 16 + 8));
+        // D fragment: (row g, n = 2c, 2c+1), (row g+8, same n) -> word c of the voxel's 16-byte vector of chunk nt
+        yw[((int64_t)nt * sp_out + qa) * 4 + c] = tc::pack_bf16x2(acc[0], acc[1]);
+        yw[((int64_t)nt * sp_out + qb) * 4 + c] = tc::pack_bf16x2(acc[2], acc[3]);
       }
     }
   }
-#pragma unroll 1
-  for (int kc = 0; kc < CH / 8; ++kc) {
-    float f0[8], f1[8];
-    unpack8(__ldg(skip + (int64_t)kc * sp_out + q0), f0);
-    unpack8(__ldg(skip + (int64_t)kc * sp_out + q0 + 1), f1);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float4* wr = reinterpret_cast<const float4*>(&s_ws[kc * 8 + k][0]);
-#pragma unroll
-      for (int o4 = 0; o4 < 4; ++o4) {
-        const float4 wv = wr[o4];
-        acc[0][4 * o4] = fmaf(f0[k], wv.x, acc[0][4 * o4]);
-        acc[0][4 * o4 + 1] = fmaf(f0[k], wv.y, acc[0][4 * o4 + 1]);
-        acc[0][4 * o4 + 2] = fmaf(f0[k], wv.z, acc[0][4 * o4 + 2]);
-        acc[0][4 * o4 + 3] = fmaf(f0[k], wv.w, acc[0][4 * o4 + 3]);
-        acc[1][4 * o4] = fmaf(f1[k], wv.x, acc[1][4 * o4]);
-        acc[1][4 * o4 + 1] = fmaf(f1[k], wv.y, acc[1][4 * o4 + 1]);
-        acc[1][4 * o4 + 2] = fmaf(f1[k], wv.z, acc[1][4 * o4 + 2]);
-        acc[1][4 * o4 + 3] = fmaf(f1[k], wv.w, acc[1][4 * o4 + 3]);
-      }
-    }
+}
+
+template <int CIN>
+static int launch_deup_mma(const uint4* x, const uint4* skip, const float* mt, const float* w3a, const float* bt, uint4* y,
+                           int gi, cudaStream_t st) {
+  constexpr int CH = CIN / 2;
+  constexpr int smem = (2 * CH * (CIN + 8) + CH * (CH + 8)) * 2 + 2 * CH * 4;
+  static bool configured = false;
+  if (!configured) {
+    DCL_CUDA_OK(cudaFuncSetAttribute(deup_mma_b_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
   }
-#pragma unroll
-  for (int hf = 0; hf < 2; ++hf) {
-    float a0[8], a1[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { a0[k] = acc[0][8 * hf + k]; a1[k] = acc[1][8 * hf + k]; }
-    uint4* dst = y + (int64_t)(og * 2 + hf) * sp_out + q0;
-    dst[0] = pack8(a0);
-    dst[1] = pack8(a1);
-  }
+  const int64_t n_tiles = (int64_t)gi * gi * gi / 16;
+  int gx = (int)((n_tiles + 7) / 8);
+  if (gx > 148) gx = 148;                          // x 4 (kd,kh) CTAs of 8 warps: persistent over the parent tiles
+  deup_mma_b_kernel<CIN><<<dim3(gx, 4), 256, smem, st>>>(x, skip, mt, w3a, bt, y, gi);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const float* w3a, const float* bt, void* y,
                         int cin, int gi, cudaStream_t st) {
-  const int64_t sp_in = (int64_t)gi * gi * gi;
-  dim3 grid((unsigned)((sp_in + 127) / 128), 4, cin / 2 / 16);
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* sp = reinterpret_cast<const uint4*>(skip);
   uint4* yp = reinterpret_cast<uint4*>(y);
-  if (cin == 32) deup_fused_b_kernel<32><<<grid, 128, 0, st>>>(xp, sp, mt, w3a, bt, yp, gi);
-  else if (cin == 64) deup_fused_b_kernel<64><<<grid, 128, 0, st>>>(xp, sp, mt, w3a, bt, yp, gi);
-  else if (cin == 128) deup_fused_b_kernel<128><<<grid, 128, 0, st>>>(xp, sp, mt, w3a, bt, yp, gi);
-  else { set_error("deup_fused: cin must be 32, 64 or 128"); return -1; }
-  ++g_launches;
-  DCL_CUDA_OK(cudaGetLastError());
-  return 0;
+  if (gi % 16 != 0) { set_error("deup_fused: grid must be a multiple of 16"); return -1; }
+  if (cin == 32) return launch_deup_mma<32>(xp, sp, mt, w3a, bt, yp, gi, st);
+  if (cin == 64) return launch_deup_mma<64>(xp, sp, mt, w3a, bt, yp, gi, st);
+  if (cin == 128) return launch_deup_mma<128>(xp, sp, mt, w3a, bt, yp, gi, st);
+  set_error("deup_fused: cin must be 32, 64 or 128");
+  return -1;
 }
 
 // ---- endconv (1x1, 16 -> 4) + Softmax(dim=1) (cls_wise_former.py:662-663): B -> fp32 NCDHW ----------
