@@ -47,6 +47,8 @@ __device__ __forceinline__ void chunk_norm_to_smem(const BNorm& n, int kc, float
 __global__ void __launch_bounds__(256)
 norm_act_b_kernel(const uint4* __restrict__ x, BNorm n, const uint4* __restrict__ res, uint4* __restrict__ y,
                   int64_t spatial) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   __shared__ float s_mean[8], s_rstd[8];
   const int kc = blockIdx.y;
   chunk_norm_to_smem(n, kc, s_mean, s_rstd);
@@ -70,9 +72,9 @@ int launch_norm_act_b(const void* x, const BNorm& n, const void* res, void* y, i
                       cudaStream_t st) {
   unsigned gx = (unsigned)((spatial + 255) / 256);
   if (gx > 4096) gx = 4096;
-  norm_act_b_kernel<<<dim3(gx, channels / 8), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), n,
+  DCL_CUDA_OK(launch_pdl(norm_act_b_kernel, dim3(dim3(gx, channels / 8)), dim3(256), (size_t)(0), st, reinterpret_cast<const uint4*>(x), n,
                                                           reinterpret_cast<const uint4*>(res),
-                                                          reinterpret_cast<uint4*>(y), spatial);
+                                                          reinterpret_cast<uint4*>(y), spatial));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -104,6 +106,8 @@ int launch_unblock(const void* x, float* y, int channels, int64_t spatial, cudaS
 __global__ void __launch_bounds__(256)
 tokenise_b_kernel(const uint4* __restrict__ x, BNorm n, int chunk0, float* __restrict__ tokens,
                   float* __restrict__ dense, int channels, int g, int p0, int p1, int p2) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   __shared__ float s_mean[8], s_rstd[8];
   const int kc = blockIdx.y;                       // chunk within this region's channels
   chunk_norm_to_smem(n, chunk0 + kc, s_mean, s_rstd);
@@ -133,8 +137,8 @@ tokenise_b_kernel(const uint4* __restrict__ x, BNorm n, int chunk0, float* __res
 int launch_tokenise_b(const void* x, const BNorm& n, int chunk0, float* tokens, float* dense_or_null, int channels,
                       int grid, int p0, int p1, int p2, cudaStream_t st) {
   const int64_t spatial = (int64_t)grid * grid * grid;
-  tokenise_b_kernel<<<dim3((unsigned)((spatial + 255) / 256), channels / 8), 256, 0, st>>>(
-      reinterpret_cast<const uint4*>(x), n, chunk0, tokens, dense_or_null, channels, grid, p0, p1, p2);
+  DCL_CUDA_OK(launch_pdl(tokenise_b_kernel, dim3(dim3((unsigned)((spatial + 255) / 256), channels / 8)), dim3(256), (size_t)(0), st, 
+      reinterpret_cast<const uint4*>(x), n, chunk0, tokens, dense_or_null, channels, grid, p0, p1, p2));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -144,6 +148,8 @@ int launch_tokenise_b(const void* x, const BNorm& n, int chunk0, float* tokens, 
 __global__ void __launch_bounds__(256)
 untokenise_b_kernel(const float* __restrict__ tokens, const float* __restrict__ class_token, uint4* __restrict__ y,
                     int channels, int g, int p0, int p1, int p2) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const int kc = blockIdx.y;
   const int64_t spatial = (int64_t)g * g * g;
   const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -168,8 +174,8 @@ untokenise_b_kernel(const float* __restrict__ tokens, const float* __restrict__ 
 int launch_untokenise_b(const float* tokens, const float* class_token, void* y, int channels, int grid, int p0, int p1,
                         int p2, cudaStream_t st) {
   const int64_t spatial = (int64_t)grid * grid * grid;
-  untokenise_b_kernel<<<dim3((unsigned)((spatial + 255) / 256), channels / 8), 256, 0, st>>>(
-      tokens, class_token, reinterpret_cast<uint4*>(y), channels, grid, p0, p1, p2);
+  DCL_CUDA_OK(launch_pdl(untokenise_b_kernel, dim3(dim3((unsigned)((spatial + 255) / 256), channels / 8)), dim3(256), (size_t)(0), st, 
+      tokens, class_token, reinterpret_cast<uint4*>(y), channels, grid, p0, p1, p2));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -196,6 +202,8 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, const float* __restrict__ mt,
                   const float* __restrict__ w3a, const float* __restrict__ bt, uint4* __restrict__ y, int gi) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   constexpr int CH = CIN / 2;                       // skip / output channels
   constexpr int NT = CH / 8, KX = CIN / 16, KS = CH / 16;
   constexpr int LDM = CIN + 8, LDS_ = CH + 8;       // padded row lengths (elements)
@@ -286,7 +294,7 @@ static int launch_deup_mma(const uint4* x, const uint4* skip, const float* mt, c
   const int64_t n_tiles = (int64_t)gi * gi * gi / 16;
   int gx = (int)((n_tiles + 7) / 8);
   if (gx > 148) gx = 148;                          // x 4 (kd,kh) CTAs of 8 warps: persistent over the parent tiles
-  deup_mma_b_kernel<CIN><<<dim3(gx, 4), 256, smem, st>>>(x, skip, mt, w3a, bt, y, gi);
+  DCL_CUDA_OK(launch_pdl(deup_mma_b_kernel<CIN>, dim3(dim3(gx, 4)), dim3(256), (size_t)(smem), st, x, skip, mt, w3a, bt, y, gi));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -309,6 +317,8 @@ int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const 
 __global__ void __launch_bounds__(256)
 endconv_softmax_b_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                          float* __restrict__ probs, int64_t spatial) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   __shared__ float s_w[4][16];
   __shared__ float s_b[4];
   if (threadIdx.x < 64) s_w[threadIdx.x / 16][threadIdx.x % 16] = __ldg(w + threadIdx.x);   // (4,16) row-major
@@ -344,8 +354,8 @@ endconv_softmax_b_kernel(const uint4* __restrict__ x, const float* __restrict__ 
 
 int launch_endconv_softmax_b(const void* x, const float* w, const float* b, float* probs, int64_t spatial,
                              cudaStream_t st) {
-  endconv_softmax_b_kernel<<<(unsigned)((spatial + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x), w, b,
-                                                                            probs, spatial);
+  DCL_CUDA_OK(launch_pdl(endconv_softmax_b_kernel, dim3((unsigned)((spatial + 255) / 256)), dim3(256), (size_t)(0), st, reinterpret_cast<const uint4*>(x), w, b,
+                                                                            probs, spatial));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

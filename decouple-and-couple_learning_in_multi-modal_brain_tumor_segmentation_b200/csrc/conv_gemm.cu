@@ -289,6 +289,8 @@ __device__ __forceinline__ void drain_stages(uint64_t* bar_full, int total, int 
 template <int G_NS>
 __global__ void __launch_bounds__(G_THREADS, 2)
 conv_gemm_kernel(GemmConvParams p) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   constexpr int LAG = G_NS - 2;
   extern __shared__ __align__(128) uint8_t smem[];
   const int a_bytes = 2 * p.kstage * 2048;               // [chunk][128 rows][16 B]
@@ -510,6 +512,8 @@ __device__ __forceinline__ void slab_xf_run(uint4* base, int n_vec, int lane, co
 
 __global__ void __launch_bounds__(S_THREADS, 1)
 conv_slab_kernel(SlabParams sp) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const GemmConvParams& p = sp.g;
   extern __shared__ __align__(128) uint8_t smem[];
   const int W = p.W, H = p.H, D = p.D;
@@ -888,7 +892,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
     configured = true;
   }
   dim3 grid((unsigned)(m_total / (sp.mt * 128)), p.cout_pad / p.n_tile);
-  conv_slab_kernel<<<grid, S_THREADS, smem_bytes, st>>>(sp);
+  DCL_CUDA_OK(launch_pdl(conv_slab_kernel, dim3(grid), dim3(S_THREADS), (size_t)(smem_bytes), st, sp));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -927,10 +931,10 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((unsigned)m_tiles, p.cout_pad / p.n_tile);
-  if (ns == 8) conv_gemm_kernel<8><<<grid, G_THREADS, smem_bytes, st>>>(p);
-  else if (ns == 6) conv_gemm_kernel<6><<<grid, G_THREADS, smem_bytes, st>>>(p);
-  else if (ns == 4) conv_gemm_kernel<4><<<grid, G_THREADS, smem_bytes, st>>>(p);
-  else conv_gemm_kernel<3><<<grid, G_THREADS, smem_bytes, st>>>(p);
+  if (ns == 8) DCL_CUDA_OK(launch_pdl(conv_gemm_kernel<8>, dim3(grid), dim3(G_THREADS), (size_t)(smem_bytes), st, p));
+  else if (ns == 6) DCL_CUDA_OK(launch_pdl(conv_gemm_kernel<6>, dim3(grid), dim3(G_THREADS), (size_t)(smem_bytes), st, p));
+  else if (ns == 4) DCL_CUDA_OK(launch_pdl(conv_gemm_kernel<4>, dim3(grid), dim3(G_THREADS), (size_t)(smem_bytes), st, p));
+  else DCL_CUDA_OK(launch_pdl(conv_gemm_kernel<3>, dim3(grid), dim3(G_THREADS), (size_t)(smem_bytes), st, p));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -943,6 +947,8 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
 __global__ void __launch_bounds__(256)
 prep_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  int rows, uint4* __restrict__ out) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -981,7 +987,7 @@ prep_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st) {
-  prep_rows_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, gamma, beta, rows, reinterpret_cast<uint4*>(out));
+  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, x, gamma, beta, rows, reinterpret_cast<uint4*>(out)));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

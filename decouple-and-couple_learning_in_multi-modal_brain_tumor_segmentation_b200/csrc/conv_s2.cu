@@ -59,6 +59,8 @@ struct S2Params {
 
 __global__ void __launch_bounds__(s2::THREADS, 1)
 conv3d_k3s2_roll_kernel(S2Params prm) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   using namespace s2;
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_bias = reinterpret_cast<float*>(smem + OFF_BIAS);
@@ -264,7 +266,7 @@ int launch_s2_roll_conv(const void* xb, const TcWeights& w, const float* bias, v
   p.stats = stats;
   const int htiles = s2::GO / s2::TH;
   p.dsplit = 148 / htiles;
-  conv3d_k3s2_roll_kernel<<<htiles * p.dsplit, s2::THREADS, s2::SMEM_BYTES, st>>>(p);
+  DCL_CUDA_OK(launch_pdl(conv3d_k3s2_roll_kernel, dim3(htiles * p.dsplit), dim3(s2::THREADS), (size_t)(s2::SMEM_BYTES), st, p));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

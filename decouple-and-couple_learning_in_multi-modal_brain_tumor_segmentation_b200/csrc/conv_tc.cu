@@ -93,6 +93,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 template <class Cfg>
 __global__ void __launch_bounds__(ROLL_THREADS, 1)
 conv3d_k3_roll_kernel(RollParams prm) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, W = Cfg::W, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
   constexpr int ROWS = Cfg::ROWS, KC = Cfg::KC;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -527,7 +529,7 @@ static int launch_roll(RollParams& prm, cudaStream_t st) {
   if (dsplit < 1) dsplit = 1;
   if (dsplit > Cfg::G) dsplit = Cfg::G;
   prm.dsplit = dsplit;
-  conv3d_k3_roll_kernel<Cfg><<<htiles * dsplit, ROLL_THREADS, Cfg::SMEM_BYTES, st>>>(prm);
+  DCL_CUDA_OK(launch_pdl(conv3d_k3_roll_kernel<Cfg>, dim3(htiles * dsplit), dim3(ROLL_THREADS), (size_t)(Cfg::SMEM_BYTES), st, prm));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

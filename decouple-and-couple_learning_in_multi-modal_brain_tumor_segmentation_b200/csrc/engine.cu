@@ -24,6 +24,10 @@ cudaError_t trace_set_conv_gemm(long long* p, int cta);
 thread_local std::string g_error;
 thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_error = msg; }
+bool pdl_enabled() {
+  static const bool on = getenv("DCL_PDL") != nullptr;
+  return on;
+}
 
 #define DCL_TRY(expr)            \
   do {                           \
@@ -204,9 +208,11 @@ struct dcl_handle {
   double* stat_accum;                            // (2*512)
   void* blk = nullptr;                           // bf16 channel-blocked conv input (DCL_BF16 only)
   void *tok_a = nullptr, *tok_b = nullptr;       // bf16 blocked token matrices feeding the linear GEMMs
-  TokScratch ts[3];                              // [0] aliases the buffers above
+  TokScratch ts[6];                              // [0] aliases the buffers above; region r works in ts[2r], ts[2r+1]
   cudaStream_t aux_stream[3] = {nullptr, nullptr, nullptr};   // [2] = capture stream of the forward graph
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaStream_t tok_stream[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // coupler lanes 1..5 (lane 0 = caller's stream)
+  cudaEvent_t ev_tok[3][3] = {}, ev_tok_join[5] = {};                           // per region: A1 done, A2 done, A4 done
   // ---- bf16 pipeline (DCL_BF16): B-format activations = bf16 [C/8][spatial][8] ----
   void *b_t0[4], *b_a[4], *b_t1[4], *b_x[4];     // encoder levels (16@128, 32@64, 64@32, 128@16)
   void *b_x4, *b_edown, *b_eraw, *b_sraw, *b_fused, *b_enc, *b_nrm;
@@ -345,7 +351,7 @@ static int allocate_workspace(dcl_handle* h) {
   DCL_TRY(dev_alloc(h, (void**)&h->counts_dev, 16 * sizeof(unsigned long long)));
   h->ts[0] = TokScratch{h->score, {h->seq[0], h->seq[1], h->seq[2], h->seq[3]}, h->ln_a, h->ln_b, h->qbuf, h->kvbuf, h->obuf,
                         h->eqs, h->sqe, h->cross, h->ffn_ln, h->ffn_h, h->tok_a, h->tok_b};
-  for (int i = 1; i < 3; ++i) {
+  for (int i = 1; i < 6; ++i) {
     TokScratch& t = h->ts[i];
     DCL_TRY(falloc(h, &t.score, 2048));
     for (int k = 0; k < 4; ++k) DCL_TRY(falloc(h, &t.seq[k], SEQ * 512));
@@ -986,34 +992,46 @@ struct Fwd16 {
     // ---- Edge-supported Intra-region Couplers: the three regions are independent until the cross-region
     // coupler, and each is a chain of small latency-bound kernels, so they run on three concurrent streams
     // (region 0 on the caller's stream, regions 1-2 on the handle's auxiliary streams, own scratch each)
-    cudaEvent_t ev_tok = h->profiling ? h->prof_begin(st) : nullptr;
+    // Within a region the edge half (selects 0,1 -> A1) and the semantic half (selects 2,3 -> A2) are independent,
+    // and so are the two cross attentions A3 / A4: every region runs on TWO lanes with private scratch, six lanes
+    // in all (lane 0 = the caller's stream).  In the captured graph these are plain parallel branches.
+    cudaEvent_t ev_tokp = h->profiling ? h->prof_begin(st) : nullptr;
     DCL_CUDA_OK(cudaEventRecord(h->ev_fork, st));
     for (int r = 0; r < 3; ++r) {
-      cudaStream_t sr = r == 0 ? st : h->aux_stream[r - 1];
-      if (r > 0) DCL_CUDA_OK(cudaStreamWaitEvent(sr, h->ev_fork, 0));
-      Fwd fr{h, sr, &h->ts[r]};
-      TokScratch* ts = &h->ts[r];
+      cudaStream_t sa = r == 0 ? st : h->tok_stream[2 * r - 1];
+      cudaStream_t sb = h->tok_stream[2 * r];
+      if (r > 0) DCL_CUDA_OK(cudaStreamWaitEvent(sa, h->ev_fork, 0));
+      DCL_CUDA_OK(cudaStreamWaitEvent(sb, h->ev_fork, 0));
+      TokScratch *ta = &h->ts[2 * r], *tb = &h->ts[2 * r + 1];
+      Fwd fa{h, sa, ta}, fb{h, sb, tb};
       const Transformer& t = h->tr[r];
       float *E = h->E[r], *S = h->S[r], *out = h->coupler_out[r];
-      DCL_TRY(fr.select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, ts->seq[0]));
-      DCL_TRY(fr.select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, ts->seq[1]));
-      DCL_TRY(fr.select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, ts->seq[2]));
-      DCL_TRY(fr.select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, ts->seq[3]));
-      DCL_TRY(fr.attn_block(t, ts->seq[0], ts->seq[1], SEQ, SEQ, ts->eqs));
-      DCL_TRY(fr.attn_block(t, ts->seq[2], ts->seq[3], SEQ, SEQ, ts->sqe));
-      DCL_TRY(fr.attn_block(t, ts->eqs, ts->sqe, SEQ, SEQ, ts->cross));
-      DCL_TRY(fr.attn_block(t, ts->sqe, ts->eqs, SEQ, SEQ, ts->cross + SEQ * 512));
-      DCL_TRY(fr.ffn_block(t, ts->cross, 2 * SEQ, out));
-      DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, sr));
-      DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, sr));
+      DCL_TRY(fa.select_build(h->e_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 0, ta->seq[0]));   // edge
+      DCL_TRY(fb.select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, tb->seq[2]));   // semantic
+      DCL_TRY(fa.select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, ta->seq[1]));   // semantic supplement
+      DCL_TRY(fb.select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, tb->seq[3]));   // edge supplement
+      DCL_TRY(fa.attn_block(t, ta->seq[0], ta->seq[1], SEQ, SEQ, ta->eqs));
+      DCL_TRY(fb.attn_block(t, tb->seq[2], tb->seq[3], SEQ, SEQ, tb->sqe));
+      DCL_CUDA_OK(cudaEventRecord(h->ev_tok[r][0], sa));
+      DCL_CUDA_OK(cudaEventRecord(h->ev_tok[r][1], sb));
+      DCL_CUDA_OK(cudaStreamWaitEvent(sa, h->ev_tok[r][1], 0));
+      DCL_CUDA_OK(cudaStreamWaitEvent(sb, h->ev_tok[r][0], 0));
+      DCL_TRY(fa.attn_block(t, ta->eqs, tb->sqe, SEQ, SEQ, ta->cross));
+      DCL_TRY(fb.attn_block(t, tb->sqe, ta->eqs, SEQ, SEQ, ta->cross + SEQ * 512));
+      DCL_CUDA_OK(cudaEventRecord(h->ev_tok[r][2], sb));
+      DCL_CUDA_OK(cudaStreamWaitEvent(sa, h->ev_tok[r][2], 0));
+      DCL_TRY(fa.ffn_block(t, ta->cross, 2 * SEQ, out));
+      DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, sa));
+      DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, sa));
       if (want_aux) {
-        DCL_TRY(launch_scale_untokenise(E, out, h->sup_edge[r], 32, 32, 4, 2, 2, sr));
-        DCL_TRY(launch_scale_untokenise(S, out + SEQ * 512, h->sup_sem[r], 128, 16, 2, 2, 1, sr));
+        DCL_TRY(launch_scale_untokenise(E, out, h->sup_edge[r], 32, 32, 4, 2, 2, sa));
+        DCL_TRY(launch_scale_untokenise(S, out + SEQ * 512, h->sup_sem[r], 128, 16, 2, 2, 1, sa));
       }
-      if (r > 0) DCL_CUDA_OK(cudaEventRecord(h->ev_join[r - 1], sr));
+      if (r > 0) {
+        DCL_CUDA_OK(cudaEventRecord(h->ev_tok_join[2 * r - 1], sa));
+        DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_tok_join[2 * r - 1], 0));
+      }
     }
-    DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join[0], 0));
-    DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_join[1], 0));
     if (want_aux) {
       for (int r = 0; r < 3; ++r) {
         std::string n = REGION_NUM[r];
@@ -1033,7 +1051,7 @@ struct Fwd16 {
     DCL_TRY(f.ffn_block(h->tr[3], h->ts[0].eqs, SEQ, h->coupler_out[3]));
     DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
     DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st));
-    if (ev_tok) h->prof_end(ev_tok, 8, 0.0, st);
+    if (ev_tokp) h->prof_end(ev_tokp, 8, 0.0, st);
     DCL_TRY(conv(h->b_fused, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, nullptr, nullptr, h->b_enc, nullptr));
 
     // ---- decoder ----
@@ -1216,6 +1234,16 @@ DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
     }
   }
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) { dcl_destroy(h); set_error("dcl_create: event creation failed"); return DCL_ERR_CUDA; }
+  for (int i = 0; i < 5; ++i)
+    if (cudaStreamCreateWithFlags(&h->tok_stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_tok_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      dcl_destroy(h); set_error("dcl_create: stream / event creation failed"); return DCL_ERR_CUDA;
+    }
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k)
+      if (cudaEventCreateWithFlags(&h->ev_tok[r][k], cudaEventDisableTiming) != cudaSuccess) {
+        dcl_destroy(h); set_error("dcl_create: event creation failed"); return DCL_ERR_CUDA;
+      }
   register_stages(h);
   *out = h;
   return DCL_OK;
@@ -1235,6 +1263,13 @@ DCL_API int dcl_destroy(dcl_handle* h) {
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
   }
   if (h->aux_stream[2]) cudaStreamDestroy(h->aux_stream[2]);
+  for (int i = 0; i < 5; ++i) {
+    if (h->tok_stream[i]) cudaStreamDestroy(h->tok_stream[i]);
+    if (h->ev_tok_join[i]) cudaEventDestroy(h->ev_tok_join[i]);
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int k = 0; k < 3; ++k)
+      if (h->ev_tok[r][k]) cudaEventDestroy(h->ev_tok[r][k]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);

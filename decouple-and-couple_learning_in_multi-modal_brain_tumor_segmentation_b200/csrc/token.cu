@@ -21,6 +21,8 @@ __device__ __forceinline__ float warp_max_t(float v) {
 __global__ void __launch_bounds__(256)
 score_kernel(const float* __restrict__ token, const float* __restrict__ feats, int n_tokens,
              float* __restrict__ score) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= n_tokens) return;
@@ -45,6 +47,8 @@ constexpr int TOPK_EPW = 4;                         // elements per warp
 constexpr int TOPK_EPB = 8 * TOPK_EPW;              // elements per block
 __global__ void __launch_bounds__(256)
 topk_kernel(const float* __restrict__ score, int n, int* __restrict__ idx_out) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float key[64];                                    // key[t] = score[lane + 32 t]
 #pragma unroll
@@ -75,8 +79,8 @@ topk_kernel(const float* __restrict__ score, int n, int* __restrict__ idx_out) {
 int launch_select_topk(const float* token, const float* feats, int n_tokens, float* score_scratch, int* idx_out,
                        cudaStream_t st) {
   if (n_tokens > 2048 || n_tokens < TOP_NUM) { set_error("select_topk: 128 <= n_tokens <= 2048 required"); return -1; }
-  score_kernel<<<(n_tokens + 7) / 8, 256, 0, st>>>(token, feats, n_tokens, score_scratch);
-  topk_kernel<<<(n_tokens + TOPK_EPB - 1) / TOPK_EPB, 256, 0, st>>>(score_scratch, n_tokens, idx_out);
+  DCL_CUDA_OK(launch_pdl(score_kernel, dim3((n_tokens + 7) / 8), dim3(256), (size_t)(0), st, token, feats, n_tokens, score_scratch));
+  DCL_CUDA_OK(launch_pdl(topk_kernel, dim3((n_tokens + TOPK_EPB - 1) / TOPK_EPB), dim3(256), (size_t)(0), st, score_scratch, n_tokens, idx_out));
   g_launches += 2;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -87,6 +91,8 @@ int launch_select_topk(const float* token, const float* feats, int n_tokens, flo
 __global__ void __launch_bounds__(128)
 build_sequence_kernel(const float* __restrict__ class_token, const float* __restrict__ feats,
                       const int* __restrict__ idx, const float* __restrict__ pe_row, float* __restrict__ seq) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const int r = blockIdx.x;
   float4 v;
   if (r == 0) {
@@ -101,7 +107,7 @@ build_sequence_kernel(const float* __restrict__ class_token, const float* __rest
 
 int launch_build_sequence(const float* class_token, const float* feats, const int* idx, const float* pe_row,
                           float* seq, cudaStream_t st) {
-  build_sequence_kernel<<<SEQ, 128, 0, st>>>(class_token, feats, idx, pe_row, seq);
+  DCL_CUDA_OK(launch_pdl(build_sequence_kernel, dim3(SEQ), dim3(128), (size_t)(0), st, class_token, feats, idx, pe_row, seq));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -217,6 +223,8 @@ constexpr int ATT_KG = ATT_MAXK / 32;     // key groups per lane
 
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int mq, int mk) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* ks = sm;                              // [mk][68]
   float* vs = ks + mk * ATT_KP;                // [mk][64]
@@ -312,7 +320,7 @@ int launch_attention(const float* q, const float* kv, float* out, int mq, int mk
     DCL_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  attention_kernel<<<dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8), 128, smem, st>>>(q, kv, out, mq, mk);
+  DCL_CUDA_OK(launch_pdl(attention_kernel, dim3(dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8)), dim3(128), (size_t)(smem), st, q, kv, out, mq, mk));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -322,13 +330,15 @@ int launch_attention(const float* q, const float* kv, float* out, int mq, int mk
 __global__ void __launch_bounds__(128)
 scatter_rows_kernel(float* __restrict__ feats, const int* __restrict__ idx, const float* __restrict__ rows,
                     int row_stride) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   const int i = blockIdx.x;
   float4 v = __ldg(reinterpret_cast<const float4*>(rows + (int64_t)i * row_stride) + threadIdx.x);
   reinterpret_cast<float4*>(feats + (int64_t)idx[i] * TOKEN_DIM)[threadIdx.x] = v;
 }
 
 int launch_scatter_rows(float* feats, const int* idx, const float* rows, int row_stride, cudaStream_t st) {
-  scatter_rows_kernel<<<TOP_NUM, 128, 0, st>>>(feats, idx, rows, row_stride);
+  DCL_CUDA_OK(launch_pdl(scatter_rows_kernel, dim3(TOP_NUM), dim3(128), (size_t)(0), st, feats, idx, rows, row_stride));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -337,6 +347,8 @@ int launch_scatter_rows(float* feats, const int* idx, const float* rows, int row
 __global__ void __launch_bounds__(256)
 add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
             float* __restrict__ y, int64_t n4) {
+  pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
+  pdl_trigger();
   int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n4) return;
   float4 u = __ldg(reinterpret_cast<const float4*>(a) + i);
@@ -348,7 +360,7 @@ add3_kernel(const float* __restrict__ a, const float* __restrict__ b, const floa
 
 int launch_add3(const float* a, const float* b, const float* c, float* y, int64_t n, cudaStream_t st) {
   if (n % 4 != 0) { set_error("add3: n must be a multiple of 4"); return -1; }
-  add3_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(a, b, c, y, n / 4);
+  DCL_CUDA_OK(launch_pdl(add3_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), (size_t)(0), st, a, b, c, y, n / 4));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
