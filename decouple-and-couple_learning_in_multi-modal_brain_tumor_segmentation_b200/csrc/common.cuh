@@ -123,6 +123,8 @@ struct PatchDesc {
   long long sc, sd, sh;     // element strides of (C, X, Y); the Z stride is 1
   float keep[16];
 };
+// debug: dst[idx] = %globaltimer (ns); DCL_STAMPS=1 places these between the stages of the forward
+int launch_stamp(unsigned long long* dst, int idx, cudaStream_t st);
 // *dst = v, passed by value (one tiny launch per patch, outside the graph)
 int launch_patch_desc(PatchDesc* dst, const PatchDesc& v, cudaStream_t st);
 // dst[0..16) = v, passed by value (keeps the per-patch dropout scale off the memcpy path)

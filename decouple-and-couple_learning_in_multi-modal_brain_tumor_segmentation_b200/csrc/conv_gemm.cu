@@ -352,6 +352,35 @@ conv_gemm_kernel(GemmConvParams p) {
     const int64_t delta1 = p.a1 ? (p.a1 - p.a) - (int64_t)p.c0_chunks * sp_in : 0;
     const uint32_t b_seg = (uint32_t)p.n_tile * 16;        // bytes of one chunk row block of B
     int it = 0;
+    if (p.taps == 1 && p.stride == 1 && p.a1 == nullptr) {
+      // pointwise conv / linear layer: the 128 rows of a chunk are 2 KB of contiguous global memory, so a stage is
+      // 2 x n_chunks bulk async copies issued by one thread (rows past m_total of a tail tile stay unwritten: GEMM
+      // rows are independent and those rows are never stored)
+      const uint32_t a_chunk = (uint32_t)(m_total - m0 < 128 ? m_total - m0 : 128) * 16u;
+      for (int kg = 0; kg < cpt; ++kg, ++it) {
+        const int s = it % G_NS;
+        mbar_wait(&bar_empty[s], ((uint32_t)(it / G_NS) & 1u) ^ 1u);
+        if (pt == 0) {
+          const int kc0 = kg * n_chunks;
+          const uint32_t st_base = smem_base + (uint32_t)(s * stage_bytes);
+          const uint32_t bar = smem_u32(&bar_full[s]);
+          asm volatile("mbarrier.expect_tx.shared::cta.b64 [%1], %0;" ::"r"((uint32_t)n_chunks * (b_seg + a_chunk)), "r"(bar) : "memory");
+          const uint4* b_src = p.w + (int64_t)kc0 * p.cout_pad + n0;
+          const uint4* a_src = p.a + (int64_t)kc0 * sp_in + m0;
+          for (int c = 0; c < n_chunks; ++c) {
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             st_base + (uint32_t)a_bytes + (uint32_t)c * b_seg),
+                         "l"(b_src + (int64_t)c * p.cout_pad), "r"(b_seg), "r"(bar)
+                         : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             st_base + (uint32_t)(c * 2048)),
+                         "l"(a_src + (int64_t)c * sp_in), "r"(a_chunk), "r"(bar)
+                         : "memory");
+          }
+        }
+        mbar_arrive(&bar_full[s]);
+      }
+    } else {
     for (int tap = 0; tap < p.taps; ++tap) {
       int kd = 0, kh = 0, kw = 0;
       if (p.taps == 27) { kd = tap / 9; kh = (tap - kd * 9) / 3; kw = tap - kd * 9 - kh * 3; }
@@ -394,6 +423,7 @@ conv_gemm_kernel(GemmConvParams p) {
       }
     }
     drain_stages<LAG - 1>(bar_full, total, G_NS);
+    }
   } else if (warp == G_EPI_WARPS) {
     // =============================== MMA issuer ==================================================
     {   // all 32 lanes run the loop; the elected lane issues

@@ -227,6 +227,8 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
       }
     }
     if (prm.stats != nullptr) {
+      // CTA-level reduction (fixed order), then one pair of atomics per channel and CTA
+      float* s_red = reinterpret_cast<float*>(smem);      // the staged planes are dead by now: [4 warps][32][2]
 #pragma unroll
       for (int c = 0; c < CO; ++c) {
         float a = st_s[c], q = st_q[c];
@@ -235,7 +237,15 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
           a += __shfl_xor_sync(0xffffffffu, a, o);
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        if (lane == 0) stat_add(prm.stats, c, a, q);
+        if (lane == 0) { s_red[(warp * CO + c) * 2] = a; s_red[(warp * CO + c) * 2 + 1] = q; }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      if (warp == 0) {
+        const int c = lane;      // CO == 32
+        float a = 0.f, q = 0.f;
+#pragma unroll
+        for (int w4 = 0; w4 < EPI_WARPS; ++w4) { a += s_red[(w4 * CO + c) * 2]; q += s_red[(w4 * CO + c) * 2 + 1]; }
+        stat_add(prm.stats, c, a, q);
       }
     }
   }

@@ -59,11 +59,18 @@ struct RollCfg {
   static constexpr uint32_t mask2(int j) { return W == 128 ? (j == 3 ? 0x80000000u : 0u) : ((j & 1) == 1 ? 0x80000000u : 0u); }
 };
 
-constexpr int EPI_WARPS = 4;
-constexpr int PROD_WARPS = 8;
-constexpr int ROLL_THREADS = (EPI_WARPS + 1 + PROD_WARPS) * 32;
-constexpr int PROD_T0 = (EPI_WARPS + 1) * 32;
+// warp roles (16 warps): 0-3 epilogue group A, 4 MMA issuer, 5-7 producers, 8-11 epilogue group B, 12-15 producers.
+// An epilogue warp may only read the TMEM lanes 32*(warp%4)..+31, hence the two groups sit at warps 0-3 and 8-11;
+// they take alternate (tile, 16-channel group) items, which halves the epilogue latency per plane (the kernel is
+// epilogue-bound as soon as residual + statistics are fused in: 81 vs 54 us for the 16-channel layer).
+constexpr int EPI_WARPS = 4;          // per group
+constexpr int EPI_GROUPS = 2;
+constexpr int MMA_WARP = 4;
+constexpr int PROD_WARPS = 7;
+constexpr int ROLL_THREADS = 16 * 32;
 constexpr int NPROD = PROD_WARPS * 32;
+__device__ __forceinline__ bool roll_is_epilogue(int warp) { return warp < 4 || (warp >= 8 && warp < 12); }
+__device__ __forceinline__ int roll_prod_index(int warp) { return warp < 8 ? warp - 5 : warp - 9; }   // 5,6,7,12..15 -> 0..6
 
 // Arguments of the rolling kernel.  All activation tensors are "B-format": bf16, channel-blocked
 // [C/8][G^3][8] (one 16-byte vector per voxel and 8-channel chunk).
@@ -149,10 +156,10 @@ conv3d_k3_roll_kernel(RollParams prm) {
   }
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); mbar_init(&bar_land[s], 1); }
-    for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_WARPS * 32); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_GROUPS * EPI_WARPS * 32); }
     fence_barrier_init();
   }
-  if (warp == EPI_WARPS) tmem_alloc(s_tmem, Cfg::TMEM_COLS);
+  if (warp == MMA_WARP) tmem_alloc(s_tmem, Cfg::TMEM_COLS);
   fence_proxy_async();   // weights / pads were written through the generic proxy
   tc_fence_before();
   __syncthreads();
@@ -160,10 +167,10 @@ conv3d_k3_roll_kernel(RollParams prm) {
   const uint32_t tmem_base = *s_tmem;
   if (tid == 0) trace_event(tbuf, 1, 0);     // setup done
 
-  if (warp >= EPI_WARPS + 1) {
+  if (warp != MMA_WARP && !roll_is_epilogue(warp)) {
     // =============================== producers ===================================================
-    const int pt = tid - PROD_T0;
-    const int pw = warp - (EPI_WARPS + 1);
+    const int pw = roll_prod_index(warp);
+    const int pt = pw * 32 + lane;
     const int act = prm.act;
     const bool identity = !has_norm && act == ACT_NONE;
     const uint32_t smem_base = smem_u32(smem);
@@ -173,30 +180,33 @@ conv3d_k3_roll_kernel(RollParams prm) {
       // InstanceNorm + activation is then applied in place, warp-per-row (conflict-free 16-byte accesses).
       constexpr int AHEAD = NSLOT - 3;
       constexpr uint32_t ROW_BYTES = (uint32_t)W * 16u;
+      // staged rows have no halo columns, so the in-range rows h0-1 .. h0+TH of one (chunk, plane) are ONE contiguous
+      // run in global memory and in the slot: a plane is KC bulk copies (plus zero fill of out-of-range rows)
+      const int r_lo = h0 == 0 ? 1 : 0;
+      const int r_hi = h0 + TH >= G ? ROWS - 2 : ROWS - 1;
+      const uint32_t run_bytes = (uint32_t)(r_hi - r_lo + 1) * ROW_BYTES;
       auto issue = [&](int j) {     // producer warp 0 only
         const int d_in = d0 - 1 + j;
         const bool d_ok = (unsigned)d_in < (unsigned)G;
         const int s = j % NSLOT;
         const uint32_t bar = smem_u32(&bar_land[s]);
-        int vh = 0;
-        for (int r = 0; r < ROWS; ++r) vh += (unsigned)(h0 - 1 + r) < (unsigned)G ? 1 : 0;
         if (lane == 0)
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(d_ok ? vh * KC : 0) * ROW_BYTES), "r"(bar)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(d_ok ? (uint32_t)KC * run_bytes : 0u), "r"(bar)
                        : "memory");
         __syncwarp();
-        for (int e = lane; e < KC * ROWS; e += 32) {
+        if (d_ok && lane < KC) {
+          const uint4* src = prm.xb + (int64_t)lane * SP + ((int64_t)d_in * G + (h0 - 1 + r_lo)) * G;
+          const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (lane * NPOS + 1 + r_lo * W) * 16);
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                       "l"(src), "r"(run_bytes), "r"(bar)
+                       : "memory");
+        }
+        // rows / planes outside the volume are zero padding
+        for (int e = 0; e < KC * ROWS; ++e) {
           const int kc = e / ROWS, r = e - kc * ROWS;
-          const int h_in = h0 - 1 + r;
-          const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (kc * NPOS + 1 + r * W) * 16);
-          if (d_ok && (unsigned)h_in < (unsigned)G) {
-            const uint4* src = prm.xb + (int64_t)kc * SP + ((int64_t)d_in * G + h_in) * G;
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                         "l"(src), "r"(ROW_BYTES), "r"(bar)
-                         : "memory");
-          } else {
-            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + 1 + r * W) * 16);
-            for (int i = 0; i < W; ++i) z[i] = make_uint4(0u, 0u, 0u, 0u);
-          }
+          if (d_ok && r >= r_lo && r <= r_hi) continue;
+          uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + 1 + r * W) * 16);
+          for (int i = lane; i < W; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
       };
       if (pw == 0)
@@ -274,7 +284,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
         mbar_arrive(&bar_full[s]);
       }
     }
-  } else if (warp == EPI_WARPS) {
+  } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ==================================================
     {   // all 32 lanes run the loop; the elected lane issues (see umma_bf16_ws)
       constexpr uint32_t idesc = umma_idesc_bf16(128, C);
@@ -374,86 +384,117 @@ conv3d_k3_roll_kernel(RollParams prm) {
     __syncwarp();
   } else {
     // =============================== epilogue ====================================================
-    float st_s[C], st_q[C];
+    // Work item = (tile, 16-channel group); the two epilogue groups take alternate items, so with C = 32 a group owns
+    // a fixed channel half (16 statistics accumulators per thread) and with C = 16 it owns every other tile.
+    constexpr int G16 = C / 16;
+    constexpr int ITEMS = Cfg::NT * G16;                // items per plane
+    static_assert(ITEMS % EPI_GROUPS == 0, "items must split evenly over the epilogue groups");
+    const int grp_id = warp >> 3;                       // 0: warps 0-3, 1: warps 8-11
+    const int ew = warp & 3;                            // TMEM lane quarter
+    const int g16 = G16 == 1 ? 0 : grp_id;              // channel group of this thread (fixed)
+    float st_s[16], st_q[16], bias_r[16], osc_r[16];
 #pragma unroll
-    for (int c = 0; c < C; ++c) { st_s[c] = 0.f; st_q[c] = 0.f; }
-    const int m = warp * 32 + lane;   // accumulator row (TMEM lane) of this thread
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int k = 0; k < 16; ++k) { st_s[k] = 0.f; st_q[k] = 0.f; bias_r[k] = s_bias[g16 * 16 + k]; osc_r[k] = s_oscale[g16 * 16 + k]; }
+    const int m = ew * 32 + lane;     // accumulator row (TMEM lane) of this thread
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(ew * 32) << 16);
+    const int wpos = m % W;
+    const uint4* res0 = prm.resb != nullptr ? prm.resb + (int64_t)(2 * g16) * SP : nullptr;
+    uint4* y0 = prm.yb + (int64_t)(2 * g16) * SP;
     for (int i = 0; i < n_out; ++i) {
       const int b = i & 1;
       const int d = d0 + i;
-      // the residual of the NEXT plane is pulled into L2 now (no registers held), so that its loads in the tile
-      // loop below cost an L2 hit instead of an HBM round trip per tile
-      if (prm.resb != nullptr) {
+      // the residual of the NEXT plane is pulled into L2 now (no registers held), so that its loads in the item
+      // loop below cost an L2 hit instead of an HBM round trip
+      if (res0 != nullptr) {
         for (int dd = (i == 0 ? d : d + 1); dd <= d + 1 && dd < d1; ++dd) {
 #pragma unroll
-          for (int t = 0; t < Cfg::NT; ++t) {
-            const int64_t off = ((int64_t)dd * G + (h0 + t * Cfg::TROWS + m / W)) * G + (m % W);
-#pragma unroll
-            for (int kc = 0; kc < C / 8; ++kc)
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(prm.resb + (int64_t)kc * SP + off));
+          for (int t = (G16 == 1 ? grp_id : 0); t < Cfg::NT; t += (G16 == 1 ? EPI_GROUPS : 1)) {
+            const int64_t off = ((int64_t)dd * G + (h0 + t * Cfg::TROWS + m / W)) * G + wpos;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res0 + off));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res0 + SP + off));
           }
         }
       }
-      mbar_wait(&bar_acc_full[b], (uint32_t)(i >> 1) & 1u);
-      tc_fence_after();
-      if (tid == 0) trace_event(tbuf, 6, i);   // epilogue: accumulator of step i complete
+      bool waited = false;
 #pragma unroll 1
-      for (int t = 0; t < Cfg::NT; ++t) {
-        uint32_t acc[C / 16][16];
-#pragma unroll
-        for (int k = 0; k < C / 16; ++k) tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * C + 16 * k), acc[k]);
+      for (int it = grp_id; it < ITEMS; it += EPI_GROUPS) {
+        const int t = it / G16;
+        const int r = t * Cfg::TROWS + m / W;
+        const int64_t off = ((int64_t)d * G + (h0 + r)) * G + wpos;
+        uint4 rv0 = make_uint4(0u, 0u, 0u, 0u), rv1 = rv0;
+        if (res0 != nullptr) {             // issued before the accumulator wait / load: the latency overlaps them
+          rv0 = __ldg(res0 + off);
+          rv1 = __ldg(res0 + SP + off);
+        }
+        if (!waited) {
+          mbar_wait(&bar_acc_full[b], (uint32_t)(i >> 1) & 1u);
+          tc_fence_after();
+          waited = true;
+          if (tid == 0) trace_event(tbuf, 6, i);   // epilogue: accumulator of plane i complete
+        }
+        uint32_t acc[16];
+        tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * C + 16 * g16), acc);
         tmem_ld_wait();
-        if (t == Cfg::NT - 1) {   // all of this thread's TMEM reads of buffer b are done
+        if (it + EPI_GROUPS >= ITEMS) {   // all of this thread's TMEM reads of buffer b are done
           tc_fence_before();
           mbar_arrive(&bar_acc_empty[b]);
         }
-        const int r = t * Cfg::TROWS + m / W;
-        const int w = m % W;
-        const int64_t off = ((int64_t)d * G + (h0 + r)) * G + w;
+        float val[16];
 #pragma unroll
-        for (int kc = 0; kc < C / 8; ++kc) {
-          float val[8];
+        for (int k = 0; k < 16; ++k) val[k] = (__uint_as_float(acc[k]) + bias_r[k]) * osc_r[k];
+        if (res0 != nullptr) {
+          const uint32_t* p0 = reinterpret_cast<const uint32_t*>(&rv0);
+          const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&rv1);
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int c = kc * 8 + k;
-            val[k] = (__uint_as_float(acc[c / 16][c % 16]) + s_bias[c]) * s_oscale[c];
+          for (int k = 0; k < 4; ++k) {
+            const float2 f0 = unpack_bf16x2(p0[k]), f1 = unpack_bf16x2(p1[k]);
+            val[2 * k] += f0.x; val[2 * k + 1] += f0.y;
+            val[8 + 2 * k] += f1.x; val[8 + 2 * k + 1] += f1.y;
           }
-          if (prm.resb != nullptr) {
-            const uint4 rv = __ldg(prm.resb + (int64_t)kc * SP + off);
-            const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = unpack_bf16x2(pr[k]);
-              val[2 * k] += f.x;
-              val[2 * k + 1] += f.y;
-            }
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            st_s[kc * 8 + k] += val[k];
-            st_q[kc * 8 + k] += val[k] * val[k];
-          }
-          uint4 o;
-          o.x = pack_bf16x2(val[0], val[1]);
-          o.y = pack_bf16x2(val[2], val[3]);
-          o.z = pack_bf16x2(val[4], val[5]);
-          o.w = pack_bf16x2(val[6], val[7]);
-          prm.yb[(int64_t)kc * SP + off] = o;
         }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          st_s[k] += val[k];
+          st_q[k] += val[k] * val[k];
+        }
+        uint4 o0, o1;
+        o0.x = pack_bf16x2(val[0], val[1]);   o0.y = pack_bf16x2(val[2], val[3]);
+        o0.z = pack_bf16x2(val[4], val[5]);   o0.w = pack_bf16x2(val[6], val[7]);
+        o1.x = pack_bf16x2(val[8], val[9]);   o1.y = pack_bf16x2(val[10], val[11]);
+        o1.z = pack_bf16x2(val[12], val[13]); o1.w = pack_bf16x2(val[14], val[15]);
+        y0[off] = o0;
+        y0[SP + off] = o1;
       }
     }
     if (tid == 0) trace_event(tbuf, 7, n_out);   // epilogue: all planes stored
     if (prm.stats != nullptr) {
+      // CTA-level reduction first (fixed order), then ONE pair of atomics per channel and CTA: 144 CTAs finishing
+      // together on 32 addresses made the per-warp atomics cost ~18 us per launch
+      float* s_red = reinterpret_cast<float*>(smem);      // the staged planes are dead by now: [8 warps][16][2]
+      const int ewarp = grp_id * EPI_WARPS + ew;
 #pragma unroll
-      for (int c = 0; c < C; ++c) {
+      for (int c = 0; c < 16; ++c) {
         float a = st_s[c], q = st_q[c];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
           a += __shfl_xor_sync(0xffffffffu, a, o);
           q += __shfl_xor_sync(0xffffffffu, q, o);
         }
-        if (lane == 0) stat_add(prm.stats, c, a, q);
+        if (lane == 0) { s_red[(ewarp * 16 + c) * 2] = a; s_red[(ewarp * 16 + c) * 2 + 1] = q; }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUPS * EPI_WARPS * 32) : "memory");
+      if (warp == 0 && lane < C) {
+        const int c = lane;
+        float a = 0.f, q = 0.f;
+        if (G16 == 1) {
+#pragma unroll
+          for (int w8 = 0; w8 < 8; ++w8) { a += s_red[(w8 * 16 + c) * 2]; q += s_red[(w8 * 16 + c) * 2 + 1]; }
+        } else {
+          const int gsel = c >> 4;
+#pragma unroll
+          for (int w4 = 0; w4 < 4; ++w4) { a += s_red[((gsel * 4 + w4) * 16 + (c & 15)) * 2]; q += s_red[((gsel * 4 + w4) * 16 + (c & 15)) * 2 + 1]; }
+        }
+        stat_add(prm.stats, c, a, q);
       }
     }
   }
@@ -461,7 +502,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   // ---- teardown ---------------------------------------------------------------------------------
   tc_fence_before();
   __syncthreads();
-  if (warp == EPI_WARPS) {
+  if (warp == MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }

@@ -201,6 +201,7 @@ struct dcl_handle {
   float* probs;                                  // (4,128^3)
   float* keep_dev;                               // (16)  (bf16 mode: aliases patch_desc->keep)
   PatchDesc* patch_desc = nullptr;               // per-patch arguments of the graph-replayed bf16 forward
+  unsigned long long* stamps = nullptr;          // debug (DCL_STAMPS=1): %globaltimer between the stages of the forward
   cudaGraphExec_t fwd_graph = nullptr;           // the captured bf16 forward (no aux outputs)
   int64_t fwd_graph_launches = 0;
   int fwd_eager_runs = 0;
@@ -339,6 +340,7 @@ static int allocate_workspace(dcl_handle* h) {
     DCL_TRY(dev_alloc(h, (void**)&h->stat_arena, (int64_t)STAT_SLOTS * 1024 * sizeof(stat_t)));
   }
   if (h->cfg.precision == DCL_BF16) {
+    DCL_TRY(dev_alloc(h, (void**)&h->stamps, 16 * sizeof(unsigned long long)));
     DCL_TRY(dev_alloc(h, (void**)&h->patch_desc, sizeof(PatchDesc)));
     h->keep_dev = h->dry_run ? nullptr : h->patch_desc->keep;
   } else {
@@ -938,6 +940,9 @@ struct Fwd16 {
     const bool dense_feats = want_aux || h->cfg.keep_stages;
     Fwd f{h, st, &h->ts[0]};   // token-path and auxiliary-head helpers are shared with the fp32 schedule
     h->stat_used = 0;
+    static const bool stamps_on = getenv("DCL_STAMPS") != nullptr;
+    auto stamp = [&](int i) -> int { return stamps_on ? launch_stamp(h->stamps, i, st) : 0; };
+    DCL_TRY(stamp(0));
     DCL_CUDA_OK(cudaMemsetAsync(h->stat_arena, 0, (size_t)STAT_SLOTS * 1024 * sizeof(stat_t), st));
     const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
 
@@ -967,6 +972,7 @@ struct Fwd16 {
                    l < 3 ? s_in : nullptr));
     }
 
+    DCL_TRY(stamp(1));
     // ---- Anatomy-induced Region Decoupler (the 3 sibling convs of each branch merged) ----
     DCL_TRY(conv(h->b_x[1], 32, nullptr, 0, 64, h->conv.at("conv_64_to_32"), 2, nullptr, nullptr, nullptr, h->b_edown,
                  nullptr));
@@ -996,6 +1002,7 @@ struct Fwd16 {
     // and so are the two cross attentions A3 / A4: every region runs on TWO lanes with private scratch, six lanes
     // in all (lane 0 = the caller's stream).  In the captured graph these are plain parallel branches.
     cudaEvent_t ev_tokp = h->profiling ? h->prof_begin(st) : nullptr;
+    DCL_TRY(stamp(2));
     DCL_CUDA_OK(cudaEventRecord(h->ev_fork, st));
     for (int r = 0; r < 3; ++r) {
       cudaStream_t sa = r == 0 ? st : h->tok_stream[2 * r - 1];
@@ -1043,6 +1050,7 @@ struct Fwd16 {
     }
 
     // ---- Mutual Cross-region Coupler ----
+    DCL_TRY(stamp(3));
     DCL_TRY(launch_add3(h->coupler_out[0] + SEQ * 512, h->coupler_out[1] + SEQ * 512, h->coupler_out[2] + SEQ * 512,
                         h->f_tok, 512, st));
     DCL_TRY(launch_add3(h->S[0], h->S[1], h->S[2], h->f_fea, 1024 * 512, st));
@@ -1052,6 +1060,7 @@ struct Fwd16 {
     DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
     DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st));
     if (ev_tokp) h->prof_end(ev_tokp, 8, 0.0, st);
+    DCL_TRY(stamp(4));
     DCL_TRY(conv(h->b_fused, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, nullptr, nullptr, h->b_enc, nullptr));
 
     // ---- decoder ----
@@ -1063,6 +1072,7 @@ struct Fwd16 {
                              {"decoder.DeBlock2", "decoder.DeBlock2_1"}};
     const void* cur = h->b_d8[4];
     for (int l = 0; l < 3; ++l) {
+      DCL_TRY(stamp(5 + l));
       const int cin = 128 >> l, g_in = 16 << l, c = cin / 2, g = g_in * 2;
       void** b = h->b_dl[l];
       {
@@ -1073,8 +1083,12 @@ struct Fwd16 {
       DCL_TRY(post_block(b[3], c, g, dbn[l][1], b[1], b[2], b[4]));
       cur = b[4];
     }
-    dcl_handle::ProfScope ps(h, st, 9);
-    DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
+    DCL_TRY(stamp(8));
+    {
+      dcl_handle::ProfScope ps(h, st, 9);
+      DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
+    }
+    DCL_TRY(stamp(9));
     return 0;
   }
 };
@@ -1496,6 +1510,13 @@ DCL_API int dcl_profile_read(dcl_handle* h, int32_t cls, double* ms_total, int64
 
 int64_t dcl_launch_count(const dcl_handle* h) { return h ? h->launches : 0; }
 
+// debug: the 16 %globaltimer stamps of the last bf16 forward (needs DCL_STAMPS=1 in the environment)
+DCL_API int dcl_debug_stamps(dcl_handle* h, uint64_t* out_host) {
+  if (!h || !out_host || !h->stamps) { set_error("dcl_debug_stamps: no stamps (bf16 handle needed)"); return DCL_ERR_ARG; }
+  DCL_CUDA_OK(cudaMemcpy(out_host, h->stamps, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return DCL_OK;
+}
+
 // debug: in-kernel timeline of CTA (0,0) of the tcgen05 kernels (tools/trace_kernel.py)
 DCL_API int dcl_trace_enable(int32_t on) {
   const size_t bytes = (1 + 2 * TRACE_CAP_HOST) * sizeof(long long);
@@ -1545,14 +1566,15 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
   for (int it = 0; it < reps + 3 && rc == 0; ++it) {
     if (it == 3) cudaEventRecord(e0, 0);
     if (roll) {
-      RollArgs a; a.xb = x; if (mode) { a.norm = bn; a.resb = r; a.stats = sout; }
+      RollArgs a; a.xb = x; if (mode & 1) a.norm = bn; if (mode & 2) a.resb = r; if (mode & 4) a.stats = sout;
       a.bias = bias; a.yb = y;
       rc = launch_roll_conv(a, tw, cout, g, 0);
     } else {
       GemmArgs ga; ga.a0 = x; ga.c0 = cin_pad; ga.D = g; ga.H = g; ga.W = g; ga.stride = stride; ga.taps = 27;
       ga.bias = bias; ga.out_mode = 2; ga.y = y;
-      if (mode) { ga.residual = r; ga.stats = sout; }
-      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && g <= 32) rc = launch_slab_conv(ga, mode ? &bn : nullptr, tw, 0);
+      if (mode & 2) ga.residual = r;
+      if (mode & 4) ga.stats = sout;
+      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && g <= 32) rc = launch_slab_conv(ga, (mode & 1) ? &bn : nullptr, tw, 0);
       else if (stride == 2 && s2_roll_supported(cin, cout, g)) rc = launch_s2_roll_conv(x, tw, bias, y, mode ? sout : nullptr, 0);
       else rc = launch_gemm_conv(ga, tw, 0);
     }

@@ -177,6 +177,17 @@ int launch_scale_untokenise(const float* tokens, const float* class_token, float
 
 __global__ void fill16_kernel(float* __restrict__ dst, Floats16 v) { dst[threadIdx.x] = v.v[threadIdx.x]; }
 
+__global__ void stamp_kernel(unsigned long long* __restrict__ dst, int idx) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  dst[idx] = t;
+}
+int launch_stamp(unsigned long long* dst, int idx, cudaStream_t st) {
+  stamp_kernel<<<1, 1, 0, st>>>(dst, idx);
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 __global__ void patch_desc_kernel(PatchDesc* __restrict__ dst, PatchDesc v) {
   if (threadIdx.x == 0) { dst->x = v.x; dst->sc = v.sc; dst->sd = v.sd; dst->sh = v.sh; }
   if (threadIdx.x < 16) dst->keep[threadIdx.x] = v.keep[threadIdx.x];

@@ -177,6 +177,11 @@ DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spat
  * forward picks for a cubic g^3 3x3x3 convolution (mode 1 = fused input norm + residual + statistics) */
 DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stride, int32_t mode, int32_t reps);
 
+/* debug: 16 %globaltimer stamps (ns) written between the stages of the last bf16 forward when DCL_STAMPS=1 is set:
+ * 0 start, 1 encoder done, 2 decoupler + tokenise done, 3 region couplers done, 4 cross-region coupler done,
+ * 5/6/7 decoder level starts, 8 decoder done, 9 end */
+DCL_API int dcl_debug_stamps(dcl_handle* h, uint64_t* out_host);
+
 /* ---- debug: in-kernel timeline of CTA (0,0) of the tcgen05 kernels (tools/trace_kernel.py) ---- */
 DCL_API int dcl_trace_enable(int32_t on);
 /* Copies up to `cap` (tag<<32|step, SM clock) pairs recorded since the last read; returns the count. */

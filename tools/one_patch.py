@@ -33,6 +33,17 @@ def main():
     dt = (time.perf_counter() - t0) / n
     print(f"precision={prec.name} forwards={n} ms_per_patch={dt * 1e3:.3f} launches_per_patch={(eng.launch_count - l0) // n} "
           f"checksum={float(p.double().sum()):.6f}")
+    if os.environ.get("DCL_STAMPS"):
+        import numpy as np
+        import ctypes as C
+        from dcl_b200 import _native as N
+        st = np.zeros(16, dtype=np.uint64)
+        N.check(N.load_library().dcl_debug_stamps(eng._h, st.ctypes.data_as(C.c_void_p)))
+        names = ["encoder", "decoupler+tokenise", "region couplers", "cross-region coupler + sum_fusion...", "decoder 16^3",
+                 "decoder 32^3", "decoder 64^3", "decoder 128^3", "endconv"]
+        for i, nm in enumerate(names):
+            print(f"  stage {nm:38s} {(int(st[i + 1]) - int(st[i])) / 1e3:8.1f} us")
+        print(f"  total {(int(st[9]) - int(st[0])) / 1e3:8.1f} us")
     if len(sys.argv) > 3 and sys.argv[3] == "prof":
         names = {0: "all k3 convs", 2: "roll16@128", 3: "roll32@64", 4: "slab", 5: "gemm conv", 6: "deup", 7: "norm_act_b",
                  8: "token path", 9: "endconv", 10: "tokenise", 11: "1x1 conv"}
