@@ -776,6 +776,13 @@ conv_slab_kernel(SlabParams sp) {
 
 // n_tile: a multiple of 16 that divides cout_pad, <= 256, chosen so the grid has enough CTAs
 static int pick_n_tile(int cout_pad, int64_t m_tiles) {
+  if (m_tiles <= 4) {
+    // the couplers' linear layers (129 / 258 rows): six of them run concurrently on different lanes, so a launch
+    // should be a handful of light CTAs (16-wide tiles gave 64-128 CTAs of 147 KB shared memory each, one per SM,
+    // queueing behind each other: ~18 us per linear)
+    for (int n = 64; n >= 16; n -= 16)
+      if (cout_pad % n == 0) return n;
+  }
   int best = 16;
   for (int n = 16; n <= 256 && n <= cout_pad; n += 16) {
     if (cout_pad % n != 0) continue;
@@ -950,6 +957,7 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
   const int total_stages = p.taps * (p.cin_pad / (16 * p.kstage));
   int ns = stage_bytes <= 12 * 1024 ? 8 : stage_bytes <= 16 * 1024 ? 6 : stage_bytes <= 26 * 1024 ? 4 : 3;
   if (total_stages <= 8 && 8 * stage_bytes <= 150 * 1024) ns = 8;
+  if (m_tiles <= 4) ns = 4;      // small concurrent GEMMs: keep the footprint at two CTAs per SM
   const int smem_bytes = ns * stage_bytes + (2 * ns + 1) * 8 + 16 + 10 * p.n_tile * 4;
   if (smem_bytes > 160 * 1024) { set_error("conv_gemm: stage does not fit shared memory"); return -1; }
   static bool configured = false;
@@ -974,11 +982,17 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
 // Linear layers of the couplers (nn.Linear in SelfAttention.py:62-66, ResidualNorm.py:38-44) as the same
 // GEMM: rows = tokens.  prep_rows fuses the preceding nn.LayerNorm(512) (ResidualNorm.py:14-32).
 // ---------------------------------------------------------------------------------------------
+struct PrepRowsSrc { const float* x; const float* gamma; const float* beta; int rows; uint4* out; };
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 int rows, uint4* __restrict__ out) {
+prep_rows_kernel(PrepRowsSrc s0, PrepRowsSrc s1) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
+  const PrepRowsSrc& sr = blockIdx.y == 0 ? s0 : s1;
+  const float* __restrict__ x = sr.x;
+  const float* __restrict__ gamma = sr.gamma;
+  const float* __restrict__ beta = sr.beta;
+  const int rows = sr.rows;
+  uint4* __restrict__ out = sr.out;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -1017,14 +1031,26 @@ prep_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, c
 }
 
 int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st) {
-  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, x, gamma, beta, rows, reinterpret_cast<uint4*>(out)));
+  PrepRowsSrc s0{x, gamma, beta, rows, reinterpret_cast<uint4*>(out)};
+  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, s0, s0));
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// two independent (LayerNorm +) conversions in one launch (the two inputs of a DualSelfAttention block)
+int launch_prep_rows2(const float* x0, const float* g0, const float* b0, int rows0, void* out0, const float* x1, const float* g1,
+                      const float* b1, int rows1, void* out1, cudaStream_t st) {
+  PrepRowsSrc s0{x0, g0, b0, rows0, reinterpret_cast<uint4*>(out0)}, s1{x1, g1, b1, rows1, reinterpret_cast<uint4*>(out1)};
+  const int rows = rows0 > rows1 ? rows0 : rows1;
+  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8, 2), dim3(256), (size_t)(0), st, s0, s1));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
-                     int m, int n, int k, bool gelu, cudaStream_t st) {
+                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked) {
   if (n % 16 != 0 || k % 16 != 0) { set_error("linear_tc: n and k must be multiples of 16"); return -1; }
   TcWeights w;
   w.dev = const_cast<void*>(w_packed); w.cin = k; w.cout = n;
@@ -1033,6 +1059,10 @@ int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* b
   g.D = 1; g.H = 1; g.W = m; g.stride = 1; g.taps = 1;
   g.bias = bias; g.residual = residual; g.y = y;
   g.out_mode = 1; g.gelu = gelu ? 1 : 0;
+  if (y_blocked != nullptr) {      // bf16 [n/8][m][8]: feeds the next GEMM directly (no residual in this mode)
+    if (residual != nullptr) { set_error("linear_tc: blocked output takes no residual"); return -1; }
+    g.y = y_blocked; g.out_mode = 2;
+  }
   return launch_gemm_conv(g, w, st);
 }
 

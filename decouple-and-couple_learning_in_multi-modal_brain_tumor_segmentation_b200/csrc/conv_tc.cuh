@@ -91,8 +91,11 @@ int launch_endconv_softmax_b(const void* x, const float* w, const float* b, floa
 
 // fp32 [rows][512] (optionally LayerNorm'ed) -> bf16 blocked [64][rows][8]
 int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st);
+int launch_prep_rows2(const float* x0, const float* g0, const float* b0, int rows0, void* out0, const float* x1, const float* g1,
+                      const float* b1, int rows1, void* out1, cudaStream_t st);
 // y[m][n] = a[m][:] . w[n][:] + bias (+GELU) (+residual), a blocked bf16, w packed by tc_pack_weights(taps = 1)
+// y_blocked != nullptr: the result goes out as bf16 [n/8][m][8] (the next GEMM's A operand) instead of fp32 `y`
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
-                     int m, int n, int k, bool gelu, cudaStream_t st);
+                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked = nullptr);
 
 }  // namespace dcl

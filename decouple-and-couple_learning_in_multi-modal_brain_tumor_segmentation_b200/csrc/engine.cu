@@ -634,12 +634,10 @@ struct Fwd {
   // Residual(PreNormDrop(DualSelfAttention)) (ResidualNorm.py:4-32, SelfAttention.py:74-102)
   int attn_block(const Transformer& t, const float* x, const float* x2, int mq, int mk, float* out) {
     if (h->cfg.precision == DCL_BF16) {   // LayerNorm fused into the bf16 operand prep, linears on tcgen05
-      DCL_TRY(launch_prep_rows(x, t.n1w, t.n1b, mq, ts->tok_a, st));
-      DCL_TRY(launch_prep_rows(x2, t.n2w, t.n2b, mk, ts->tok_b, st));
+      DCL_TRY(launch_prep_rows2(x, t.n1w, t.n1b, mq, ts->tok_a, x2, t.n2w, t.n2b, mk, ts->tok_b, st));
       DCL_TRY(launch_linear_tc(ts->tok_a, t.pq, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st));
       DCL_TRY(launch_linear_tc(ts->tok_b, t.pkv, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st));
-      DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, ts->obuf, mq, mk, st));
-      DCL_TRY(launch_prep_rows(ts->obuf, nullptr, nullptr, mq, ts->tok_a, st));
+      DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, nullptr, mq, mk, st, ts->tok_a));     // bf16 blocked, straight into the GEMM
       DCL_TRY(launch_linear_tc(ts->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st));
       return 0;
     }
@@ -656,8 +654,7 @@ struct Fwd {
   int ffn_block(const Transformer& t, const float* x, int m, float* out) {
     if (h->cfg.precision == DCL_BF16) {
       DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, ts->tok_a, st));
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, ts->ffn_h, m, 512, 512, true, st));
-      DCL_TRY(launch_prep_rows(ts->ffn_h, nullptr, nullptr, m, ts->tok_b, st));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, nullptr, m, 512, 512, true, st, ts->tok_b));   // GELU, bf16 blocked out
       DCL_TRY(launch_linear_tc(ts->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st));
       return 0;
     }
@@ -1017,17 +1014,21 @@ struct Fwd16 {
       DCL_TRY(fb.select_build(h->s_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 2, tb->seq[2]));   // semantic
       DCL_TRY(fa.select_build(h->e_tok[r], h->s_tok[r], S, 1024, h->pe[r], 4 * r + 1, ta->seq[1]));   // semantic supplement
       DCL_TRY(fb.select_build(h->s_tok[r], h->e_tok[r], E, 2048, h->pe[r], 4 * r + 3, tb->seq[3]));   // edge supplement
+      if (r == 0 && stamps_on) DCL_TRY(launch_stamp(h->stamps, 10, sa));
       DCL_TRY(fa.attn_block(t, ta->seq[0], ta->seq[1], SEQ, SEQ, ta->eqs));
+      if (r == 0 && stamps_on) DCL_TRY(launch_stamp(h->stamps, 11, sa));
       DCL_TRY(fb.attn_block(t, tb->seq[2], tb->seq[3], SEQ, SEQ, tb->sqe));
       DCL_CUDA_OK(cudaEventRecord(h->ev_tok[r][0], sa));
       DCL_CUDA_OK(cudaEventRecord(h->ev_tok[r][1], sb));
       DCL_CUDA_OK(cudaStreamWaitEvent(sa, h->ev_tok[r][1], 0));
       DCL_CUDA_OK(cudaStreamWaitEvent(sb, h->ev_tok[r][0], 0));
       DCL_TRY(fa.attn_block(t, ta->eqs, tb->sqe, SEQ, SEQ, ta->cross));
+      if (r == 0 && stamps_on) DCL_TRY(launch_stamp(h->stamps, 12, sa));
       DCL_TRY(fb.attn_block(t, tb->sqe, ta->eqs, SEQ, SEQ, ta->cross + SEQ * 512));
       DCL_CUDA_OK(cudaEventRecord(h->ev_tok[r][2], sb));
       DCL_CUDA_OK(cudaStreamWaitEvent(sa, h->ev_tok[r][2], 0));
       DCL_TRY(fa.ffn_block(t, ta->cross, 2 * SEQ, out));
+      if (r == 0 && stamps_on) DCL_TRY(launch_stamp(h->stamps, 13, sa));
       DCL_TRY(launch_scatter_rows(E, h->topk + (4 * r + 0) * TOP_NUM, out + 512, 512, sa));
       DCL_TRY(launch_scatter_rows(S, h->topk + (4 * r + 2) * TOP_NUM, out + (SEQ + 1) * 512, 512, sa));
       if (want_aux) {

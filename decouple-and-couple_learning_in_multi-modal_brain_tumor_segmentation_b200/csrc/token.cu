@@ -1,6 +1,7 @@
 // Token path of the region couplers: score + top-k selection, sequence assembly, LayerNorm, linear
 // layers, 8-head attention over 129-token sequences, row scatter.  All fp32 (the discrete
 // top-k makes low precision fragile here).
+#include <cuda_bf16.h>
 #include <float.h>
 #include "common.cuh"
 
@@ -222,7 +223,8 @@ constexpr int ATT_KP = ATT_HD + 4;
 constexpr int ATT_KG = ATT_MAXK / 32;     // key groups per lane
 
 __global__ void __launch_bounds__(128)
-attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int mq, int mk) {
+attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
+                 unsigned short* __restrict__ out_blocked, int mq, int mk) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
@@ -306,13 +308,21 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
   for (int r = 0; r < 4; ++r) {
     const int row = row0 + warp * 4 + r;
     if (row < mq) {
-      out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o[r][0] * inv[r];
-      out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32] = o[r][1] * inv[r];
+      if (out_blocked != nullptr) {
+        // bf16, channel-blocked [64 chunks][mq rows][8]: exactly the A operand of the out-projection GEMM, so the
+        // separate fp32 -> blocked conversion pass is skipped
+        const int c0 = head * ATT_HD + lane, c1 = c0 + 32;
+        out_blocked[((int64_t)(c0 >> 3) * mq + row) * 8 + (c0 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(o[r][0] * inv[r]));
+        out_blocked[((int64_t)(c1 >> 3) * mq + row) * 8 + (c1 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(o[r][1] * inv[r]));
+      } else {
+        out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o[r][0] * inv[r];
+        out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32] = o[r][1] * inv[r];
+      }
     }
   }
 }
 
-int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st) {
+int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st, void* out_blocked) {
   if (mk > ATT_MAXK) { set_error("attention: at most 160 keys"); return -1; }
   size_t smem = (size_t)(mk * ATT_KP + mk * ATT_HD + ATT_QCHUNK * ATT_HD + ATT_QCHUNK * ATT_MAXK) * sizeof(float);
   static bool configured = false;
@@ -320,7 +330,7 @@ int launch_attention(const float* q, const float* kv, float* out, int mq, int mk
     DCL_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  DCL_CUDA_OK(launch_pdl(attention_kernel, dim3(dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8)), dim3(128), (size_t)(smem), st, q, kv, out, mq, mk));
+  DCL_CUDA_OK(launch_pdl(attention_kernel, dim3(dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8)), dim3(128), (size_t)(smem), st, q, kv, out, reinterpret_cast<unsigned short*>(out_blocked), mq, mk));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

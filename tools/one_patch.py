@@ -44,6 +44,9 @@ def main():
         for i, nm in enumerate(names):
             print(f"  stage {nm:38s} {(int(st[i + 1]) - int(st[i])) / 1e3:8.1f} us")
         print(f"  total {(int(st[9]) - int(st[0])) / 1e3:8.1f} us")
+        if st[10]:
+            for a, b, nm in ((2, 10, "region 0 lane A: 2 selects"), (10, 11, "A1 block"), (11, 12, "wait A2 + A3 block"), (12, 13, "wait A4 + FFN")):
+                print(f"  coupler {nm:30s} {(int(st[b]) - int(st[a])) / 1e3:8.1f} us")
     if len(sys.argv) > 3 and sys.argv[3] == "prof":
         names = {0: "all k3 convs", 2: "roll16@128", 3: "roll32@64", 4: "slab", 5: "gemm conv", 6: "deup", 7: "norm_act_b",
                  8: "token path", 9: "endconv", 10: "tokenise", 11: "1x1 conv"}
