@@ -235,6 +235,11 @@ struct dcl_handle {
   float* stage_probs = nullptr; int64_t stage_probs_cap = 0;
   uint8_t* stage_labels = nullptr; uint8_t* stage_target = nullptr; int64_t stage_lab_cap = 0;
   unsigned long long* counts_dev = nullptr;
+  // host entry point: the volume is uploaded on a copy stream in three x-slabs, patches wait only for the slab they need
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_st = nullptr;
+  int up_bound[3] = {0, 0, 0};      // slab k has landed when x < up_bound[k] is on the device; 0 = no staged upload
+  bool up_active = false;
 
   std::map<std::string, std::pair<const float*, int64_t>> stages;
 
@@ -1192,8 +1197,14 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
   Fwd f{h, st, &h->ts[0]};
   Fwd16 f16{h, st};
+  int up_have = -1;     // staged upload (host entry point): highest x-slab this stream already waits for
   for (int i = first; i < first + count; ++i) {
     const PlanItem& p = plan[i];
+    if (h->up_active) {
+      int need = 0;
+      while (need < 2 && h->up_bound[need] < p.start[0] + 128) ++need;
+      for (; up_have < need; ++up_have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[up_have + 1], 0));
+    }
     const float* x = vol + (int64_t)p.start[0] * xs[1] + (int64_t)p.start[1] * xs[2] + p.start[2];
     if (h->cfg.precision == DCL_BF16)
       DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
@@ -1210,6 +1221,8 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
     }
     if (h->profiling) h->prof_end(ev, 1, bytes, st);
   }
+  if (h->up_active)      // the tail (finalize, target) needs the whole upload
+    for (; up_have < 2; ++up_have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[up_have + 1], 0));
   return 0;
 }
 
@@ -1286,6 +1299,9 @@ DCL_API int dcl_destroy(dcl_handle* h) {
     for (int k = 0; k < 3; ++k)
       if (h->ev_tok[r][k]) cudaEventDestroy(h->ev_tok[r][k]);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (int k = 0; k < 3; ++k) if (h->ev_up[k]) cudaEventDestroy(h->ev_up[k]);
+  if (h->ev_st) cudaEventDestroy(h->ev_st);
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);
   if (h->stage_vol) cudaFree(h->stage_vol);
@@ -1439,12 +1455,39 @@ DCL_API int dcl_predict_volume_host(dcl_handle* h, const float* vol_host, const 
     DCL_CUDA_OK(cudaMalloc((void**)&h->stage_target, (size_t)V));
     h->stage_lab_cap = V;
   }
-  DCL_CUDA_OK(cudaMemcpyAsync(h->stage_vol, vol_host, 4 * vin * 4, cudaMemcpyHostToDevice, st));
-  if (target_host) DCL_CUDA_OK(cudaMemcpyAsync(h->stage_target, target_host, (size_t)V, cudaMemcpyHostToDevice, st));
+  // upload in three x-slabs on the copy stream (x < 128 is all the first patches of the z-major plan need), so the
+  // first forward starts after ~half of the host-to-device copy and the rest overlaps with compute
+  if (!h->copy_stream) {
+    DCL_CUDA_OK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 3; ++k) DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_up[k], cudaEventDisableTiming));
+    DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_st, cudaEventDisableTiming));
+  }
+  DCL_CUDA_OK(cudaEventRecord(h->ev_st, st));                       // the copies follow the work already queued on st
+  DCL_CUDA_OK(cudaStreamWaitEvent(h->copy_stream, h->ev_st, 0));
+  {
+    const int X = shape[0];
+    const int64_t row = (int64_t)shape[1] * shape[2];
+    h->up_bound[0] = X < 128 ? X : 128; h->up_bound[1] = X < 192 ? X : 192; h->up_bound[2] = X;
+    int x0 = 0;
+    for (int k = 0; k < 3; ++k) {
+      const int x1 = h->up_bound[k];
+      if (x1 > x0)
+        for (int c = 0; c < 4; ++c)
+          DCL_CUDA_OK(cudaMemcpyAsync(h->stage_vol + c * vin + x0 * row, vol_host + c * vin + x0 * row, (size_t)(x1 - x0) * row * 4,
+                                      cudaMemcpyHostToDevice, h->copy_stream));
+      if (k == 2 && target_host)
+        DCL_CUDA_OK(cudaMemcpyAsync(h->stage_target, target_host, (size_t)V, cudaMemcpyHostToDevice, h->copy_stream));
+      DCL_CUDA_OK(cudaEventRecord(h->ev_up[k], h->copy_stream));
+      x0 = x1;
+    }
+  }
   if (probs_out_host) DCL_TRY(grow(h, (void**)&h->stage_probs, &h->stage_probs_cap, 4 * V * 4));
-  DCL_TRY(dcl_predict_volume(h, h->stage_vol, shape, mode, n_patches, starts_host, keep_scale_host,
+  h->up_active = true;
+  const int rc_pv = dcl_predict_volume(h, h->stage_vol, shape, mode, n_patches, starts_host, keep_scale_host,
                              probs_out_host ? h->stage_probs : nullptr, h->stage_labels, target_host ? h->stage_target : nullptr,
-                             counts_out_host ? (uint64_t*)h->counts_dev : nullptr, stream));
+                             counts_out_host ? (uint64_t*)h->counts_dev : nullptr, stream);
+  h->up_active = false;
+  if (rc_pv != 0) { cudaStreamSynchronize(h->copy_stream); return rc_pv; }
   if (labels_out_host) DCL_CUDA_OK(cudaMemcpyAsync(labels_out_host, h->stage_labels, (size_t)V, cudaMemcpyDeviceToHost, st));
   if (counts_out_host) DCL_CUDA_OK(cudaMemcpyAsync(counts_out_host, h->counts_dev, 13 * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
   if (probs_out_host) DCL_CUDA_OK(cudaMemcpyAsync(probs_out_host, h->stage_probs, 4 * V * 4, cudaMemcpyDeviceToHost, st));
