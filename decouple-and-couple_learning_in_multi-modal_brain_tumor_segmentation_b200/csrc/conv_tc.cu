@@ -35,7 +35,10 @@ struct RollCfg {
   static constexpr bool KHN = KHN_;               // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
   static constexpr int W = G;                     // staged rows have NO halo columns (kw = 0/2 use lane masks)
   static constexpr int ROWS = TH + 2;
-  static constexpr int NPOS = ROWS * W + 2;       // positions per channel chunk of one plane (+1 pad front/back)
+  static constexpr int PAD = 8;                   // pad positions in front of / behind the rows: 128 bytes, so that the staged rows
+                                                  // (and the bulk copies that fill them) stay 128-byte aligned - a 16-byte offset
+                                                  // destination made the plane copies land at ~9 instead of ~45 B/clk
+  static constexpr int NPOS = ROWS * W + 2 * PAD; // positions per channel chunk of one plane
   static constexpr int KC = C / 8;                // 16-byte channel chunks
   static constexpr int KS = C / 16;               // K = 16 MMA steps per tap
   static constexpr int SLOT_BYTES = KC * NPOS * 16;
@@ -49,7 +52,7 @@ struct RollCfg {
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
   static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // scale[C], shift[C], bias[C], out_scale[C] floats
   static constexpr int OFF_BAR = OFF_SMALL + 4 * C * 4;      // 16-byte aligned (C multiple of 16)
-  static constexpr int SMEM_BYTES = OFF_BAR + (3 * NSLOT + 4) * 8 + 16;
+  static constexpr int SMEM_BYTES = OFF_BAR + (3 * NSLOT + 5) * 8 + 16;
   static_assert(W == 64 || W == 128, "rows must tile 128-voxel M tiles");
   static_assert(!KHN || TROWS == 1, "kh stacking needs one-row M tiles");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
@@ -114,7 +117,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
   uint64_t* bar_land = bar_empty + NSLOT;                                  // bulk copies of the plane landed
   uint64_t* bar_acc_full = bar_land + NSLOT;
   uint64_t* bar_acc_empty = bar_acc_full + 2;
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
+  uint64_t* bar_w = bar_acc_empty + 2;                                     // the weights have landed
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 1);
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -133,11 +137,9 @@ conv3d_k3_roll_kernel(RollParams prm) {
   constexpr int64_t SP = (int64_t)G * G * G;
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  for (int i = tid; i < Cfg::W_BYTES / 16; i += ROLL_THREADS)
-    reinterpret_cast<uint4*>(smem + Cfg::OFF_W)[i] = __ldg(prm.w + i);
   for (int i = tid; i < NSLOT * KC * 2; i += ROLL_THREADS) {   // the pad positions of every slot chunk stay zero
     const int sc = i >> 1;
-    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KC) * Cfg::SLOT_BYTES + (size_t)((sc % KC) * NPOS + ((i & 1) ? NPOS - 1 : 0)) * 16) =
+    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KC) * Cfg::SLOT_BYTES + (size_t)((sc % KC) * NPOS + ((i & 1) ? NPOS - Cfg::PAD : Cfg::PAD - 1)) * 16) =
         make_uint4(0u, 0u, 0u, 0u);
   }
   const bool has_norm = prm.sums != nullptr || prm.mean != nullptr;
@@ -157,7 +159,14 @@ conv3d_k3_roll_kernel(RollParams prm) {
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); mbar_init(&bar_land[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&bar_acc_full[b], 1); mbar_init(&bar_acc_empty[b], EPI_GROUPS * EPI_WARPS * 32); }
+    mbar_init(bar_w, 1);
     fence_barrier_init();
+    // the weights (constant across the forward) come in with one bulk async copy; only the MMA warp waits for it
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)Cfg::W_BYTES), "r"(smem_u32(bar_w)) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem + Cfg::OFF_W)),
+                 "l"(prm.w), "r"((uint32_t)Cfg::W_BYTES), "r"(smem_u32(bar_w))
+                 : "memory");
   }
   if (warp == MMA_WARP) tmem_alloc(s_tmem, Cfg::TMEM_COLS);
   fence_proxy_async();   // weights / pads were written through the generic proxy
@@ -196,24 +205,36 @@ conv3d_k3_roll_kernel(RollParams prm) {
         __syncwarp();
         if (d_ok && lane < KC) {
           const uint4* src = prm.xb + (int64_t)lane * SP + ((int64_t)d_in * G + (h0 - 1 + r_lo)) * G;
-          const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (lane * NPOS + 1 + r_lo * W) * 16);
+          const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (lane * NPOS + Cfg::PAD + r_lo * W) * 16);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                        "l"(src), "r"(run_bytes), "r"(bar)
                        : "memory");
         }
-        // rows / planes outside the volume are zero padding
-        for (int e = 0; e < KC * ROWS; ++e) {
-          const int kc = e / ROWS, r = e - kc * ROWS;
-          if (d_ok && r >= r_lo && r <= r_hi) continue;
-          uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + 1 + r * W) * 16);
-          for (int i = lane; i < W; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        // rows / planes outside the volume are zero padding (at most one row at either end, or the whole plane)
+        if (!d_ok) {
+          for (int kc = 0; kc < KC; ++kc) {
+            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + Cfg::PAD) * 16);
+            for (int i = lane; i < ROWS * W; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else if (r_lo != 0 || r_hi != ROWS - 1) {
+          const int r = r_lo != 0 ? 0 : ROWS - 1;      // a strip touches at most one border (TH < G)
+          for (int kc = 0; kc < KC; ++kc) {
+            uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + Cfg::PAD + r * W) * 16);
+            for (int i = lane; i < W; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
       };
-      if (pw == 0)
-        for (int j = 0; j < AHEAD && j < n_in; ++j) issue(j);
+      // every slot is free at kernel start: the first NSLOT planes are fetched at once, so the prologue (three planes
+      // before the first MMA) costs one copy latency instead of three
+      const int burst = n_in < NSLOT ? n_in : NSLOT;
+      if (pw == 0) {
+        for (int j = 0; j < burst; ++j) issue(j);
+        if (pt == 0) trace_event(tbuf, 10, burst);   // producer: first planes requested
+      }
       for (int j = 0; j < n_in; ++j) {
         const int s = j % NSLOT;
         mbar_wait(&bar_land[s], (uint32_t)(j / NSLOT) & 1u);
+        if (pt == 0) trace_event(tbuf, 9, j);    // producer: bulk copies of plane j landed
         if (!identity) {
           const int d_in = d0 - 1 + j;
           if ((unsigned)d_in < (unsigned)G) {
@@ -224,7 +245,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
               const float4 sh0 = *reinterpret_cast<const float4*>(s_shift + kc * 8), sh1 = *reinterpret_cast<const float4*>(s_shift + kc * 8 + 4);
               const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
               const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-              uint4* q = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + 1 + r * W) * 16);
+              uint4* q = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + Cfg::PAD + r * W) * 16);
               uint4 v[W / 32];
 #pragma unroll
               for (int i = 0; i < W / 32; ++i) v[i] = q[lane + 32 * i];
@@ -248,7 +269,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
         mbar_arrive(&bar_full[s]);
         if (pt == 0) trace_event(tbuf, 3, j);    // producer: plane j staged (this thread)
         const int jn = j + AHEAD;
-        if (pw == 0 && jn < n_in) {
+        if (pw == 0 && jn < n_in && jn >= burst) {
           mbar_wait(&bar_empty[jn % NSLOT], ((uint32_t)(jn / NSLOT) & 1u) ^ 1u);
           if (pt == 0) trace_event(tbuf, 2, jn);  // producer: slot free, fetching plane jn
           issue(jn);
@@ -275,10 +296,10 @@ conv3d_k3_roll_kernel(RollParams prm) {
             o.x = pack_bf16x2(__ldg(p), __ldg(p + prm.s4c));
             o.y = pack_bf16x2(__ldg(p + 2 * prm.s4c), __ldg(p + 3 * prm.s4c));
           }
-          *reinterpret_cast<uint4*>(slot + (size_t)(1 + e) * 16) = o;
+          *reinterpret_cast<uint4*>(slot + (size_t)(Cfg::PAD + e) * 16) = o;
 #pragma unroll
           for (int kc = 1; kc < KC; ++kc)
-            *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + 1 + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + Cfg::PAD + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
         fence_proxy_async();
         mbar_arrive(&bar_full[s]);
@@ -293,6 +314,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
       for (int i = 0; i < n_out; ++i) {
         const int b = i & 1;
         if (i == 0) {
+          mbar_wait(bar_w, 0);
+          if (lane == 0) trace_event(tbuf, 8, 0);          // MMA: weights landed
           mbar_wait(&bar_full[0], 0);
           mbar_wait(&bar_full[1], 0);
         }
@@ -333,7 +356,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
                 const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
-                  const uint64_t ad = a_kd[kd] + (uint64_t)(1 + rho * W + (kw - 1) + ks * 2 * NPOS);
+                  const uint64_t ad = a_kd[kd] + (uint64_t)(Cfg::PAD + rho * W + (kw - 1) + ks * 2 * NPOS);
                   const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * C * 16 + ks * 2 * B_LBO) >> 4);
                   if (n_acc > 0) {
                     if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
@@ -365,7 +388,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
                   const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
 #pragma unroll
                   for (int ks = 0; ks < Cfg::KS; ++ks) {
-                    const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(1 + (t * Cfg::TROWS + kh) * W + (kw - 1) + ks * 2 * NPOS);
+                    const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(Cfg::PAD + (t * Cfg::TROWS + kh) * W + (kw - 1) + ks * 2 * NPOS);
                     const uint64_t bd = b_base + (uint64_t)((tap * C * C * 2 + ks * 2 * C * 16) >> 4);
                     const uint32_t accum = (kd | kh | kwi | ks) != 0 ? 1u : 0u;
                     if (kw == 1) umma_bf16_ws(d_tmem, ad, bd, idesc, accum);

@@ -29,7 +29,7 @@ def show(title, recs, names):
     t0 = min(r[2] for r in recs)
     print(f"== {title}: {len(recs)} records, span {max(r[2] for r in recs) - t0} clk")
     for tag, step, t in sorted(recs, key=lambda r: r[2]):
-        print(f"  {t - t0:9d}  {names.get(tag, tag):28s} {step}")
+        print(f"  {t - t0:9d}  {str(names.get(tag, tag)):28s} {step}")
 
 
 def conv_case(c, g, cout=None, stride=1, norm=True):
@@ -50,8 +50,8 @@ def conv_case(c, g, cout=None, stride=1, norm=True):
 
 
 K1 = {0: "entry", 1: "setup done", 2: "prod: slot free, stage", 3: "prod: staged", 4: "mma: issue step", 5: "mma: issued",
-      6: "epi: acc complete", 7: "epi: all stored", 8: "epi: item ld issued", 9: "epi: item acc in regs",
-      10: "epi: item exchanged", 11: "epi: item stored"}
+      6: "epi: acc complete", 7: "epi: all stored", 8: "mma: weights landed", 9: "prod: plane landed",
+      10: "prod: burst issued", 11: "epi: item stored"}
 K2 = {0: "entry", 1: "setup done", 2: "prod: stage issued", 3: "mma: stage landed", 4: "epi: acc complete", 5: "epi: done",
       10: "wgt: stage free, issue tap", 11: "slab: cp.async issued", 12: "slab: landed", 13: "slab: published",
       14: "mma: tap weights landed", 15: "epi: acc complete", 16: "all roles done"}
