@@ -124,6 +124,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   const int warp = tid >> 5;
   const int lane = tid & 31;
   long long* const tbuf = trace_begin();
+  if (tid == 0) trace_grid_extent(false);
   if (tid == 0) trace_event(tbuf, 0, 0);     // kernel entry
 
   const int dsplit = prm.dsplit;
@@ -529,6 +530,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (tid == 0) trace_grid_extent(true);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -29,6 +29,18 @@ __device__ __forceinline__ void trace_event(long long* buf, int tag, int step) {
   }
 }
 
+// whole-grid extent in %globaltimer ns (every CTA, thread 0): slot of tag 30 holds 2^62 - min(entry), tag 31 max(exit)
+__device__ __forceinline__ void trace_grid_extent(bool at_exit) {
+  long long* buf = g_trace_buf;
+  if (buf != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    const int i = (at_exit ? 31 : 30) * 128;
+    buf[1 + 2 * i] = (long long)(at_exit ? 31 : 30) << 32;
+    atomicMax(buf + 2 + 2 * i, at_exit ? (long long)t : (1ll << 62) - (long long)t);
+  }
+}
+
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

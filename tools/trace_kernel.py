@@ -26,6 +26,10 @@ def show(title, recs, names):
     if not recs:
         print(title, ": no records")
         return
+    ext = {r[0]: r[2] for r in recs if r[0] >= 30}
+    recs = [r for r in recs if r[0] < 30]
+    if 30 in ext and 31 in ext:
+        print(f"{title}: grid extent (first CTA entry -> last CTA exit) {(ext[31] + ext[30] - (1 << 62)) / 1e3:.2f} us")
     t0 = min(r[2] for r in recs)
     print(f"== {title}: {len(recs)} records, span {max(r[2] for r in recs) - t0} clk")
     for tag, step, t in sorted(recs, key=lambda r: r[2]):
