@@ -50,3 +50,33 @@ def test_bf16_forward_is_deterministic(engine_bf16, golden_patch):
     b = engine_bf16.forward(x, golden_patch["keep_scale"])
     torch.cuda.synchronize()
     assert torch.equal(a, b)
+
+
+def test_bf16_volume_graph_replay_matches_per_patch_forwards(engine_bf16):
+    """The sliding-window driver in bf16 mode replays the forward as a CUDA graph with per-patch arguments in device
+    memory, accumulates with the vectorised kernel and (host entry point) uploads the volume in x-slabs while the first
+    patches already run.  All of that must be pure plumbing: the blended probabilities equal the oracle blend of the
+    per-patch forwards (same kernels, bit-reproducible), host and device entry points agree bit for bit."""
+    from dcl_b200 import StitchMode, patch_starts
+    from oracle import stitch_oracle as S
+    from tests.util import volume_input, volume_target
+    vol_h = volume_input(0)
+    vol = vol_h.cuda()
+    starts = patch_starts((240, 240, 155), 96)
+    keeps = np.ones((len(starts), 16), np.float32)
+    keeps[1, 3] = 0.0
+    keeps[2, 7] = 1.25
+    probs = []
+    for (sx, sy, sz), k in zip(starts, keeps):
+        probs.append(engine_bf16.forward(vol[..., sx:sx + 128, sy:sy + 128, sz:sz + 128], k)[0].cpu().numpy())
+    want = S.accumulate_from_probs(probs, starts, "uniform")
+    tgt = torch.from_numpy(volume_target(0).astype(np.uint8))
+    dev = engine_bf16.predict_volume(vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt.cuda())
+    got = dev["probs"][0].cpu().numpy()
+    assert np.abs(got - want).max() < 2e-6
+    labels = S.labels_from_probs(got)
+    assert np.array_equal(dev["labels"].cpu().numpy(), labels.astype(np.uint8))
+    host = engine_bf16.predict_volume_host(vol_h[0].pin_memory(), StitchMode.UNIFORM, starts=starts, keep_scales=keeps,
+                                           target_host=tgt.pin_memory())
+    assert np.array_equal(host["labels"].numpy(), dev["labels"].cpu().numpy())
+    assert np.array_equal(host["counts"], dev["counts"].cpu().numpy())
