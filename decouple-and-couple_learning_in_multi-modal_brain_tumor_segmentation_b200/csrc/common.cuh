@@ -149,6 +149,11 @@ int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, i
                            float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
                            cudaStream_t st);
 
+// 8-flip TTA (predict_cls.py:180-203): dst = flip(src[..., :Zd]) along the selected axes; out (+)= softmax_c(flip(yf))
+int launch_flip_volume(const float* src, float* dst, int X, int Y, int Zs, int Zd, int fx, int fy, int fz, cudaStream_t st);
+int launch_tta_accumulate(const float* yf, float* out, int X, int Y, int Z, int fx, int fy, int fz, int first, int last,
+                          cudaStream_t st);
+
 extern thread_local int64_t g_launches;   // incremented by every launcher
 
 // ---- programmatic dependent launch (PDL) ------------------------------------------------------

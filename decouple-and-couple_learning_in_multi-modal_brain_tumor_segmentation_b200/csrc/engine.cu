@@ -231,6 +231,8 @@ struct dcl_handle {
   // ---- volume level ----
   float* vol_probs = nullptr;  int64_t vol_probs_cap = 0;
   float* vol_wsum = nullptr;   int64_t vol_wsum_cap = 0;
+  float* tta_vol = nullptr;    int64_t tta_vol_cap = 0;      // flipped copy of the volume (TTA)
+  float* tta_sum = nullptr;    int64_t tta_sum_cap = 0;      // running sum of the un-flipped softmaxes (TTA)
   float* stage_vol = nullptr;  int64_t stage_vol_cap = 0;
   float* stage_probs = nullptr; int64_t stage_probs_cap = 0;
   uint8_t* stage_labels = nullptr; uint8_t* stage_target = nullptr; int64_t stage_lab_cap = 0;
@@ -1304,6 +1306,8 @@ DCL_API int dcl_destroy(dcl_handle* h) {
   if (h->ev_st) cudaEventDestroy(h->ev_st);
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);
+  if (h->tta_vol) cudaFree(h->tta_vol);
+  if (h->tta_sum) cudaFree(h->tta_sum);
   if (h->stage_vol) cudaFree(h->stage_vol);
   if (h->stage_probs) cudaFree(h->stage_probs);
   if (h->stage_labels) cudaFree(h->stage_labels);
@@ -1431,6 +1435,48 @@ DCL_API int dcl_predict_volume(dcl_handle* h, const float* vol_dev, const int32_
     if (h->profiling)
       h->prof_end(ev, 1, (double)V * (16 + (wsum ? 4 : 0) + (weighted && probs_out_dev ? 16 : 0) +
                                       (labels_out_dev ? 1 : 0) + (target_dev ? 1 : 0)), st);
+  }
+  h->launches += g_launches - before;
+  return rc;
+}
+
+
+// 8-flip test-time augmentation around the reference tiling: predict_cls.py:180-203.
+//   keep_scale_host: NULL, or 8 flips x 8 patches x 16 dropout scales in the order the reference draws them
+//   (flip order: none, X, Y, Z, XY, XZ, YZ, XYZ = dims (2,), (3,), (4,), (2,3), (2,4), (3,4), (2,3,4)).
+DCL_API int dcl_predict_volume_tta(dcl_handle* h, const float* vol_dev, const int32_t shape[3], const float* keep_scale_host,
+                           float* probs_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
+                           uint64_t* counts_out_dev, void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!vol_dev || !shape) { set_error("dcl_predict_volume_tta: null argument"); return DCL_ERR_ARG; }
+  if (shape[0] != 240 || shape[1] != 240 || shape[2] < 155) {
+    set_error("the reference tiling needs a (4,240,240,>=155) volume (predict_overlap.py:34-41)");
+    return DCL_ERR_ARG;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int X = shape[0], Y = shape[1], Z = 155;
+  const int64_t V = (int64_t)X * Y * Z;
+  DCL_TRY(grow(h, (void**)&h->tta_vol, &h->tta_vol_cap, 4 * V * 4));
+  DCL_TRY(grow(h, (void**)&h->vol_probs, &h->vol_probs_cap, 4 * V * 4));
+  float* sum = probs_out_dev;
+  if (!sum) { DCL_TRY(grow(h, (void**)&h->tta_sum, &h->tta_sum_cap, 4 * V * 4)); sum = h->tta_sum; }
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  const int32_t fshape[3] = {X, Y, Z};
+  DCL_TRY(build_plan(DCL_STITCH_REFERENCE, fshape, 8, nullptr, &plan, &zout));
+  static const int FLIPS[8][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};
+  const int64_t before = g_launches;
+  for (int f = 0; f < 8; ++f) {
+    const int* fl = FLIPS[f];
+    DCL_TRY(launch_flip_volume(vol_dev, h->tta_vol, X, Y, shape[2], Z, fl[0], fl[1], fl[2], st));     // x[..., :155].flip(dims)
+    DCL_TRY(run_patches(h, h->tta_vol, fshape, DCL_STITCH_REFERENCE, plan, 0, 8, keep_scale_host ? keep_scale_host + f * 8 * 16 : nullptr,
+                        zout, h->vol_probs, nullptr, st));                                           // tailor_and_concat
+    DCL_TRY(launch_tta_accumulate(h->vol_probs, sum, X, Y, Z, fl[0], fl[1], fl[2], f == 0, f == 7, st));   // += softmax(.flip(dims))
+  }
+  int rc = 0;
+  if (labels_out_dev || counts_out_dev) {
+    if (counts_out_dev) DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, 13 * sizeof(uint64_t), st));
+    rc = launch_finalize_labels(sum, nullptr, V, 0, V, nullptr, labels_out_dev, target_dev, (unsigned long long*)counts_out_dev, st);
   }
   h->launches += g_launches - before;
   return rc;

@@ -230,4 +230,70 @@ int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, i
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 8-flip test-time augmentation around the tiling (predict_cls.py:180-203):
+//   logit  = softmax(T(x));  logit += softmax(flip_f(T(flip_f(x))))  for the 7 flips;  output = logit / 8
+// where T = tailor_and_concat.  flip_volume_kernel builds flip_f(x[..., :155]); tta_accumulate_kernel adds the
+// un-flipped softmax (note: a softmax of what already are probabilities - the reference does exactly that).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flip_volume_kernel(const float* __restrict__ src, float* __restrict__ dst, int X, int Y, int Zs, int Zd, int fx, int fy,
+                   int fz) {
+  const int64_t n = (int64_t)X * Y * Zd;
+  const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (v >= n) return;
+  const int z = (int)(v % Zd);
+  const int y = (int)((v / Zd) % Y);
+  const int x = (int)(v / ((int64_t)Zd * Y));
+  const int sx = fx ? X - 1 - x : x, sy = fy ? Y - 1 - y : y, sz = fz ? Zd - 1 - z : z;
+  const int64_t s = ((int64_t)sx * Y + sy) * Zs + sz;
+  const int64_t sp_s = (int64_t)X * Y * Zs;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) dst[c * n + v] = __ldg(src + c * sp_s + s);
+}
+
+int launch_flip_volume(const float* src, float* dst, int X, int Y, int Zs, int Zd, int fx, int fy, int fz, cudaStream_t st) {
+  const int64_t n = (int64_t)X * Y * Zd;
+  flip_volume_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, dst, X, Y, Zs, Zd, fx, fy, fz);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+__global__ void __launch_bounds__(256)
+tta_accumulate_kernel(const float* __restrict__ yf, float* __restrict__ out, int X, int Y, int Z, int fx, int fy, int fz,
+                      int first, int last) {
+  const int64_t n = (int64_t)X * Y * Z;
+  const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (v >= n) return;
+  const int z = (int)(v % Z);
+  const int y = (int)((v / Z) % Y);
+  const int x = (int)(v / ((int64_t)Z * Y));
+  const int sx = fx ? X - 1 - x : x, sy = fy ? Y - 1 - y : y, sz = fz ? Z - 1 - z : z;
+  const int64_t s = ((int64_t)sx * Y + sy) * Z + sz;
+  float p[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) p[c] = __ldg(yf + c * n + s);
+  const float m = fmaxf(fmaxf(p[0], p[1]), fmaxf(p[2], p[3]));
+  float e[4], sum = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) { e[c] = expf(p[c] - m); sum += e[c]; }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    float o = e[c] / sum;
+    if (!first) o += out[c * n + v];
+    if (last) o = o / 8.0f;
+    out[c * n + v] = o;
+  }
+}
+
+int launch_tta_accumulate(const float* yf, float* out, int X, int Y, int Z, int fx, int fy, int fz, int first, int last,
+                          cudaStream_t st) {
+  const int64_t n = (int64_t)X * Y * Z;
+  tta_accumulate_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(yf, out, X, Y, Z, fx, fy, fz, first, last);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace dcl

@@ -164,6 +164,32 @@ class Engine:
             _ptr(probs), _ptr(labels), _ptr(target), _ptr(counts), _stream()))
         return {"probs": probs, "labels": labels, "counts": counts}
 
+    def predict_volume_tta(self, vol, keep_scales=None, target=None, want_probs=True, want_labels=True):
+        """8-flip test-time augmentation around the reference tiling (predict_cls.py:180-203) on a CUDA
+        (4,240,240,>=155) / (1,4,...) fp32 volume.  keep_scales: None or (8 flips, 8 patches, 16).
+        Returns dict(probs (1,4,240,240,155) | None, labels uint8 (240,240,155) | None, counts int64[13])."""
+        if vol.dim() == 5:
+            vol = vol[0]
+        if vol.dim() != 4 or vol.shape[0] != 4 or vol.dtype != torch.float32 or not vol.is_cuda:
+            raise DclError("vol must be a CUDA fp32 (4,X,Y,Z) tensor")
+        vol = vol.contiguous()
+        X, Y, Z = (int(v) for v in vol.shape[1:])
+        shape = (C.c_int32 * 3)(X, Y, Z)
+        k_arr = None
+        if keep_scales is not None:
+            k_arr = np.ascontiguousarray(np.asarray(keep_scales, dtype=np.float32).reshape(8, 8, 16))
+        probs = torch.empty((1, 4, X, Y, 155), dtype=torch.float32, device=vol.device) if want_probs else None
+        labels = torch.empty((X, Y, 155), dtype=torch.uint8, device=vol.device) if want_labels else None
+        counts = torch.zeros(13, dtype=torch.int64, device=vol.device)
+        if target is not None:
+            target = target.to(device=vol.device, dtype=torch.uint8).contiguous()
+            if tuple(target.shape) != (X, Y, 155):
+                raise DclError(f"target must have shape {(X, Y, 155)}")
+        N.check(self._lib.dcl_predict_volume_tta(
+            self._h, _ptr(vol), shape, k_arr.ctypes.data_as(C.c_void_p) if k_arr is not None else C.c_void_p(0),
+            _ptr(probs), _ptr(labels), _ptr(target), _ptr(counts), _stream()))
+        return {"probs": probs, "labels": labels, "counts": counts}
+
     def predict_volume_host(self, vol_host, mode=StitchMode.REFERENCE, starts=None, keep_scales=None,
                             target_host=None, labels_out=None, probs_out=None):
         """The end-to-end call: HOST (ideally pinned) fp32 volume in, HOST uint8 labels + 13 counters out;

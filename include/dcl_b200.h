@@ -130,6 +130,14 @@ DCL_API int dcl_predict_volume_host(dcl_handle* h, const float* vol_host, const 
                             float* probs_out_host, uint8_t* labels_out_host, const uint8_t* target_host,
                             uint64_t counts_out_host[13], void* stream);
 
+/* 8-flip test-time augmentation around the reference tiling: replaces predict_cls.py:180-203:
+ *   logit = softmax(T(x)) + sum over the 7 flips f of softmax(flip_f(T(flip_f(x)))),  output = logit / 8,  T = tailor_and_concat,
+ * on x[..., :155], flips in the reference's order (none, X, Y, Z, XY, XZ, YZ, XYZ).  keep_scale_host: NULL or 8 x 8 x 16
+ * dropout scales in draw order.  probs_out_dev: NULL or (4,240,240,155); labels / target / counts as dcl_predict_volume. */
+DCL_API int dcl_predict_volume_tta(dcl_handle* h, const float* vol_dev, const int32_t shape[3], const float* keep_scale_host,
+                           float* probs_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
+                           uint64_t* counts_out_dev, void* stream);
+
 /* ---- multi-GPU: a rank runs only patches [first, first+count) of the plan into its
  * private fp32 accumulator (acc: 4 x X x Y x Zout weighted sums, wsum: X x Y x Zout); the
  * accumulators are then summed across ranks by the caller (NCCL reduce-scatter / all-reduce

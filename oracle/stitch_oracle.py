@@ -97,6 +97,39 @@ def accumulate_from_probs(probs_list, starts, mode="uniform", shape=(240, 240, 1
     return acc / wsum[None]
 
 
+# ---- 8-flip test-time augmentation around the tiling (predict_cls.py:180-203) ------------
+# flipped dims of the (N,C,X,Y,Z) tensor in the reference's order: none, H(2), W(3), D(4), HW, HD, WD, HWD
+TTA_FLIPS = [(), (2,), (3,), (4,), (2, 3), (2, 4), (3, 4), (2, 3, 4)]
+
+
+def softmax4(a):
+    """F.softmax(., 1) on a (C, ...) fp32 array: exp(x - max) / sum, all in fp32."""
+    a = np.asarray(a, dtype=np.float32)
+    e = np.exp(a - a.max(axis=0, keepdims=True), dtype=np.float32)
+    return e / e.sum(axis=0, keepdims=True, dtype=np.float32)
+
+
+def tta_average_from_stitched(stitched):
+    """predict_cls.py:182-203 given the 8 stitched outputs T(flip_f(x)) (each (C,X,Y,155), flip order TTA_FLIPS):
+    logit = softmax(T(x));  logit += softmax(T(flip_f(x)).flip(f)) for the 7 flips;  output = logit / 8.
+    (The softmax is applied to what already are probabilities - as the reference does.)"""
+    logit = softmax4(stitched[0])
+    for y, dims in zip(stitched[1:], TTA_FLIPS[1:]):
+        logit = logit + softmax4(np.flip(y, axis=tuple(d - 1 for d in dims)))
+    return logit / np.float32(8.0)
+
+
+@torch.no_grad()
+def tta_tailor_and_concat(x, missing_modal, model):
+    """predict_cls.py:180-203 as a function: x (1,4,240,240,>=155) -> (1,4,240,240,155) averaged probabilities."""
+    import torch.nn.functional as F
+    x = x[..., :155]
+    logit = F.softmax(tailor_and_concat(x, missing_modal, model), 1)
+    for dims in TTA_FLIPS[1:]:
+        logit += F.softmax(tailor_and_concat(x.flip(dims=dims), missing_modal, model).flip(dims=dims), 1)
+    return logit / 8.0
+
+
 def labels_from_probs(probs):
     """predict_overlap.py:141-143: numpy argmax over the class axis (first maximum wins)."""
     return np.asarray(probs).argmax(0)

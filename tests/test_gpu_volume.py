@@ -200,3 +200,49 @@ def test_sharded_two_gpus_nccl_equals_one_gpu(engine, vol, seed0_state_dict, tmp
     wl = want["labels"].cpu().numpy()
     assert (r0["labels"] != wl).mean() <= 1e-4
     assert np.abs(r0["counts"][:4] - want["counts"].cpu().numpy()[:4]).sum() <= 2e-4 * wl.size
+
+
+def test_tta_matches_oracle_algebra(engine, vol):
+    """dcl_predict_volume_tta (flip -> tiling -> un-flip -> softmax -> mean, predict_cls.py:180-203) against the oracle
+    algebra fed with the library's own stitched outputs of the flipped volumes."""
+    from dcl_b200 import StitchMode
+    from oracle import stitch_oracle as S
+    keeps = np.ones((8, 8, 16), np.float32)
+    keeps[3, 2, 5] = 0.0
+    x155 = vol[..., :155]
+    stitched = []
+    for f, dims in enumerate(S.TTA_FLIPS):
+        xf = x155.flip(dims=dims).contiguous() if dims else x155.contiguous()     # test-side input preparation only
+        stitched.append(engine.predict_volume(xf, StitchMode.REFERENCE, keep_scales=keeps[f])["probs"][0].cpu().numpy())
+    want = S.tta_average_from_stitched(stitched)
+    tgt_np = volume_target(0)
+    out = engine.predict_volume_tta(vol, keep_scales=keeps, target=torch.from_numpy(tgt_np.astype(np.uint8)).cuda())
+    got = out["probs"][0].cpu().numpy()
+    assert got.shape == (4, 240, 240, 155)
+    assert np.abs(got - want).max() < 1e-6
+    labels = S.labels_from_probs(got)
+    assert np.array_equal(out["labels"].cpu().numpy(), labels.astype(np.uint8))
+    counts = out["counts"].cpu().numpy().tolist()
+    assert counts[:4] == S.label_histogram(labels)
+    assert counts[4:] == [v for c in S.region_counts(labels, tgt_np) for v in c]
+
+
+def test_tta_reference_golden(engine, vol):
+    """End to end against the UNMODIFIED reference run on CPU (tests/golden/make_golden_tta.py): averaged probabilities
+    within 1e-3, <= 1e-4 of the voxels with a different label, Dice within 1e-3."""
+    import os
+    from dcl_b200.engine import dice_from_counts
+    path = os.path.join(os.path.dirname(__file__), "golden", "volume_tta_seed1000.npz")
+    if not os.path.exists(path):
+        pytest.skip("TTA golden not generated")
+    g = np.load(path)
+    tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
+    out = engine.predict_volume_tta(vol, keep_scales=g["keep_scale"].reshape(8, 8, 16), target=tgt)
+    torch.cuda.synchronize()
+    check_digest("tta", out["probs"], g, 1e-3)
+    counts = out["counts"].cpu().numpy()
+    V = 240 * 240 * 155
+    assert np.abs(counts[:4] - g["labels_hist"]).sum() <= 2e-4 * V
+    samp = out["labels"].cpu().numpy().ravel()[:: V // 4096][:4096]
+    assert (samp != g["labels_sample"]).mean() <= 1e-3
+    assert np.allclose(dice_from_counts(counts), g["dice"], atol=1e-3)
