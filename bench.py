@@ -30,7 +30,8 @@ import torch  # noqa: E402
 SHAPE = (240, 240, 155)
 VOXELS = SHAPE[0] * SHAPE[1] * SHAPE[2]
 FLOPS_PER_PATCH = 523.35e9 + 0.44e9      # conv+linear without aux heads + attention
-WORKLOADS = {"overlap50": ("UNIFORM", 64), "overlap75": ("UNIFORM", 32), "reference8": ("REFERENCE", None)}
+WORKLOADS = {"overlap50": ("UNIFORM", 64), "overlap75": ("UNIFORM", 32), "reference8": ("REFERENCE", None),
+             "tta8": ("TTA", None)}
 
 
 def seed0_weights():
@@ -106,6 +107,8 @@ class ClockSampler:
 def workload_plan(name):
     from dcl_b200 import StitchMode, patch_starts
     mode_name, stride = WORKLOADS[name]
+    if mode_name == "TTA":
+        return "TTA", None, 64
     if stride is None:
         return StitchMode.REFERENCE, None, 8
     starts = patch_starts(SHAPE, stride)
@@ -121,6 +124,8 @@ def cpu_reference_volumes_per_s(workload, n_sample_patches, threads, steps=1, wa
     torch.set_num_threads(threads)
     sd = seed0_weights()
     mode_name, stride = WORKLOADS[workload]
+    if mode_name == "TTA":
+        raise SystemExit("the CPU arm of the tta8 workload is 8 x the reference8 workload; run --workload reference8")
     starts = S.REFERENCE_STARTS if stride is None else S.patch_starts(SHAPE, stride)
     x = synth_volume(0)
     tgt = synth_target(0).numpy()
@@ -182,7 +187,8 @@ def workload_name(w):
     return {"overlap50": "predict_overlap sliding window, one 4x240x240x155 volume, 128^3 patches at 50% overlap "
                          "(stride 64, 18 patches, uniform blend)",
             "overlap75": "4x240x240x155 volume, 128^3 patches at 75% overlap (stride 32, 50 patches, uniform blend)",
-            "reference8": "predict_overlap.py 8-corner tiling + crop-overwrite stitch, one 4x240x240x155 volume"}[w]
+            "reference8": "predict_overlap.py 8-corner tiling + crop-overwrite stitch, one 4x240x240x155 volume",
+            "tta8": "predict_cls.py 8-flip TTA around the 8-corner tiling (64 patch forwards), one 4x240x240x155 volume"}[w]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -237,6 +243,21 @@ def run_ours(args):
             if rank == 0:
                 lab_h.copy_(out["labels"], non_blocking=True)
                 out["counts"].cpu()
+            torch.cuda.synchronize()
+            return out
+    elif mode == "TTA":
+        stage = torch.empty_like(vols_d[0])
+
+        def step_dev(i):
+            j = i % n_rot
+            return eng.predict_volume_tta(vols_d[j], keep_scales=keeps[j], target=tgts_d[j], want_probs=False)
+
+        def step_e2e(i):
+            j = i % n_rot
+            stage.copy_(vols_h[j], non_blocking=True)
+            out = eng.predict_volume_tta(stage, keep_scales=keeps[j], target=tgts_h[j].cuda(non_blocking=True), want_probs=False)
+            lab_h.copy_(out["labels"], non_blocking=True)
+            out["counts"].cpu()
             torch.cuda.synchronize()
             return out
     else:
