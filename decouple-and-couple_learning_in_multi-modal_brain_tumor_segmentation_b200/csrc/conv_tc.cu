@@ -281,26 +281,37 @@ conv3d_k3_roll_kernel(RollParams prm) {
       if (prm.desc != nullptr) {
         prm.x4 = prm.desc->x; prm.s4c = prm.desc->sc; prm.s4d = prm.desc->sd; prm.s4h = prm.desc->sh;
       }
+      constexpr int ITER = (ROWS * W + NPROD - 1) / NPROD;
       for (int j = 0; j < n_in; ++j) {
         const int s = j % NSLOT;
-        mbar_wait(&bar_empty[s], ((uint32_t)(j / NSLOT) & 1u) ^ 1u);
         const int d_in = d0 - 1 + j;
         const bool d_ok = (unsigned)d_in < (unsigned)G;
-        uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
-        for (int e = pt; e < ROWS * W; e += NPROD) {
+        // all global loads of the plane are issued BEFORE the wait for the ring slot: their latency overlaps it
+        float v[ITER][4];
+#pragma unroll
+        for (int it = 0; it < ITER; ++it) {
+          const int e = pt + it * NPROD;
           const int r = e / W;
           const int w_in = e - r * W;
           const int h_in = h0 - 1 + r;
-          uint4 o = make_uint4(0u, 0u, 0u, 0u);
-          if (d_ok && (unsigned)h_in < (unsigned)G) {
+          v[it][0] = v[it][1] = v[it][2] = v[it][3] = 0.f;
+          if (e < ROWS * W && d_ok && (unsigned)h_in < (unsigned)G) {
             const float* p = prm.x4 + (int64_t)d_in * prm.s4d + (int64_t)h_in * prm.s4h + w_in;
-            o.x = pack_bf16x2(__ldg(p), __ldg(p + prm.s4c));
-            o.y = pack_bf16x2(__ldg(p + 2 * prm.s4c), __ldg(p + 3 * prm.s4c));
+            v[it][0] = __ldg(p); v[it][1] = __ldg(p + prm.s4c); v[it][2] = __ldg(p + 2 * prm.s4c); v[it][3] = __ldg(p + 3 * prm.s4c);
           }
-          *reinterpret_cast<uint4*>(slot + (size_t)(Cfg::PAD + e) * 16) = o;
+        }
+        mbar_wait(&bar_empty[s], ((uint32_t)(j / NSLOT) & 1u) ^ 1u);
+        uint8_t* slot = smem + s * Cfg::SLOT_BYTES;
 #pragma unroll
-          for (int kc = 1; kc < KC; ++kc)
-            *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + Cfg::PAD + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
+        for (int it = 0; it < ITER; ++it) {
+          const int e = pt + it * NPROD;
+          if (e < ROWS * W) {
+            uint4 o = make_uint4(pack_bf16x2(v[it][0], v[it][1]), pack_bf16x2(v[it][2], v[it][3]), 0u, 0u);
+            *reinterpret_cast<uint4*>(slot + (size_t)(Cfg::PAD + e) * 16) = o;
+#pragma unroll
+            for (int kc = 1; kc < KC; ++kc)
+              *reinterpret_cast<uint4*>(slot + (size_t)(kc * NPOS + Cfg::PAD + e) * 16) = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
         fence_proxy_async();
         mbar_arrive(&bar_full[s]);
