@@ -315,26 +315,46 @@ int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const 
 
 // ---- endconv (1x1, 16 -> 4) + Softmax(dim=1) (cls_wise_former.py:662-663): B -> fp32 NCDHW ----------
 __global__ void __launch_bounds__(256)
-endconv_softmax_b_kernel(const uint4* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                         float* __restrict__ probs, int64_t spatial) {
+endconv_softmax_b_kernel(const uint4* __restrict__ x, BNorm n, const uint4* __restrict__ res, const float* __restrict__ w,
+                         const float* __restrict__ b, float* __restrict__ probs, int64_t spatial) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   __shared__ float s_w[4][16];
   __shared__ float s_b[4];
+  __shared__ float s_mean[16], s_rstd[16];
   if (threadIdx.x < 64) s_w[threadIdx.x / 16][threadIdx.x % 16] = __ldg(w + threadIdx.x);   // (4,16) row-major
   if (threadIdx.x < 4) s_b[threadIdx.x] = __ldg(b + threadIdx.x);
+  const bool fused = n.sums != nullptr || n.mean != nullptr;       // input = act(norm(x)) + res (the DeBlock tail)
+  if (fused && threadIdx.x >= 64 && threadIdx.x < 80) {
+    const int c = threadIdx.x - 64;
+    float m, r;
+    if (n.sums != nullptr) stat_mean_rstd(n.sums, c, n.inv_n, &m, &r);
+    else { m = n.mean[c]; r = n.rstd[c]; }
+    s_mean[c] = m; s_rstd[c] = r;
+  }
   __syncthreads();
-  const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (p >= spatial) return;
-  float f[16];
-  {
+  for (int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x; p < spatial; p += (int64_t)gridDim.x * 256) {   // persistent: the
+  float f[16];                                                                 // per-block prologue (fp64 statistics) amortises
+#pragma unroll
+  for (int kc = 0; kc < 2; ++kc) {
     float t[8];
-    unpack8(__ldg(x + p), t);
+    unpack8(__ldg(x + kc * spatial + p), t);
+    if (fused) {
+      // exactly norm_act_b_kernel's arithmetic, including the bf16 rounding of its stored result, so the fused and
+      // the unfused (keep_stages) schedules give bit-identical probabilities
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = t[k];
-    unpack8(__ldg(x + spatial + p), t);
+      for (int k = 0; k < 8; ++k) t[k] = apply_act((t[k] - s_mean[kc * 8 + k]) * s_rstd[kc * 8 + k], n.act);
+      if (res != nullptr) {
+        float r[8];
+        unpack8(__ldg(res + kc * spatial + p), r);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[8 + k] = t[k];
+        for (int k = 0; k < 8; ++k) t[k] += r[k];
+      }
+      const uint4 q = pack8(t);
+      unpack8(q, t);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[kc * 8 + k] = t[k];
   }
   float l[4];
 #pragma unroll
@@ -350,12 +370,17 @@ endconv_softmax_b_kernel(const uint4* __restrict__ x, const float* __restrict__ 
   for (int c = 0; c < 4; ++c) { l[c] = expf(l[c] - m); s += l[c]; }
 #pragma unroll
   for (int c = 0; c < 4; ++c) probs[(int64_t)c * spatial + p] = l[c] / s;
+  }
 }
 
 int launch_endconv_softmax_b(const void* x, const float* w, const float* b, float* probs, int64_t spatial,
-                             cudaStream_t st) {
-  DCL_CUDA_OK(launch_pdl(endconv_softmax_b_kernel, dim3((unsigned)((spatial + 255) / 256)), dim3(256), (size_t)(0), st, reinterpret_cast<const uint4*>(x), w, b,
-                                                                            probs, spatial));
+                             cudaStream_t st, const BNorm* norm, const void* res) {
+  BNorm n;
+  if (norm) n = *norm;
+  unsigned gx = (unsigned)((spatial + 255) / 256);
+  if (gx > 148 * 8) gx = 148 * 8;
+  DCL_CUDA_OK(launch_pdl(endconv_softmax_b_kernel, dim3(gx), dim3(256), (size_t)(0), st,
+                         reinterpret_cast<const uint4*>(x), n, reinterpret_cast<const uint4*>(res), w, b, probs, spatial));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

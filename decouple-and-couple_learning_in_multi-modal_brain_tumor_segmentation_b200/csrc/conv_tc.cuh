@@ -86,8 +86,10 @@ int launch_untokenise_b(const float* tokens, const float* class_token, void* y, 
 int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const float* w3a, const float* bt, void* y,
                         int cin, int gi, cudaStream_t st);
 // probs (fp32 NCDHW, 4 classes) = softmax(endconv(x)), x B-format 16 channels
+// norm != nullptr: the input is act(norm(x)) + res, i.e. the DeBlock tail is applied while loading (bit-identical to
+// running launch_norm_act_b first, including its bf16 rounding)
 int launch_endconv_softmax_b(const void* x, const float* w, const float* b, float* probs, int64_t spatial,
-                             cudaStream_t st);
+                             cudaStream_t st, const BNorm* norm = nullptr, const void* res = nullptr);
 
 // fp32 [rows][512] (optionally LayerNorm'ed) -> bf16 blocked [64][rows][8]
 int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st);

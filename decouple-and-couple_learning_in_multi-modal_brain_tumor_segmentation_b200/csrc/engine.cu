@@ -878,12 +878,15 @@ struct Fwd16 {
   }
 
   // EnBlock2 / DeBlock: y = lrelu(IN(conv2(lrelu(IN(conv1(x)))))) + x
-  int post_block(const void* x, int c, int g, const std::string& name, void* a, void* b, void* y) {
+  // tail_out != nullptr: the trailing norm + act + residual is NOT run; its description (input b, statistics) is
+  // returned so that the consumer applies it while loading (endconv)
+  int post_block(const void* x, int c, int g, const std::string& name, void* a, void* b, void* y, BNorm* tail_out = nullptr) {
     const int64_t sp = (int64_t)g * g * g;
     stat_t *sa = new_stats(), *sb = new_stats();
     DCL_TRY(conv(x, c, nullptr, 0, g, h->conv.at(name + ".conv1"), 1, nullptr, nullptr, nullptr, a, sa));
     BNorm n1 = norm_of(sa, sp, ACT_LRELU);
     DCL_TRY(conv(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &n1, nullptr, nullptr, b, sb));
+    if (tail_out != nullptr) { *tail_out = norm_of(sb, sp, ACT_LRELU); return 0; }
     dcl_handle::ProfScope ps(h, st, 7);
     DCL_TRY(launch_norm_act_b(b, norm_of(sb, sp, ACT_LRELU), x, y, c, sp, st));
     return 0;
@@ -1079,6 +1082,8 @@ struct Fwd16 {
     const char* dbn[3][2] = {{"decoder.DeBlock4", "decoder.DeBlock4_1"}, {"decoder.DeBlock3", "decoder.DeBlock3_1"},
                              {"decoder.DeBlock2", "decoder.DeBlock2_1"}};
     const void* cur = h->b_d8[4];
+    BNorm end_tail;
+    const void *end_src = nullptr, *end_res = nullptr;
     for (int l = 0; l < 3; ++l) {
       DCL_TRY(stamp(5 + l));
       const int cin = 128 >> l, g_in = 16 << l, c = cin / 2, g = g_in * 2;
@@ -1088,13 +1093,17 @@ struct Fwd16 {
         DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st));
       }
       DCL_TRY(post_block(b[0], c, g, dbn[l][0], b[1], b[2], b[3]));
-      DCL_TRY(post_block(b[3], c, g, dbn[l][1], b[1], b[2], b[4]));
+      // the very last DeBlock tail (16 channels @ 128^3) is folded into endconv's load unless the stage is to be kept
+      const bool fold = l == 2 && !h->cfg.keep_stages;
+      DCL_TRY(post_block(b[3], c, g, dbn[l][1], b[1], b[2], b[4], fold ? &end_tail : nullptr));
       cur = b[4];
+      if (fold) { end_src = b[2]; end_res = b[3]; }
     }
     DCL_TRY(stamp(8));
     {
       dcl_handle::ProfScope ps(h, st, 9);
-      DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
+      if (end_src != nullptr) DCL_TRY(launch_endconv_softmax_b(end_src, h->end_w, h->end_b, probs_out, P3, st, &end_tail, end_res));
+      else DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
     }
     DCL_TRY(stamp(9));
     return 0;

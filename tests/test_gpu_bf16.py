@@ -80,3 +80,17 @@ def test_bf16_volume_graph_replay_matches_per_patch_forwards(engine_bf16):
                                            target_host=tgt.pin_memory())
     assert np.array_equal(host["labels"].numpy(), dev["labels"].cpu().numpy())
     assert np.array_equal(host["counts"], dev["counts"].cpu().numpy())
+
+
+def test_bf16_production_schedule_equals_stage_keeping_schedule(engine_bf16, seed0_state_dict, golden_patch):
+    """Without keep_stages the last DeBlock tail is folded into endconv's load; the probabilities must not change by a bit."""
+    import dcl_b200
+    eng = dcl_b200.Engine(dcl_b200.Precision.BF16)
+    eng.load_state_dict(seed0_state_dict)
+    x = config1_input().cuda()
+    a = engine_bf16.forward(x, golden_patch["keep_scale"])
+    b = eng.forward(x, golden_patch["keep_scale"])      # eager launches
+    c = eng.forward(x, golden_patch["keep_scale"])      # captured graph
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(b, c)
+    eng.close()
