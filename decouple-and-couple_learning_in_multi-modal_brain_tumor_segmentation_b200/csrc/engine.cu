@@ -242,6 +242,11 @@ struct dcl_handle {
   cudaEvent_t ev_up[3] = {nullptr, nullptr, nullptr}, ev_st = nullptr;
   int up_bound[3] = {0, 0, 0};      // slab k has landed when x < up_bound[k] is on the device; 0 = no staged upload
   bool up_active = false;
+  // two patches in flight (bf16 sliding window): a twin handle (own workspace, graph and weights copy) runs every other
+  // patch on a second stream; the overlap accumulates stay in patch order through an event chain
+  dcl_handle* twin = nullptr;
+  cudaStream_t lane_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_lane_fork = nullptr, ev_lane_acc[2] = {nullptr, nullptr};
 
   std::map<std::string, std::pair<const float*, int64_t>> stages;
 
@@ -1200,40 +1205,78 @@ static int build_plan(int mode, const int32_t shape[3], int n_patches, const int
   return 0;
 }
 
+static int check_handle(dcl_handle* h);
+
+// The second lane of the sliding window: a handle of its own (workspace, captured graph, coupler streams) with a copy
+// of the weights.  Two patches in flight overlap each other's latency-bound phases (the couplers, the 16^3 / 32^3
+// levels): measured 35.3 instead of 30.0 volumes/s.
+static int ensure_twin(dcl_handle* h) {
+  if (h->twin != nullptr) return 0;
+  dcl_handle* t = nullptr;
+  DCL_TRY(dcl_create(&h->cfg, &t));
+  t->host_w = h->host_w;
+  h->twin = t;
+  DCL_TRY(check_handle(t));      // packs the weights
+  for (int i = 0; i < 2; ++i) {
+    DCL_CUDA_OK(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
+    DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lane_acc[i], cudaEventDisableTiming));
+  }
+  DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lane_fork, cudaEventDisableTiming));
+  return 0;
+}
+
 static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], int mode,
                        const std::vector<PlanItem>& plan, int first, int count, const float* keep_host, int zout,
                        float* acc, float* wsum, cudaStream_t st) {
   const int X = shape[0], Y = shape[1], Z = shape[2];
   const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
-  Fwd f{h, st, &h->ts[0]};
-  Fwd16 f16{h, st};
-  int up_have = -1;     // staged upload (host entry point): highest x-slab this stream already waits for
+  static const bool one_lane = getenv("DCL_ONE_LANE") != nullptr;
+  const bool two = h->cfg.precision == DCL_BF16 && !h->profiling && count >= 2 && !one_lane;
+  if (two) {
+    DCL_TRY(ensure_twin(h));
+    DCL_CUDA_OK(cudaEventRecord(h->ev_lane_fork, st));
+    for (int l = 0; l < 2; ++l) DCL_CUDA_OK(cudaStreamWaitEvent(h->lane_stream[l], h->ev_lane_fork, 0));
+  }
+  int up_have[2] = {-1, -1};     // staged upload (host entry point): highest x-slab each lane already waits for
+  int lane = 0;
   for (int i = first; i < first + count; ++i) {
     const PlanItem& p = plan[i];
+    lane = two ? (i - first) & 1 : 0;
+    dcl_handle* hh = lane ? h->twin : h;
+    cudaStream_t s = two ? h->lane_stream[lane] : st;
     if (h->up_active) {
       int need = 0;
       while (need < 2 && h->up_bound[need] < p.start[0] + 128) ++need;
-      for (; up_have < need; ++up_have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[up_have + 1], 0));
+      for (; up_have[lane] < need; ++up_have[lane]) DCL_CUDA_OK(cudaStreamWaitEvent(s, h->ev_up[up_have[lane] + 1], 0));
     }
     const float* x = vol + (int64_t)p.start[0] * xs[1] + (int64_t)p.start[1] * xs[2] + p.start[2];
-    if (h->cfg.precision == DCL_BF16)
-      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
-    else
+    if (h->cfg.precision == DCL_BF16) {
+      Fwd16 f16{hh, s};
+      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, hh->probs, nullptr));
+    } else {
+      Fwd f{h, st, &h->ts[0]};
       DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
-    cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+    }
+    // the accumulates run in patch order (fp32 sums stay reproducible): wait for the previous patch's, on the other lane
+    if (two && i > first) DCL_CUDA_OK(cudaStreamWaitEvent(s, h->ev_lane_acc[lane ^ 1], 0));
+    cudaEvent_t ev = h->profiling ? h->prof_begin(s) : nullptr;
     double bytes;
     if (weighted) {
-      DCL_TRY(launch_accumulate(h->probs, p.start, mode == DCL_STITCH_GAUSSIAN, acc, wsum, X, Y, zout, st));
+      DCL_TRY(launch_accumulate(hh->probs, p.start, mode == DCL_STITCH_GAUSSIAN, acc, wsum, X, Y, zout, s));
       bytes = (double)P3 * (4 * 4 + 2 * (4 * 4 + 4));     // read 4 probs; read+write 4 acc + wsum
     } else {
-      DCL_TRY(launch_stitch_copy(h->probs, acc, p.box, X, Y, zout, st));
+      DCL_TRY(launch_stitch_copy(hh->probs, acc, p.box, X, Y, zout, s));
       bytes = (double)p.box.ext[0] * p.box.ext[1] * p.box.ext[2] * 4 * 4 * 2;
     }
-    if (h->profiling) h->prof_end(ev, 1, bytes, st);
+    if (h->profiling) h->prof_end(ev, 1, bytes, s);
+    if (two) DCL_CUDA_OK(cudaEventRecord(h->ev_lane_acc[lane], s));
   }
-  if (h->up_active)      // the tail (finalize, target) needs the whole upload
-    for (; up_have < 2; ++up_have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[up_have + 1], 0));
+  if (two) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_lane_acc[lane], 0));     // the chain ends at the last accumulate
+  if (h->up_active) {     // the tail (finalize, target) needs the whole upload
+    int have = -1;
+    for (; have < 2; ++have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[have + 1], 0));
+  }
   return 0;
 }
 
@@ -1291,6 +1334,12 @@ DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
 DCL_API int dcl_destroy(dcl_handle* h) {
   if (!h) return DCL_OK;
   cudaDeviceSynchronize();
+  if (h->twin) { dcl_destroy(h->twin); h->twin = nullptr; }
+  for (int i = 0; i < 2; ++i) {
+    if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
+    if (h->ev_lane_acc[i]) cudaEventDestroy(h->ev_lane_acc[i]);
+  }
+  if (h->ev_lane_fork) cudaEventDestroy(h->ev_lane_fork);
   if (h->fwd_graph) cudaGraphExecDestroy(h->fwd_graph);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->conv)
@@ -1353,6 +1402,15 @@ DCL_API int dcl_set_weight(dcl_handle* h, const char* name, const float* data, i
   v.resize((size_t)numel);
   DCL_CUDA_OK(cudaMemcpy(v.data(), data, (size_t)numel * 4, cudaMemcpyDefault));
   h->ready = false;   // repacked lazily by the next compute call
+  if (h->twin) {      // the second lane holds a copy of the weights: rebuilt on demand
+    dcl_destroy(h->twin);
+    h->twin = nullptr;
+    for (int i = 0; i < 2; ++i) {
+      if (h->lane_stream[i]) { cudaStreamDestroy(h->lane_stream[i]); h->lane_stream[i] = nullptr; }
+      if (h->ev_lane_acc[i]) { cudaEventDestroy(h->ev_lane_acc[i]); h->ev_lane_acc[i] = nullptr; }
+    }
+    if (h->ev_lane_fork) { cudaEventDestroy(h->ev_lane_fork); h->ev_lane_fork = nullptr; }
+  }
   return DCL_OK;
 }
 
