@@ -244,9 +244,11 @@ struct dcl_handle {
   bool up_active = false;
   // two patches in flight (bf16 sliding window): a twin handle (own workspace, graph and weights copy) runs every other
   // patch on a second stream; the overlap accumulates stay in patch order through an event chain
-  dcl_handle* twin = nullptr;
-  cudaStream_t lane_stream[2] = {nullptr, nullptr};
-  cudaEvent_t ev_lane_fork = nullptr, ev_lane_acc[2] = {nullptr, nullptr};
+  static constexpr int MAX_LANES = 4;
+  dcl_handle* twin[MAX_LANES - 1] = {nullptr, nullptr, nullptr};
+  int lanes = 0;                                   // lanes built so far (0 = none)
+  cudaStream_t lane_stream[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_lane_fork = nullptr, ev_lane_acc[MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
 
   std::map<std::string, std::pair<const float*, int64_t>> stages;
 
@@ -1206,22 +1208,47 @@ static int build_plan(int mode, const int32_t shape[3], int n_patches, const int
 }
 
 static int check_handle(dcl_handle* h);
+static void free_lanes(dcl_handle* h);
 
 // The second lane of the sliding window: a handle of its own (workspace, captured graph, coupler streams) with a copy
 // of the weights.  Two patches in flight overlap each other's latency-bound phases (the couplers, the 16^3 / 32^3
 // levels): measured 35.3 instead of 30.0 volumes/s.
-static int ensure_twin(dcl_handle* h) {
-  if (h->twin != nullptr) return 0;
-  dcl_handle* t = nullptr;
-  DCL_TRY(dcl_create(&h->cfg, &t));
-  t->host_w = h->host_w;
-  h->twin = t;
-  DCL_TRY(check_handle(t));      // packs the weights
-  for (int i = 0; i < 2; ++i) {
-    DCL_CUDA_OK(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
-    DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lane_acc[i], cudaEventDisableTiming));
+static int lane_count() {      // DCL_LANES = 1..4 (default 3: measured 29.9 / 36.6 / 38.2 / 38.5 volumes/s with 1 / 2 / 3 / 4 lanes)
+  static const int n = [] {
+    const char* e = getenv("DCL_LANES");
+    int v = e ? atoi(e) : 3;
+    if (getenv("DCL_ONE_LANE")) v = 1;
+    return v < 1 ? 1 : (v > dcl_handle::MAX_LANES ? dcl_handle::MAX_LANES : v);
+  }();
+  return n;
+}
+
+static void free_lanes(dcl_handle* h) {
+  for (int i = 0; i < dcl_handle::MAX_LANES - 1; ++i)
+    if (h->twin[i]) { dcl_destroy(h->twin[i]); h->twin[i] = nullptr; }
+  for (int i = 0; i < dcl_handle::MAX_LANES; ++i) {
+    if (h->lane_stream[i]) { cudaStreamDestroy(h->lane_stream[i]); h->lane_stream[i] = nullptr; }
+    if (h->ev_lane_acc[i]) { cudaEventDestroy(h->ev_lane_acc[i]); h->ev_lane_acc[i] = nullptr; }
   }
-  DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lane_fork, cudaEventDisableTiming));
+  if (h->ev_lane_fork) { cudaEventDestroy(h->ev_lane_fork); h->ev_lane_fork = nullptr; }
+  h->lanes = 0;
+}
+
+static int ensure_lanes(dcl_handle* h, int n) {
+  if (h->lanes >= n) return 0;
+  if (!h->ev_lane_fork) DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lane_fork, cudaEventDisableTiming));
+  for (int i = 0; i < n; ++i) {
+    if (!h->lane_stream[i]) DCL_CUDA_OK(cudaStreamCreateWithFlags(&h->lane_stream[i], cudaStreamNonBlocking));
+    if (!h->ev_lane_acc[i]) DCL_CUDA_OK(cudaEventCreateWithFlags(&h->ev_lane_acc[i], cudaEventDisableTiming));
+    if (i > 0 && !h->twin[i - 1]) {
+      dcl_handle* t = nullptr;
+      DCL_TRY(dcl_create(&h->cfg, &t));
+      t->host_w = h->host_w;
+      h->twin[i - 1] = t;
+      DCL_TRY(check_handle(t));      // packs the weights
+    }
+  }
+  h->lanes = n;
   return 0;
 }
 
@@ -1231,19 +1258,20 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
   const int X = shape[0], Y = shape[1], Z = shape[2];
   const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
-  static const bool one_lane = getenv("DCL_ONE_LANE") != nullptr;
-  const bool two = h->cfg.precision == DCL_BF16 && !h->profiling && count >= 2 && !one_lane;
+  int L = lane_count();
+  if (L > count) L = count;
+  const bool two = h->cfg.precision == DCL_BF16 && !h->profiling && L >= 2;
   if (two) {
-    DCL_TRY(ensure_twin(h));
+    DCL_TRY(ensure_lanes(h, L));
     DCL_CUDA_OK(cudaEventRecord(h->ev_lane_fork, st));
-    for (int l = 0; l < 2; ++l) DCL_CUDA_OK(cudaStreamWaitEvent(h->lane_stream[l], h->ev_lane_fork, 0));
+    for (int l = 0; l < L; ++l) DCL_CUDA_OK(cudaStreamWaitEvent(h->lane_stream[l], h->ev_lane_fork, 0));
   }
-  int up_have[2] = {-1, -1};     // staged upload (host entry point): highest x-slab each lane already waits for
+  int up_have[dcl_handle::MAX_LANES] = {-1, -1, -1, -1};     // staged upload: highest x-slab each lane already waits for
   int lane = 0;
   for (int i = first; i < first + count; ++i) {
     const PlanItem& p = plan[i];
-    lane = two ? (i - first) & 1 : 0;
-    dcl_handle* hh = lane ? h->twin : h;
+    lane = two ? (i - first) % L : 0;
+    dcl_handle* hh = lane ? h->twin[lane - 1] : h;
     cudaStream_t s = two ? h->lane_stream[lane] : st;
     if (h->up_active) {
       int need = 0;
@@ -1259,7 +1287,7 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
       DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
     }
     // the accumulates run in patch order (fp32 sums stay reproducible): wait for the previous patch's, on the other lane
-    if (two && i > first) DCL_CUDA_OK(cudaStreamWaitEvent(s, h->ev_lane_acc[lane ^ 1], 0));
+    if (two && i > first) DCL_CUDA_OK(cudaStreamWaitEvent(s, h->ev_lane_acc[(lane + L - 1) % L], 0));
     cudaEvent_t ev = h->profiling ? h->prof_begin(s) : nullptr;
     double bytes;
     if (weighted) {
@@ -1334,12 +1362,7 @@ DCL_API int dcl_create(const dcl_config* cfg, dcl_handle** out) {
 DCL_API int dcl_destroy(dcl_handle* h) {
   if (!h) return DCL_OK;
   cudaDeviceSynchronize();
-  if (h->twin) { dcl_destroy(h->twin); h->twin = nullptr; }
-  for (int i = 0; i < 2; ++i) {
-    if (h->lane_stream[i]) cudaStreamDestroy(h->lane_stream[i]);
-    if (h->ev_lane_acc[i]) cudaEventDestroy(h->ev_lane_acc[i]);
-  }
-  if (h->ev_lane_fork) cudaEventDestroy(h->ev_lane_fork);
+  free_lanes(h);
   if (h->fwd_graph) cudaGraphExecDestroy(h->fwd_graph);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->conv)
@@ -1402,15 +1425,7 @@ DCL_API int dcl_set_weight(dcl_handle* h, const char* name, const float* data, i
   v.resize((size_t)numel);
   DCL_CUDA_OK(cudaMemcpy(v.data(), data, (size_t)numel * 4, cudaMemcpyDefault));
   h->ready = false;   // repacked lazily by the next compute call
-  if (h->twin) {      // the second lane holds a copy of the weights: rebuilt on demand
-    dcl_destroy(h->twin);
-    h->twin = nullptr;
-    for (int i = 0; i < 2; ++i) {
-      if (h->lane_stream[i]) { cudaStreamDestroy(h->lane_stream[i]); h->lane_stream[i] = nullptr; }
-      if (h->ev_lane_acc[i]) { cudaEventDestroy(h->ev_lane_acc[i]); h->ev_lane_acc[i] = nullptr; }
-    }
-    if (h->ev_lane_fork) { cudaEventDestroy(h->ev_lane_fork); h->ev_lane_fork = nullptr; }
-  }
+  free_lanes(h);      // the extra lanes hold copies of the weights: rebuilt on demand
   return DCL_OK;
 }
 
