@@ -1217,7 +1217,6 @@ static int lane_count() {      // DCL_LANES = 1..4 (default 3: measured 29.9 / 3
   static const int n = [] {
     const char* e = getenv("DCL_LANES");
     int v = e ? atoi(e) : 3;
-    if (getenv("DCL_ONE_LANE")) v = 1;
     return v < 1 ? 1 : (v > dcl_handle::MAX_LANES ? dcl_handle::MAX_LANES : v);
   }();
   return n;

@@ -13,7 +13,9 @@
  *     Z is the contiguous axis (predict_overlap.py:34-41 slices it last)
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream)
  *   - a handle is bound to the CUDA device that was current in dcl_create and is not
- *     thread safe; use one handle per stream
+ *     thread safe; use one handle per stream (different handles may be used from different threads)
+ *   - environment: DCL_LANES=1..4 patches in flight per volume call (default 3), DCL_PDL=1 programmatic dependent
+ *     launch, DCL_STAMPS=1 / DCL_DEBUG=1 debug aids
  *   - pointers named *_dev are device pointers, *_host host pointers; the caller owns all of them
  */
 #ifndef DCL_B200_H
@@ -49,7 +51,7 @@ typedef enum dcl_status {
 /* Arithmetic mode of the convolution / GEMM kernels. */
 typedef enum dcl_precision {
   DCL_FP32 = 0,            /* fp32 FFMA kernels: the parity mode (1e-3 rel. to the reference) */
-  DCL_BF16X3 = 1,          /* tcgen05 bf16 MMA on split operands (hi+lo), fp32 accumulate: fp32-class accuracy */
+  DCL_BF16X3 = 1,          /* reserved for split-operand (hi+lo) bf16 MMAs; currently runs the fp32 kernels of DCL_FP32 */
   DCL_BF16 = 2             /* tcgen05 bf16 MMA, fp32 accumulate (2e-2 rel.) */
 } dcl_precision;
 
