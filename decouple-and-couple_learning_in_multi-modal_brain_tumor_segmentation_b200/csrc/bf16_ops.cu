@@ -212,13 +212,13 @@ deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, c
   __nv_bfloat16* s_ws = s_wm + 2 * CH * LDM;                                   // [CH][LDS_]
   float* s_b = reinterpret_cast<float*>(s_ws + CH * LDS_);                     // [2 kw][CH]
   const int kdh = blockIdx.y;                       // kd*2 + kh
-  for (int e = threadIdx.x; e < 2 * CH * CIN; e += 256) {
-    const int c = e % CIN, o = (e / CIN) % CH, kw = e / (CIN * CH);
-    s_wm[(kw * CH + o) * LDM + c] = __float2bfloat16_rn(__ldg(mt + ((int64_t)(kdh * 2 + kw) * CH + o) * CIN + c));   // mt[t][o][c]
-  }
-  for (int e = threadIdx.x; e < CH * CH; e += 256) {
-    const int sc = e % CH, o = e / CH;
-    s_ws[o * LDS_ + sc] = __float2bfloat16_rn(__ldg(w3a + (int64_t)o * CH + sc));                                     // w3a[o][s]
+  {   // mt / w3a arrive as the bf16 padded image built at weight-load time: [8 taps][CH][LDM] and [CH][LDS_]
+    const uint4* src_m = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(mt) + (size_t)(kdh * 2) * CH * LDM);
+    uint4* dst_m = reinterpret_cast<uint4*>(s_wm);
+    for (int e = threadIdx.x; e < 2 * CH * LDM / 8; e += 256) dst_m[e] = __ldg(src_m + e);
+    const uint4* src_s = reinterpret_cast<const uint4*>(w3a);
+    uint4* dst_s = reinterpret_cast<uint4*>(s_ws);
+    for (int e = threadIdx.x; e < CH * LDS_ / 8; e += 256) dst_s[e] = __ldg(src_s + e);
   }
   for (int e = threadIdx.x; e < 2 * CH; e += 256) s_b[e] = __ldg(bt + (int64_t)(kdh * 2) * CH + e);                   // bt[t][o]
   __syncthreads();

@@ -221,7 +221,7 @@ struct dcl_handle {
   void *b_dl[3][5];                              // decoder levels: in, a, b, 1, 2
   stat_t* stat_arena = nullptr;                  // STAT_SLOTS x 1024 fixed-point sums, zeroed once per forward
   int stat_used = 0;
-  struct DeUpW { float *mt, *w3a, *bt; } deup[3];
+  struct DeUpW { float *mt, *w3a, *bt; } deup[3];     // mt / w3a: bf16 rows padded by 8 elements (the kernel's smem image)
   float *end_w = nullptr, *end_b = nullptr;
   struct BStage { const void* p; int c; int64_t spatial; };
   std::map<std::string, BStage> bstages;
@@ -556,7 +556,23 @@ static int prepare(dcl_handle* h) {
           }
         }
       }
-      DCL_TRY(upload(h, mt, &h->deup[l].mt)); DCL_TRY(upload(h, w3a, &h->deup[l].w3a)); DCL_TRY(upload(h, btc, &h->deup[l].bt));
+      // the kernel keeps these as bf16 with rows padded by 8 elements (conflict-free fragment reads): store exactly that
+      // image, so its prologue is a straight 16-byte copy instead of thousands of scalar loads + conversions per CTA
+      auto to_bf16_padded = [](const std::vector<float>& src, int rows, int cols) {
+        std::vector<float> out((size_t)rows * (cols + 8) / 2, 0.f);      // 2 bf16 per float slot
+        uint16_t* o = reinterpret_cast<uint16_t*>(out.data());
+        for (int r = 0; r < rows; ++r)
+          for (int c = 0; c < cols; ++c) {
+            uint32_t u; float f = src[(size_t)r * cols + c];
+            memcpy(&u, &f, 4);
+            u += 0x7fffu + ((u >> 16) & 1u);
+            o[(size_t)r * (cols + 8) + c] = (uint16_t)(u >> 16);
+          }
+        return out;
+      };
+      DCL_TRY(upload(h, to_bf16_padded(mt, 8 * CH, C), &h->deup[l].mt));
+      DCL_TRY(upload(h, to_bf16_padded(w3a, CH, CH), &h->deup[l].w3a));
+      DCL_TRY(upload(h, btc, &h->deup[l].bt));
     }
     DCL_TRY(upload(h, h->host_w.at("decoder.endconv.weight"), &h->end_w));
     DCL_TRY(upload(h, h->host_w.at("decoder.endconv.bias"), &h->end_b));
