@@ -74,6 +74,20 @@ _SIGNATURES = {
                                          C.c_void_p]),
     "dcl_finalize_labels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcl_export_labels": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcl_snapshot_frames": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcl_slice_counts": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
+    "dcl_write_nifti": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "dcl_write_npy_labels": (C.c_int, [C.c_char_p, C.c_void_p, C.POINTER(C.c_int32)]),
+    "dcl_write_png_rgb": (C.c_int, [C.c_char_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "dcl_read_nifti_header": (C.c_int, [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
+    "dcl_read_nifti_f32": (C.c_int64, [C.c_char_p, C.c_void_p, C.c_int64]),
+    "dcl_preprocess_volume": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dcl_reorder_labels": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "dcl_hausdorff_workspace_bytes": (C.c_int64, [C.POINTER(C.c_int32)]),
+    "dcl_hausdorff": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_int64, C.POINTER(C.c_double),
+                                C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_void_p]),
+    "dcl_percentile_from_hist": (C.c_double, [C.c_void_p, C.c_int64, C.c_double]),
     "dcl_read_stage": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "dcl_read_topk": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcl_launch_count": (C.c_int64, [C.c_void_p]),

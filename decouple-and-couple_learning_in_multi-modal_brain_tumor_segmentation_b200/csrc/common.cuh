@@ -123,6 +123,7 @@ struct PatchDesc {
   const float* x;           // first element of the (4,128,128,128) view
   long long sc, sd, sh;     // element strides of (C, X, Y); the Z stride is 1
   float keep[16];
+  float* probs;             // nullptr, or where this patch's probabilities go instead of the handle's buffer
 };
 // debug: dst[idx] = %globaltimer (ns); DCL_STAMPS=1 places these between the stages of the forward
 int launch_stamp(unsigned long long* dst, int idx, cudaStream_t st);
@@ -144,6 +145,15 @@ struct StitchBox {      // one rectangular copy of the crop-and-overwrite plan
 int launch_stitch_copy(const float* probs, float* out, const StitchBox& box, int X, int Y, int Zout, cudaStream_t st);
 int launch_accumulate(const float* probs, const int start[3], int gaussian, float* acc, float* wsum, int X, int Y,
                       int Z, cudaStream_t st);
+// gather form of the weighted stitch: patch i keeps its probabilities at patch_probs + i * 4 * 128^3
+struct GatherPlan {
+  static constexpr int MAX = 128;
+  int n;
+  int start[MAX][3];
+};
+int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,
+                           float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                           cudaStream_t st);
 // probs (4 x total) [+ wsum] -> labels / normalised probs / 13 counters over voxels [v0, v0+nvox)
 int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, int64_t v0, int64_t nvox,
                            float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,

@@ -15,6 +15,12 @@ __device__ __forceinline__ float4 ld_stream4(const float* p) {
   return r;
 }
 
+__device__ __forceinline__ float ld_stream1(const float* p) {
+  float r;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+  return r;
+}
+
 // out[c, dst+e] = probs[c, src+e] for e in the box.  Thread = one (x,y,z) of the box, all 4 classes;
 // z is contiguous in both tensors so warps read and write full sectors.
 __global__ void __launch_bounds__(256)
@@ -225,6 +231,93 @@ int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, i
   if (blocks > persistent) blocks = persistent;
   finalize_labels_kernel<<<(unsigned)blocks, 256, 0, st>>>(acc, wsum, total, v0, nvox, probs_out, labels, target,
                                                           counts);
+  ++g_launches;
+  DCL_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gather form of the weighted stitch (extension modes): every patch keeps its probabilities in its own slot of
+// `pp` (P x 4 x 128^3) and ONE kernel forms, per output voxel, sum_i w_i p_i / sum_i w_i over the patches that
+// cover it, the arg-max label and the counters.  Against accumulate + finalize this drops the accumulator round
+// trip: P x 33.5 MB read + 1 B / voxel written (613 MB for 18 patches) instead of P x 117 MB + 196 MB (2.3 GB).
+// The sums run in patch order with the same FMA as accumulate_kernel, so the result is bit-identical to it.
+// CTA = one (x,y) row of the volume: the patches covering (x,y) are listed once per CTA (in patch order), each
+// thread then owns one z and tests only the z range; loads are coalesced along z in every patch slot.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussian, int Y, int Z,
+                       float* __restrict__ probs_out, uint8_t* __restrict__ labels, const uint8_t* __restrict__ target,
+                       unsigned long long* __restrict__ counts) {
+  __shared__ int s_n;
+  __shared__ short s_idx[GatherPlan::MAX];
+  __shared__ float s_wxy[GatherPlan::MAX];
+  __shared__ unsigned s_cnt[13];
+  const int row = blockIdx.x;                       // x * Y + y
+  const int x = row / Y, y = row - x * Y;
+  if (threadIdx.x < 13) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x < 32) {                           // warp 0 compacts the covering patches, keeping their order
+    int base = 0;
+    for (int i0 = 0; i0 < plan.n; i0 += 32) {
+      const int i = i0 + threadIdx.x;
+      bool hit = false;
+      if (i < plan.n) {
+        const int lx = x - plan.start[i][0], ly = y - plan.start[i][1];
+        hit = (unsigned)lx < (unsigned)P && (unsigned)ly < (unsigned)P;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int k = base + __popc(m & ((1u << threadIdx.x) - 1u));
+        s_idx[k] = (short)i;
+        s_wxy[k] = blend_w1(x - plan.start[i][0], gaussian) * blend_w1(y - plan.start[i][1], gaussian);
+      }
+      base += __popc(m);
+    }
+    if (threadIdx.x == 0) s_n = base;
+  }
+  __syncthreads();
+  const int n = s_n;
+  const int64_t plane = (int64_t)gridDim.x * Z;     // voxels of the volume
+  LabelCounts k;
+#pragma unroll
+  for (int i = 0; i < 13; ++i) k.v[i] = 0;
+  for (int z = threadIdx.x; z < Z; z += 256) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ws = 0.f;
+    for (int j = 0; j < n; ++j) {
+      const int i = s_idx[j];
+      const int lz = z - plan.start[i][2];
+      if ((unsigned)lz >= (unsigned)P) continue;
+      const float w = s_wxy[j] * blend_w1(lz, gaussian);
+      const float* p = pp + (int64_t)i * 4 * P3 + ((int64_t)(x - plan.start[i][0]) * P + (y - plan.start[i][1])) * P + lz;
+      const float p0 = ld_stream1(p), p1 = ld_stream1(p + P3), p2 = ld_stream1(p + 2 * P3), p3 = ld_stream1(p + 3 * P3);
+      a0 = __fmaf_rn(w, p0, a0); a1 = __fmaf_rn(w, p1, a1); a2 = __fmaf_rn(w, p2, a2); a3 = __fmaf_rn(w, p3, a3);
+      ws += w;
+    }
+    a0 /= ws; a1 /= ws; a2 /= ws; a3 /= ws;
+    const int64_t v = (int64_t)row * Z + z;
+    if (probs_out) { probs_out[v] = a0; probs_out[plane + v] = a1; probs_out[2 * plane + v] = a2; probs_out[3 * plane + v] = a3; }
+    const int l = argmax4(a0, a1, a2, a3);
+    if (labels) labels[v] = (uint8_t)l;
+    if (counts) count_label(k, l, target ? target[v] : 0, target != nullptr);
+  }
+  if (counts) {
+#pragma unroll
+    for (int i = 0; i < 13; ++i) {
+      unsigned r = __reduce_add_sync(0xffffffffu, k.v[i]);
+      if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_cnt[i], r);
+    }
+    __syncthreads();
+    if (threadIdx.x < 13 && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+  }
+}
+
+int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,
+                           float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                           cudaStream_t st) {
+  if (plan.n < 1 || plan.n > GatherPlan::MAX) { set_error("gather_finalize: 1..128 patches"); return -1; }
+  const int threads = Z >= 224 ? 256 : Z > 160 ? 224 : Z > 128 ? 160 : 128;
+  gather_finalize_kernel<<<(unsigned)(X * Y), threads, 0, st>>>(patch_probs, plan, gaussian, Y, Z, probs_out, labels,
+                                                               target, counts);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

@@ -152,6 +152,58 @@ DCL_API int dcl_finalize_labels(const float* acc_dev, const float* wsum_dev, int
                         int64_t nvox, float* probs_out_dev, uint8_t* labels_out_dev,
                         const uint8_t* target_dev, uint64_t* counts_out_dev, void* stream);
 
+/* ---- label export: the savepath / save_format / snapshot block of validate_softmax
+ * (predict.py:310-350) and the per-slice pictures / tables of predict_simple.py:186-278 ---- */
+/* labels_dev (X,Y,Z) uint8 in {0..3}.  seg_out_dev: NULL or (X,Y,Z) with label 3 written as 4 (predict.py:322-324);
+ * seg_nifti_dev: NULL or the same values in NIfTI storage order (x fastest = the array nibabel writes for seg_img);
+ * counts_out_dev: NULL or 6 uint64: voxels of label 1, 2, 4, then WT, TC, ET (the verbose print, predict.py:325-328). */
+DCL_API int dcl_export_labels(const uint8_t* labels_dev, const int32_t shape[3], uint8_t* seg_out_dev,
+                      uint8_t* seg_nifti_dev, uint64_t* counts_out_dev, void* stream);
+/* frames_out_dev (Z, X, Y, 3) uint8: frame z = Snapshot_img[:, :, :, z] of predict.py:338-350 with
+ * palette[label][rgb]; the reference's schemes are {255,0,0, 0,0,0, 0,255,0, 0,0,255} (predict.py:342-344) and
+ * {0,0,0, 250,250,149, 244,130,128, 97,136,200} (predict_simple.py:193-197). */
+DCL_API int dcl_snapshot_frames(const uint8_t* labels_dev, const int32_t shape[3], const uint8_t palette[12],
+                        uint8_t* frames_out_dev, void* stream);
+/* counts_out_dev (Z, 9) uint64: per z slice (|o|,|t|,|o&t|) for WT, TC, ET = the integers behind the per-frame
+ * softmax_output_dice of output_excel (predict_simple.py:224-243); Z <= 256. */
+DCL_API int dcl_slice_counts(const uint8_t* labels_dev, const uint8_t* target_dev, const int32_t shape[3],
+                     uint64_t* counts_out_dev, void* stream);
+/* Host-side writers (no device needed).  dcl_write_nifti: NIfTI-1 single file, gzip when the path ends in ".gz";
+ * data_host in storage order (x fastest), datatype = NIfTI code (2 uint8, 4 int16, 16 float32, ...); header as
+ * nibabel's Nifti1Image(data, None): unit voxels, qform_code = sform_code = 0 (predict.py:329, nibabel itself is
+ * absent from this image).  dcl_write_npy_labels: np.save of the int64 arg-max map (predict.py:313-314), byte-identical
+ * to numpy 2.x.  dcl_write_png_rgb: one (height, width, 3) frame (imageio.imwrite, predict.py:350). */
+DCL_API int dcl_write_nifti(const char* path, const void* data_host, int32_t datatype, const int32_t shape[3]);
+DCL_API int dcl_write_npy_labels(const char* path, const uint8_t* labels_host, const int32_t shape[3]);
+DCL_API int dcl_write_png_rgb(const char* path, const uint8_t* rgb_host, int32_t height, int32_t width);
+
+/* ---- input side: what data/ClsWiseBraTS128Test.BraDataSet128 (test_overlap.py:14,94-97, not shipped
+ * by the reference) hands to predict_overlap.py:132-135 ---- */
+DCL_API int dcl_read_nifti_header(const char* path, int32_t shape_out[3], int32_t* datatype_out, float pixdim_out[3]);
+/* voxel data as float32 in storage order (x fastest), scl_slope / scl_inter applied; returns the element count */
+DCL_API int64_t dcl_read_nifti_f32(const char* path, float* data_out_host, int64_t capacity);
+/* modalities_dev (4, Z, Y, X) float32 = four NIfTI arrays as stored (FLAIR, T1ce, T1, T2 in the caller's order) ->
+ * vol_out_dev (4, X, Y, z_pad): mask = sum over modalities > 0, per modality (x - mean) / std over the mask (population
+ * std), other voxels unchanged, z in [Z, z_pad) zero.  stats_dev: 17 doubles of device scratch; on completion
+ * [8] = mask voxels, [9..12] = mean, [13..16] = std. */
+DCL_API int dcl_preprocess_volume(const float* modalities_dev, const int32_t shape[3], int32_t z_pad, float* vol_out_dev,
+                          double* stats_dev, void* stream);
+/* seg_nifti_dev (Z, Y, X) uint8 as stored -> target_out_dev (X, Y, z_pad), optionally 4 -> 3 (predict_overlap.py:150-152) */
+DCL_API int dcl_reorder_labels(const uint8_t* seg_nifti_dev, const int32_t shape[3], int32_t z_pad, int32_t map4to3,
+                       uint8_t* target_out_dev, void* stream);
+
+/* ---- surface-distance metrics: cal_hausdorff (predict_simple.py:121-144) ->
+ * utils/hausdorff.py:86-123 -> medpy.metric.binary.hd95 / hd (medpy is absent: its published algorithm is restated in
+ * csrc/hausdorff.cu) for the WT, TC and ET regions of two (X,Y,Z) uint8 label maps in {0..3}.  Exact integer squared
+ * distance transform + histogram on the device, numpy's "linear" percentile on the host; 0 for an empty or full mask.
+ * The call synchronises the stream.  surface_voxels_out_host: NULL or the number of surface distances per region. */
+DCL_API int64_t dcl_hausdorff_workspace_bytes(const int32_t shape[3]);
+DCL_API int dcl_hausdorff(const uint8_t* labels_dev, const uint8_t* target_dev, const int32_t shape[3], void* workspace_dev,
+                  int64_t workspace_bytes, double hd95_out_host[3], double hd_out_host[3],
+                  uint64_t surface_voxels_out_host[3], void* stream);
+/* numpy.percentile(a, q) ("linear") of the multiset {sqrt(i) repeated hist[i] times}; pure host code */
+DCL_API double dcl_percentile_from_hist(const uint32_t* hist_host, int64_t nbins, double q_percent);
+
 /* ---- introspection used by the parity tests (tests/) and the bench ---- */
 /* Copies the named intermediate tensor of the last dcl_forward into out_dev (dense NCDHW / row
  * major).  Returns its element count, or a negative status.  Requires cfg.keep_stages. */
