@@ -12,6 +12,7 @@ from ._native import (DclError, Precision, StitchMode, abi_version, build_librar
                       weight_catalogue, workspace_bytes)
 from .engine import Engine, patch_starts, reference_starts
 from . import sharded
+from . import volio
 
 __all__ = ["DclError", "Precision", "StitchMode", "Engine", "abi_version", "build_library", "library_path",
-           "load_library", "weight_catalogue", "workspace_bytes", "patch_starts", "reference_starts", "sharded"]
+           "load_library", "weight_catalogue", "workspace_bytes", "patch_starts", "reference_starts", "sharded", "volio"]

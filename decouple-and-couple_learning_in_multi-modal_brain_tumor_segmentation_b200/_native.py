@@ -99,6 +99,7 @@ _SIGNATURES = {
                                    C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "dcl_op_instnorm_stats": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcl_bench_conv": (C.c_double, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "dcl_bench_stitch": (C.c_double, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "dcl_debug_stamps": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dcl_trace_enable": (C.c_int, [C.c_int32]),
     "dcl_trace_read": (C.c_int64, [C.c_void_p, C.c_int64]),

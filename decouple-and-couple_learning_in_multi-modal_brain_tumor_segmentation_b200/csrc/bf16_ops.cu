@@ -316,9 +316,13 @@ int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const 
 // ---- endconv (1x1, 16 -> 4) + Softmax(dim=1) (cls_wise_former.py:662-663): B -> fp32 NCDHW ----------
 __global__ void __launch_bounds__(256)
 endconv_softmax_b_kernel(const uint4* __restrict__ x, BNorm n, const uint4* __restrict__ res, const float* __restrict__ w,
-                         const float* __restrict__ b, float* __restrict__ probs, int64_t spatial) {
+                         const float* __restrict__ b, float* __restrict__ probs_fixed, int64_t spatial,
+                         const PatchDesc* __restrict__ desc) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
+  // the replayed graph bakes probs_fixed in; a per-patch destination (gather-form stitch, caller's buffer) comes
+  // through the device-side patch descriptor instead
+  float* __restrict__ probs = (desc != nullptr && desc->probs != nullptr) ? desc->probs : probs_fixed;
   __shared__ float s_w[4][16];
   __shared__ float s_b[4];
   __shared__ float s_mean[16], s_rstd[16];
@@ -374,13 +378,13 @@ endconv_softmax_b_kernel(const uint4* __restrict__ x, BNorm n, const uint4* __re
 }
 
 int launch_endconv_softmax_b(const void* x, const float* w, const float* b, float* probs, int64_t spatial,
-                             cudaStream_t st, const BNorm* norm, const void* res) {
+                             cudaStream_t st, const BNorm* norm, const void* res, const PatchDesc* desc) {
   BNorm n;
   if (norm) n = *norm;
   unsigned gx = (unsigned)((spatial + 255) / 256);
   if (gx > 148 * 8) gx = 148 * 8;
   DCL_CUDA_OK(launch_pdl(endconv_softmax_b_kernel, dim3(gx), dim3(256), (size_t)(0), st,
-                         reinterpret_cast<const uint4*>(x), n, reinterpret_cast<const uint4*>(res), w, b, probs, spatial));
+                         reinterpret_cast<const uint4*>(x), n, reinterpret_cast<const uint4*>(res), w, b, probs, spatial, desc));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

@@ -89,7 +89,8 @@ int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const 
 // norm != nullptr: the input is act(norm(x)) + res, i.e. the DeBlock tail is applied while loading (bit-identical to
 // running launch_norm_act_b first, including its bf16 rounding)
 int launch_endconv_softmax_b(const void* x, const float* w, const float* b, float* probs, int64_t spatial,
-                             cudaStream_t st, const BNorm* norm = nullptr, const void* res = nullptr);
+                             cudaStream_t st, const BNorm* norm = nullptr, const void* res = nullptr,
+                             const PatchDesc* desc = nullptr);
 
 // fp32 [rows][512] (optionally LayerNorm'ed) -> bf16 blocked [64][rows][8]
 int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st);

@@ -231,6 +231,7 @@ struct dcl_handle {
   // ---- volume level ----
   float* vol_probs = nullptr;  int64_t vol_probs_cap = 0;
   float* vol_wsum = nullptr;   int64_t vol_wsum_cap = 0;
+  float* gather_buf = nullptr; int64_t gather_cap = 0;      // gather-form stitch: one probability slot per patch
   float* tta_vol = nullptr;    int64_t tta_vol_cap = 0;      // flipped copy of the volume (TTA)
   float* tta_sum = nullptr;    int64_t tta_sum_cap = 0;      // running sum of the un-flipped softmaxes (TTA)
   float* stage_vol = nullptr;  int64_t stage_vol_cap = 0;
@@ -921,6 +922,7 @@ struct Fwd16 {
     PatchDesc d;
     d.x = x; d.sc = xs[0]; d.sd = xs[1]; d.sh = xs[2];
     for (int i = 0; i < 16; ++i) d.keep[i] = keep_host ? keep_host[i] : 1.f;
+    d.probs = probs_out;      // endconv writes here (the captured graph only knows h->probs)
     DCL_TRY(launch_patch_desc(h->patch_desc, d, st));
     const bool graphable = aux == nullptr && !h->profiling && !h->fwd_graph_off;
     if (!graphable) return body(probs_out, aux);
@@ -960,8 +962,6 @@ struct Fwd16 {
     }
     DCL_CUDA_OK(cudaGraphLaunch(h->fwd_graph, st));
     g_launches += h->fwd_graph_launches;
-    if (probs_out != h->probs)
-      DCL_CUDA_OK(cudaMemcpyAsync(probs_out, h->probs, 4 * P3 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     return 0;
   }
 
@@ -1125,8 +1125,8 @@ struct Fwd16 {
     DCL_TRY(stamp(8));
     {
       dcl_handle::ProfScope ps(h, st, 9);
-      if (end_src != nullptr) DCL_TRY(launch_endconv_softmax_b(end_src, h->end_w, h->end_b, probs_out, P3, st, &end_tail, end_res));
-      else DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st));
+      if (end_src != nullptr) DCL_TRY(launch_endconv_softmax_b(end_src, h->end_w, h->end_b, probs_out, P3, st, &end_tail, end_res, h->patch_desc));
+      else DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st, nullptr, nullptr, h->patch_desc));
     }
     DCL_TRY(stamp(9));
     return 0;
@@ -1269,7 +1269,7 @@ static int ensure_lanes(dcl_handle* h, int n) {
 
 static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], int mode,
                        const std::vector<PlanItem>& plan, int first, int count, const float* keep_host, int zout,
-                       float* acc, float* wsum, cudaStream_t st) {
+                       float* acc, float* wsum, cudaStream_t st, float* gather = nullptr) {
   const int X = shape[0], Y = shape[1], Z = shape[2];
   const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
@@ -1294,12 +1294,19 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
       for (; up_have[lane] < need; ++up_have[lane]) DCL_CUDA_OK(cudaStreamWaitEvent(s, h->ev_up[up_have[lane] + 1], 0));
     }
     const float* x = vol + (int64_t)p.start[0] * xs[1] + (int64_t)p.start[1] * xs[2] + p.start[2];
+    // gather form: the patch keeps its probabilities in its own slot; nothing is accumulated here and the lanes
+    // never wait for each other
+    float* dst = gather ? gather + (int64_t)(i - first) * 4 * P3 : nullptr;
     if (h->cfg.precision == DCL_BF16) {
       Fwd16 f16{hh, s};
-      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, hh->probs, nullptr));
+      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : hh->probs, nullptr));
     } else {
       Fwd f{h, st, &h->ts[0]};
-      DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, h->probs, nullptr));
+      DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : h->probs, nullptr));
+    }
+    if (gather) {
+      if (two) DCL_CUDA_OK(cudaEventRecord(h->ev_lane_acc[lane], s));
+      continue;
     }
     // the accumulates run in patch order (fp32 sums stay reproducible): wait for the previous patch's, on the other lane
     if (two && i > first) DCL_CUDA_OK(cudaStreamWaitEvent(s, h->ev_lane_acc[(lane + L - 1) % L], 0));
@@ -1315,7 +1322,11 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
     if (h->profiling) h->prof_end(ev, 1, bytes, s);
     if (two) DCL_CUDA_OK(cudaEventRecord(h->ev_lane_acc[lane], s));
   }
-  if (two) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_lane_acc[lane], 0));     // the chain ends at the last accumulate
+  if (two && gather) {
+    for (int l = 0; l < L; ++l) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_lane_acc[l], 0));   // every lane's last patch
+  } else if (two) {
+    DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_lane_acc[lane], 0));     // the chain ends at the last accumulate
+  }
   if (h->up_active) {     // the tail (finalize, target) needs the whole upload
     int have = -1;
     for (; have < 2; ++have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[have + 1], 0));
@@ -1402,6 +1413,7 @@ DCL_API int dcl_destroy(dcl_handle* h) {
   if (h->ev_st) cudaEventDestroy(h->ev_st);
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);
+  if (h->gather_buf) cudaFree(h->gather_buf);
   if (h->tta_vol) cudaFree(h->tta_vol);
   if (h->tta_sum) cudaFree(h->tta_sum);
   if (h->stage_vol) cudaFree(h->stage_vol);
@@ -1511,6 +1523,30 @@ DCL_API int dcl_predict_volume(dcl_handle* h, const float* vol_dev, const int32_
   DCL_TRY(build_plan(mode, shape, n_patches, starts_host, &plan, &zout));
   const int64_t V = (int64_t)shape[0] * shape[1] * zout;
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
+  // weighted modes: gather form by default (one slot per patch, no accumulator round trip; bit-identical to the
+  // accumulate form, which DCL_GATHER=0 selects and the multi-GPU path keeps using)
+  const char* genv = getenv("DCL_GATHER");
+  const bool gather = weighted && (int)plan.size() <= GatherPlan::MAX && !(genv && genv[0] == '0');
+  if (gather) {
+    const int np = (int)plan.size();
+    DCL_TRY(grow(h, (void**)&h->gather_buf, &h->gather_cap, (int64_t)np * 4 * P3 * 4));
+    const int64_t before = g_launches;
+    int rc = run_patches(h, vol_dev, shape, mode, plan, 0, np, keep_scale_host, zout, nullptr, nullptr, st, h->gather_buf);
+    if (rc == 0 && (labels_out_dev || counts_out_dev || probs_out_dev)) {
+      if (counts_out_dev) DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, 13 * sizeof(uint64_t), st));
+      GatherPlan gp;
+      gp.n = np;
+      for (int i = 0; i < np; ++i) for (int a = 0; a < 3; ++a) gp.start[i][a] = plan[i].start[a];
+      cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+      rc = launch_gather_finalize(h->gather_buf, gp, mode == DCL_STITCH_GAUSSIAN, shape[0], shape[1], zout, probs_out_dev,
+                                  labels_out_dev, target_dev, (unsigned long long*)counts_out_dev, st);
+      if (h->profiling)
+        h->prof_end(ev, 1, (double)np * 4 * P3 * 4 + (double)V * ((probs_out_dev ? 16 : 0) + (labels_out_dev ? 1 : 0) +
+                                                                  (target_dev ? 1 : 0)), st);
+    }
+    h->launches += g_launches - before;
+    return rc;
+  }
   DCL_TRY(grow(h, (void**)&h->vol_probs, &h->vol_probs_cap, 4 * V * 4));
   float* acc = h->vol_probs;
   float* wsum = nullptr;
@@ -1772,6 +1808,53 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(x); cudaFree(y); cudaFree(r); cudaFree(bias); cudaFree(sin); cudaFree(sout);
   tc_free_weights(&tw);
+  return rc == 0 ? (double)ms * 1e3 / reps : -1.0;
+}
+
+// Isolated device timing of the weighted stitch on one X x Y x Z volume with the sliding-window plan of `stride`:
+// form 0 = gather (one gather_finalize launch over the per-patch slots), form 1 = accumulate (two memsets, one accumulate
+// launch per patch, finalize).  Slots hold a constant; labels + counters are produced.  Returns us per volume.
+DCL_API double dcl_bench_stitch(const int32_t shape[3], int32_t stride, int32_t gaussian, int32_t form, int32_t reps,
+                                int32_t* n_patches_out) {
+  if (!shape || stride < 1 || reps < 1) return -1.0;
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  std::vector<int32_t> starts;
+  auto axis = [&](int n) { std::vector<int> v; for (int s = 0; s < n - 128; s += stride) v.push_back(s); v.push_back(n - 128); return v; };
+  const std::vector<int> xs = axis(shape[0]), ys = axis(shape[1]), zs = axis(shape[2]);
+  for (int z : zs) for (int x : xs) for (int y : ys) { starts.push_back(x); starts.push_back(y); starts.push_back(z); }
+  const int np = (int)starts.size() / 3;
+  if (build_plan(DCL_STITCH_UNIFORM, shape, np, starts.data(), &plan, &zout) != 0 || np > GatherPlan::MAX) return -1.0;
+  if (n_patches_out) *n_patches_out = np;
+  const int64_t V = (int64_t)shape[0] * shape[1] * zout;
+  float *slots = nullptr, *acc = nullptr, *wsum = nullptr;
+  uint8_t* labels = nullptr;
+  unsigned long long* counts = nullptr;
+  if (cudaMalloc((void**)&slots, (size_t)np * 4 * P3 * 4) != cudaSuccess) return -1.0;
+  cudaMalloc((void**)&acc, 4 * V * 4); cudaMalloc((void**)&wsum, V * 4); cudaMalloc((void**)&labels, V); cudaMalloc((void**)&counts, 13 * 8);
+  cudaMemset(slots, 0x3e, (size_t)np * 4 * P3 * 4);
+  GatherPlan gp;
+  gp.n = np;
+  for (int i = 0; i < np; ++i) for (int a = 0; a < 3; ++a) gp.start[i][a] = plan[i].start[a];
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  for (int it = 0; it < reps + 3 && rc == 0; ++it) {
+    if (it == 3) cudaEventRecord(e0, 0);
+    cudaMemsetAsync(counts, 0, 13 * 8, 0);
+    if (form == 0) {
+      rc = launch_gather_finalize(slots, gp, gaussian, shape[0], shape[1], zout, nullptr, labels, nullptr, counts, 0);
+    } else {
+      cudaMemsetAsync(acc, 0, 4 * V * 4, 0); cudaMemsetAsync(wsum, 0, V * 4, 0);
+      for (int i = 0; i < np && rc == 0; ++i)
+        rc = launch_accumulate(slots + (int64_t)i * 4 * P3, plan[i].start, gaussian, acc, wsum, shape[0], shape[1], zout, 0);
+      if (rc == 0) rc = launch_finalize_labels(acc, wsum, V, 0, V, nullptr, labels, nullptr, counts, 0);
+    }
+  }
+  cudaEventRecord(e1, 0);
+  cudaEventSynchronize(e1);
+  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(slots); cudaFree(acc); cudaFree(wsum); cudaFree(labels); cudaFree(counts);
   return rc == 0 ? (double)ms * 1e3 / reps : -1.0;
 }
 

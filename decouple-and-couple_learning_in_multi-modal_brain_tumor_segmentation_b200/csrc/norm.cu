@@ -189,7 +189,7 @@ int launch_stamp(unsigned long long* dst, int idx, cudaStream_t st) {
 }
 
 __global__ void patch_desc_kernel(PatchDesc* __restrict__ dst, PatchDesc v) {
-  if (threadIdx.x == 0) { dst->x = v.x; dst->sc = v.sc; dst->sd = v.sd; dst->sh = v.sh; }
+  if (threadIdx.x == 0) { dst->x = v.x; dst->sc = v.sc; dst->sd = v.sd; dst->sh = v.sh; dst->probs = v.probs; }
   if (threadIdx.x < 16) dst->keep[threadIdx.x] = v.keep[threadIdx.x];
 }
 

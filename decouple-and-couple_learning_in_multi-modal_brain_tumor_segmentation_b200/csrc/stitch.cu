@@ -149,7 +149,7 @@ __device__ __forceinline__ int argmax4(float a, float b, float c, float d) {
 }
 
 __device__ __forceinline__ void count_label(LabelCounts& k, int l, int t, bool has_target) {
-  k.v[l] += 1;
+  k.v[0] += l == 0; k.v[1] += l == 1; k.v[2] += l == 2; k.v[3] += l == 3;     // no dynamic index: stays in registers
   const bool owt = l > 0, otc = (l == 1) | (l == 3), oet = l == 3;
   k.v[4] += owt; k.v[7] += otc; k.v[10] += oet;
   if (has_target) {
@@ -242,69 +242,92 @@ int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, i
 // cover it, the arg-max label and the counters.  Against accumulate + finalize this drops the accumulator round
 // trip: P x 33.5 MB read + 1 B / voxel written (613 MB for 18 patches) instead of P x 117 MB + 196 MB (2.3 GB).
 // The sums run in patch order with the same FMA as accumulate_kernel, so the result is bit-identical to it.
-// CTA = one (x,y) row of the volume: the patches covering (x,y) are listed once per CTA (in patch order), each
-// thread then owns one z and tests only the z range; loads are coalesced along z in every patch slot.
+// A WARP owns one (x,y) row of the volume at a time (persistent grid striding over the rows): it lists the patches
+// that cover (x,y) with one ballot per 32 plan entries (patch order preserved), then lane l handles z = l, l+32, ...
+// testing only the z range; loads are coalesced along z in every patch slot, four patches (16 loads) in flight per
+// lane.  Counters stay in registers until the CTA's single flush.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussian, int Y, int Z,
+constexpr int GATHER_WARPS = 8;
+__global__ void __launch_bounds__(GATHER_WARPS * 32)
+gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussian, int rows, int Y, int Z,
                        float* __restrict__ probs_out, uint8_t* __restrict__ labels, const uint8_t* __restrict__ target,
                        unsigned long long* __restrict__ counts) {
-  __shared__ int s_n;
-  __shared__ short s_idx[GatherPlan::MAX];
-  __shared__ float s_wxy[GatherPlan::MAX];
+  __shared__ int s_base[GATHER_WARPS][GatherPlan::MAX];     // slot offset of (x, y, z = 0) relative to pp, in floats
+  __shared__ short s_sz[GATHER_WARPS][GatherPlan::MAX];     // z origin of the patch
+  __shared__ float s_wxy[GATHER_WARPS][GatherPlan::MAX];
   __shared__ unsigned s_cnt[13];
-  const int row = blockIdx.x;                       // x * Y + y
-  const int x = row / Y, y = row - x * Y;
+  __shared__ float s_wz[P];                                 // blend_w1 along z, computed once (same expression, same bits)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (threadIdx.x < 13) s_cnt[threadIdx.x] = 0;
-  if (threadIdx.x < 32) {                           // warp 0 compacts the covering patches, keeping their order
-    int base = 0;
+  if (threadIdx.x < P) s_wz[threadIdx.x] = blend_w1(threadIdx.x, gaussian);
+  __syncthreads();
+  const int64_t plane = (int64_t)rows * Z;          // voxels of the volume
+  LabelCounts k;
+#pragma unroll
+  for (int i = 0; i < 13; ++i) k.v[i] = 0;
+  for (int row = blockIdx.x * GATHER_WARPS + w; row < rows; row += gridDim.x * GATHER_WARPS) {
+    const int x = row / Y, y = row - x * Y;
+    int n = 0;
     for (int i0 = 0; i0 < plan.n; i0 += 32) {
-      const int i = i0 + threadIdx.x;
+      const int i = i0 + lane;
       bool hit = false;
+      int lx = 0, ly = 0;
       if (i < plan.n) {
-        const int lx = x - plan.start[i][0], ly = y - plan.start[i][1];
+        lx = x - plan.start[i][0]; ly = y - plan.start[i][1];
         hit = (unsigned)lx < (unsigned)P && (unsigned)ly < (unsigned)P;
       }
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
-        const int k = base + __popc(m & ((1u << threadIdx.x) - 1u));
-        s_idx[k] = (short)i;
-        s_wxy[k] = blend_w1(x - plan.start[i][0], gaussian) * blend_w1(y - plan.start[i][1], gaussian);
+        const int j = n + __popc(m & ((1u << lane) - 1u));
+        s_base[w][j] = i * (4 * (int)P3) + (lx * P + ly) * P - plan.start[i][2];
+        s_sz[w][j] = (short)plan.start[i][2];
+        s_wxy[w][j] = blend_w1(lx, gaussian) * blend_w1(ly, gaussian);
       }
-      base += __popc(m);
+      n += __popc(m);
     }
-    if (threadIdx.x == 0) s_n = base;
-  }
-  __syncthreads();
-  const int n = s_n;
-  const int64_t plane = (int64_t)gridDim.x * Z;     // voxels of the volume
-  LabelCounts k;
+    __syncwarp();
+    for (int z = lane; z < Z; z += 32) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ws = 0.f;
+      // four patches per trip, branch-free: a patch that does not cover z contributes w = 0, p = 0 (fma(0, 0, a) == a,
+      // so the sums keep accumulate_kernel's bits); the 16 loads of a trip are in flight before the first FMA
+      for (int j0 = 0; j0 < n; j0 += 4) {
+        float wt[4], p[4][4];
 #pragma unroll
-  for (int i = 0; i < 13; ++i) k.v[i] = 0;
-  for (int z = threadIdx.x; z < Z; z += 256) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ws = 0.f;
-    for (int j = 0; j < n; ++j) {
-      const int i = s_idx[j];
-      const int lz = z - plan.start[i][2];
-      if ((unsigned)lz >= (unsigned)P) continue;
-      const float w = s_wxy[j] * blend_w1(lz, gaussian);
-      const float* p = pp + (int64_t)i * 4 * P3 + ((int64_t)(x - plan.start[i][0]) * P + (y - plan.start[i][1])) * P + lz;
-      const float p0 = ld_stream1(p), p1 = ld_stream1(p + P3), p2 = ld_stream1(p + 2 * P3), p3 = ld_stream1(p + 3 * P3);
-      a0 = __fmaf_rn(w, p0, a0); a1 = __fmaf_rn(w, p1, a1); a2 = __fmaf_rn(w, p2, a2); a3 = __fmaf_rn(w, p3, a3);
-      ws += w;
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u;
+          wt[u] = 0.f;
+          p[u][0] = p[u][1] = p[u][2] = p[u][3] = 0.f;
+          if (j < n) {
+            const int lz = z - s_sz[w][j];
+            if ((unsigned)lz < (unsigned)P) {
+              wt[u] = s_wxy[w][j] * s_wz[lz];
+              const float* q = pp + ((int64_t)s_base[w][j] + z);
+              p[u][0] = ld_stream1(q); p[u][1] = ld_stream1(q + P3); p[u][2] = ld_stream1(q + 2 * P3); p[u][3] = ld_stream1(q + 3 * P3);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          a0 = __fmaf_rn(wt[u], p[u][0], a0); a1 = __fmaf_rn(wt[u], p[u][1], a1);
+          a2 = __fmaf_rn(wt[u], p[u][2], a2); a3 = __fmaf_rn(wt[u], p[u][3], a3);
+          ws += wt[u];
+        }
+      }
+      a0 /= ws; a1 /= ws; a2 /= ws; a3 /= ws;
+      const int64_t v = (int64_t)row * Z + z;
+      if (probs_out) { probs_out[v] = a0; probs_out[plane + v] = a1; probs_out[2 * plane + v] = a2; probs_out[3 * plane + v] = a3; }
+      const int l = argmax4(a0, a1, a2, a3);
+      if (labels) labels[v] = (uint8_t)l;
+      if (counts) count_label(k, l, target ? target[v] : 0, target != nullptr);
     }
-    a0 /= ws; a1 /= ws; a2 /= ws; a3 /= ws;
-    const int64_t v = (int64_t)row * Z + z;
-    if (probs_out) { probs_out[v] = a0; probs_out[plane + v] = a1; probs_out[2 * plane + v] = a2; probs_out[3 * plane + v] = a3; }
-    const int l = argmax4(a0, a1, a2, a3);
-    if (labels) labels[v] = (uint8_t)l;
-    if (counts) count_label(k, l, target ? target[v] : 0, target != nullptr);
+    __syncwarp();
   }
   if (counts) {
+    __syncthreads();
 #pragma unroll
     for (int i = 0; i < 13; ++i) {
       unsigned r = __reduce_add_sync(0xffffffffu, k.v[i]);
-      if ((threadIdx.x & 31) == 0 && r) atomicAdd(&s_cnt[i], r);
+      if (lane == 0 && r) atomicAdd(&s_cnt[i], r);
     }
     __syncthreads();
     if (threadIdx.x < 13 && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
@@ -315,9 +338,18 @@ int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int
                            float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
                            cudaStream_t st) {
   if (plan.n < 1 || plan.n > GatherPlan::MAX) { set_error("gather_finalize: 1..128 patches"); return -1; }
-  const int threads = Z >= 224 ? 256 : Z > 160 ? 224 : Z > 128 ? 160 : 128;
-  gather_finalize_kernel<<<(unsigned)(X * Y), threads, 0, st>>>(patch_probs, plan, gaussian, Y, Z, probs_out, labels,
-                                                               target, counts);
+  const int rows = X * Y;
+  int blocks = (rows + GATHER_WARPS - 1) / GATHER_WARPS;
+  static const int resident = [] {                 // persistent: exactly one wave of resident CTAs
+    int per_sm = 0, dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gather_finalize_kernel, GATHER_WARPS * 32, 0) != cudaSuccess || per_sm < 1) per_sm = 4;
+    return per_sm * sms;
+  }();
+  if (blocks > resident) blocks = resident;
+  gather_finalize_kernel<<<blocks, GATHER_WARPS * 32, 0, st>>>(patch_probs, plan, gaussian, rows, Y, Z, probs_out, labels,
+                                                              target, counts);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

@@ -38,34 +38,41 @@ export_labels_kernel(const uint8_t* __restrict__ lab, int A, int B, int Cn, uint
   __shared__ uint8_t tile[32][33];
   __shared__ unsigned s_cnt[3];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c0 = blockIdx.x * 32, a0 = blockIdx.y * 32, b = blockIdx.z;
   if (threadIdx.x < 3) s_cnt[threadIdx.x] = 0;
   unsigned n1 = 0, n2 = 0, n4 = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int a = a0 + ty + 8 * i, c = c0 + tx;
-    uint8_t v = 0;
-    if (a < A && c < Cn) {
-      const int64_t idx = ((int64_t)a * B + b) * Cn + c;
-      const uint8_t l = lab[idx];
-      v = l == 3 ? (uint8_t)4 : l;                         // seg_img[output == 3] = 4 (predict.py:322-324)
-      n1 += v == 1; n2 += v == 2; n4 += v == 4;
-      if (plain) plain[idx] = v;
-    }
-    tile[ty + 8 * i][tx] = v;
-  }
-  __syncthreads();
-  if (turned) {
+  // persistent CTAs walk the tiles (c fastest), so the label counters cost six global atomics per CTA, not per tile
+  const int tc = (Cn + 31) / 32, ta = (A + 31) / 32;
+  const int64_t tiles = (int64_t)tc * ta * B;
+  for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+    const int c0 = (int)(t % tc) * 32, a0 = (int)((t / tc) % ta) * 32, b = (int)(t / ((int64_t)tc * ta));
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int c = c0 + ty + 8 * i, a = a0 + tx;
-      if (a < A && c < Cn) turned[((int64_t)c * B + b) * A + a] = tile[tx][ty + 8 * i];
+      const int a = a0 + ty + 8 * i, c = c0 + tx;
+      uint8_t v = 0;
+      if (a < A && c < Cn) {
+        const int64_t idx = ((int64_t)a * B + b) * Cn + c;
+        const uint8_t l = lab[idx];
+        v = l == 3 ? (uint8_t)4 : l;                       // seg_img[output == 3] = 4 (predict.py:322-324)
+        n1 += v == 1; n2 += v == 2; n4 += v == 4;
+        if (plain) plain[idx] = v;
+      }
+      tile[ty + 8 * i][tx] = v;
     }
+    __syncthreads();
+    if (turned) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + ty + 8 * i, a = a0 + tx;
+        if (a < A && c < Cn) turned[((int64_t)c * B + b) * A + a] = tile[tx][ty + 8 * i];
+      }
+    }
+    __syncthreads();
   }
   if (counts) {
     n1 = __reduce_add_sync(0xffffffffu, n1);
     n2 = __reduce_add_sync(0xffffffffu, n2);
     n4 = __reduce_add_sync(0xffffffffu, n4);
+    __syncthreads();
     if (tx == 0) {
       if (n1) atomicAdd(&s_cnt[0], n1);
       if (n2) atomicAdd(&s_cnt[1], n2);
@@ -109,25 +116,45 @@ snapshot_kernel(const uint8_t* __restrict__ lab, int X, int Y, int Z, Palette pa
 }
 
 // per z-slice (|o|, |t|, |o&t|) for WT, TC, ET: the counters behind output_excel's per-frame Dice
-// (predict_simple.py:224-243).  Persistent grid; shared-memory counters per slice, flushed once per CTA.
+// (predict_simple.py:224-243).  A warp owns whole (x,y) rows: lane l always sees z = l, l+32, ... so its counters
+// live in registers (NZ slices x 9) while the persistent grid strides over the rows; one atomic flush per warp.
 constexpr int SLICE_MAX = 256;
+template <int NZ>
 __global__ void __launch_bounds__(256)
-slice_counts_kernel(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ tgt, int64_t n, int Z,
+slice_counts_kernel(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ tgt, int64_t rows, int Z,
                     unsigned long long* __restrict__ out) {
-  __shared__ unsigned s[SLICE_MAX * 9];
-  for (int i = threadIdx.x; i < Z * 9; i += 256) s[i] = 0;
-  __syncthreads();
-  for (int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x; v < n; v += (int64_t)gridDim.x * 256) {
-    const int z = (int)(v % Z);
-    const int l = lab[v], t = tgt[v];
-    const bool o3[3] = {l > 0, l == 1 || l == 3, l == 3};
-    const bool t3[3] = {t > 0, t == 1 || t == 3, t == 3};
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (int64_t)gridDim.x * 8;
+  unsigned cnt[NZ][9];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      if (o3[r]) atomicAdd(&s[z * 9 + 3 * r], 1u);
-      if (t3[r]) atomicAdd(&s[z * 9 + 3 * r + 1], 1u);
-      if (o3[r] & t3[r]) atomicAdd(&s[z * 9 + 3 * r + 2], 1u);
+  for (int k = 0; k < NZ; ++k)
+#pragma unroll
+    for (int j = 0; j < 9; ++j) cnt[k][j] = 0;
+  for (int64_t r = warp; r < rows; r += nwarps) {
+    const uint8_t* lr = lab + r * Z;
+    const uint8_t* tr = tgt + r * Z;
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) {
+      const int z = 32 * k + lane;
+      if (z < Z) {
+        const int l = lr[z], t = tr[z];
+        const unsigned o0 = l > 0, o1 = (l == 1) | (l == 3), o2 = l == 3;
+        const unsigned t0 = t > 0, t1 = (t == 1) | (t == 3), t2 = t == 3;
+        cnt[k][0] += o0; cnt[k][1] += t0; cnt[k][2] += o0 & t0;
+        cnt[k][3] += o1; cnt[k][4] += t1; cnt[k][5] += o1 & t1;
+        cnt[k][6] += o2; cnt[k][7] += t2; cnt[k][8] += o2 & t2;
+      }
     }
+  }
+  __shared__ unsigned s[NZ * 32 * 9];                     // CTA-level sum first: one global atomic per slot and CTA
+  for (int i = threadIdx.x; i < NZ * 32 * 9; i += 256) s[i] = 0;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < NZ; ++k) {
+    const int z = 32 * k + lane;
+#pragma unroll
+    for (int j = 0; j < 9; ++j)
+      if (cnt[k][j]) atomicAdd(&s[z * 9 + j], cnt[k][j]);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < Z * 9; i += 256)
@@ -329,8 +356,10 @@ DCL_API int dcl_export_labels(const uint8_t* labels_dev, const int32_t shape[3],
   const int X = shape[0], Y = shape[1], Z = shape[2];
   cudaStream_t st = (cudaStream_t)stream;
   if (counts_out_dev) DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, 6 * sizeof(uint64_t), st));
-  export_labels_kernel<<<dim3((Z + 31) / 32, (X + 31) / 32, Y), 256, 0, st>>>(
-      labels_dev, X, Y, Z, seg_out_dev, seg_nifti_dev, (unsigned long long*)counts_out_dev);
+  int64_t tiles = (int64_t)((Z + 31) / 32) * ((X + 31) / 32) * Y;
+  if (tiles > 148 * 8) tiles = 148 * 8;
+  export_labels_kernel<<<(unsigned)tiles, 256, 0, st>>>(labels_dev, X, Y, Z, seg_out_dev, seg_nifti_dev,
+                                                        (unsigned long long*)counts_out_dev);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return DCL_OK;
@@ -358,13 +387,15 @@ DCL_API int dcl_slice_counts(const uint8_t* labels_dev, const uint8_t* target_de
     set_error("dcl_slice_counts: bad argument (Z <= 256)");
     return DCL_ERR_ARG;
   }
-  const int64_t n = (int64_t)shape[0] * shape[1] * shape[2];
   cudaStream_t st = (cudaStream_t)stream;
   DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, (size_t)shape[2] * 9 * sizeof(uint64_t), st));
-  int64_t blocks = (n + 255) / 256;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  slice_counts_kernel<<<(unsigned)blocks, 256, 0, st>>>(labels_dev, target_dev, n, shape[2],
-                                                        (unsigned long long*)counts_out_dev);
+  const int64_t rows = (int64_t)shape[0] * shape[1];
+  int64_t blocks = (rows + 7) / 8;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  unsigned long long* out = (unsigned long long*)counts_out_dev;
+  const int nz = (shape[2] + 31) / 32;
+  if (nz <= 5) slice_counts_kernel<5><<<(unsigned)blocks, 256, 0, st>>>(labels_dev, target_dev, rows, shape[2], out);
+  else slice_counts_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(labels_dev, target_dev, rows, shape[2], out);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return DCL_OK;

@@ -7,7 +7,7 @@ Reference: predict_overlap.py:31-58 (8-corner tiling + crop-and-overwrite stitch
 import numpy as np
 import torch
 
-from dcl_b200 import StitchMode
+from dcl_b200 import StitchMode, volio
 from dcl_b200.engine import dice_from_counts
 
 
@@ -56,6 +56,11 @@ def validate_softmax(valid_loader, model, load_file, multimodel, savepath='', na
         print('0标签:{},1标签:{},2标签:{},3标签:{},索引最大值: {}'.format(
             counts[0], counts[1], counts[2], counts[3], int(np.max(np.nonzero(counts[:4])[0]))))
         wt_dices.append(soft[0]); tc_dices.append(soft[1]); et_dices.append(soft[2])
+        if savepath:
+            # the export block the reference keeps (commented out) in predict.py:310-350: '.npy' for ensembling,
+            # '.nii.gz' with label 3 -> 4 for submission, optional per-frame snapshots
+            volio.save_prediction(out["labels"], savepath, name, save_format or 'nii', snapshot=snapshot,
+                                  visual=visual, verbose=verbose)
     print('WT Dice: %.4f' % np.mean(wt_dices))
     print('TC Dice: %.4f' % np.mean(tc_dices))
     print('ET Dice: %.4f' % np.mean(et_dices))

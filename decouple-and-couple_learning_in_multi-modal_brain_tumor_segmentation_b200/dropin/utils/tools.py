@@ -18,3 +18,27 @@ def softmax_output_dice(output, target):
         (output == 3, target == 3),                                           # enhancing
     )
     return [dice_score(o, t) for o, t in regions]
+
+
+def mIOU(o, t, eps=1e-8):
+    """predict_simple.py:66-69"""
+    num = (o * t).sum() + eps
+    den = (o | t).sum() + eps
+    return num / den
+
+
+def softmax_output_mIou(output, target):
+    """predict_simple.py:100-118"""
+    output, target = np.asarray(output), np.asarray(target)
+    return [mIOU(output > 0, target > 0),
+            mIOU((output == 1) | (output == 3), (target == 1) | (target == 3)),
+            mIOU(output == 3, target == 3)]
+
+
+def cal_hausdorff(output, target):
+    """predict_simple.py:121-144: HD95 of WT / TC / ET on the device (label maps may be numpy or CUDA tensors)."""
+    import torch
+    from dcl_b200 import volio
+    lab = output if isinstance(output, torch.Tensor) else torch.from_numpy(np.asarray(output).astype(np.uint8))
+    tgt = target if isinstance(target, torch.Tensor) else torch.from_numpy(np.asarray(target).astype(np.uint8))
+    return volio.cal_hausdorff(lab.to("cuda", torch.uint8), tgt.to("cuda", torch.uint8))

@@ -239,6 +239,12 @@ DCL_API int dcl_op_instnorm_stats(const float* x, int32_t channels, int64_t spat
  * forward picks for a cubic g^3 3x3x3 convolution (mode 1 = fused input norm + residual + statistics) */
 DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stride, int32_t mode, int32_t reps);
 
+/* bench helper (tools/stitch_time.py): device time in us per volume of the weighted stitch in isolation on a
+ * shape[0] x shape[1] x shape[2] volume with the sliding-window plan of `stride`; form 0 = gather (per-patch slots + one
+ * gather_finalize launch), form 1 = accumulate (memsets + one accumulate launch per patch + finalize) */
+DCL_API double dcl_bench_stitch(const int32_t shape[3], int32_t stride, int32_t gaussian, int32_t form, int32_t reps,
+                        int32_t* n_patches_out);
+
 /* debug: 16 %globaltimer stamps (ns) written between the stages of the last bf16 forward when DCL_STAMPS=1 is set:
  * 0 start, 1 encoder done, 2 decoupler + tokenise done, 3 region couplers done, 4 cross-region coupler done,
  * 5/6/7 decoder level starts, 8 decoder done, 9 end */

@@ -80,6 +80,15 @@ def test_bf16_volume_graph_replay_matches_per_patch_forwards(engine_bf16):
                                            target_host=tgt.pin_memory())
     assert np.array_equal(host["labels"].numpy(), dev["labels"].cpu().numpy())
     assert np.array_equal(host["counts"], dev["counts"].cpu().numpy())
+    # the accumulate form (DCL_GATHER=0, what the multi-GPU path uses) gives the same bits as the default gather form
+    import os
+    os.environ["DCL_GATHER"] = "0"
+    try:
+        acc = engine_bf16.predict_volume(vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt.cuda())
+    finally:
+        del os.environ["DCL_GATHER"]
+    assert torch.equal(acc["probs"], dev["probs"]) and torch.equal(acc["labels"], dev["labels"])
+    assert torch.equal(acc["counts"], dev["counts"])
 
 
 def test_bf16_production_schedule_equals_stage_keeping_schedule(engine_bf16, seed0_state_dict, golden_patch):

@@ -174,3 +174,40 @@ def test_hausdorff_edge_cases():
     b[8:20, 5:15, 0:10] = 2
     got = check_hausdorff(a, b)
     assert got["hd95"][1:] == [0.0, 0.0] and got["hd95"][0] > 0
+
+
+def test_dropin_validate_softmax_exports_and_metrics(seed0_state_dict, tmp_path):
+    """validate_softmax(..., savepath, save_format='nii', snapshot=True) through the drop-in modules writes what the
+    reference's export block describes (predict.py:310-350); utils.hausdorff / utils.tools keep their signatures."""
+    import predict_overlap
+    from models.clswiseformer.cls_wise_former import get_cls_wise_former
+    from tests.util import volume_input, volume_target
+    from utils import hausdorff as H
+    from utils.tools import cal_hausdorff, softmax_output_mIou
+    model = get_cls_wise_former("brats", True, "fixed", 0)
+    model.load_state_dict(seed0_state_dict)
+    model.precision = __import__("dcl_b200").Precision.BF16
+    model.compute_aux = False
+    model.deterministic = True
+    x = torch.cat([volume_input(0), torch.zeros(1, 4, 240, 240, 5)], -1)              # the loader pads 155 -> 160
+    target = torch.from_numpy(np.pad(volume_target(0), ((0, 0), (0, 0), (0, 5))))[None]
+    loader = [(x, target)]
+    with torch.no_grad():
+        wt, tc, et = predict_overlap.validate_softmax(loader, model, None, False, savepath=str(tmp_path / "out"),
+                                                      names=["case0"], save_format="nii", snapshot=True,
+                                                      visual=str(tmp_path / "vis"), valid_in_train=True)
+    seg = O.parse_nifti(str(tmp_path / "out" / "case0.nii.gz"))["data"]
+    assert seg.shape == (240, 240, 155) and set(np.unique(seg)) <= {0, 1, 2, 4}
+    lab = np.where(seg == 4, 3, seg)
+    d = O.softmax_output_dice(lab, volume_target(0))
+    assert np.allclose([wt, tc, et], d, atol=1e-12)
+    assert len(os.listdir(tmp_path / "vis" / "case0")) == 155
+    from PIL import Image
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "vis" / "case0" / "77.png")), O.snapshot_predict(lab)[:, :, :, 77])
+    # metrics drop-ins on the exported map
+    small_o, small_t = lab[60:140, 60:140, 40:100], volume_target(0)[60:140, 60:140, 40:100]
+    assert cal_hausdorff(small_o, small_t) == O.cal_hausdorff(small_o, small_t)
+    assert softmax_output_mIou(small_o, small_t) == [float(v) for v in O.softmax_output_mIou(small_o, small_t)]
+    a, b = blob_labels(RAGGED, 60, 1.0) > 0, blob_labels(RAGGED, 61, 1.0) > 0
+    assert H.hausdorff_distance_95(a, b) == float(O.medpy_hd95(a, b)) and H.hausdorff_distance(a, b) == float(O.medpy_hd(a, b))
+    assert H.hausdorff_distance_95(np.zeros_like(a), b) == 0

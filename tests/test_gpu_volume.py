@@ -105,6 +105,23 @@ def test_weighted_accumulate_matches_oracle(engine, vol, mode_name, stride):
     assert np.abs(got.sum(0) - 1).max() < 1e-5       # blended probabilities still sum to one
 
 
+@pytest.mark.parametrize("mode_name", ["UNIFORM", "GAUSSIAN"])
+def test_gather_form_is_bit_identical_to_accumulate_form(engine, vol, mode_name, monkeypatch):
+    """the default gather-form stitch (one slot per patch + gather_finalize_kernel) against accumulate + finalize"""
+    from dcl_b200 import StitchMode, patch_starts
+    starts = patch_starts((240, 240, 155), 64)
+    keeps = np.ones((len(starts), 16), np.float32)
+    tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
+    monkeypatch.setenv("DCL_GATHER", "0")
+    ref = engine.predict_volume(vol, StitchMode[mode_name], starts=starts, keep_scales=keeps, target=tgt)
+    monkeypatch.delenv("DCL_GATHER")
+    got = engine.predict_volume(vol, StitchMode[mode_name], starts=starts, keep_scales=keeps, target=tgt)
+    assert torch.equal(got["probs"], ref["probs"])
+    assert torch.equal(got["labels"], ref["labels"]) and torch.equal(got["counts"], ref["counts"])
+    only_labels = engine.predict_volume(vol, StitchMode[mode_name], starts=starts, keep_scales=keeps, want_probs=False)
+    assert torch.equal(only_labels["labels"], ref["labels"])
+
+
 def test_host_entry_point_equals_device_entry_point(engine, vol, golden_volume):
     from dcl_b200 import StitchMode
     keeps = golden_volume["keep_scale"]

@@ -58,11 +58,29 @@ def main():
         rows.append({"kernel": name, "us": round(us, 2), "algorithmic_bytes": nbytes, "GB/s": round(nbytes / us / 1e3, 1),
                      "frac_of_copy_peak": round(nbytes / us / 1e3 / peak, 3), "peak": peak, "peak_source": src, "note": note})
 
-    row("export_labels_kernel", timed(lambda i: V.export_labels(labs[i % nbuf])), V_ * 3, "1 B read + 2 x 1 B written per voxel")
-    row("snapshot_kernel", timed(lambda i: V.snapshot_frames(labs[i % nbuf])), V_ * 4, "1 B read + 3 B written per voxel")
-    row("slice_counts_kernel", timed(lambda i: V.slice_counts(labs[i % nbuf], tgts[i % 2])), V_ * 2, "2 B read per voxel")
+    # the C entry points are called directly on preallocated outputs (the torch allocations of the Python wrappers
+    # cost more host time than these kernels take on the device)
+    import ctypes as C
+    from dcl_b200 import _native as N
+    lib = N.load_library()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    sh = (C.c_int32 * 3)(*shape)
+    P = lambda t: C.c_void_p(t.data_ptr())
+    seg, turned = torch.empty_like(labs[0]), torch.empty((155, 240, 240), dtype=torch.uint8, device="cuda")
+    cnt = torch.zeros(6, dtype=torch.int64, device="cuda")
+    row("export_labels_kernel", timed(lambda i: lib.dcl_export_labels(P(labs[i % nbuf]), sh, P(seg), P(turned), P(cnt), st)),
+        V_ * 3, "1 B read + 2 x 1 B written per voxel")
+    frames = torch.empty((155, 240, 240, 3), dtype=torch.uint8, device="cuda")
+    pal = (C.c_uint8 * 12)(*V.PALETTE_PREDICT)
+    row("snapshot_kernel", timed(lambda i: lib.dcl_snapshot_frames(P(labs[i % nbuf]), sh, pal, P(frames), st)), V_ * 4,
+        "1 B read + 3 B written per voxel")
+    sc = torch.zeros((155, 9), dtype=torch.int64, device="cuda")
+    row("slice_counts_kernel", timed(lambda i: lib.dcl_slice_counts(P(labs[i % nbuf]), P(tgts[i % 2]), sh, P(sc), st)), V_ * 2,
+        "2 B read per voxel")
     mri = [torch.from_numpy(np.ascontiguousarray(synthetic_mri(shape, 50 + i).transpose(3, 2, 1, 0))).cuda() for i in range(2)]
-    row("mask_stats + normalise_reorder", timed(lambda i: V.preprocess_volume(mri[i % 2], 160)),
+    vol = torch.empty((4, 240, 240, 160), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(17, dtype=torch.float64, device="cuda")
+    row("mask_stats + normalise_reorder", timed(lambda i: lib.dcl_preprocess_volume(P(mri[i % 2]), sh, 160, P(vol), P(stats), st)),
         V_ * 16 * 2 + 240 * 240 * 160 * 16, "two 16 B/voxel reads + one 16 B/voxel write (2 x 143 MB inputs > L2)")
     for name, lab, tgt in (("blobs", tgts[0], tgts[1]), ("random vs blobs", labs[0], tgts[0])):
         torch.cuda.synchronize()
