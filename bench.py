@@ -308,6 +308,21 @@ def run_ours(args):
              3: "conv3d_k3_roll_kernel<32ch @64^3>", 4: "conv_slab_kernel", 5: "conv_gemm_kernel (stride 2)",
              12: "conv3d_k3s2_roll_kernel"}
     per_kind = {k: eng.profile_read(k) for k in kinds}
+    # the overlap stitch alone (dcl_bench_stitch: 20 back-to-back volumes of per-patch slots, > L2), both forms
+    stitch_iso = None
+    stride = WORKLOADS[args.workload][1]
+    if rank == 0 and mode != "TTA" and stride is not None:
+        import ctypes as C
+        from dcl_b200 import _native as N
+        lib, npat = N.load_library(), C.c_int32()
+        shp = (C.c_int32 * 3)(*SHAPE)
+        us_g = lib.dcl_bench_stitch(shp, stride, 0, 0, 20, C.byref(npat))
+        us_a = lib.dcl_bench_stitch(shp, stride, 0, 1, 20, C.byref(npat))
+        algo = npat.value * 4 * 128 ** 3 * 4 + VOXELS        # every patch probability once + one label byte per voxel
+        hbm = peaks()["hbm"]
+        stitch_iso = {"algorithmic_bytes": algo, "gather_form_us": us_g, "gather_form_GB/s": algo / us_g / 1e3,
+                      "gather_form_frac": algo / us_g / 1e3 / hbm, "accumulate_form_us": us_a,
+                      "accumulate_form_frac": algo / us_a / 1e3 / hbm}
 
     # ---- end to end through the host-buffer C-ABI call ----
     # The call is synchronous (upload, compute, download, sync), so a throughput-minded caller keeps two volumes in
@@ -390,8 +405,13 @@ def run_ours(args):
                                       "share_of_step": conv_ms / prof_ms, "peak_source": pk["source"] + " sustained bf16 dense"},
             "roofline_accumulate": {"bound": "hbm", "achieved": tail_gbs, "peak": pk["hbm"], "unit": "GB/s",
                                     "frac": tail_gbs / pk["hbm"], "launches": tail_n,
-                                    "kernel": "accumulate / stitch_copy / finalize_labels",
-                                    "share_of_step": tail_ms / prof_ms, "peak_source": pk["source"] + " copy"},
+                                    "kernel": ("gather_finalize_kernel (overlap blend + normalise + arg-max + counters in one "
+                                               "pass over the per-patch probability slots)"
+                                               if (stitch_iso and not by_patch and os.environ.get("DCL_GATHER", "1") != "0")
+                                               else "accumulate / stitch_copy / finalize_labels"),
+                                    "share_of_step": tail_ms / prof_ms, "peak_source": pk["source"] + " copy",
+                                    "note": "timed inside the profiled steps, right after the last patch forward",
+                                    **({"isolated": stitch_iso} if stitch_iso else {})},
             "clocks": clocks,
             "label_hist": counts[:4].tolist(),
         }

@@ -149,6 +149,7 @@ int launch_accumulate(const float* probs, const int start[3], int gaussian, floa
 struct GatherPlan {
   static constexpr int MAX = 128;
   int n;
+  int slot_planes;          // 128^3 planes per patch slot: 4, or 16 when the six final auxiliary heads travel along
   int start[MAX][3];
 };
 int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,

@@ -765,8 +765,10 @@ struct Fwd {
     if (want_aux) {   // mid heads (cls_wise_former.py:332-333)
       for (int r = 0; r < 3; ++r) {
         std::string n = REGION_NUM[r];
+        if (aux[6 + r] != nullptr)
         DCL_TRY(aux_branch(h->sem_dense[r], 128, 16, "mid_supervise_label.supervise_label_" + n,
                            "mid_supervise_label.down_label_" + n, aux[6 + r]));
+        if (aux[9 + r] != nullptr)
         DCL_TRY(aux_branch(h->edge_dense[r], 32, 32, "mid_edge_supervise_label.edge_supervise_label_" + n,
                            "mid_edge_supervise_label.edge_down_label_" + n, aux[9 + r]));
       }
@@ -795,8 +797,10 @@ struct Fwd {
     if (want_aux) {   // final heads (cls_wise_former.py:545-546)
       for (int r = 0; r < 3; ++r) {
         std::string n = REGION_NUM[r];
+        if (aux[0 + r] != nullptr)
         DCL_TRY(aux_branch(h->sup_sem[r], 128, 16, "supervise_label.supervise_label_" + n,
                            "supervise_label.down_label_" + n, aux[0 + r]));
+        if (aux[3 + r] != nullptr)
         DCL_TRY(aux_branch(h->sup_edge[r], 32, 32, "edge_supervise_label.edge_supervise_label_" + n,
                            "edge_supervise_label.edge_down_label_" + n, aux[3 + r]));
       }
@@ -1018,9 +1022,11 @@ struct Fwd16 {
     if (want_aux) {
       for (int r = 0; r < 3; ++r) {
         std::string n = REGION_NUM[r];
-        DCL_TRY(f.aux_branch(h->sem_dense[r], 128, 16, "mid_supervise_label.supervise_label_" + n,
+        if (aux[6 + r] != nullptr)
+          DCL_TRY(f.aux_branch(h->sem_dense[r], 128, 16, "mid_supervise_label.supervise_label_" + n,
                              "mid_supervise_label.down_label_" + n, aux[6 + r]));
-        DCL_TRY(f.aux_branch(h->edge_dense[r], 32, 32, "mid_edge_supervise_label.edge_supervise_label_" + n,
+        if (aux[9 + r] != nullptr)
+          DCL_TRY(f.aux_branch(h->edge_dense[r], 32, 32, "mid_edge_supervise_label.edge_supervise_label_" + n,
                              "mid_edge_supervise_label.edge_down_label_" + n, aux[9 + r]));
       }
     }
@@ -1076,9 +1082,11 @@ struct Fwd16 {
     if (want_aux) {
       for (int r = 0; r < 3; ++r) {
         std::string n = REGION_NUM[r];
-        DCL_TRY(f.aux_branch(h->sup_sem[r], 128, 16, "supervise_label.supervise_label_" + n,
+        if (aux[0 + r] != nullptr)
+          DCL_TRY(f.aux_branch(h->sup_sem[r], 128, 16, "supervise_label.supervise_label_" + n,
                              "supervise_label.down_label_" + n, aux[0 + r]));
-        DCL_TRY(f.aux_branch(h->sup_edge[r], 32, 32, "edge_supervise_label.edge_supervise_label_" + n,
+        if (aux[3 + r] != nullptr)
+          DCL_TRY(f.aux_branch(h->sup_edge[r], 32, 32, "edge_supervise_label.edge_supervise_label_" + n,
                              "edge_supervise_label.edge_down_label_" + n, aux[3 + r]));
       }
     }
@@ -1269,7 +1277,7 @@ static int ensure_lanes(dcl_handle* h, int n) {
 
 static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], int mode,
                        const std::vector<PlanItem>& plan, int first, int count, const float* keep_host, int zout,
-                       float* acc, float* wsum, cudaStream_t st, float* gather = nullptr) {
+                       float* acc, float* wsum, cudaStream_t st, float* gather = nullptr, int slot_planes = 4) {
   const int X = shape[0], Y = shape[1], Z = shape[2];
   const int64_t xs[4] = {(int64_t)X * Y * Z, (int64_t)Y * Z, Z, 1};
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
@@ -1296,13 +1304,19 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
     const float* x = vol + (int64_t)p.start[0] * xs[1] + (int64_t)p.start[1] * xs[2] + p.start[2];
     // gather form: the patch keeps its probabilities in its own slot; nothing is accumulated here and the lanes
     // never wait for each other
-    float* dst = gather ? gather + (int64_t)(i - first) * 4 * P3 : nullptr;
+    float* dst = gather ? gather + (int64_t)(i - first) * slot_planes * P3 : nullptr;
+    // 16-plane slots: the six final auxiliary heads (supervise / edge x {01,02,04}, two classes each) follow the four
+    // class planes; the mid heads (forward()[3..4]) are not computed
+    float* aux_ptr[DCL_NUM_AUX] = {};
+    if (dst && slot_planes == 16)
+      for (int j = 0; j < 6; ++j) aux_ptr[j] = dst + (int64_t)(4 + 2 * j) * P3;
+    float* const* aux = (dst && slot_planes == 16) ? aux_ptr : nullptr;
     if (h->cfg.precision == DCL_BF16) {
       Fwd16 f16{hh, s};
-      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : hh->probs, nullptr));
+      DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : hh->probs, aux));
     } else {
       Fwd f{h, st, &h->ts[0]};
-      DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : h->probs, nullptr));
+      DCL_TRY(f.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : h->probs, aux));
     }
     if (gather) {
       if (two) DCL_CUDA_OK(cudaEventRecord(h->ev_lane_acc[lane], s));
@@ -1332,6 +1346,42 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
     for (; have < 2; ++have) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_up[have + 1], 0));
   }
   return 0;
+}
+
+// Weighted stitch in gather form: every patch of the plan keeps its probabilities (and, with aux_out_dev, the six final
+// auxiliary heads) in a slot of its own; gather_finalize_kernel then blends, normalises and labels the volume.
+static int predict_volume_gather(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                                 const std::vector<PlanItem>& plan, int zout, const float* keep_scale_host,
+                                 float* probs_out_dev, float* aux_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
+                                 uint64_t* counts_out_dev, cudaStream_t st) {
+  const int np = (int)plan.size();
+  const int planes = aux_out_dev ? 16 : 4;
+  const int64_t V = (int64_t)shape[0] * shape[1] * zout;
+  if ((int64_t)np * planes * P3 >= ((int64_t)1 << 31)) { set_error("predict_volume: too many patches for the gather form"); return DCL_ERR_ARG; }
+  DCL_TRY(grow(h, (void**)&h->gather_buf, &h->gather_cap, (int64_t)np * planes * P3 * 4));
+  const int64_t before = g_launches;
+  int rc = run_patches(h, vol_dev, shape, mode, plan, 0, np, keep_scale_host, zout, nullptr, nullptr, st, h->gather_buf, planes);
+  if (rc == 0 && (labels_out_dev || counts_out_dev || probs_out_dev || aux_out_dev)) {
+    if (counts_out_dev) DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, 13 * sizeof(uint64_t), st));
+    GatherPlan gp;
+    gp.n = np;
+    gp.slot_planes = planes;
+    for (int i = 0; i < np; ++i) for (int a = 0; a < 3; ++a) gp.start[i][a] = plan[i].start[a];
+    const int gaussian = mode == DCL_STITCH_GAUSSIAN;
+    cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
+    if (labels_out_dev || counts_out_dev || probs_out_dev)
+      rc = launch_gather_finalize(h->gather_buf, gp, gaussian, shape[0], shape[1], zout, probs_out_dev, labels_out_dev,
+                                  target_dev, (unsigned long long*)counts_out_dev, st);
+    if (h->profiling)
+      h->prof_end(ev, 1, (double)np * 4 * P3 * 4 + (double)V * ((probs_out_dev ? 16 : 0) + (labels_out_dev ? 1 : 0) +
+                                                                (target_dev ? 1 : 0)), st);
+    // the auxiliary planes, four at a time (two heads per launch), with the same weights
+    for (int g = 0; rc == 0 && aux_out_dev && g < 3; ++g)
+      rc = launch_gather_finalize(h->gather_buf + (int64_t)(4 + 4 * g) * P3, gp, gaussian, shape[0], shape[1], zout,
+                                  aux_out_dev + (int64_t)g * 4 * V, nullptr, nullptr, nullptr, st);
+  }
+  h->launches += g_launches - before;
+  return rc;
 }
 
 }  // namespace dcl
@@ -1527,26 +1577,9 @@ DCL_API int dcl_predict_volume(dcl_handle* h, const float* vol_dev, const int32_
   // accumulate form, which DCL_GATHER=0 selects and the multi-GPU path keeps using)
   const char* genv = getenv("DCL_GATHER");
   const bool gather = weighted && (int)plan.size() <= GatherPlan::MAX && !(genv && genv[0] == '0');
-  if (gather) {
-    const int np = (int)plan.size();
-    DCL_TRY(grow(h, (void**)&h->gather_buf, &h->gather_cap, (int64_t)np * 4 * P3 * 4));
-    const int64_t before = g_launches;
-    int rc = run_patches(h, vol_dev, shape, mode, plan, 0, np, keep_scale_host, zout, nullptr, nullptr, st, h->gather_buf);
-    if (rc == 0 && (labels_out_dev || counts_out_dev || probs_out_dev)) {
-      if (counts_out_dev) DCL_CUDA_OK(cudaMemsetAsync(counts_out_dev, 0, 13 * sizeof(uint64_t), st));
-      GatherPlan gp;
-      gp.n = np;
-      for (int i = 0; i < np; ++i) for (int a = 0; a < 3; ++a) gp.start[i][a] = plan[i].start[a];
-      cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
-      rc = launch_gather_finalize(h->gather_buf, gp, mode == DCL_STITCH_GAUSSIAN, shape[0], shape[1], zout, probs_out_dev,
-                                  labels_out_dev, target_dev, (unsigned long long*)counts_out_dev, st);
-      if (h->profiling)
-        h->prof_end(ev, 1, (double)np * 4 * P3 * 4 + (double)V * ((probs_out_dev ? 16 : 0) + (labels_out_dev ? 1 : 0) +
-                                                                  (target_dev ? 1 : 0)), st);
-    }
-    h->launches += g_launches - before;
-    return rc;
-  }
+  if (gather)
+    return predict_volume_gather(h, vol_dev, shape, mode, plan, zout, keep_scale_host, probs_out_dev, nullptr, labels_out_dev,
+                                 target_dev, counts_out_dev, st);
   DCL_TRY(grow(h, (void**)&h->vol_probs, &h->vol_probs_cap, 4 * V * 4));
   float* acc = h->vol_probs;
   float* wsum = nullptr;
@@ -1573,6 +1606,27 @@ DCL_API int dcl_predict_volume(dcl_handle* h, const float* vol_dev, const int32_
   return rc;
 }
 
+
+// BASELINE config 4 ("WT/TC/ET + edge outputs"): the weighted sliding window with the six final auxiliary heads
+// (forward()[1] = supervise {01,02,04}, forward()[2] = edge {01,02,04}; cls_wise_former.py:545-546, :585-592) blended
+// alongside the class probabilities.  aux_out_dev: (6, 2, X, Y, Z) in that order.  Needs cfg.want_aux.
+DCL_API int dcl_predict_volume_aux(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode, int32_t n_patches,
+                           const int32_t* starts_host, const float* keep_scale_host, float* probs_out_dev,
+                           float* aux_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
+                           uint64_t* counts_out_dev, void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!vol_dev || !shape || !aux_out_dev) { set_error("dcl_predict_volume_aux: null argument"); return DCL_ERR_ARG; }
+  if (!h->cfg.want_aux) { set_error("dcl_predict_volume_aux: the handle was created without want_aux"); return DCL_ERR_ARG; }
+  if (mode != DCL_STITCH_UNIFORM && mode != DCL_STITCH_GAUSSIAN) {
+    set_error("dcl_predict_volume_aux: weighted stitch modes only (the crop-and-overwrite plan needs 4 output channels, predict_overlap.py:43)");
+    return DCL_ERR_ARG;
+  }
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  DCL_TRY(build_plan(mode, shape, n_patches, starts_host, &plan, &zout));
+  return predict_volume_gather(h, vol_dev, shape, mode, plan, zout, keep_scale_host, probs_out_dev, aux_out_dev, labels_out_dev,
+                               target_dev, counts_out_dev, (cudaStream_t)stream);
+}
 
 // 8-flip test-time augmentation around the reference tiling: predict_cls.py:180-203.
 //   keep_scale_host: NULL, or 8 flips x 8 patches x 16 dropout scales in the order the reference draws them
@@ -1835,6 +1889,7 @@ DCL_API double dcl_bench_stitch(const int32_t shape[3], int32_t stride, int32_t 
   cudaMemset(slots, 0x3e, (size_t)np * 4 * P3 * 4);
   GatherPlan gp;
   gp.n = np;
+  gp.slot_planes = 4;
   for (int i = 0; i < np; ++i) for (int a = 0; a < 3; ++a) gp.start[i][a] = plan[i].start[a];
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   int rc = 0;

@@ -279,7 +279,7 @@ gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussi
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int j = n + __popc(m & ((1u << lane) - 1u));
-        s_base[w][j] = i * (4 * (int)P3) + (lx * P + ly) * P - plan.start[i][2];
+        s_base[w][j] = i * (plan.slot_planes * (int)P3) + (lx * P + ly) * P - plan.start[i][2];
         s_sz[w][j] = (short)plan.start[i][2];
         s_wxy[w][j] = blend_w1(lx, gaussian) * blend_w1(ly, gaussian);
       }
@@ -337,7 +337,11 @@ gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussi
 int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,
                            float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
                            cudaStream_t st) {
-  if (plan.n < 1 || plan.n > GatherPlan::MAX) { set_error("gather_finalize: 1..128 patches"); return -1; }
+  if (plan.n < 1 || plan.n > GatherPlan::MAX || plan.slot_planes < 4 ||
+      (int64_t)plan.n * plan.slot_planes * P3 >= ((int64_t)1 << 31)) {
+    set_error("gather_finalize: 1..128 patches and fewer than 2^31 floats of slots");
+    return -1;
+  }
   const int rows = X * Y;
   int blocks = (rows + GATHER_WARPS - 1) / GATHER_WARPS;
   static const int resident = [] {                 // persistent: exactly one wave of resident CTAs

@@ -164,6 +164,38 @@ class Engine:
             _ptr(probs), _ptr(labels), _ptr(target), _ptr(counts), _stream()))
         return {"probs": probs, "labels": labels, "counts": counts}
 
+    def predict_volume_aux(self, vol, mode=StitchMode.UNIFORM, starts=None, keep_scales=None, target=None,
+                           want_probs=True, want_labels=True):
+        """BASELINE config 4: the weighted sliding window with the six final auxiliary heads blended alongside
+        (forward()[1] and [2]: supervise / edge x {'01','02','04'}).  Returns predict_volume's dict plus
+        'supervise' and 'edge': dicts of (1,2,X,Y,Z) tensors keyed like the reference's outputs."""
+        if not self.want_aux:
+            raise DclError("engine was created without want_aux")
+        if vol.dim() == 5:
+            vol = vol[0]
+        if vol.dim() != 4 or vol.shape[0] != 4 or vol.dtype != torch.float32 or not vol.is_cuda:
+            raise DclError("vol must be a CUDA fp32 (4,X,Y,Z) tensor")
+        vol = vol.contiguous()
+        mode, n, s_arr, k_arr = self._plan_args(mode, starts, keep_scales)
+        if s_arr is None:
+            raise DclError("predict_volume_aux needs a weighted stitch mode and a patch list")
+        X, Y, Z = (int(v) for v in vol.shape[1:])
+        shape = (C.c_int32 * 3)(X, Y, Z)
+        probs = torch.empty((1, 4, X, Y, Z), dtype=torch.float32, device=vol.device) if want_probs else None
+        aux = torch.empty((6, 2, X, Y, Z), dtype=torch.float32, device=vol.device)
+        labels = torch.empty((X, Y, Z), dtype=torch.uint8, device=vol.device) if want_labels else None
+        counts = torch.zeros(13, dtype=torch.int64, device=vol.device)
+        if target is not None:
+            target = target.to(device=vol.device, dtype=torch.uint8).contiguous()
+        N.check(self._lib.dcl_predict_volume_aux(
+            self._h, _ptr(vol), shape, int(mode), n, s_arr.ctypes.data_as(C.c_void_p),
+            k_arr.ctypes.data_as(C.c_void_p) if k_arr is not None else C.c_void_p(0),
+            _ptr(probs), _ptr(aux), _ptr(labels), _ptr(target), _ptr(counts), _stream()))
+        out = {"probs": probs, "labels": labels, "counts": counts, "supervise": {}, "edge": {}}
+        for j, (head, key) in enumerate(AUX_ORDER[:6]):
+            out[head][key] = aux[j][None]
+        return out
+
     def predict_volume_tta(self, vol, keep_scales=None, target=None, want_probs=True, want_labels=True):
         """8-flip test-time augmentation around the reference tiling (predict_cls.py:180-203) on a CUDA
         (4,240,240,>=155) / (1,4,...) fp32 volume.  keep_scales: None or (8 flips, 8 patches, 16).

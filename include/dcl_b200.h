@@ -132,6 +132,14 @@ DCL_API int dcl_predict_volume_host(dcl_handle* h, const float* vol_host, const 
                             float* probs_out_host, uint8_t* labels_out_host, const uint8_t* target_host,
                             uint64_t counts_out_host[13], void* stream);
 
+/* BASELINE config 4 ("WT/TC/ET + edge outputs"): dcl_predict_volume in a weighted mode with the six final auxiliary heads
+ * (forward()[1] = supervise {01,02,04}, forward()[2] = edge {01,02,04}; cls_wise_former.py:545-546, :585-592) blended with
+ * the same weights.  aux_out_dev: (6, 2, X, Y, Z) fp32 in that order; requires cfg.want_aux; UNIFORM / GAUSSIAN only. */
+DCL_API int dcl_predict_volume_aux(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                           int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                           float* probs_out_dev, float* aux_out_dev, uint8_t* labels_out_dev,
+                           const uint8_t* target_dev, uint64_t* counts_out_dev, void* stream);
+
 /* 8-flip test-time augmentation around the reference tiling: replaces predict_cls.py:180-203:
  *   logit = softmax(T(x)) + sum over the 7 flips f of softmax(flip_f(T(flip_f(x)))),  output = logit / 8,  T = tailor_and_concat,
  * on x[..., :155], flips in the reference's order (none, X, Y, Z, XY, XZ, YZ, XYZ).  keep_scale_host: NULL or 8 x 8 x 16
