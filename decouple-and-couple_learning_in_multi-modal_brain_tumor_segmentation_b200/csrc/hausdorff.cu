@@ -138,23 +138,40 @@ edt_z_kernel(const uint8_t* __restrict__ border, uint16_t* __restrict__ g1, int6
 __global__ void __launch_bounds__(256)
 edt_y_kernel(const uint16_t* __restrict__ g1, int* __restrict__ g2, int Y, int Z, int64_t n) {
   extern __shared__ int sq[];                              // Y * 32
+  __shared__ int s_any[32];                                // does column tz hold any border voxel at all?
   const int tz = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int z = blockIdx.x * 32 + tz, x = blockIdx.y, set = blockIdx.z;
   const int64_t base = (int64_t)set * n + (int64_t)x * Y * Z;
+  if (threadIdx.x < 32) s_any[threadIdx.x] = 0;
+  __syncthreads();
+  bool any = false;
   for (int y = ty; y < Y; y += 8) {
     int d = INF_G1;
     if (z < Z) d = g1[base + (int64_t)y * Z + z];
+    any |= d < INF_G1;
     sq[y * 32 + tz] = d >= INF_G1 ? INF_SQ : d * d;
   }
+  if (any) s_any[tz] = 1;                                  // benign race: every writer stores 1
   __syncthreads();
   if (z >= Z) return;
+  if (!s_any[tz]) {                                        // sparse masks: most (x, z) columns are empty - no scan
+    for (int y = ty; y < Y; y += 8) g2[base + (int64_t)y * Z + z] = INF_SQ;
+    return;
+  }
   for (int y = ty; y < Y; y += 8) {
     int best = sq[y * 32 + tz];
-    for (int dy = 1; dy < Y; ++dy) {
-      const int dd = dy * dy;
-      if (dd >= best) break;
-      if (y - dy >= 0) best = min(best, sq[(y - dy) * 32 + tz] + dd);
-      if (y + dy < Y) best = min(best, sq[(y + dy) * 32 + tz] + dd);
+    // four steps per trip: the extra candidates of a trip are legitimate ones (the minimum stays exact), and the
+    // eight shared-memory reads no longer wait for the previous step's comparison
+    for (int dy = 1; dy < Y && dy * dy < best; dy += 4) {
+      int c[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int d = dy + u, lo = y - d, hi = y + d;
+        c[2 * u] = lo >= 0 ? sq[lo * 32 + tz] + d * d : INF_SQ;
+        c[2 * u + 1] = hi < Y ? sq[hi * 32 + tz] + d * d : INF_SQ;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) best = min(best, c[u]);
     }
     g2[base + (int64_t)y * Z + z] = best;
   }
@@ -179,11 +196,16 @@ edt_x_hist_kernel(const uint8_t* __restrict__ border, const int* __restrict__ g2
         if (!(b & (1 << q))) continue;
         const int* g = g2 + (int64_t)(1 - q) * n;          // o's border queries t's transform (set 1), t's queries o's
         int best = g[v];
-        for (int dx = 1; dx < X; ++dx) {
-          const int dd = dx * dx;
-          if (dd >= best) break;
-          if (x - dx >= 0) best = min(best, __ldg(g + v - dx * sx) + dd);
-          if (x + dx < X) best = min(best, __ldg(g + v + dx * sx) + dd);
+        for (int dx = 1; dx < X && dx * dx < best; dx += 4) {      // four steps (eight independent L2 loads) per trip
+          int c[8];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int d = dx + u;
+            c[2 * u] = x - d >= 0 ? __ldg(g + v - d * sx) + d * d : INF_SQ;
+            c[2 * u + 1] = x + d < X ? __ldg(g + v + d * sx) + d * d : INF_SQ;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) best = min(best, c[u]);
         }
         if (best < INF_SQ) {                               // INF: the other border is empty (host returns 0 then)
           dmax = max(dmax, best);
