@@ -19,6 +19,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")     # see dcl_b200/__init__.py; before the CUDA context exists
 PKG = os.path.join(ROOT, "decouple-and-couple_learning_in_multi-modal_brain_tumor_segmentation_b200")
 for p in (ROOT, os.path.join(PKG, "dropin")):
     if p not in sys.path:
@@ -66,42 +67,95 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled every 20 ms DURING the timed region, in-process through NVML
+    (nvidia-ml-py; the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons...` prints).  A polling
+    `nvidia-smi -lms` child process was used first: roughly one run in four one of its queries stalled for ~80 ms and the
+    device-resident loop with it (33-37 instead of 25.4 ms per volume; tools/host_enqueue.py, which has no sampler, never
+    showed it).  NVML is initialised before the warm-up; only samples taken inside the timed region are reported.
+    Falls back to one `nvidia-smi` query right after the region when the NVML module is unavailable."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.nvml, self.handle = index, None, None
+        self.samples, self.thread, self.running = [], None, False
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
-        except OSError:
-            self.proc = None
+            if os.environ.get("BENCH_NO_CLOCKS"):       # diagnostic switch: no sampling at all
+                raise RuntimeError("sampling disabled")
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode())
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self._read()          # first call pays the lazy initialisation
+        except Exception:
+            self.nvml = None
+
+    def _read(self):
+        n = self.nvml
+        sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+        return float(sm), float(mx), int(mask)
+
+    def _loop(self):
+        while self.running:
+            try:
+                self.samples.append(self._read())
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def region_begin(self):
+        if self.nvml is not None:
+            self.running = True
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+
+    def region_end(self):
+        if self.thread is not None:
+            self.running = False
+            self.thread.join()
+            try:
+                self.samples.append(self._read())
+            except Exception:
+                pass
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [v.strip() for v in ln.split(",")]
-            if len(f) < 6:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+        if self.nvml is None:
+            return self._nvidia_smi_once()
+        sm = [s[0] for s in self.samples]
+        mx = [s[1] for s in self.samples]
+        mask = 0
+        for s in self.samples:
+            mask |= s[2]
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(name for bit, name in self.REASONS if mask & bit), "samples": len(sm),
+                "source": "NVML, 20 ms period, inside the timed region"}
+
+    def _nvidia_smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                 capture_output=True, text=True, timeout=20).stdout
+            f = [v.strip() for v in out.strip().splitlines()[0].split(",")]
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            return {"sm_mhz": float(f[0]), "sm_max_mhz": float(f[1]),
+                    "reasons": [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")], "samples": 1,
+                    "source": "nvidia-smi, one query right after the timed region (NVML module unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
 
 
 def workload_plan(name):
@@ -272,19 +326,21 @@ def run_ours(args):
                                            labels_out=lab_h)
 
     # ---- device-resident throughput (no per-kernel events inside this region) ----
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()          # before the warm-up: its start-up must not land in the timed region
     for i in range(args.warmup):
         step_dev(i)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = eng.launch_count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.region_begin()
     ev0.record()
     for i in range(args.steps):
         out = step_dev(i)
     ev1.record()
     barrier()
+    sampler.region_end()
     ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count - l0
     clocks = sampler.stop() if rank == 0 else None
