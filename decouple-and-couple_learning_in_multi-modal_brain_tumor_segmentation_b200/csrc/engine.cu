@@ -1757,7 +1757,7 @@ DCL_API int dcl_read_topk(dcl_handle* h, int32_t* out_host, void* stream) {
   return DCL_OK;
 }
 
-DCL_API DCL_API int dcl_profile_enable(dcl_handle* h, int32_t on) {
+DCL_API int dcl_profile_enable(dcl_handle* h, int32_t on) {
   if (!h) { set_error("null handle"); return DCL_ERR_ARG; }
   if (on) {   // a new measurement window: recycle the recorded events
     cudaDeviceSynchronize();

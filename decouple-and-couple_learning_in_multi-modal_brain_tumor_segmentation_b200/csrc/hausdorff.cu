@@ -13,7 +13,9 @@
 //   g2[x,y,z] = min_y' g1[x,y',z] + (y-y')^2                             (edt_y_kernel, shared-memory lines)
 //   d2[x,y,z] = min_x' g2[x',y,z] + (x-x')^2                             (edt_x_hist_kernel, only at query voxels)
 // and the two minimisations walk outwards from the voxel and stop once the step alone exceeds the best distance found,
-// so the cost follows the actual distances (brute force would be 240 candidates per voxel and pass).  The surface
+// so the cost follows the actual distances (brute force would be 240 candidates per voxel and pass).  The second pass
+// is evaluated only at the (y, z) positions the third pass will read (the yz projection of the other set's border) and
+// skips columns without any border voxel.  The surface
 // distances are never materialised: edt_x_hist_kernel adds each query voxel's d2 to one integer histogram per region
 // (both directions share it = the hstack), and the host takes the 95th percentile from the histogram with numpy's
 // "linear" rule in the same double arithmetic (percentile_from_hist), so the result equals numpy's bit for bit.
@@ -41,7 +43,7 @@ __device__ __forceinline__ bool in_region(int l, int region) {
 // summary[0] += |o|, summary[1] += |t|.
 __global__ void __launch_bounds__(256)
 border_kernel(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ tgt, uint8_t* __restrict__ border, int X,
-              int Y, int Z, int region, unsigned long long* __restrict__ summary) {
+              int Y, int Z, int region, unsigned long long* __restrict__ summary, uint8_t* __restrict__ proj) {
   const int64_t n = (int64_t)X * Y * Z;
   const int64_t v = (int64_t)blockIdx.x * 256 + threadIdx.x;
   unsigned no = 0, nt = 0;
@@ -67,6 +69,10 @@ border_kernel(const uint8_t* __restrict__ lab, const uint8_t* __restrict__ tgt, 
       if (!interior) b |= 2;
     }
     border[v] = b;
+    // yz projection of the two borders (zeroed by the host): the transform of one set is only ever read at the (y, z) of
+    // the OTHER set's border voxels, so edt_y_kernel skips every other (y, z).  Racing writers all store 1.
+    if (b & 1) proj[(int64_t)y * Z + z] = 1;
+    if (b & 2) proj[(int64_t)Y * Z + (int64_t)y * Z + z] = 1;
   }
   no = __reduce_add_sync(0xffffffffu, no);
   nt = __reduce_add_sync(0xffffffffu, nt);
@@ -136,7 +142,8 @@ edt_z_kernel(const uint8_t* __restrict__ border, uint16_t* __restrict__ g1, int6
 
 // block = one x, 32 consecutive z, all y of one set; shared sq[y][32] = g1^2; thread (ty, tz) minimises over y'
 __global__ void __launch_bounds__(256)
-edt_y_kernel(const uint16_t* __restrict__ g1, int* __restrict__ g2, int Y, int Z, int64_t n) {
+edt_y_kernel(const uint16_t* __restrict__ g1, int* __restrict__ g2, int Y, int Z, int64_t n,
+             const uint8_t* __restrict__ proj) {
   extern __shared__ int sq[];                              // Y * 32
   __shared__ int s_any[32];                                // does column tz hold any border voxel at all?
   const int tz = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -154,11 +161,15 @@ edt_y_kernel(const uint16_t* __restrict__ g1, int* __restrict__ g2, int Y, int Z
   if (any) s_any[tz] = 1;                                  // benign race: every writer stores 1
   __syncthreads();
   if (z >= Z) return;
+  // the transform of set `set` is queried by the border voxels of the other set only
+  const uint8_t* need = proj + (int64_t)(1 - set) * Y * Z;
   if (!s_any[tz]) {                                        // sparse masks: most (x, z) columns are empty - no scan
-    for (int y = ty; y < Y; y += 8) g2[base + (int64_t)y * Z + z] = INF_SQ;
+    for (int y = ty; y < Y; y += 8)
+      if (need[(int64_t)y * Z + z]) g2[base + (int64_t)y * Z + z] = INF_SQ;
     return;
   }
   for (int y = ty; y < Y; y += 8) {
+    if (!need[(int64_t)y * Z + z]) continue;               // never read by edt_x_hist_kernel
     int best = sq[y * 32 + tz];
     // four steps per trip: the extra candidates of a trip are legitimate ones (the minimum stays exact), and the
     // eight shared-memory reads no longer wait for the previous step's comparison
@@ -226,7 +237,7 @@ inline int64_t align256(int64_t v) { return (v + 255) & ~(int64_t)255; }
 
 struct HdLayout {
   int64_t n, nbins;
-  int64_t off_border, off_g1, off_g2, off_hist, off_summary, total;
+  int64_t off_border, off_g1, off_g2, off_hist, off_summary, off_proj, total;
 };
 
 HdLayout hd_layout(const int32_t shape[3]) {
@@ -240,6 +251,7 @@ HdLayout hd_layout(const int32_t shape[3]) {
   L.off_g2 = o; o += align256(2 * L.n * 4);
   L.off_hist = o; o += align256(L.nbins * 4);
   L.off_summary = o; o += 256;
+  L.off_proj = o; o += align256(2 * (int64_t)shape[1] * shape[2]);
   L.total = o;
   return L;
 }
@@ -310,6 +322,7 @@ DCL_API int dcl_hausdorff(const uint8_t* labels_dev, const uint8_t* target_dev, 
   int* g2 = (int*)(ws + L.off_g2);
   unsigned* hist = (unsigned*)(ws + L.off_hist);
   unsigned long long* summary = (unsigned long long*)(ws + L.off_summary);
+  uint8_t* proj = (uint8_t*)(ws + L.off_proj);
   const size_t smem_y = (size_t)Y * 32 * sizeof(int);
   if (smem_y > 48 * 1024) DCL_CUDA_OK(cudaFuncSetAttribute(edt_y_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_y));
   std::vector<uint32_t> h(L.nbins);
@@ -317,10 +330,11 @@ DCL_API int dcl_hausdorff(const uint8_t* labels_dev, const uint8_t* target_dev, 
   for (int region = 0; region < 3; ++region) {
     DCL_CUDA_OK(cudaMemsetAsync(hist, 0, L.nbins * 4, st));
     DCL_CUDA_OK(cudaMemsetAsync(summary, 0, 32, st));
-    border_kernel<<<vblocks, 256, 0, st>>>(labels_dev, target_dev, border, X, Y, Z, region, summary);
+    DCL_CUDA_OK(cudaMemsetAsync(proj, 0, 2 * (size_t)Y * Z, st));
+    border_kernel<<<vblocks, 256, 0, st>>>(labels_dev, target_dev, border, X, Y, Z, region, summary, proj);
     const int64_t lines = (int64_t)X * Y;
     edt_z_kernel<<<(unsigned)((lines + 7) / 8), 256, 0, st>>>(border, g1, lines, Z, L.n);
-    edt_y_kernel<<<dim3((Z + 31) / 32, X, 2), 256, smem_y, st>>>(g1, g2, Y, Z, L.n);
+    edt_y_kernel<<<dim3((Z + 31) / 32, X, 2), 256, smem_y, st>>>(g1, g2, Y, Z, L.n, proj);
     edt_x_hist_kernel<<<vblocks, 256, 0, st>>>(border, g2, X, Y, Z, L.n, hist, L.nbins, summary);
     g_launches += 4;
     DCL_CUDA_OK(cudaGetLastError());
