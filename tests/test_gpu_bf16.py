@@ -155,3 +155,35 @@ def test_config4_volume_with_wt_tc_et_and_edge_outputs(seed0_state_dict, golden_
                 assert err <= 1e-1, (gname, key, err)
     finally:
         eng.close()
+
+
+def test_overlap75_plan_matches_oracle_and_both_stitch_forms(engine_bf16):
+    """BASELINE config 5 (MSD-style 75 % overlap: stride 32, 50 patches, up to 32 patches covering one voxel) with the
+    gaussian blend: the volume call equals the oracle blend of the 50 per-patch forwards, and the gather form equals the
+    accumulate form bit for bit."""
+    import os
+    from dcl_b200 import StitchMode, patch_starts
+    from oracle import stitch_oracle as S
+    from tests.util import volume_input, volume_target
+    vol = volume_input(1).cuda()
+    starts = patch_starts((240, 240, 155), 32)
+    assert len(starts) == 50 and starts == S.patch_starts((240, 240, 155), 32)
+    probs = [engine_bf16.forward(vol[..., sx:sx + 128, sy:sy + 128, sz:sz + 128], None)[0].cpu().numpy()
+             for sx, sy, sz in starts]
+    want = S.accumulate_from_probs(probs, starts, "gaussian")
+    tgt = torch.from_numpy(volume_target(1).astype(np.uint8)).cuda()
+    got = engine_bf16.predict_volume(vol, StitchMode.GAUSSIAN, starts=starts, target=tgt)
+    g = got["probs"][0].cpu().numpy()
+    assert np.abs(g - want).max() < 2e-6
+    labels = S.labels_from_probs(g)
+    assert np.array_equal(got["labels"].cpu().numpy(), labels.astype(np.uint8))
+    counts = got["counts"].cpu().numpy().tolist()
+    assert counts[:4] == S.label_histogram(labels)
+    assert counts[4:] == [v for c in S.region_counts(labels, volume_target(1)) for v in c]
+    os.environ["DCL_GATHER"] = "0"
+    try:
+        acc = engine_bf16.predict_volume(vol, StitchMode.GAUSSIAN, starts=starts, target=tgt)
+    finally:
+        del os.environ["DCL_GATHER"]
+    assert torch.equal(acc["probs"], got["probs"]) and torch.equal(acc["labels"], got["labels"])
+    assert torch.equal(acc["counts"], got["counts"])
