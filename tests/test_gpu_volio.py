@@ -211,3 +211,16 @@ def test_dropin_validate_softmax_exports_and_metrics(seed0_state_dict, tmp_path)
     a, b = blob_labels(RAGGED, 60, 1.0) > 0, blob_labels(RAGGED, 61, 1.0) > 0
     assert H.hausdorff_distance_95(a, b) == float(O.medpy_hd95(a, b)) and H.hausdorff_distance(a, b) == float(O.medpy_hd(a, b))
     assert H.hausdorff_distance_95(np.zeros_like(a), b) == 0
+
+
+def test_device_metrics_match_reference_goldens():
+    """HD95 / HD on the device against the values the reference's own cal_hausdorff / hausdorff_distance glue produced in
+    the build container (tests/golden/make_golden_metrics.py; only medpy itself substituted): bit-exact doubles."""
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gold = json.load(open(os.path.join(here, "metrics_golden.json")))
+    arrays = np.load(os.path.join(here, "metrics_cases.npz"))
+    for name, g in gold.items():
+        got = V.hausdorff(dev(arrays[name + "/output"]), dev(arrays[name + "/target"]))
+        assert got["hd95"] == g["cal_hausdorff"], (name, got)
+        assert got["hd"] == g["hausdorff_distance"], (name, got)

@@ -141,3 +141,25 @@ def test_no_gpu_means_error_not_fallback():
         V.export_labels(torch.zeros(4, 4, 4, dtype=torch.uint8))
     with pytest.raises(DclError):
         V.hausdorff(torch.zeros(4, 4, 4, dtype=torch.uint8), torch.zeros(4, 4, 4, dtype=torch.uint8))
+
+
+def _metric_goldens():
+    import json
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    return json.load(open(os.path.join(here, "metrics_golden.json"))), np.load(os.path.join(here, "metrics_cases.npz"))
+
+
+def test_metrics_oracle_and_counter_formulas_match_reference_goldens():
+    """tests/golden/make_golden_metrics.py ran the reference's own cal_hausdorff / softmax_output_mIou /
+    softmax_output_dice (only medpy itself substituted): the oracle and the counter-based host formulas reproduce them."""
+    from dcl_b200.engine import dice_from_counts
+    from oracle import stitch_oracle as S
+    gold, arrays = _metric_goldens()
+    assert len(gold) == 7
+    for name, g in gold.items():
+        o, t = arrays[name + "/output"], arrays[name + "/target"]
+        assert O.cal_hausdorff(o, t) == g["cal_hausdorff"], name
+        assert O.cal_hd(o, t) == g["hausdorff_distance"], name
+        counts = [int(np.sum(o == k)) for k in range(4)] + [v for c in S.region_counts(o, t) for v in c]
+        assert V.miou_from_counts(counts) == g["softmax_output_mIou"], name
+        assert dice_from_counts(counts) == g["softmax_output_dice"], name
