@@ -163,3 +163,23 @@ def test_metrics_oracle_and_counter_formulas_match_reference_goldens():
         counts = [int(np.sum(o == k)) for k in range(4)] + [v for c in S.region_counts(o, t) for v in c]
         assert V.miou_from_counts(counts) == g["softmax_output_mIou"], name
         assert dice_from_counts(counts) == g["softmax_output_dice"], name
+
+
+def test_host_entry_points_reject_bad_arguments(tmp_path):
+    import ctypes as C
+    from dcl_b200 import _native as N
+    lib = N.load_library()
+    bad = (C.c_int32 * 3)(0, 4, 4)
+    ok = (C.c_int32 * 3)(240, 240, 155)
+    assert lib.dcl_hausdorff_workspace_bytes(bad) < 0
+    ws = lib.dcl_hausdorff_workspace_bytes(ok)
+    assert 100e6 < ws < 200e6                                      # border 9 MB + 16-bit and 32-bit transforms of two sets
+    a = np.zeros((4, 4, 4), np.float32)
+    assert lib.dcl_write_nifti(str(tmp_path / "x.nii").encode(), a.ctypes.data_as(C.c_void_p), 3, (C.c_int32 * 3)(4, 4, 4)) < 0
+    assert b"datatype" in lib.dcl_last_error()
+    assert lib.dcl_write_nifti(b"/nonexistent_dir/x.nii", a.ctypes.data_as(C.c_void_p), 16, (C.c_int32 * 3)(4, 4, 4)) < 0
+    assert lib.dcl_write_png_rgb(str(tmp_path / "x.png").encode(), a.ctypes.data_as(C.c_void_p), 0, 4) < 0
+    with pytest.raises(DclError):
+        V.write_png(str(tmp_path / "y.png"), np.zeros((4, 4), np.uint8))
+    with pytest.raises(DclError):
+        V.write_nifti_storage(str(tmp_path / "z.nii"), np.zeros((2, 2, 2), np.complex64))
