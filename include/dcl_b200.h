@@ -15,7 +15,8 @@
  *   - a handle is bound to the CUDA device that was current in dcl_create and is not
  *     thread safe; use one handle per stream (different handles may be used from different threads)
  *   - environment: DCL_LANES=1..4 patches in flight per volume call (default 3), DCL_GATHER=0 accumulate-form stitch
- *     instead of the gather form, DCL_PDL=1 programmatic dependent launch, DCL_STAMPS=1 / DCL_DEBUG=1 debug aids.
+ *     instead of the gather form, DCL_S2GEN=0 im2col GEMM instead of the rolling kernel for the stride-2 convolutions of
+ *     the 64^3 level, DCL_PDL=1 programmatic dependent launch, DCL_STAMPS=1 / DCL_DEBUG=1 debug aids.
  *     Set CUDA_DEVICE_MAX_CONNECTIONS=32 before the CUDA context is created (the Python package does): with the
  *     driver's default of 8 hardware work queues the lane streams of a volume call can share a queue and serialise
  *     (measured: one process in four ran 33-42 instead of 25.5 ms per volume)
