@@ -28,7 +28,7 @@ cudaError_t trace_set_conv_gemm(long long* p, int cta) { return trace_set_local(
 // prep: norm + act + bf16 + channel blocking (zero-pads channels up to a multiple of 16)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-prep_blocked_kernel(ConvSrc src, int64_t spatial, int in_h, int in_w, uint4* __restrict__ out) {
+prep_blocked_kernel(ConvSrc src, int64_t spatial, int in_h, int in_w, uint4* __restrict__ out, int64_t lo_off) {
   const int kc = blockIdx.y;
   const int cin = src.c0 + src.c1;
   const int64_t p = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -60,18 +60,25 @@ prep_blocked_kernel(ConvSrc src, int64_t spatial, int in_h, int in_w, uint4* __r
     v[k] = x;
   }
   uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]);
-  o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]);
-  o.w = pack_bf16x2(v[6], v[7]);
+  if (lo_off != 0) {      // split-bf16: hi planes, then lo planes
+    uint4 l;
+    split8(v, o, l);
+    out[lo_off + (int64_t)kc * spatial + p] = l;
+  } else {
+    o.x = pack_bf16x2(v[0], v[1]);
+    o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]);
+    o.w = pack_bf16x2(v[6], v[7]);
+  }
   out[(int64_t)kc * spatial + p] = o;
 }
 
-int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* out, cudaStream_t st) {
+int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* out, cudaStream_t st, bool x3) {
   const int cin_pad = (src.c0 + src.c1 + 15) / 16 * 16;
   const int64_t spatial = (int64_t)in_d * in_h * in_w;
   dim3 grid((unsigned)((spatial + 255) / 256), cin_pad / 8);
-  prep_blocked_kernel<<<grid, 256, 0, st>>>(src, spatial, in_h, in_w, reinterpret_cast<uint4*>(out));
+  prep_blocked_kernel<<<grid, 256, 0, st>>>(src, spatial, in_h, in_w, reinterpret_cast<uint4*>(out),
+                                            x3 ? (int64_t)(cin_pad / 8) * spatial : 0);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -94,6 +101,11 @@ struct GemmConvParams {
   int D, H, W, OD, OH, OW, stride, taps, kstage;
   int out_mode;            // 0: fp32 NCDHW [cout][m]   1: fp32 row-major [m][cout]   2: B-format bf16
   int gelu;                // exact (erf) GELU after the bias
+  // split-bf16 (DCL_BF16X3): the lo planes of a source follow its hi planes (chunk kc of source 0 at + c0_chunks *
+  // spatial, of source 1 at + c1 chunks * spatial), the lo weight image sits w_lo 16-byte units behind the hi image,
+  // B-format outputs / residuals carry their lo planes cout_pad / 8 chunks behind the hi planes
+  int x3;
+  int64_t w_lo;
 };
 
 constexpr int G_EPI_WARPS = 4;
@@ -217,20 +229,34 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint
         for (int hf = 0; hf < 2; ++hf) {
           const int kc = (n0 + c0) / 8 + hf;
           if (kc * 8 < p.cout_pad) {
+            const int64_t lo_off = p.x3 ? (int64_t)(p.cout_pad / 8) * m_total : 0;
             if (rb) {
-              const uint4 rv = __ldg(rb + (int64_t)kc * m_total + m);
-              const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                v[8 * hf + 2 * k] += __uint_as_float(pr[k] << 16);
-                v[8 * hf + 2 * k + 1] += __uint_as_float(pr[k] & 0xffff0000u);
+              for (int part = 0; part < 2; ++part) {
+                if (part == 1 && !p.x3) break;
+                const uint4 rv = __ldg(rb + (part ? lo_off : 0) + (int64_t)kc * m_total + m);
+                const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  v[8 * hf + 2 * k] += __uint_as_float(pr[k] << 16);
+                  v[8 * hf + 2 * k + 1] += __uint_as_float(pr[k] & 0xffff0000u);
+                }
               }
             }
             uint4 o;
-            o.x = pack_bf16x2(v[8 * hf], v[8 * hf + 1]);
-            o.y = pack_bf16x2(v[8 * hf + 2], v[8 * hf + 3]);
-            o.z = pack_bf16x2(v[8 * hf + 4], v[8 * hf + 5]);
-            o.w = pack_bf16x2(v[8 * hf + 6], v[8 * hf + 7]);
+            if (p.x3) {
+              uint4 l;
+              split_bf16x2(v[8 * hf], v[8 * hf + 1], o.x, l.x);
+              split_bf16x2(v[8 * hf + 2], v[8 * hf + 3], o.y, l.y);
+              split_bf16x2(v[8 * hf + 4], v[8 * hf + 5], o.z, l.z);
+              split_bf16x2(v[8 * hf + 6], v[8 * hf + 7], o.w, l.w);
+              yb[lo_off + (int64_t)kc * m_total + m] = l;
+            } else {
+              o.x = pack_bf16x2(v[8 * hf], v[8 * hf + 1]);
+              o.y = pack_bf16x2(v[8 * hf + 2], v[8 * hf + 3]);
+              o.z = pack_bf16x2(v[8 * hf + 4], v[8 * hf + 5]);
+              o.w = pack_bf16x2(v[8 * hf + 6], v[8 * hf + 7]);
+            }
             yb[(int64_t)kc * m_total + m] = o;
           }
         }
@@ -293,8 +319,10 @@ conv_gemm_kernel(GemmConvParams p) {
   pdl_trigger();
   constexpr int LAG = G_NS - 2;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int a_bytes = 2 * p.kstage * 2048;               // [chunk][128 rows][16 B]
-  const int b_bytes = 2 * p.kstage * p.n_tile * 16;      // [chunk][n_tile rows][16 B]
+  const int a_half = 2 * p.kstage * 2048;                // [chunk][128 rows][16 B]
+  const int b_half = 2 * p.kstage * p.n_tile * 16;       // [chunk][n_tile rows][16 B]
+  const int a_bytes = a_half << p.x3;                    // split-bf16: the lo chunks follow the hi chunks
+  const int b_bytes = b_half << p.x3;
   const int stage_bytes = a_bytes + b_bytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + G_NS * stage_bytes);
   uint64_t* bar_empty = bar_full + G_NS;
@@ -350,6 +378,7 @@ conv_gemm_kernel(GemmConvParams p) {
     const int n_chunks = 2 * p.kstage;
     // chunk kc of the (virtually concatenated) input lives at a + kc*sp_in (+ delta1 once past source 0)
     const int64_t delta1 = p.a1 ? (p.a1 - p.a) - (int64_t)p.c0_chunks * sp_in : 0;
+    const int64_t lo0 = (int64_t)p.c0_chunks * sp_in, lo1 = (int64_t)(p.cin_pad / 8 - p.c0_chunks) * sp_in;   // x3 only
     const uint32_t b_seg = (uint32_t)p.n_tile * 16;        // bytes of one chunk row block of B
     int it = 0;
     if (p.taps == 1 && p.stride == 1 && p.a1 == nullptr) {
@@ -364,18 +393,22 @@ conv_gemm_kernel(GemmConvParams p) {
           const int kc0 = kg * n_chunks;
           const uint32_t st_base = smem_base + (uint32_t)(s * stage_bytes);
           const uint32_t bar = smem_u32(&bar_full[s]);
-          asm volatile("mbarrier.expect_tx.shared::cta.b64 [%1], %0;" ::"r"((uint32_t)n_chunks * (b_seg + a_chunk)), "r"(bar) : "memory");
+          asm volatile("mbarrier.expect_tx.shared::cta.b64 [%1], %0;" ::"r"(((uint32_t)n_chunks * (b_seg + a_chunk)) << p.x3), "r"(bar) : "memory");
           const uint4* b_src = p.w + (int64_t)kc0 * p.cout_pad + n0;
           const uint4* a_src = p.a + (int64_t)kc0 * sp_in + m0;
-          for (int c = 0; c < n_chunks; ++c) {
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             st_base + (uint32_t)a_bytes + (uint32_t)c * b_seg),
-                         "l"(b_src + (int64_t)c * p.cout_pad), "r"(b_seg), "r"(bar)
-                         : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             st_base + (uint32_t)(c * 2048)),
-                         "l"(a_src + (int64_t)c * sp_in), "r"(a_chunk), "r"(bar)
-                         : "memory");
+          for (int part = 0; part <= p.x3; ++part) {
+            const uint4* bs = b_src + (part ? p.w_lo : 0);
+            const uint4* as = a_src + (part ? lo0 : 0);
+            for (int c = 0; c < n_chunks; ++c) {
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                               st_base + (uint32_t)a_bytes + (uint32_t)(part * b_half) + (uint32_t)c * b_seg),
+                           "l"(bs + (int64_t)c * p.cout_pad), "r"(b_seg), "r"(bar)
+                           : "memory");
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                               st_base + (uint32_t)(part * a_half) + (uint32_t)(c * 2048)),
+                           "l"(as + (int64_t)c * sp_in), "r"(a_chunk), "r"(bar)
+                           : "memory");
+            }
           }
         }
         mbar_arrive(&bar_full[s]);
@@ -397,20 +430,24 @@ conv_gemm_kernel(GemmConvParams p) {
         if (pt == 0) {
           // weights: one bulk async copy (UBLKCP) per 8-channel chunk, completion counted in bytes on full[s]
           const uint32_t bar = smem_u32(&bar_full[s]);
-          asm volatile("mbarrier.expect_tx.shared::cta.b64 [%1], %0;" ::"r"((uint32_t)n_chunks * b_seg), "r"(bar) : "memory");
+          asm volatile("mbarrier.expect_tx.shared::cta.b64 [%1], %0;" ::"r"(((uint32_t)n_chunks * b_seg) << p.x3), "r"(bar) : "memory");
           const uint4* b_src = b_tap + (int64_t)kc0 * p.cout_pad;
-          for (int c = 0; c < n_chunks; ++c)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                             st_base + (uint32_t)a_bytes + (uint32_t)c * b_seg),
-                         "l"(b_src + (int64_t)c * p.cout_pad), "r"(b_seg), "r"(bar)
-                         : "memory");
+          for (int part = 0; part <= p.x3; ++part)
+            for (int c = 0; c < n_chunks; ++c)
+              asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                               st_base + (uint32_t)a_bytes + (uint32_t)(part * b_half) + (uint32_t)c * b_seg),
+                           "l"(b_src + (part ? p.w_lo : 0) + (int64_t)c * p.cout_pad), "r"(b_seg), "r"(bar)
+                           : "memory");
         }
         // activations: this thread's row, one 16-byte zero-filling cp.async per chunk
         const uint32_t a_dst = st_base + (uint32_t)(pt * 16);
         const int64_t step = ok ? sp_in : 0, d1 = ok ? delta1 : 0;   // masked rows never form an out-of-range address
         const uint4* a_src = a_row + (int64_t)kc0 * step;
         for (int c = 0; c < n_chunks; ++c) {
-          cp_async16(a_dst + (uint32_t)(c * 2048), a_src + (kc0 + c >= p.c0_chunks ? d1 : 0), a_bytes_ok);
+          const bool second = kc0 + c >= p.c0_chunks;
+          const uint4* srcp = a_src + (second ? d1 : 0);
+          cp_async16(a_dst + (uint32_t)(c * 2048), srcp, a_bytes_ok);
+          if (p.x3) cp_async16(a_dst + (uint32_t)(a_half + c * 2048), srcp + (ok ? (second ? lo1 : lo0) : 0), a_bytes_ok);
           a_src += step;
         }
         cp_async_commit();
@@ -441,6 +478,10 @@ conv_gemm_kernel(GemmConvParams p) {
         uint64_t bd = b_desc0 + (uint64_t)((uint32_t)(s * stage_bytes) >> 4);
         for (int ks = 0; ks < p.kstage; ++ks) {
           umma_bf16_ws(tmem_base, ad, bd, idesc, (it | ks) != 0 ? 1u : 0u);
+          if (p.x3) {                       // + a_lo * w_hi + a_hi * w_lo
+            umma_bf16_ws(tmem_base, ad + (uint64_t)((uint32_t)a_half >> 4), bd, idesc, 1u);
+            umma_bf16_ws(tmem_base, ad, bd + (uint64_t)((uint32_t)b_half >> 4), idesc, 1u);
+          }
           ad += 256u;                       // 2 chunks x 2048 B
           bd += (uint64_t)(b_lbo >> 3);     // 2 chunks x n_tile*16 B, in 16-byte units
         }
@@ -496,6 +537,7 @@ conv_gemm_kernel(GemmConvParams p) {
 struct SlabParams {
   GemmConvParams g;         // a / a1 / c0_chunks / bias / residual / y / stats / cout / n_tile / D,H,W / out_mode
   const uint4* wslab;       // repacked weights
+  int64_t wslab_lo;         // split-bf16: 16-byte units from the hi image to the lo image
   const stat_t* sums;       // fused input InstanceNorm (+ activation), as in the rolling kernel
   float inv_n;
   const float* mean;
@@ -527,6 +569,27 @@ __device__ __forceinline__ uint4 slab_xf(uint4 v, const float (&sc)[8], const fl
   return v;
 }
 
+// split-bf16 variant: value = hi + lo -> norm + act -> split again
+template <int ACT>
+__device__ __forceinline__ void slab_xf_run_x3(uint4* bh, uint4* bl, int n_vec, int lane, const float (&sc)[8], const float (&sh)[8]) {
+  for (int i = lane; i < n_vec; i += 32) {
+    float f[8];
+    unpack8_acc<false>(bh[i], f);
+    unpack8_acc<true>(bl[i], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v = fmaf(f[k], sc[k], sh[k]);
+      if (ACT == ACT_RELU) v = fmaxf(v, 0.f);
+      else if (ACT == ACT_LRELU) v = fmaxf(v, 0.01f * v);
+      f[k] = v;
+    }
+    uint4 h, l;
+    split8(f, h, l);
+    bh[i] = h;
+    bl[i] = l;
+  }
+}
+
 template <int ACT>
 __device__ __forceinline__ void slab_xf_run(uint4* base, int n_vec, int lane, const float (&sc)[8], const float (&sh)[8]) {
   int i = lane;
@@ -549,9 +612,11 @@ conv_slab_kernel(SlabParams sp) {
   const int W = p.W, H = p.H, D = p.D;
   const int R = sp.rows;
   const int npos = 3 * (R + 2) * W;                      // 16-byte positions per channel chunk
-  const int slab_bytes = sp.kc_pass * npos * 16;
+  const int kcp = sp.kc_pass;                            // channel chunks per pass
+  const int kcs = kcp << p.x3;                           // staged chunks per pass: split-bf16 keeps the lo chunks behind the hi chunks
+  const int slab_bytes = kcs * npos * 16;
   const int nst = 3 * p.n_tile;                          // stacked N
-  const int b_stage = sp.kc_pass * nst * 16;             // ring stage = one (kd,kh): [chunk][kw][n_tile] x 16 B
+  const int b_stage = kcs * nst * 16;                    // ring stage = one (kd,kh): [hi|lo][chunk][kw][n_tile] x 16 B
   uint64_t* bar_bfull = reinterpret_cast<uint64_t*>(smem + slab_bytes + sp.nb * b_stage);
   uint64_t* bar_bempty = bar_bfull + sp.nb;
   uint64_t* bar_slab_full = bar_bempty + sp.nb;          // slab transformed (one arrive per transform warp)
@@ -614,6 +679,7 @@ conv_slab_kernel(SlabParams sp) {
     // =============================== loader: slab + weight ring ==================================
     const int64_t sp_in = m_total;
     const int64_t delta1 = p.a1 ? (p.a1 - p.a) - (int64_t)p.c0_chunks * sp_in : 0;
+    const int64_t lo0 = (int64_t)p.c0_chunks * sp_in, lo1 = (int64_t)(kcs_total - p.c0_chunks) * sp_in;   // x3 only
     const uint32_t run_bytes = (uint32_t)((r_hi - r_lo + 1) * W) * 16u;
     int vd = 0;
     for (int pl = 0; pl < 3; ++pl) vd += (unsigned)(d_out - 1 + pl) < (unsigned)D ? 1 : 0;
@@ -623,17 +689,20 @@ conv_slab_kernel(SlabParams sp) {
       const int kc_base = pass * sp.kc_pass;
       if (pass > 0) mbar_wait(bar_slab_empty, (uint32_t)(pass - 1) & 1u);   // MMAs of the previous pass are done
       if (lane == 0)
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(vd * sp.kc_pass) * run_bytes),
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)(vd * kcs) * run_bytes),
                      "r"(smem_u32(bar_slab_land))
                      : "memory");
       __syncwarp();
-      for (int e = lane; e < sp.kc_pass * 3; e += 32) {
-        const int c = e / 3, pl = e - c * 3;
+      for (int e = lane; e < kcs * 3; e += 32) {
+        const int cc = e / 3, pl = e - cc * 3;             // staged chunk (hi chunks, then lo chunks), plane
         const int d_in = d_out - 1 + pl;
         if ((unsigned)d_in >= (unsigned)D) continue;
-        const int kc = kc_base + c;
-        const uint4* src = p.a + (int64_t)kc * sp_in + (kc >= p.c0_chunks ? delta1 : 0) + ((int64_t)d_in * H + (h0 - 1 + r_lo)) * W;
-        const uint32_t dst = smem_base + (uint32_t)((c * npos + (pl * (R + 2) + r_lo) * W) * 16);
+        const int part = cc >= kcp ? 1 : 0;
+        const int kc = kc_base + cc - part * kcp;
+        const bool second = kc >= p.c0_chunks;
+        const uint4* src = p.a + (int64_t)kc * sp_in + (second ? delta1 : 0) + (part ? (second ? lo1 : lo0) : 0) +
+                           ((int64_t)d_in * H + (h0 - 1 + r_lo)) * W;
+        const uint32_t dst = smem_base + (uint32_t)((cc * npos + (pl * (R + 2) + r_lo) * W) * 16);
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                      "l"(src), "r"(run_bytes), "r"(smem_u32(bar_slab_land))
                      : "memory");
@@ -646,10 +715,12 @@ conv_slab_kernel(SlabParams sp) {
           trace_event(tbuf, 10, bit);   // weight stage free, issuing (kd,kh)
           const uint32_t bar = smem_u32(&bar_bfull[s]);
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"((uint32_t)b_stage), "r"(bar) : "memory");
-          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                           smem_base + (uint32_t)(slab_bytes + s * b_stage)),
-                       "l"(wsrc + ((int64_t)kdh * kcs_total + kc_base) * nst), "r"((uint32_t)b_stage), "r"(bar)
-                       : "memory");
+          const uint32_t half = (uint32_t)(kcp * nst * 16);
+          for (int part = 0; part <= p.x3; ++part)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_base + (uint32_t)(slab_bytes + s * b_stage) + (uint32_t)part * half),
+                         "l"(wsrc + (part ? sp.wslab_lo : 0) + ((int64_t)kdh * kcs_total + kc_base) * nst), "r"(half), "r"(bar)
+                         : "memory");
         }
         __syncwarp();
       }
@@ -663,6 +734,7 @@ conv_slab_kernel(SlabParams sp) {
       const uint64_t b_desc0 = umma_desc(smem_base + (uint32_t)slab_bytes, (uint32_t)nst * 16, 128);
       const uint32_t a_ks = 2u * (uint32_t)npos, b_ks = 2u * (uint32_t)nst;    // K-step strides in 16-byte units
       const int nks = sp.kc_pass / 2;
+      const uint64_t a_lo = (uint64_t)((uint32_t)kcp * (uint32_t)npos), b_lo = (uint64_t)((uint32_t)kcp * (uint32_t)nst);   // 16-byte units
       int bit = 0;
       for (int pass = 0; pass < sp.npass; ++pass) {
         mbar_wait(bar_slab_full, (uint32_t)pass & 1u);
@@ -682,6 +754,10 @@ conv_slab_kernel(SlabParams sp) {
             uint32_t acc_t = accum;
             for (int ks = 0; ks < nks; ++ks) {
               umma_bf16_ws(d_tmem, ad, bd, idesc, acc_t);
+              if (p.x3) {                   // + a_lo * w_hi + a_hi * w_lo
+                umma_bf16_ws(d_tmem, ad + a_lo, bd, idesc, 1u);
+                umma_bf16_ws(d_tmem, ad, bd + b_lo, idesc, 1u);
+              }
               ad += a_ks; bd += b_ks; acc_t = 1u;
             }
           }
@@ -697,7 +773,7 @@ conv_slab_kernel(SlabParams sp) {
     const int xw = warp < G_EPI_WARPS ? warp : warp - 1;    // 0..11
     const bool identity = !has_norm && sp.act == ACT_NONE;
     // rows / planes outside the volume are zero padding: written once, never touched by the bulk copies
-    for (int q = xw; q < sp.kc_pass * 3; q += S_XF_WARPS) {
+    for (int q = xw; q < kcs * 3; q += S_XF_WARPS) {
       const int c = q / 3, pl = q - c * 3;
       uint4* chunk = reinterpret_cast<uint4*>(smem + (size_t)(c * npos + pl * (R + 2) * W) * 16);
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
@@ -723,7 +799,12 @@ conv_slab_kernel(SlabParams sp) {
           const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
           const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
           uint4* base = reinterpret_cast<uint4*>(smem + (size_t)(c * npos + (pl * (R + 2) + r_lo) * W) * 16);
-          if (sp.act == ACT_RELU) slab_xf_run<ACT_RELU>(base, n_vec, lane, sc, sh);
+          if (p.x3) {
+            uint4* bl = base + (size_t)kcp * npos;
+            if (sp.act == ACT_RELU) slab_xf_run_x3<ACT_RELU>(base, bl, n_vec, lane, sc, sh);
+            else if (sp.act == ACT_LRELU) slab_xf_run_x3<ACT_LRELU>(base, bl, n_vec, lane, sc, sh);
+            else slab_xf_run_x3<ACT_NONE>(base, bl, n_vec, lane, sc, sh);
+          } else if (sp.act == ACT_RELU) slab_xf_run<ACT_RELU>(base, n_vec, lane, sc, sh);
           else if (sp.act == ACT_LRELU) slab_xf_run<ACT_LRELU>(base, n_vec, lane, sc, sh);
           else slab_xf_run<ACT_NONE>(base, n_vec, lane, sc, sh);
         }
@@ -814,6 +895,9 @@ int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st) {
   p.D = g.D; p.H = g.H; p.W = g.W;
   p.stride = g.stride; p.taps = g.taps;
   p.out_mode = g.out_mode; p.gelu = g.gelu;
+  p.x3 = g.x3 ? 1 : 0;
+  p.w_lo = w.lo_off / 16;
+  if (g.x3 && (w.lo_off == 0 || (w.cin % 16) != 0 && g.a1 != nullptr)) { set_error("gemm_conv: split-bf16 needs split weights"); return -1; }
   p.OD = (g.D - 1) / g.stride + 1; p.OH = (g.H - 1) / g.stride + 1; p.OW = (g.W - 1) / g.stride + 1;
   if (p.out_mode == 1 && (p.cout % 16) != 0) { set_error("gemm_conv: row-major output needs cout % 16 == 0"); return -1; }
   return launch_gemm_params(p, st);
@@ -866,6 +950,10 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   p.D = g.D; p.H = g.H; p.W = g.W; p.OD = g.D; p.OH = g.H; p.OW = g.W;
   p.stride = 1; p.taps = 27; p.kstage = 1;
   p.out_mode = g.out_mode; p.gelu = g.gelu;
+  p.x3 = g.x3 ? 1 : 0;
+  p.w_lo = w.lo_off / 16;
+  if (g.x3 && w.lo_off == 0) { set_error("slab_conv: split-bf16 needs split weights"); return -1; }
+  const int xs = p.x3;
   sp.sums = norm ? norm->sums : nullptr;
   sp.inv_n = norm ? norm->inv_n : 0.f;
   sp.mean = norm ? norm->mean : nullptr;
@@ -885,11 +973,11 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
     const int npos = 3 * (rows + 2) * g.W;
     for (int nt = 16; 3 * nt <= 256 && nt <= p.cout_pad; nt += 16) {
       if (p.cout_pad % nt != 0 || mt * 3 * nt > 512) continue;
-      for (int npass = 1; npass <= 2; ++npass) {
+      for (int npass = 1; npass <= 4; ++npass) {
         if ((cin_pad / 16) % npass != 0) continue;
         const int kc_pass = cin_pad / 8 / npass;
-        const int slab = kc_pass * npos * 16;
-        const int b_stage = kc_pass * 3 * nt * 16;
+        const int slab = (kc_pass * npos * 16) << xs;
+        const int b_stage = (kc_pass * 3 * nt * 16) << xs;
         const int fixed = (2 * 6 + 4) * 8 + 16 + 18 * nt * 4 + 2 * cin_pad * 4 + 2048 + 64;
         int nb = (smem_cap - slab - fixed) / b_stage;
         if (nb > 6) nb = 6;
@@ -897,8 +985,8 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
         const double ctas = (double)m_ctas * (p.cout_pad / nt);
         const double waves = ceil(ctas / 148.0);
         const double per_mma = 3 * nt <= 96 ? 50.0 : 3 * nt / 2.0 + 4.0;
-        const double mma = (double)npass * 9 * mt * (kc_pass / 2) * per_mma;
-        const double wstream = 27.0 * cin_pad * nt * 2 / 40.0;
+        const double mma = (double)npass * 9 * mt * (kc_pass / 2) * per_mma * (xs ? 3.0 : 1.0);
+        const double wstream = 27.0 * cin_pad * nt * 2 / 40.0 * (xs ? 2.0 : 1.0);
         const double cost = waves * (6000.0 + (double)npass * (slab / 40.0 + slab / 60.0) + (mma > wstream ? mma : wstream) +
                                      (nb < 3 ? 3000.0 : 0.0) + mt * nt * 6.0);
         if (cost < best_cost) { best_cost = cost; best_mt = mt; best_nt = nt; best_pass = npass; best_nb = nb; }
@@ -910,18 +998,21 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   sp.idesc = umma_idesc_bf16(128, 3 * best_nt);
   sp.rows = best_mt * 128 / g.W;
   sp.kc_pass = cin_pad / 8 / best_pass;
+  const int64_t n16 = (int64_t)27 * (cin_pad / 8) * p.cout_pad;
   if (w.slab_dev == nullptr || w.slab_ntile != best_nt) {   // one-time repack for this tile width (cached in w)
     if (w.slab_dev) { cudaStreamSynchronize(st); cudaFree(w.slab_dev); w.slab_dev = nullptr; }
-    const int64_t n16 = (int64_t)27 * (cin_pad / 8) * p.cout_pad;
-    DCL_CUDA_OK(cudaMalloc(&w.slab_dev, (size_t)n16 * 16));
-    slab_repack_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(p.w, reinterpret_cast<uint4*>(w.slab_dev), cin_pad / 8,
-                                                                   p.cout_pad, best_nt);
+    DCL_CUDA_OK(cudaMalloc(&w.slab_dev, (size_t)(n16 << xs) * 16));
+    for (int part = 0; part <= xs; ++part)     // split-bf16: the lo image is repacked the same way, behind the hi image
+      slab_repack_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(p.w + (part ? p.w_lo : 0),
+                                                                     reinterpret_cast<uint4*>(w.slab_dev) + (part ? n16 : 0),
+                                                                     cin_pad / 8, p.cout_pad, best_nt);
     DCL_CUDA_OK(cudaGetLastError());
     w.slab_ntile = best_nt;
   }
   sp.wslab = reinterpret_cast<const uint4*>(w.slab_dev);
+  sp.wslab_lo = n16;
   const int npos = 3 * (sp.rows + 2) * g.W;
-  const int smem_bytes = sp.kc_pass * npos * 16 + sp.nb * sp.kc_pass * 3 * p.n_tile * 16 + (2 * sp.nb + 4) * 8 + 16 + 16 +
+  const int smem_bytes = ((sp.kc_pass * npos * 16 + sp.nb * sp.kc_pass * 3 * p.n_tile * 16) << xs) + (2 * sp.nb + 4) * 8 + 16 + 16 +
                          18 * p.n_tile * 4 + 2 * cin_pad * 4 + 2048 + 64;
   static bool configured = false;
   if (!configured) {
@@ -937,8 +1028,9 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
 
 // fp32-NCDHW-out convenience wrapper used by the mixed pipeline (prep kernel output as the only source)
 int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
-                     int stride, int taps, cudaStream_t st) {
+                     int stride, int taps, cudaStream_t st, bool x3) {
   GemmArgs g;
+  g.x3 = x3;
   g.a0 = a_blocked; g.c0 = (w.cin + 15) / 16 * 16;
   g.D = in_d; g.H = in_h; g.W = in_w; g.stride = stride; g.taps = taps;
   g.bias = dst.bias; g.out_scale = dst.out_scale; g.residual = dst.residual; g.y = dst.y; g.stats = dst.stats;
@@ -952,7 +1044,9 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
   const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
   const int64_t m_tiles = (m_total + 127) / 128;
   p.n_tile = pick_n_tile(p.cout_pad, m_tiles);
-  const int stage_bytes = 2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16;
+  // split-bf16 stages are twice as large: halve the K depth of a stage until three of them fit
+  while (p.x3 && p.kstage % 2 == 0 && ((2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16) << 1) > 64 * 1024) p.kstage /= 2;
+  const int stage_bytes = (2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16) << p.x3;
   // deep enough to cover the L2 round trip with small stages; short K loops (linears) take all stages at once
   const int total_stages = p.taps * (p.cin_pad / (16 * p.kstage));
   int ns = stage_bytes <= 12 * 1024 ? 8 : stage_bytes <= 16 * 1024 ? 6 : stage_bytes <= 26 * 1024 ? 4 : 3;
@@ -984,7 +1078,7 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 struct PrepRowsSrc { const float* x; const float* gamma; const float* beta; int rows; uint4* out; };
 __global__ void __launch_bounds__(256)
-prep_rows_kernel(PrepRowsSrc s0, PrepRowsSrc s1) {
+prep_rows_kernel(PrepRowsSrc s0, PrepRowsSrc s1, int x3) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   const PrepRowsSrc& sr = blockIdx.y == 0 ? s0 : s1;
@@ -1022,17 +1116,26 @@ prep_rows_kernel(PrepRowsSrc s0, PrepRowsSrc s1) {
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     uint4 o;
-    o.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
-    o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
-    o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
-    o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    if (x3) {
+      uint4 l;
+      split_bf16x2(v[8 * c], v[8 * c + 1], o.x, l.x);
+      split_bf16x2(v[8 * c + 2], v[8 * c + 3], o.y, l.y);
+      split_bf16x2(v[8 * c + 4], v[8 * c + 5], o.z, l.z);
+      split_bf16x2(v[8 * c + 6], v[8 * c + 7], o.w, l.w);
+      out[(int64_t)(TOKEN_DIM / 8 + lane * 2 + c) * rows + row] = l;
+    } else {
+      o.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);
+      o.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+      o.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]);
+      o.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+    }
     out[(int64_t)(lane * 2 + c) * rows + row] = o;
   }
 }
 
-int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st) {
+int launch_prep_rows(const float* x, const float* gamma, const float* beta, int rows, void* out, cudaStream_t st, bool x3) {
   PrepRowsSrc s0{x, gamma, beta, rows, reinterpret_cast<uint4*>(out)};
-  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, s0, s0));
+  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8), dim3(256), (size_t)(0), st, s0, s0, x3 ? 1 : 0));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
@@ -1040,21 +1143,23 @@ int launch_prep_rows(const float* x, const float* gamma, const float* beta, int 
 
 // two independent (LayerNorm +) conversions in one launch (the two inputs of a DualSelfAttention block)
 int launch_prep_rows2(const float* x0, const float* g0, const float* b0, int rows0, void* out0, const float* x1, const float* g1,
-                      const float* b1, int rows1, void* out1, cudaStream_t st) {
+                      const float* b1, int rows1, void* out1, cudaStream_t st, bool x3) {
   PrepRowsSrc s0{x0, g0, b0, rows0, reinterpret_cast<uint4*>(out0)}, s1{x1, g1, b1, rows1, reinterpret_cast<uint4*>(out1)};
   const int rows = rows0 > rows1 ? rows0 : rows1;
-  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8, 2), dim3(256), (size_t)(0), st, s0, s1));
+  DCL_CUDA_OK(launch_pdl(prep_rows_kernel, dim3((rows + 7) / 8, 2), dim3(256), (size_t)(0), st, s0, s1, x3 ? 1 : 0));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
-                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked) {
+                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked, bool x3) {
   if (n % 16 != 0 || k % 16 != 0) { set_error("linear_tc: n and k must be multiples of 16"); return -1; }
   TcWeights w;
   w.dev = const_cast<void*>(w_packed); w.cin = k; w.cout = n;
+  w.lo_off = x3 ? (int64_t)n * k * 2 : 0;
   GemmArgs g;
+  g.x3 = x3;
   g.a0 = a_blocked; g.c0 = k;
   g.D = 1; g.H = 1; g.W = m; g.stride = 1; g.taps = 1;
   g.bias = bias; g.residual = residual; g.y = y;

@@ -25,9 +25,12 @@ namespace dcl {
 
 using namespace tc;
 
-template <int CI_, int CO_, int GI_, int NT_, int NSLOT_>
+// X3_: split-bf16 (DCL_BF16X3): staged planes and weights carry their lo halves behind the hi halves (as in global
+// memory), every (tap, K step) issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
+template <int CI_, int CO_, int GI_, int NT_, int NSLOT_, bool X3_ = false>
 struct S2Cfg {
   static constexpr int CI = CI_, CO = CO_, GI = GI_, GO = GI_ / 2, NT = NT_, NSLOT = NSLOT_;
+  static constexpr bool X3 = X3_;
   static constexpr int RPT = 128 / GO;                      // output rows per 128-row MMA tile
   static constexpr int TH = RPT * NT;                       // output rows per CTA
   static constexpr int ROWS = 2 * TH + 1;                   // staged input rows 2*oh0-1 .. 2*oh0+2*TH-1
@@ -38,11 +41,13 @@ struct S2Cfg {
   static constexpr int B_EE = B_EO + N_ODD * GO;
   static constexpr int NPOS = B_EE + N_EVEN * GO;           // 16-byte positions per channel chunk
   static constexpr int KC = CI / 8;
+  static constexpr int KCS = X3 ? 2 * KC : KC;              // staged chunks
   static constexpr int KSTEPS = CI / 16;                    // K = 16 MMAs per tap
-  static constexpr int SLOT_BYTES = KC * NPOS * 16;
+  static constexpr int SLOT_BYTES = KCS * NPOS * 16;
   static constexpr int ACC_COLS = NT * CO;
   static constexpr int TMEM_COLS = 2 * ACC_COLS < 32 ? 32 : 2 * ACC_COLS;     // two accumulator buffers
-  static constexpr int W_BYTES = 27 * CI * CO * 2;
+  static constexpr int W_HALF = 27 * CI * CO * 2;
+  static constexpr int W_BYTES = X3 ? 2 * W_HALF : W_HALF;
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
   static constexpr int OFF_BIAS = OFF_W + W_BYTES;
   static constexpr int OFF_RED = OFF_BIAS + CO * 4;         // [4 epilogue warps][CO][2] partial statistics
@@ -75,7 +80,8 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   constexpr int CI = C::CI, CO = C::CO, GI = C::GI, GO = C::GO, NT = C::NT, NSLOT = C::NSLOT, RPT = C::RPT, TH = C::TH;
-  constexpr int ROWS = C::ROWS, NPOS = C::NPOS, KC = C::KC, SLOT_BYTES = C::SLOT_BYTES, ACC_COLS = C::ACC_COLS;
+  constexpr int ROWS = C::ROWS, NPOS = C::NPOS, KC = C::KC, KCS = C::KCS, SLOT_BYTES = C::SLOT_BYTES, ACC_COLS = C::ACC_COLS;
+  constexpr bool X3 = C::X3;
   constexpr int EPI_WARPS = C::EPI_WARPS, THREADS = C::THREADS, NPROD = C::NPROD;
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_bias = reinterpret_cast<float*>(smem + C::OFF_BIAS);
@@ -97,9 +103,9 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
   constexpr int64_t SPI = (int64_t)GI * GI * GI, SPO = (int64_t)GO * GO * GO;
 
   for (int i = tid; i < C::W_BYTES / 16; i += THREADS) reinterpret_cast<uint4*>(smem + C::OFF_W)[i] = __ldg(prm.w + i);
-  for (int i = tid; i < NSLOT * KC * 8; i += THREADS) {   // the pad positions of every slot chunk (read by masked lanes only)
+  for (int i = tid; i < NSLOT * KCS * 8; i += THREADS) {   // the pad positions of every slot chunk (read by masked lanes only)
     const int sc = i >> 3;
-    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KC) * SLOT_BYTES + (size_t)((sc % KC) * NPOS + (i & 7)) * 16) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KCS) * SLOT_BYTES + (size_t)((sc % KCS) * NPOS + (i & 7)) * 16) = make_uint4(0u, 0u, 0u, 0u);
   }
   for (int i = tid; i < CO; i += THREADS) s_bias[i] = prm.bias ? prm.bias[i] : 0.f;
   for (int i = tid; i < 4 * CO * 2; i += THREADS) s_red[i] = 0.f;
@@ -125,7 +131,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
       const bool d_ok = d_in >= 0;                  // the high side never leaves the volume (2*(GO-1)+1 = GI-1)
       uint8_t* slot = smem + (size_t)s * SLOT_BYTES;
       // item = (chunk, staged row, w): consecutive threads read consecutive 16-byte vectors of one row
-      constexpr int ITEMS = KC * ROWS * GI;
+      constexpr int ITEMS = KCS * ROWS * GI;      // (split-bf16: global chunk KC + k is the lo half of chunk k, as in the slot)
       for (int e0 = pt; e0 < ITEMS; e0 += 4 * NPROD) {
         uint4 v[4];
         int pos[4];
@@ -188,12 +194,15 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
               const int tap = (kd * 3 + kh) * 3 + kw;
 #pragma unroll
               for (int ks = 0; ks < C::KSTEPS; ++ks) {
-                const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(base + ridx * GO - (kw == 0 ? 1 : 0) + ks * 2 * NPOS);
-                const uint64_t bd = b_base + (uint64_t)((tap * CI * CO * 2 + ks * 2 * CO * 16) >> 4);
-                const uint32_t accum = (kd | kh | kwi | ks) != 0 ? 1u : 0u;
-                if (kw == 0)      // ow = 0: the M rows that are multiples of GO
-                  umma_bf16_masked_ws(d_tmem, ad, bd, idesc, accum, C::mask_word(0), C::mask_word(1), C::mask_word(2), C::mask_word(3));
-                else umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
+#pragma unroll
+                for (int v = 0; v < (X3 ? 3 : 1); ++v) {
+                  const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(base + ridx * GO - (kw == 0 ? 1 : 0) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
+                  const uint64_t bd = b_base + (uint64_t)((tap * CI * CO * 2 + ks * 2 * CO * 16 + (v == 2 ? C::W_HALF : 0)) >> 4);
+                  const uint32_t accum = (kd | kh | kwi | ks | v) != 0 ? 1u : 0u;
+                  if (kw == 0)      // ow = 0: the M rows that are multiples of GO
+                    umma_bf16_masked_ws(d_tmem, ad, bd, idesc, accum, C::mask_word(0), C::mask_word(1), C::mask_word(2), C::mask_word(3));
+                  else umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
+                }
               }
             }
           }
@@ -239,10 +248,19 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             uint4 o;
-            o.x = pack_bf16x2(val[h8 * 8 + 0], val[h8 * 8 + 1]);
-            o.y = pack_bf16x2(val[h8 * 8 + 2], val[h8 * 8 + 3]);
-            o.z = pack_bf16x2(val[h8 * 8 + 4], val[h8 * 8 + 5]);
-            o.w = pack_bf16x2(val[h8 * 8 + 6], val[h8 * 8 + 7]);
+            if constexpr (X3) {
+              uint4 l;
+              split_bf16x2(val[h8 * 8 + 0], val[h8 * 8 + 1], o.x, l.x);
+              split_bf16x2(val[h8 * 8 + 2], val[h8 * 8 + 3], o.y, l.y);
+              split_bf16x2(val[h8 * 8 + 4], val[h8 * 8 + 5], o.z, l.z);
+              split_bf16x2(val[h8 * 8 + 6], val[h8 * 8 + 7], o.w, l.w);
+              prm.yb[(int64_t)(CO / 8 + g16 * 2 + h8) * SPO + off] = l;
+            } else {
+              o.x = pack_bf16x2(val[h8 * 8 + 0], val[h8 * 8 + 1]);
+              o.y = pack_bf16x2(val[h8 * 8 + 2], val[h8 * 8 + 3]);
+              o.z = pack_bf16x2(val[h8 * 8 + 4], val[h8 * 8 + 5]);
+              o.w = pack_bf16x2(val[h8 * 8 + 6], val[h8 * 8 + 7]);
+            }
             prm.yb[(int64_t)(g16 * 2 + h8) * SPO + off] = o;
           }
           if constexpr (PER_THREAD) {
@@ -307,11 +325,15 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
 using S2EnDown1 = S2Cfg<16, 32, 128, 2, 5>;     // 16 -> 32 @ 128^3
 using S2EnDown2 = S2Cfg<32, 64, 64, 1, 3>;      // 32 -> 64 @ 64^3: 110 KB of weights leave room for three staged planes
 using S2Edge = S2Cfg<32, 32, 64, 1, 4>;         // conv_64_to_32: 32 -> 32 @ 64^3
+using S2EnDown1X3 = S2Cfg<16, 32, 128, 1, 4, true>;   // split-bf16: two output rows per CTA, 221 KB (the 64^3 layers' split
+                                                      // weights alone are 221 KB: they stay on the GEMM kernel)
 
 static bool s2_general_enabled() {      // DCL_S2GEN=0 sends the 64^3 layers back to the im2col GEMM
   static const bool on = [] { const char* e = getenv("DCL_S2GEN"); return e == nullptr || e[0] != '0'; }();
   return on;
 }
+
+bool s2_roll_supported_x3(int cin, int cout, int g) { return cin == 16 && cout == 32 && g == 128; }
 
 bool s2_roll_supported(int cin, int cout, int g) {
   if (cin == 16 && cout == 32 && g == 128) return true;
@@ -344,8 +366,12 @@ static int launch_s2(const void* xb, const TcWeights& w, const float* bias, void
 // xb: B-format CI channels @ GI^3, yb: B-format CO channels @ (GI/2)^3; w packed by tc_pack_weights(taps = 27,
 // roll_layout = false).  The geometry is recovered from the weights (cin, cout): 16 -> 32 is the 128^3 level, the
 // 32-input layers are the 64^3 level.
-int launch_s2_roll_conv(const void* xb, const TcWeights& w, const float* bias, void* yb, stat_t* stats, cudaStream_t st) {
+int launch_s2_roll_conv(const void* xb, const TcWeights& w, const float* bias, void* yb, stat_t* stats, cudaStream_t st, bool x3) {
   if (w.dev == nullptr) { set_error("s2_roll_conv: weights not packed"); return -1; }
+  if (x3) {
+    if (w.lo_off == 0 || !(w.cin == 16 && w.cout == 32)) { set_error("s2_roll_conv: unsupported split-bf16 layer"); return -1; }
+    return launch_s2<S2EnDown1X3>(xb, w, bias, yb, stats, st);
+  }
   if (w.cin == 16 && w.cout == 32) return launch_s2<S2EnDown1>(xb, w, bias, yb, stats, st);
   if (w.cin == 32 && w.cout == 64) return launch_s2<S2EnDown2>(xb, w, bias, yb, stats, st);
   if (w.cin == 32 && w.cout == 32) return launch_s2<S2Edge>(xb, w, bias, yb, stats, st);

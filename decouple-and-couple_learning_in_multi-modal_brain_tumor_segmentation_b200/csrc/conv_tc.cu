@@ -29,9 +29,13 @@ using namespace tc;
 
 cudaError_t trace_set_conv_tc(long long* p, int cta) { return trace_set_local(p, cta); }
 
-template <int C_, int G_, int TH_, bool KHN_, int NSLOT_>
+// X3_: split-bf16 (DCL_BF16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (exactly
+// the global layout, so a plane is still one bulk copy per chunk), the weights a hi image followed by a lo image, and
+// every (tap, K step) issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo into the same accumulator.
+template <int C_, int G_, int TH_, bool KHN_, int NSLOT_, bool X3_ = false>
 struct RollCfg {
   static constexpr int C = C_, G = G_, TH = TH_;
+  static constexpr bool X3 = X3_;
   static constexpr bool KHN = KHN_;               // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
   static constexpr int W = G;                     // staged rows have NO halo columns (kw = 0/2 use lane masks)
   static constexpr int ROWS = TH + 2;
@@ -40,15 +44,17 @@ struct RollCfg {
                                                   // destination made the plane copies land at ~9 instead of ~45 B/clk
   static constexpr int NPOS = ROWS * W + 2 * PAD; // positions per channel chunk of one plane
   static constexpr int KC = C / 8;                // 16-byte channel chunks
+  static constexpr int KCS = X3 ? 2 * KC : KC;    // staged chunks per plane
   static constexpr int KS = C / 16;               // K = 16 MMA steps per tap
-  static constexpr int SLOT_BYTES = KC * NPOS * 16;
+  static constexpr int SLOT_BYTES = KCS * NPOS * 16;
   static constexpr int NSLOT = NSLOT_;            // staged planes: 3 feeding the MMAs + (NSLOT-3) in flight
   static constexpr int TROWS = 128 / W;           // output rows per 128-voxel M tile (1 for W=128, 2 for W=64)
   static constexpr int NT = TH / TROWS;           // M tiles per plane
   static constexpr int ACC_COLS = NT * C;         // TMEM columns of one accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
                                    : 2 * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int W_BYTES = 27 * C * C * 2;
+  static constexpr int W_HALF = 27 * C * C * 2;   // one weight image
+  static constexpr int W_BYTES = X3 ? 2 * W_HALF : W_HALF;
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
   static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // scale[C], shift[C], bias[C], out_scale[C] floats
   static constexpr int OFF_BAR = OFF_SMALL + 4 * C * 4;      // 16-byte aligned (C multiple of 16)
@@ -106,7 +112,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, W = Cfg::W, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
-  constexpr int ROWS = Cfg::ROWS, KC = Cfg::KC;
+  constexpr int ROWS = Cfg::ROWS, KC = Cfg::KC, KCS = Cfg::KCS;
+  constexpr bool X3 = Cfg::X3;
   extern __shared__ __align__(128) uint8_t smem[];
   float* s_scale = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);   // rstd
   float* s_shift = s_scale + C;                                        // -mean * rstd
@@ -138,9 +145,9 @@ conv3d_k3_roll_kernel(RollParams prm) {
   constexpr int64_t SP = (int64_t)G * G * G;
 
   // ---- one-time setup ---------------------------------------------------------------------------
-  for (int i = tid; i < NSLOT * KC * 2; i += ROLL_THREADS) {   // the pad positions of every slot chunk stay zero
+  for (int i = tid; i < NSLOT * KCS * 2; i += ROLL_THREADS) {   // the pad positions of every slot chunk stay zero
     const int sc = i >> 1;
-    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KC) * Cfg::SLOT_BYTES + (size_t)((sc % KC) * NPOS + ((i & 1) ? NPOS - Cfg::PAD : Cfg::PAD - 1)) * 16) =
+    *reinterpret_cast<uint4*>(smem + (size_t)(sc / KCS) * Cfg::SLOT_BYTES + (size_t)((sc % KCS) * NPOS + ((i & 1) ? NPOS - Cfg::PAD : Cfg::PAD - 1)) * 16) =
         make_uint4(0u, 0u, 0u, 0u);
   }
   const bool has_norm = prm.sums != nullptr || prm.mean != nullptr;
@@ -201,10 +208,10 @@ conv3d_k3_roll_kernel(RollParams prm) {
         const int s = j % NSLOT;
         const uint32_t bar = smem_u32(&bar_land[s]);
         if (lane == 0)
-          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(d_ok ? (uint32_t)KC * run_bytes : 0u), "r"(bar)
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(d_ok ? (uint32_t)KCS * run_bytes : 0u), "r"(bar)
                        : "memory");
         __syncwarp();
-        if (d_ok && lane < KC) {
+        if (d_ok && lane < KCS) {      // split-bf16: chunk KC + k (lo) follows chunk k (hi) in global memory as in the slot
           const uint4* src = prm.xb + (int64_t)lane * SP + ((int64_t)d_in * G + (h0 - 1 + r_lo)) * G;
           const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (lane * NPOS + Cfg::PAD + r_lo * W) * 16);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -213,13 +220,13 @@ conv3d_k3_roll_kernel(RollParams prm) {
         }
         // rows / planes outside the volume are zero padding (at most one row at either end, or the whole plane)
         if (!d_ok) {
-          for (int kc = 0; kc < KC; ++kc) {
+          for (int kc = 0; kc < KCS; ++kc) {
             uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + Cfg::PAD) * 16);
             for (int i = lane; i < ROWS * W; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
           }
         } else if (r_lo != 0 || r_hi != ROWS - 1) {
           const int r = r_lo != 0 ? 0 : ROWS - 1;      // a strip touches at most one border (TH < G)
-          for (int kc = 0; kc < KC; ++kc) {
+          for (int kc = 0; kc < KCS; ++kc) {
             uint4* z = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + Cfg::PAD + r * W) * 16);
             for (int i = lane; i < W; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
           }
@@ -247,6 +254,28 @@ conv3d_k3_roll_kernel(RollParams prm) {
               const float sc[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
               const float sh[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
               uint4* q = reinterpret_cast<uint4*>(smem + (size_t)s * Cfg::SLOT_BYTES + (size_t)(kc * NPOS + Cfg::PAD + r * W) * 16);
+              if constexpr (X3) {
+                // value = hi + lo -> InstanceNorm + activation -> split again into the hi / lo chunks
+                uint4* ql = q + (size_t)KC * NPOS;
+#pragma unroll
+                for (int i = 0; i < W / 32; ++i) {
+                  float f[8];
+                  unpack8_acc<false>(q[lane + 32 * i], f);
+                  unpack8_acc<true>(ql[lane + 32 * i], f);
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) {
+                    float t = fmaf(f[k], sc[k], sh[k]);
+                    if (act == ACT_RELU) t = fmaxf(t, 0.f);
+                    else if (act == ACT_LRELU) t = fmaxf(t, 0.01f * t);
+                    f[k] = t;
+                  }
+                  uint4 vh, vl;
+                  split8(f, vh, vl);
+                  q[lane + 32 * i] = vh;
+                  ql[lane + 32 * i] = vl;
+                }
+                continue;
+              }
               uint4 v[W / 32];
 #pragma unroll
               for (int i = 0; i < W / 32; ++i) v[i] = q[lane + 32 * i];
@@ -307,6 +336,10 @@ conv3d_k3_roll_kernel(RollParams prm) {
           const int e = pt + it * NPROD;
           if (e < ROWS * W) {
             uint4 o = make_uint4(pack_bf16x2(v[it][0], v[it][1]), pack_bf16x2(v[it][2], v[it][3]), 0u, 0u);
+            if constexpr (X3) {   // the four lo halves ride in elements 4-7 of the same chunk (weights: see tc_pack_weights)
+              split_bf16x2(v[it][0], v[it][1], o.x, o.z);
+              split_bf16x2(v[it][2], v[it][3], o.y, o.w);
+            }
             *reinterpret_cast<uint4*>(slot + (size_t)(Cfg::PAD + e) * 16) = o;
 #pragma unroll
             for (int kc = 1; kc < KC; ++kc)
@@ -323,6 +356,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
       constexpr uint32_t idesc = umma_idesc_bf16(128, C);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t w_base = smem_base + Cfg::OFF_W;
+      const bool x4_src = prm.xb == nullptr;
       for (int i = 0; i < n_out; ++i) {
         const int b = i & 1;
         if (i == 0) {
@@ -368,15 +402,20 @@ conv3d_k3_roll_kernel(RollParams prm) {
                 const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
-                  const uint64_t ad = a_kd[kd] + (uint64_t)(Cfg::PAD + rho * W + (kw - 1) + ks * 2 * NPOS);
-                  const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * C * 16 + ks * 2 * B_LBO) >> 4);
-                  if (n_acc > 0) {
-                    if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
-                    else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u, m0, m1, m2, m3);
+#pragma unroll
+                  for (int v = 0; v < (X3 ? 3 : 1); ++v) {      // split-bf16: a_hi*w_hi, a_lo*w_hi, a_hi*w_lo
+                    // (the 4-channel fp32 source packs hi and lo into ONE chunk and pairs it with two weight images)
+                    if (X3 && v == 1 && x4_src) continue;
+                    const uint64_t ad = a_kd[kd] + (uint64_t)(Cfg::PAD + rho * W + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
+                    const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * C * 16 + ks * 2 * B_LBO + (v == 2 ? Cfg::W_HALF : 0)) >> 4);
+                    if (n_acc > 0) {
+                      if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
+                      else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u, m0, m1, m2, m3);
+                    }
+                    if (first)
+                      umma_bf16_ws(acc0 + (uint32_t)(rho * C), ad, bd + (uint64_t)((n_acc * C * 16) >> 4),
+                                   umma_idesc_bf16(128, C), (ks | v) == 0 ? 0u : 1u);
                   }
-                  if (first)
-                    umma_bf16_ws(acc0 + (uint32_t)(rho * C), ad, bd + (uint64_t)((n_acc * C * 16) >> 4),
-                                 umma_idesc_bf16(128, C), ks == 0 ? 0u : 1u);
                 }
               }
             }
@@ -400,11 +439,14 @@ conv3d_k3_roll_kernel(RollParams prm) {
                   const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
 #pragma unroll
                   for (int ks = 0; ks < Cfg::KS; ++ks) {
-                    const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(Cfg::PAD + (t * Cfg::TROWS + kh) * W + (kw - 1) + ks * 2 * NPOS);
-                    const uint64_t bd = b_base + (uint64_t)((tap * C * C * 2 + ks * 2 * C * 16) >> 4);
-                    const uint32_t accum = (kd | kh | kwi | ks) != 0 ? 1u : 0u;
-                    if (kw == 1) umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
-                    else umma_bf16_masked_ws(d_tmem, ad, bd, idesc, accum, m0, m1, m2, m3);
+#pragma unroll
+                    for (int v = 0; v < (X3 ? 3 : 1); ++v) {
+                      const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(Cfg::PAD + (t * Cfg::TROWS + kh) * W + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
+                      const uint64_t bd = b_base + (uint64_t)((tap * C * C * 2 + ks * 2 * C * 16 + (v == 2 ? Cfg::W_HALF : 0)) >> 4);
+                      const uint32_t accum = (kd | kh | kwi | ks | v) != 0 ? 1u : 0u;
+                      if (kw == 1) umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
+                      else umma_bf16_masked_ws(d_tmem, ad, bd, idesc, accum, m0, m1, m2, m3);
+                    }
                   }
                 }
               }
@@ -456,10 +498,14 @@ conv3d_k3_roll_kernel(RollParams prm) {
         const int t = it / G16;
         const int r = t * Cfg::TROWS + m / W;
         const int64_t off = ((int64_t)d * G + (h0 + r)) * G + wpos;
-        uint4 rv0 = make_uint4(0u, 0u, 0u, 0u), rv1 = rv0;
+        uint4 rv0 = make_uint4(0u, 0u, 0u, 0u), rv1 = rv0, rl0 = rv0, rl1 = rv0;
         if (res0 != nullptr) {             // issued before the accumulator wait / load: the latency overlaps them
           rv0 = __ldg(res0 + off);
           rv1 = __ldg(res0 + SP + off);
+          if constexpr (X3) {
+            rl0 = __ldg(res0 + (int64_t)KC * SP + off);
+            rl1 = __ldg(res0 + (int64_t)(KC + 1) * SP + off);
+          }
         }
         if (!waited) {
           mbar_wait(&bar_acc_full[b], (uint32_t)(i >> 1) & 1u);
@@ -486,6 +532,16 @@ conv3d_k3_roll_kernel(RollParams prm) {
             val[2 * k] += f0.x; val[2 * k + 1] += f0.y;
             val[8 + 2 * k] += f1.x; val[8 + 2 * k + 1] += f1.y;
           }
+          if constexpr (X3) {
+            const uint32_t* q0 = reinterpret_cast<const uint32_t*>(&rl0);
+            const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&rl1);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f0 = unpack_bf16x2(q0[k]), f1 = unpack_bf16x2(q1[k]);
+              val[2 * k] += f0.x; val[2 * k + 1] += f0.y;
+              val[8 + 2 * k] += f1.x; val[8 + 2 * k + 1] += f1.y;
+            }
+          }
         }
 #pragma unroll
         for (int k = 0; k < 16; ++k) {
@@ -493,10 +549,20 @@ conv3d_k3_roll_kernel(RollParams prm) {
           st_q[k] += val[k] * val[k];
         }
         uint4 o0, o1;
-        o0.x = pack_bf16x2(val[0], val[1]);   o0.y = pack_bf16x2(val[2], val[3]);
-        o0.z = pack_bf16x2(val[4], val[5]);   o0.w = pack_bf16x2(val[6], val[7]);
-        o1.x = pack_bf16x2(val[8], val[9]);   o1.y = pack_bf16x2(val[10], val[11]);
-        o1.z = pack_bf16x2(val[12], val[13]); o1.w = pack_bf16x2(val[14], val[15]);
+        if constexpr (X3) {
+          uint4 l0, l1;
+          split_bf16x2(val[0], val[1], o0.x, l0.x);     split_bf16x2(val[2], val[3], o0.y, l0.y);
+          split_bf16x2(val[4], val[5], o0.z, l0.z);     split_bf16x2(val[6], val[7], o0.w, l0.w);
+          split_bf16x2(val[8], val[9], o1.x, l1.x);     split_bf16x2(val[10], val[11], o1.y, l1.y);
+          split_bf16x2(val[12], val[13], o1.z, l1.z);   split_bf16x2(val[14], val[15], o1.w, l1.w);
+          y0[(int64_t)KC * SP + off] = l0;
+          y0[(int64_t)(KC + 1) * SP + off] = l1;
+        } else {
+          o0.x = pack_bf16x2(val[0], val[1]);   o0.y = pack_bf16x2(val[2], val[3]);
+          o0.z = pack_bf16x2(val[4], val[5]);   o0.w = pack_bf16x2(val[6], val[7]);
+          o1.x = pack_bf16x2(val[8], val[9]);   o1.y = pack_bf16x2(val[10], val[11]);
+          o1.z = pack_bf16x2(val[12], val[13]); o1.w = pack_bf16x2(val[14], val[15]);
+        }
         y0[off] = o0;
         y0[SP + off] = o1;
       }
@@ -560,12 +626,23 @@ static uint16_t f32_to_bf16_rn(float f) {
 //   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]      one stacked N = 3*cout matrix per (kd,kw)
 static int tc_weight_layout(int cin, int cout) { return (cin <= 16 && cout == 16) ? 1 : 0; }
 
-int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_layout, TcWeights* out) {
-  out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0;
+static float bf16_to_f32(uint16_t h) {
+  const uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_layout, TcWeights* out, bool x3) {
+  out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0; out->lo_off = 0;
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;   // zero padded
   const int kcs = cin_pad / 8;
-  std::vector<uint16_t> packed((size_t)taps * cin_pad * cout_pad, 0);
+  const size_t image = (size_t)taps * cin_pad * cout_pad;
+  std::vector<uint16_t> packed(x3 ? 2 * image : image, 0);       // split-bf16: hi image, then lo image
   const int layout = (roll_layout && taps == 27) ? tc_weight_layout(cin, cout) : 0;
+  // InitConv in split-bf16 mode: the rolling kernel stages the four input channels as [hi0..3 | lo0..3] in ONE chunk,
+  // so image 0 carries w_hi at k = ci AND k = ci + 4 (a_hi*w_hi + a_lo*w_hi) and image 1 carries w_lo at k = ci
+  const bool init_x3 = x3 && layout == 1 && cin == 4;
   for (int tap = 0; tap < taps; ++tap)
     for (int ci = 0; ci < cin; ++ci)
       for (int n = 0; n < cout; ++n) {
@@ -577,9 +654,16 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
           const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
           dst = (((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * cout_pad) + n) * 8 + k;
         }
-        packed[dst] = f32_to_bf16_rn(w_host[((size_t)n * cin + ci) * taps + tap]);
+        const float wv = w_host[((size_t)n * cin + ci) * taps + tap];
+        const uint16_t hi = f32_to_bf16_rn(wv);
+        packed[dst] = hi;
+        if (x3) {
+          packed[image + dst] = f32_to_bf16_rn(wv - bf16_to_f32(hi));
+          if (init_x3) packed[dst + 4] = hi;
+        }
       }
   out->bytes = (int64_t)packed.size() * 2;
+  out->lo_off = x3 ? (int64_t)image * 2 : 0;
   DCL_CUDA_OK(cudaMalloc(&out->dev, (size_t)out->bytes));
   DCL_CUDA_OK(cudaMemcpy(out->dev, packed.data(), (size_t)out->bytes, cudaMemcpyHostToDevice));
   return 0;
@@ -587,9 +671,13 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
 
 using RollC16 = RollCfg<16, 128, 8, true, 5>;
 using RollC32 = RollCfg<32, 64, 8, false, 4>;
+// split-bf16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory); the
+// 32-channel layers (110 KB of split weights) run on the slab kernel instead
+using RollC16X3 = RollCfg<16, 128, 4, true, 4, true>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
-  if (split || stride != 1) return false;
+  if (stride != 1) return false;
+  if (split) return (cin == 16 || cin == 4) && cout == 16 && g == 128;
   return (cin == 16 && cout == 16 && g == 128) || (cin == 32 && cout == 32 && g == 64) || (cin == 4 && cout == 16 && g == 128);
 }
 
@@ -614,7 +702,7 @@ static int launch_roll(RollParams& prm, cudaStream_t st) {
 
 int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cudaStream_t st) {
   const int cin = w.cin;
-  if (!tc_conv_supported(cin, cout, g, 1, false) || w.dev == nullptr || (a.xb == nullptr) == (a.x4 == nullptr && a.desc == nullptr) ||
+  if (!tc_conv_supported(cin, cout, g, 1, a.x3) || w.dev == nullptr || (a.x3 && w.lo_off == 0) || (a.xb == nullptr) == (a.x4 == nullptr && a.desc == nullptr) ||
       (cin == 4) != (a.x4 != nullptr || a.desc != nullptr)) {
     set_error("roll_conv: unsupported shape / source");
     return -1;
@@ -629,6 +717,7 @@ int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cud
   p.yb = reinterpret_cast<uint4*>(a.yb);
   p.stats = a.stats;
   p.dsplit = 1;
+  if (a.x3) return launch_roll<RollC16X3>(p, st);
   if (cout == 16) return launch_roll<RollC16>(p, st);
   return launch_roll<RollC32>(p, st);
 }

@@ -280,6 +280,10 @@ struct dcl_handle {
 
 namespace dcl {
 
+// tensor-core pipeline (B-format activations, tcgen05 kernels): DCL_BF16 and the split-bf16 mode DCL_BF16X3
+static inline bool is_tc(const dcl_handle* h) { return h->cfg.precision == DCL_BF16 || h->cfg.precision == DCL_BF16X3; }
+static inline bool is_x3(const dcl_handle* h) { return h->cfg.precision == DCL_BF16X3; }
+
 static int dev_alloc(dcl_handle* h, void** p, int64_t bytes) {
   h->alloc_bytes += (bytes + 255) / 256 * 256;
   if (h->dry_run) { *p = nullptr; return 0; }
@@ -333,28 +337,29 @@ static int allocate_workspace(dcl_handle* h) {
     DCL_TRY(falloc(h, &h->dl_1[l], n)); DCL_TRY(falloc(h, &h->dl_2[l], n));
   }
   DCL_TRY(falloc(h, &h->probs, 4 * P3));
-  if (h->cfg.precision == DCL_BF16) {
-    DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * 2));
-    DCL_TRY(dev_alloc(h, &h->tok_a, 258 * 512 * 2));
-    DCL_TRY(dev_alloc(h, &h->tok_b, 258 * 512 * 2));
+  if (is_tc(h)) {
+    const int64_t E = is_x3(h) ? 4 : 2;      // bytes per element of a B-format tensor (split-bf16: hi + lo planes)
+    DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * E));
+    DCL_TRY(dev_alloc(h, &h->tok_a, 258 * 512 * E));
+    DCL_TRY(dev_alloc(h, &h->tok_b, 258 * 512 * E));
     for (int l = 0; l < 4; ++l) {
-      int64_t bytes = (int64_t)LVL_C[l] * LVL_G[l] * LVL_G[l] * LVL_G[l] * 2;
+      int64_t bytes = (int64_t)LVL_C[l] * LVL_G[l] * LVL_G[l] * LVL_G[l] * E;
       DCL_TRY(dev_alloc(h, &h->b_t0[l], bytes)); DCL_TRY(dev_alloc(h, &h->b_a[l], bytes));
       DCL_TRY(dev_alloc(h, &h->b_t1[l], bytes)); DCL_TRY(dev_alloc(h, &h->b_x[l], bytes));
     }
     const int64_t v16 = 16 * 16 * 16, v32 = 32 * 32 * 32;
-    DCL_TRY(dev_alloc(h, &h->b_x4, 256 * v16 * 2)); DCL_TRY(dev_alloc(h, &h->b_edown, 32 * v32 * 2));
-    DCL_TRY(dev_alloc(h, &h->b_eraw, 96 * v32 * 2)); DCL_TRY(dev_alloc(h, &h->b_sraw, 384 * v16 * 2));
-    DCL_TRY(dev_alloc(h, &h->b_fused, 128 * v16 * 2)); DCL_TRY(dev_alloc(h, &h->b_enc, 256 * v16 * 2));
-    DCL_TRY(dev_alloc(h, &h->b_nrm, 32 * (P3 / 8) * 2));
-    for (int i = 0; i < 5; ++i) DCL_TRY(dev_alloc(h, &h->b_d8[i], 128 * v16 * 2));
+    DCL_TRY(dev_alloc(h, &h->b_x4, 256 * v16 * E)); DCL_TRY(dev_alloc(h, &h->b_edown, 32 * v32 * E));
+    DCL_TRY(dev_alloc(h, &h->b_eraw, 96 * v32 * E)); DCL_TRY(dev_alloc(h, &h->b_sraw, 384 * v16 * E));
+    DCL_TRY(dev_alloc(h, &h->b_fused, 128 * v16 * E)); DCL_TRY(dev_alloc(h, &h->b_enc, 256 * v16 * E));
+    DCL_TRY(dev_alloc(h, &h->b_nrm, 32 * (P3 / 8) * E));
+    for (int i = 0; i < 5; ++i) DCL_TRY(dev_alloc(h, &h->b_d8[i], 128 * v16 * E));
     for (int l = 0; l < 3; ++l) {
       int c = 64 >> l, g = 32 << l;
-      for (int i = 0; i < 5; ++i) DCL_TRY(dev_alloc(h, &h->b_dl[l][i], (int64_t)c * g * g * g * 2));
+      for (int i = 0; i < 5; ++i) DCL_TRY(dev_alloc(h, &h->b_dl[l][i], (int64_t)c * g * g * g * E));
     }
     DCL_TRY(dev_alloc(h, (void**)&h->stat_arena, (int64_t)STAT_SLOTS * 1024 * sizeof(stat_t)));
   }
-  if (h->cfg.precision == DCL_BF16) {
+  if (is_tc(h)) {
     DCL_TRY(dev_alloc(h, (void**)&h->stamps, 16 * sizeof(unsigned long long)));
     DCL_TRY(dev_alloc(h, (void**)&h->patch_desc, sizeof(PatchDesc)));
     h->keep_dev = h->dry_run ? nullptr : h->patch_desc->keep;
@@ -379,9 +384,9 @@ static int allocate_workspace(dcl_handle* h) {
     DCL_TRY(falloc(h, &t.cross, 258 * 512)); DCL_TRY(falloc(h, &t.ffn_ln, 258 * 512));
     DCL_TRY(falloc(h, &t.ffn_h, 258 * 512));
     t.tok_a = t.tok_b = nullptr;
-    if (h->cfg.precision == DCL_BF16) {
-      DCL_TRY(dev_alloc(h, &t.tok_a, 258 * 512 * 2));
-      DCL_TRY(dev_alloc(h, &t.tok_b, 258 * 512 * 2));
+    if (is_tc(h)) {
+      DCL_TRY(dev_alloc(h, &t.tok_a, 258 * 512 * (is_x3(h) ? 4 : 2)));
+      DCL_TRY(dev_alloc(h, &t.tok_b, 258 * 512 * (is_x3(h) ? 4 : 2)));
     }
   }
   return 0;
@@ -440,10 +445,11 @@ static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vec
   }
   DCL_TRY(upload(h, packed, &out->w));
   DCL_TRY(upload(h, bias, &out->b));
-  if (h->cfg.precision == DCL_BF16 && (kind == W_CONV3 || kind == W_CONV1)) {
+  if (is_tc(h) && (kind == W_CONV3 || kind == W_CONV1)) {
     if (kind == W_CONV1) raw = *ws[0];   // (cout, cin)
     DCL_TRY(tc_pack_weights(raw.data(), cout, cin, kind == W_CONV3 ? 27 : 1,
-                            kind == W_CONV3 && stride1 && tc_conv_supported(cin, cout, cin == 32 ? 64 : 128, 1, false), &out->tc));
+                            kind == W_CONV3 && stride1 && tc_conv_supported(cin, cout, cin == 32 ? 64 : 128, 1, is_x3(h)), &out->tc,
+                            is_x3(h)));
     h->allocs.push_back(out->tc.dev);
   }
   return 0;
@@ -499,11 +505,11 @@ static int prepare(dcl_handle* h) {
     t.fnw = R(f + "norm.weight"); t.fnb = R(f + "norm.bias");
     t.w0 = R(f + "fn.net.0.weight"); t.b0 = R(f + "fn.net.0.bias");
     t.w3 = R(f + "fn.net.3.weight"); t.b3 = R(f + "fn.net.3.bias");
-    if (h->cfg.precision == DCL_BF16) {
+    if (is_tc(h)) {
       const std::vector<float>& qkv = h->host_w.at(a + "fn.qkv.weight");
       auto pack = [&](const float* w, int n, void** out) -> int {
         TcWeights tw;
-        DCL_TRY(tc_pack_weights(w, n, 512, 1, false, &tw));
+        DCL_TRY(tc_pack_weights(w, n, 512, 1, false, &tw, is_x3(h)));
         h->allocs.push_back(tw.dev);
         *out = tw.dev;
         return 0;
@@ -521,7 +527,7 @@ static int prepare(dcl_handle* h) {
     h->pe[r] = R(std::string("label_") + REGION_KEY[r] + "_position_encoding.pe");
   }
   h->pe[3] = R("fusion_label_pos.pe");
-  if (h->cfg.precision == DCL_BF16) {
+  if (is_tc(h)) {
     // DeUp_Cat composed into one linear map per transposed-conv tap (see bf16_ops.cu)
     const char* upn[3] = {"decoder.DeUp4", "decoder.DeUp3", "decoder.DeUp2"};
     for (int l = 0; l < 3; ++l) {
@@ -559,15 +565,23 @@ static int prepare(dcl_handle* h) {
       }
       // the kernel keeps these as bf16 with rows padded by 8 elements (conflict-free fragment reads): store exactly that
       // image, so its prologue is a straight 16-byte copy instead of thousands of scalar loads + conversions per CTA
-      auto to_bf16_padded = [](const std::vector<float>& src, int rows, int cols) {
-        std::vector<float> out((size_t)rows * (cols + 8) / 2, 0.f);      // 2 bf16 per float slot
+      // (split-bf16: the hi image is followed by the lo image = bf16(w - hi))
+      const bool x3 = is_x3(h);
+      auto to_bf16_padded = [x3](const std::vector<float>& src, int rows, int cols) {
+        const size_t image = (size_t)rows * (cols + 8);                  // bf16 elements
+        std::vector<float> out((x3 ? 2 : 1) * image / 2, 0.f);           // 2 bf16 per float slot
         uint16_t* o = reinterpret_cast<uint16_t*>(out.data());
+        auto rn = [](float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7fffu + ((u >> 16) & 1u); return (uint16_t)(u >> 16); };
         for (int r = 0; r < rows; ++r)
           for (int c = 0; c < cols; ++c) {
-            uint32_t u; float f = src[(size_t)r * cols + c];
-            memcpy(&u, &f, 4);
-            u += 0x7fffu + ((u >> 16) & 1u);
-            o[(size_t)r * (cols + 8) + c] = (uint16_t)(u >> 16);
+            const float f = src[(size_t)r * cols + c];
+            const uint16_t hi = rn(f);
+            o[(size_t)r * (cols + 8) + c] = hi;
+            if (x3) {
+              const uint32_t hu = (uint32_t)hi << 16;
+              float hf; memcpy(&hf, &hu, 4);
+              o[image + (size_t)r * (cols + 8) + c] = rn(f - hf);
+            }
           }
         return out;
       };
@@ -603,10 +617,10 @@ struct Fwd {
     cudaEvent_t ev = nullptr;
     if (h->profiling) ev = h->prof_begin(st);
     int rc;
-    if (h->cfg.precision == DCL_BF16) {
+    if (is_tc(h)) {
       // fp32 NCDHW tensors of the auxiliary heads: blocked-bf16 prep + the general GEMM kernel
-      rc = launch_prep_blocked(s, g, g, g, h->blk, st);
-      if (rc == 0) rc = launch_conv_gemm(h->blk, w.tc, d, g, g, g, stride, 27, st);
+      rc = launch_prep_blocked(s, g, g, g, h->blk, st, is_x3(h));
+      if (rc == 0) rc = launch_conv_gemm(h->blk, w.tc, d, g, g, g, stride, 27, st, is_x3(h));
     } else {
       rc = launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, g, g, g, stride, st);
     }
@@ -621,9 +635,9 @@ struct Fwd {
             bool softmax = false) {
     ConvSrc s{x0, x1, c0, c1, spatial, 0, 0, nullptr, nullptr, ACT_NONE};
     ConvDst d{y, w.b, nullptr, nullptr};
-    if (h->cfg.precision == DCL_BF16 && !softmax) {   // pointwise conv = 1-tap GEMM over a flat "row" of voxels
-      DCL_TRY(launch_prep_blocked(s, 1, 1, (int)spatial, h->blk, st));
-      return launch_conv_gemm(h->blk, w.tc, d, 1, 1, (int)spatial, 1, 1, st);
+    if (is_tc(h) && !softmax) {   // pointwise conv = 1-tap GEMM over a flat "row" of voxels
+      DCL_TRY(launch_prep_blocked(s, 1, 1, (int)spatial, h->blk, st, is_x3(h)));
+      return launch_conv_gemm(h->blk, w.tc, d, 1, 1, (int)spatial, 1, 1, st, is_x3(h));
     }
     return launch_conv1x1(s, d, w.w, w.cout, spatial, softmax, st);
   }
@@ -664,12 +678,13 @@ struct Fwd {
 
   // Residual(PreNormDrop(DualSelfAttention)) (ResidualNorm.py:4-32, SelfAttention.py:74-102)
   int attn_block(const Transformer& t, const float* x, const float* x2, int mq, int mk, float* out) {
-    if (h->cfg.precision == DCL_BF16) {   // LayerNorm fused into the bf16 operand prep, linears on tcgen05
-      DCL_TRY(launch_prep_rows2(x, t.n1w, t.n1b, mq, ts->tok_a, x2, t.n2w, t.n2b, mk, ts->tok_b, st));
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.pq, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st));
-      DCL_TRY(launch_linear_tc(ts->tok_b, t.pkv, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st));
-      DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, nullptr, mq, mk, st, ts->tok_a));     // bf16 blocked, straight into the GEMM
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st));
+    if (is_tc(h)) {   // LayerNorm fused into the bf16 operand prep, linears on tcgen05
+      const bool x3 = is_x3(h);
+      DCL_TRY(launch_prep_rows2(x, t.n1w, t.n1b, mq, ts->tok_a, x2, t.n2w, t.n2b, mk, ts->tok_b, st, x3));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.pq, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st, nullptr, x3));
+      DCL_TRY(launch_linear_tc(ts->tok_b, t.pkv, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st, nullptr, x3));
+      DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, nullptr, mq, mk, st, ts->tok_a, x3));     // bf16 blocked, straight into the GEMM
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st, nullptr, x3));
       return 0;
     }
     DCL_TRY(launch_layernorm(x, t.n1w, t.n1b, ts->ln_a, mq, st));
@@ -683,10 +698,11 @@ struct Fwd {
 
   // Residual(PreNorm(FeedForward)) (ResidualNorm.py:35-47)
   int ffn_block(const Transformer& t, const float* x, int m, float* out) {
-    if (h->cfg.precision == DCL_BF16) {
-      DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, ts->tok_a, st));
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, nullptr, m, 512, 512, true, st, ts->tok_b));   // GELU, bf16 blocked out
-      DCL_TRY(launch_linear_tc(ts->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st));
+    if (is_tc(h)) {
+      const bool x3 = is_x3(h);
+      DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, ts->tok_a, st, x3));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, nullptr, m, 512, 512, true, st, ts->tok_b, x3));   // GELU, bf16 blocked out
+      DCL_TRY(launch_linear_tc(ts->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st, nullptr, x3));
       return 0;
     }
     DCL_TRY(launch_layernorm(x, t.fnw, t.fnb, ts->ffn_ln, m, st));
@@ -726,9 +742,9 @@ struct Fwd {
       const ConvW& w = h->conv.at("Unet_list.InitConv.conv");
       ConvDst d{h->l_t0[0], w.b, h->keep_dev, nullptr};
       cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
-      if (h->cfg.precision == DCL_BF16) {
-        DCL_TRY(launch_prep_blocked(s, 128, 128, 128, h->blk, st));
-        DCL_TRY(launch_conv_gemm(h->blk, w.tc, d, 128, 128, 128, 1, 27, st));
+      if (is_tc(h)) {
+        DCL_TRY(launch_prep_blocked(s, 128, 128, 128, h->blk, st, is_x3(h)));
+        DCL_TRY(launch_conv_gemm(h->blk, w.tc, d, 128, 128, 128, 1, 27, st, is_x3(h)));
       } else {
         DCL_TRY(launch_conv3d_k3(s, d, w.w, w.cout, w.cout_pad, 128, 128, 128, 1, st));
       }
@@ -856,33 +872,38 @@ struct Fwd16 {
            const float* out_scale, const void* resb, void* y, stat_t* stats, int taps = 27) {
     cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
     int rc, kind;
-    if (taps == 27 && x1 == nullptr && tc_conv_supported(c0, w.cout, g, stride, false)) {
+    const bool x3 = is_x3(h);
+    if (taps == 27 && x1 == nullptr && tc_conv_supported(c0, w.cout, g, stride, x3)) {
       kind = c0 == 32 ? 3 : 2;
       RollArgs a;
+      a.x3 = x3;
       a.xb = x0;
       if (norm) a.norm = *norm;
       a.bias = w.b; a.out_scale = out_scale; a.resb = resb; a.yb = y; a.stats = stats;
       rc = launch_roll_conv(a, w.tc, w.cout, g, st);
-    } else if (taps == 27 && slab_conv_supported(c0 + c1, w.cout, g, g, g, stride, taps) && g <= 32) {
+    } else if (taps == 27 && slab_conv_supported(c0 + c1, w.cout, g, g, g, stride, taps) && (g <= 32 || (x3 && g == 64))) {
+      // (split-bf16: the 32-channel 64^3 layers come here too - their split weights do not fit the rolling kernel)
       kind = 4;
       GemmArgs ga;
+      ga.x3 = x3;
       ga.a0 = x0; ga.c0 = c0; ga.a1 = x1;
       ga.D = g; ga.H = g; ga.W = g; ga.stride = 1; ga.taps = 27;
       ga.bias = w.b; ga.out_scale = out_scale; ga.out_mode = 2; ga.y = y; ga.residual = resb; ga.stats = stats;
       rc = launch_slab_conv(ga, norm, w.tc, st);
     } else if (taps == 27 && stride == 2 && x1 == nullptr && norm == nullptr && out_scale == nullptr && resb == nullptr &&
-               s2_roll_supported(c0, w.cout, g)) {
+               (x3 ? s2_roll_supported_x3(c0, w.cout, g) : s2_roll_supported(c0, w.cout, g))) {
       kind = 12;
-      rc = launch_s2_roll_conv(x0, w.tc, w.b, y, stats, st);
+      rc = launch_s2_roll_conv(x0, w.tc, w.b, y, stats, st, x3);
     } else {
       kind = 5;
       const void* src = x0;
       if (norm) {
         if (x1 != nullptr) { set_error("bf16 conv: fused norm with two sources is not used by this network"); return -1; }
-        DCL_TRY(launch_norm_act_b(x0, *norm, nullptr, h->b_nrm, c0, (int64_t)g * g * g, st));
+        DCL_TRY(launch_norm_act_b(x0, *norm, nullptr, h->b_nrm, c0, (int64_t)g * g * g, st, x3));
         src = h->b_nrm;
       }
       GemmArgs ga;
+      ga.x3 = x3;
       ga.a0 = src; ga.c0 = c0; ga.a1 = x1;
       ga.D = g; ga.H = g; ga.W = g; ga.stride = stride; ga.taps = taps;
       ga.bias = w.b; ga.out_scale = out_scale; ga.out_mode = 2; ga.y = y; ga.residual = resb; ga.stats = stats;
@@ -916,7 +937,7 @@ struct Fwd16 {
     DCL_TRY(conv(a, c, nullptr, 0, g, h->conv.at(name + ".conv2"), 1, &n1, nullptr, nullptr, b, sb));
     if (tail_out != nullptr) { *tail_out = norm_of(sb, sp, ACT_LRELU); return 0; }
     dcl_handle::ProfScope ps(h, st, 7);
-    DCL_TRY(launch_norm_act_b(b, norm_of(sb, sp, ACT_LRELU), x, y, c, sp, st));
+    DCL_TRY(launch_norm_act_b(b, norm_of(sb, sp, ACT_LRELU), x, y, c, sp, st, is_x3(h)));
     return 0;
   }
 
@@ -986,7 +1007,7 @@ struct Fwd16 {
       const ConvW& w = h->conv.at("Unet_list.InitConv.conv");
       RollArgs a;
       a.desc = h->patch_desc;
-      a.bias = w.b; a.out_scale = h->keep_dev; a.yb = h->b_t0[0]; a.stats = s_in;
+      a.bias = w.b; a.out_scale = h->keep_dev; a.yb = h->b_t0[0]; a.stats = s_in; a.x3 = is_x3(h);
       cudaEvent_t ev = h->profiling ? h->prof_begin(st) : nullptr;
       DCL_TRY(launch_roll_conv(a, w.tc, 16, 128, st));
       if (h->profiling) h->prof_end(ev, 0, 2.0 * 27.0 * 4 * 16 * (double)P3, st, 2);
@@ -1016,8 +1037,10 @@ struct Fwd16 {
     for (int r = 0; r < 3; ++r) {
       dcl_handle::ProfScope ps(h, st, 10);
       BNorm ne = norm_of(s_e, g32, ACT_LRELU), ns = norm_of(s_s, g16, ACT_LRELU);
-      DCL_TRY(launch_tokenise_b(h->b_eraw, ne, 4 * r, h->E[r], dense_feats ? h->edge_dense[r] : nullptr, 32, 32, 4, 2, 2, st));
-      DCL_TRY(launch_tokenise_b(h->b_sraw, ns, 16 * r, h->S[r], dense_feats ? h->sem_dense[r] : nullptr, 128, 16, 2, 2, 1, st));
+      DCL_TRY(launch_tokenise_b(h->b_eraw, ne, 4 * r, h->E[r], dense_feats ? h->edge_dense[r] : nullptr, 32, 32, 4, 2, 2, st,
+                                is_x3(h) ? 12 : 0));
+      DCL_TRY(launch_tokenise_b(h->b_sraw, ns, 16 * r, h->S[r], dense_feats ? h->sem_dense[r] : nullptr, 128, 16, 2, 2, 1, st,
+                                is_x3(h) ? 48 : 0));
     }
     if (want_aux) {
       for (int r = 0; r < 3; ++r) {
@@ -1100,7 +1123,7 @@ struct Fwd16 {
     DCL_TRY(f.attn_block(h->tr[3], h->ts[0].seq[0], h->ts[0].seq[0], SEQ, SEQ, h->ts[0].eqs));
     DCL_TRY(f.ffn_block(h->tr[3], h->ts[0].eqs, SEQ, h->coupler_out[3]));
     DCL_TRY(launch_scatter_rows(h->f_fea, h->topk + 12 * TOP_NUM, h->coupler_out[3] + 512, 512, st));
-    DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st));
+    DCL_TRY(launch_untokenise_b(h->f_fea, h->coupler_out[3], h->b_fused, 128, 16, 2, 2, 1, st, is_x3(h)));
     if (ev_tokp) h->prof_end(ev_tokp, 8, 0.0, st);
     DCL_TRY(stamp(4));
     DCL_TRY(conv(h->b_fused, 128, nullptr, 0, 16, h->conv.at("sum_fusion"), 1, nullptr, nullptr, nullptr, h->b_enc, nullptr));
@@ -1121,7 +1144,7 @@ struct Fwd16 {
       void** b = h->b_dl[l];
       {
         dcl_handle::ProfScope ps(h, st, 6);
-        DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st));
+        DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st, is_x3(h)));
       }
       DCL_TRY(post_block(b[0], c, g, dbn[l][0], b[1], b[2], b[3]));
       // the very last DeBlock tail (16 channels @ 128^3) is folded into endconv's load unless the stage is to be kept
@@ -1133,8 +1156,8 @@ struct Fwd16 {
     DCL_TRY(stamp(8));
     {
       dcl_handle::ProfScope ps(h, st, 9);
-      if (end_src != nullptr) DCL_TRY(launch_endconv_softmax_b(end_src, h->end_w, h->end_b, probs_out, P3, st, &end_tail, end_res, h->patch_desc));
-      else DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st, nullptr, nullptr, h->patch_desc));
+      if (end_src != nullptr) DCL_TRY(launch_endconv_softmax_b(end_src, h->end_w, h->end_b, probs_out, P3, st, &end_tail, end_res, h->patch_desc, is_x3(h)));
+      else DCL_TRY(launch_endconv_softmax_b(cur, h->end_w, h->end_b, probs_out, P3, st, nullptr, nullptr, h->patch_desc, is_x3(h)));
     }
     DCL_TRY(stamp(9));
     return 0;
@@ -1160,7 +1183,7 @@ static void register_stages(dcl_handle* h) {
   s["dec4"] = {h->dl_2[0], 64 * g32};
   s["dec3"] = {h->dl_2[1], 32 * P3 / 8};
   s["dec2"] = {h->dl_2[2], 16 * P3};
-  if (h->cfg.precision == DCL_BF16) {   // the conv-path stages live in B-format buffers in this mode
+  if (is_tc(h)) {   // the conv-path stages live in B-format buffers in this mode
     auto& b = h->bstages;
     b["init"] = {h->b_t0[0], 16, P3};
     b["x1_1"] = {h->b_x[0], 16, P3};
@@ -1283,7 +1306,7 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
   const bool weighted = mode == DCL_STITCH_UNIFORM || mode == DCL_STITCH_GAUSSIAN;
   int L = lane_count();
   if (L > count) L = count;
-  const bool two = h->cfg.precision == DCL_BF16 && !h->profiling && L >= 2;
+  const bool two = is_tc(h) && !h->profiling && L >= 2;
   if (two) {
     DCL_TRY(ensure_lanes(h, L));
     DCL_CUDA_OK(cudaEventRecord(h->ev_lane_fork, st));
@@ -1311,7 +1334,7 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
     if (dst && slot_planes == 16)
       for (int j = 0; j < 6; ++j) aux_ptr[j] = dst + (int64_t)(4 + 2 * j) * P3;
     float* const* aux = (dst && slot_planes == 16) ? aux_ptr : nullptr;
-    if (h->cfg.precision == DCL_BF16) {
+    if (is_tc(h)) {
       Fwd16 f16{hh, s};
       DCL_TRY(f16.run(x, xs, keep_host ? keep_host + 16 * i : nullptr, dst ? dst : hh->probs, aux));
     } else {
@@ -1525,7 +1548,7 @@ DCL_API int dcl_forward(dcl_handle* h, const float* x_dev, const int64_t x_strid
   if (aux_dev && !h->cfg.want_aux) { set_error("dcl_forward: aux outputs need cfg.want_aux"); return DCL_ERR_ARG; }
   int64_t before = g_launches;
   int rc;
-  if (h->cfg.precision == DCL_BF16) {
+  if (is_tc(h)) {
     Fwd16 f{h, (cudaStream_t)stream};
     rc = f.run(x_dev, x_strides, keep_scale_host, probs_dev, aux_dev);
   } else {
@@ -1736,7 +1759,7 @@ DCL_API int64_t dcl_read_stage(dcl_handle* h, const char* stage, float* out_dev,
     const int64_t n = (int64_t)bit->second.c * bit->second.spatial;
     if (out_dev) {
       if (cap < n) { set_error("dcl_read_stage: output buffer too small"); return DCL_ERR_ARG; }
-      DCL_TRY(launch_unblock(bit->second.p, out_dev, bit->second.c, bit->second.spatial, (cudaStream_t)stream));
+      DCL_TRY(launch_unblock(bit->second.p, out_dev, bit->second.c, bit->second.spatial, (cudaStream_t)stream, is_x3(h)));
     }
     return n;
   }
@@ -1827,15 +1850,17 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
   std::vector<float> w((size_t)cout * cin * 27);
   for (size_t i = 0; i < w.size(); ++i) w[i] = (float)((i * 2654435761u >> 8) & 0xffff) / 65536.f - 0.5f;
-  const bool roll = stride == 1 && tc_conv_supported(cin, cout, g, 1, false) && cin != 4;
+  const bool x3 = (mode & 8) != 0;     // split-bf16 (DCL_BF16X3) variant of the same layer
+  const int E = x3 ? 4 : 2;
+  const bool roll = stride == 1 && tc_conv_supported(cin, cout, g, 1, x3) && cin != 4;
   TcWeights tw;
-  if (tc_pack_weights(w.data(), cout, cin, 27, roll, &tw) != 0) return -1.0;
+  if (tc_pack_weights(w.data(), cout, cin, 27, roll, &tw, x3) != 0) return -1.0;
   void *x = nullptr, *y = nullptr, *r = nullptr;
   float* bias = nullptr;
   stat_t *sin = nullptr, *sout = nullptr;
-  cudaMalloc(&x, (size_t)cin_pad * sp * 2); cudaMalloc(&y, (size_t)cout_pad * osp * 2); cudaMalloc(&r, (size_t)cout_pad * osp * 2);
+  cudaMalloc(&x, (size_t)cin_pad * sp * E); cudaMalloc(&y, (size_t)cout_pad * osp * E); cudaMalloc(&r, (size_t)cout_pad * osp * E);
   cudaMalloc((void**)&bias, cout_pad * 4); cudaMalloc((void**)&sin, 2 * cin_pad * sizeof(stat_t)); cudaMalloc((void**)&sout, 2 * cout_pad * sizeof(stat_t));
-  cudaMemset(x, 0x3c, (size_t)cin_pad * sp * 2); cudaMemset(r, 0x3c, (size_t)cout_pad * osp * 2); cudaMemset(bias, 0, cout_pad * 4);
+  cudaMemset(x, 0x3c, (size_t)cin_pad * sp * E); cudaMemset(r, 0x3c, (size_t)cout_pad * osp * E); cudaMemset(bias, 0, cout_pad * 4);
   cudaMemset(sin, 0, 2 * cin_pad * sizeof(stat_t)); cudaMemset(sout, 0, 2 * cout_pad * sizeof(stat_t));
   BNorm bn; bn.sums = sin; bn.inv_n = 1.f / (float)sp; bn.act = ACT_RELU;
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1843,16 +1868,17 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
   for (int it = 0; it < reps + 3 && rc == 0; ++it) {
     if (it == 3) cudaEventRecord(e0, 0);
     if (roll) {
-      RollArgs a; a.xb = x; if (mode & 1) a.norm = bn; if (mode & 2) a.resb = r; if (mode & 4) a.stats = sout;
+      RollArgs a; a.x3 = x3; a.xb = x; if (mode & 1) a.norm = bn; if (mode & 2) a.resb = r; if (mode & 4) a.stats = sout;
       a.bias = bias; a.yb = y;
       rc = launch_roll_conv(a, tw, cout, g, 0);
     } else {
-      GemmArgs ga; ga.a0 = x; ga.c0 = cin_pad; ga.D = g; ga.H = g; ga.W = g; ga.stride = stride; ga.taps = 27;
+      GemmArgs ga; ga.x3 = x3; ga.a0 = x; ga.c0 = cin_pad; ga.D = g; ga.H = g; ga.W = g; ga.stride = stride; ga.taps = 27;
       ga.bias = bias; ga.out_mode = 2; ga.y = y;
       if (mode & 2) ga.residual = r;
       if (mode & 4) ga.stats = sout;
-      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && g <= 32) rc = launch_slab_conv(ga, (mode & 1) ? &bn : nullptr, tw, 0);
-      else if (stride == 2 && s2_roll_supported(cin, cout, g)) rc = launch_s2_roll_conv(x, tw, bias, y, mode ? sout : nullptr, 0);
+      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && (g <= 32 || (x3 && g == 64))) rc = launch_slab_conv(ga, (mode & 1) ? &bn : nullptr, tw, 0);
+      else if (stride == 2 && (x3 ? s2_roll_supported_x3(cin, cout, g) : s2_roll_supported(cin, cout, g)))
+        rc = launch_s2_roll_conv(x, tw, bias, y, (mode & 7) ? sout : nullptr, 0, x3);
       else rc = launch_gemm_conv(ga, tw, 0);
     }
   }
@@ -1950,24 +1976,26 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
     cudaStreamSynchronize(st);
     cudaFree(wp);
   } else {
-    if (impl == 1) { set_error("dcl_op_conv3d_k3: bf16x3 has no tensor-core kernel yet"); return DCL_ERR_ARG; }
+    const bool x3 = impl == 1;           // split-bf16 operands (DCL_BF16X3)
+    const int E = x3 ? 4 : 2;            // bytes per B-format element
     TcWeights tw;
     const bool cubic = in_dhw[0] == in_dhw[1] && in_dhw[1] == in_dhw[2];
-    const bool roll = cubic && x1 == nullptr && tc_conv_supported(cin, cout, in_dhw[0], stride, false) && cin != 4;
-    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, 27, roll, &tw));
+    const bool roll = cubic && x1 == nullptr && tc_conv_supported(cin, cout, in_dhw[0], stride, x3) && cin != 4;
+    DCL_TRY(tc_pack_weights(wh.data(), cout, cin, 27, roll, &tw, x3));
     if (roll) {
       // rolling kernel: B-format in / out, so convert around it (raw input; the norm is fused in the kernel)
       void *xb = nullptr, *yb = nullptr, *rb = nullptr;
-      DCL_CUDA_OK(cudaMalloc(&xb, (size_t)cin * sp * 2));
-      DCL_CUDA_OK(cudaMalloc(&yb, (size_t)cout * sp * 2));
+      DCL_CUDA_OK(cudaMalloc(&xb, (size_t)cin * sp * E));
+      DCL_CUDA_OK(cudaMalloc(&yb, (size_t)cout * sp * E));
       ConvSrc raw{x0, nullptr, c0, 0, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], nullptr, nullptr, ACT_NONE};
-      rc = launch_prep_blocked(raw, in_dhw[0], in_dhw[1], in_dhw[2], xb, st);
+      rc = launch_prep_blocked(raw, in_dhw[0], in_dhw[1], in_dhw[2], xb, st, x3);
       if (rc == 0 && residual) {
-        DCL_CUDA_OK(cudaMalloc(&rb, (size_t)cout * sp * 2));
+        DCL_CUDA_OK(cudaMalloc(&rb, (size_t)cout * sp * E));
         ConvSrc rs{residual, nullptr, cout, 0, sp, (int64_t)in_dhw[1] * in_dhw[2], in_dhw[2], nullptr, nullptr, ACT_NONE};
-        rc = launch_prep_blocked(rs, in_dhw[0], in_dhw[1], in_dhw[2], rb, st);
+        rc = launch_prep_blocked(rs, in_dhw[0], in_dhw[1], in_dhw[2], rb, st, x3);
       }
       RollArgs a;
+      a.x3 = x3;
       a.xb = xb; a.norm.mean = norm_mean; a.norm.rstd = norm_rstd; a.norm.act = act;
       stat_t* sfix = nullptr;
       if (stats_out) {
@@ -1976,7 +2004,7 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
       }
       a.bias = bias; a.resb = rb; a.yb = yb; a.stats = sfix;
       if (rc == 0) rc = launch_roll_conv(a, tw, cout, in_dhw[0], st);
-      if (rc == 0) rc = launch_unblock(yb, y, cout, sp, st);
+      if (rc == 0) rc = launch_unblock(yb, y, cout, sp, st, x3);
       cudaStreamSynchronize(st);
       if (stats_out && rc == 0) {   // decode the fixed-point sums into the caller's doubles
         std::vector<stat_t> hs(2 * cout);
@@ -1990,24 +2018,25 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
     } else {
       if (stats_out) { cudaFree(tw.dev); set_error("dcl_op_conv3d_k3: fused statistics need the rolling kernel"); return DCL_ERR_ARG; }
       void* blk = nullptr;
-      DCL_CUDA_OK(cudaMalloc(&blk, (size_t)((cin + 15) / 16 * 16) * sp * 2));
+      DCL_CUDA_OK(cudaMalloc(&blk, (size_t)((cin + 15) / 16 * 16) * sp * E));
       if (stride == 2 && cubic && x1 == nullptr && norm_mean == nullptr && act == ACT_NONE && residual == nullptr &&
-          s2_roll_supported(cin, cout, in_dhw[0])) {
+          (x3 ? s2_roll_supported_x3(cin, cout, in_dhw[0]) : s2_roll_supported(cin, cout, in_dhw[0]))) {
         // rolling stride-2 kernel (EnDown1): B-format in / out
         const int64_t osp = sp / 8;
         void* yb = nullptr;
-        DCL_CUDA_OK(cudaMalloc(&yb, (size_t)cout * osp * 2));
-        rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
-        if (rc == 0) rc = launch_s2_roll_conv(blk, tw, bias, yb, nullptr, st);
-        if (rc == 0) rc = launch_unblock(yb, y, cout, osp, st);
+        DCL_CUDA_OK(cudaMalloc(&yb, (size_t)cout * osp * E));
+        rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st, x3);
+        if (rc == 0) rc = launch_s2_roll_conv(blk, tw, bias, yb, nullptr, st, x3);
+        if (rc == 0) rc = launch_unblock(yb, y, cout, osp, st, x3);
         cudaStreamSynchronize(st);
         cudaFree(yb);
       } else if (slab_conv_supported(cin, cout, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27)) {
         // slab kernel: raw blocked input, norm fused in the kernel, fp32 NCDHW output
         ConvSrc raw = s;
         raw.mean = nullptr; raw.rstd = nullptr; raw.act = ACT_NONE;
-        rc = launch_prep_blocked(raw, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
+        rc = launch_prep_blocked(raw, in_dhw[0], in_dhw[1], in_dhw[2], blk, st, x3);
         GemmArgs ga;
+        ga.x3 = x3;
         ga.a0 = blk; ga.c0 = (cin + 15) / 16 * 16;
         ga.D = in_dhw[0]; ga.H = in_dhw[1]; ga.W = in_dhw[2]; ga.stride = 1; ga.taps = 27;
         ga.bias = bias; ga.out_mode = 0; ga.y = y; ga.residual = residual;
@@ -2015,8 +2044,8 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
         bn.mean = norm_mean; bn.rstd = norm_rstd; bn.act = act;
         if (rc == 0) rc = launch_slab_conv(ga, &bn, tw, st);
       } else {
-        rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st);
-        if (rc == 0) rc = launch_conv_gemm(blk, tw, d, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27, st);
+        rc = launch_prep_blocked(s, in_dhw[0], in_dhw[1], in_dhw[2], blk, st, x3);
+        if (rc == 0) rc = launch_conv_gemm(blk, tw, d, in_dhw[0], in_dhw[1], in_dhw[2], stride, 27, st, x3);
       }
       cudaStreamSynchronize(st);
       cudaFree(blk);

@@ -173,6 +173,29 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// ---- split-bf16 ("bf16x3") helpers: v = hi + lo, hi = bf16(v), lo = bf16(v - hi) (16 significant bits) ------
+// A product a*b is then formed as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo in the fp32 tensor-memory accumulator
+// (the dropped a_lo*b_lo term is 2^-16 relative), which gives fp32-class results on the bf16 tensor pipe.
+__device__ __forceinline__ void split_bf16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_bf16x2(a, b);
+  lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  split_bf16x2(f[0], f[1], hi.x, lo.x);
+  split_bf16x2(f[2], f[3], hi.y, lo.y);
+  split_bf16x2(f[4], f[5], hi.z, lo.z);
+  split_bf16x2(f[6], f[7], hi.w, lo.w);
+}
+// f[k] (+)= the 8 bf16 values of v
+template <bool ADD>
+__device__ __forceinline__ void unpack8_acc(const uint4& v, float (&f)[8]) {
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float a = __uint_as_float(p[k] << 16), b = __uint_as_float(p[k] & 0xffff0000u);
+    if (ADD) { f[2 * k] += a; f[2 * k + 1] += b; } else { f[2 * k] = a; f[2 * k + 1] = b; }
+  }
+}
 
 }  // namespace tc
 }  // namespace dcl

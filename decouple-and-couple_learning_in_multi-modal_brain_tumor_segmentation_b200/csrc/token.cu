@@ -224,7 +224,7 @@ constexpr int ATT_KG = ATT_MAXK / 32;     // key groups per lane
 
 __global__ void __launch_bounds__(128)
 attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out,
-                 unsigned short* __restrict__ out_blocked, int mq, int mk) {
+                 unsigned short* __restrict__ out_blocked, int mq, int mk, int x3) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
@@ -312,8 +312,14 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
         // bf16, channel-blocked [64 chunks][mq rows][8]: exactly the A operand of the out-projection GEMM, so the
         // separate fp32 -> blocked conversion pass is skipped
         const int c0 = head * ATT_HD + lane, c1 = c0 + 32;
-        out_blocked[((int64_t)(c0 >> 3) * mq + row) * 8 + (c0 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(o[r][0] * inv[r]));
-        out_blocked[((int64_t)(c1 >> 3) * mq + row) * 8 + (c1 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(o[r][1] * inv[r]));
+        const float v0 = o[r][0] * inv[r], v1 = o[r][1] * inv[r];
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        out_blocked[((int64_t)(c0 >> 3) * mq + row) * 8 + (c0 & 7)] = __bfloat16_as_ushort(h0);
+        out_blocked[((int64_t)(c1 >> 3) * mq + row) * 8 + (c1 & 7)] = __bfloat16_as_ushort(h1);
+        if (x3) {      // split-bf16: the lo planes follow the 64 hi chunks
+          out_blocked[((int64_t)(64 + (c0 >> 3)) * mq + row) * 8 + (c0 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(v0 - __bfloat162float(h0)));
+          out_blocked[((int64_t)(64 + (c1 >> 3)) * mq + row) * 8 + (c1 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        }
       } else {
         out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o[r][0] * inv[r];
         out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane + 32] = o[r][1] * inv[r];
@@ -322,7 +328,7 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
   }
 }
 
-int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st, void* out_blocked) {
+int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st, void* out_blocked, bool x3) {
   if (mk > ATT_MAXK) { set_error("attention: at most 160 keys"); return -1; }
   size_t smem = (size_t)(mk * ATT_KP + mk * ATT_HD + ATT_QCHUNK * ATT_HD + ATT_QCHUNK * ATT_MAXK) * sizeof(float);
   static bool configured = false;
@@ -330,7 +336,7 @@ int launch_attention(const float* q, const float* kv, float* out, int mq, int mk
     DCL_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  DCL_CUDA_OK(launch_pdl(attention_kernel, dim3(dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8)), dim3(128), (size_t)(smem), st, q, kv, out, reinterpret_cast<unsigned short*>(out_blocked), mq, mk));
+  DCL_CUDA_OK(launch_pdl(attention_kernel, dim3(dim3((mq + ATT_QCHUNK - 1) / ATT_QCHUNK, 8)), dim3(128), (size_t)(smem), st, q, kv, out, reinterpret_cast<unsigned short*>(out_blocked), mq, mk, x3 ? 1 : 0));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

@@ -21,10 +21,12 @@ for _k in ("01", "02", "04"):
 FP32_TOL = 1e-3     # north_star: fp32 logits within 1e-3 relative of the reference forward
 
 
-@pytest.fixture(scope="module")
-def engine(seed0_state_dict):
+# Both parity-grade modes run the whole file: DCL_FP32 (FFMA kernels) and DCL_BF16X3 (split-bf16 operands on the
+# tcgen05 kernels, the fast path) are gated at the SAME fp32 tolerances of north_star.
+@pytest.fixture(scope="module", params=["FP32", "BF16X3"])
+def engine(request, seed0_state_dict):
     import dcl_b200
-    eng = dcl_b200.Engine(dcl_b200.Precision.FP32, want_aux=True, keep_stages=True)
+    eng = dcl_b200.Engine(dcl_b200.Precision[request.param], want_aux=True, keep_stages=True)
     eng.load_state_dict(seed0_state_dict)
     yield eng
     eng.close()

@@ -9,7 +9,7 @@ from tests.util import rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _conv_case(c0, c1, cout, dims, stride, norm, act, residual, seed):
+def _conv_case(c0, c1, cout, dims, stride, norm, act, residual, seed, impl=0):
     from dcl_b200.engine import op_conv3d_k3
     g = torch.Generator().manual_seed(seed)
     x0 = torch.randn(c0, *dims, generator=g)
@@ -34,7 +34,7 @@ def _conv_case(c0, c1, cout, dims, stride, norm, act, residual, seed):
         ref = ref + res
     dev = "cuda"
     y = op_conv3d_k3(x0.to(dev), w.to(dev), b.to(dev), x1.to(dev) if c1 else None, stride,
-                     (mean.to(dev), rstd.to(dev)) if norm else None, act, res.to(dev) if residual else None, impl=0)
+                     (mean.to(dev), rstd.to(dev)) if norm else None, act, res.to(dev) if residual else None, impl=impl)
     torch.cuda.synchronize()
     return y.cpu(), ref
 
@@ -165,3 +165,29 @@ def test_conv3d_k3_gemm_bf16(case):
     assert float((y - ref).abs().mean() / ref.abs().mean()) < (2e-3 if bf16_out else 1e-4)
     if bf16_out:
         assert float((y - _bf16_round(ref)).abs().mean() / ref.abs().mean()) < 2e-4     # identical up to rare ulp flips
+
+
+@pytest.mark.parametrize("case", [
+    dict(c0=16, c1=0, cout=16, dims=(128, 128, 128), stride=1, norm=True, act=1, residual=True),    # rolling kernel, split strips
+    dict(c0=16, c1=0, cout=16, dims=(128, 128, 128), stride=1, norm=False, act=0, residual=False),
+    dict(c0=32, c1=0, cout=32, dims=(64, 64, 64), stride=1, norm=True, act=2, residual=True),       # slab kernel at 64^3
+    dict(c0=64, c1=0, cout=64, dims=(32, 32, 32), stride=1, norm=True, act=1, residual=True),       # slab
+    dict(c0=32, c1=64, cout=96, dims=(32, 32, 32), stride=1, norm=False, act=0, residual=False),    # slab, two sources
+    dict(c0=128, c1=0, cout=128, dims=(16, 16, 16), stride=1, norm=True, act=2, residual=False),    # slab, two passes
+    dict(c0=256, c1=0, cout=384, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),   # slab, four passes
+    dict(c0=128, c1=0, cout=256, dims=(16, 16, 16), stride=1, norm=False, act=0, residual=False),
+    dict(c0=16, c1=0, cout=32, dims=(128, 128, 128), stride=2, norm=False, act=0, residual=False),  # rolling stride-2 kernel
+    dict(c0=32, c1=0, cout=64, dims=(64, 64, 64), stride=2, norm=False, act=0, residual=False),     # im2col GEMM
+    dict(c0=64, c1=0, cout=128, dims=(32, 32, 32), stride=2, norm=False, act=0, residual=False),    # im2col GEMM (EnDown3)
+    dict(c0=5, c1=3, cout=19, dims=(9, 17, 18), stride=2, norm=True, act=2, residual=True),         # ragged, padded channels
+    dict(c0=32, c1=0, cout=8, dims=(16, 16, 16), stride=1, norm=True, act=2, residual=False),       # auxiliary-head shapes
+    dict(c0=8, c1=0, cout=2, dims=(20, 12, 36), stride=1, norm=False, act=0, residual=False),
+])
+def test_conv3d_k3_split_bf16(case):
+    """DCL_BF16X3 kernels (split-bf16 operands: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05, fp32 accumulate) against
+    the PLAIN fp32 torch convolution - no operand rounding is granted: 16 significant bits per operand leave ~2^-16
+    per product, and B-format outputs are stored as hi + lo (2^-17)."""
+    y, ref = _conv_case(seed=31, impl=1, **case)
+    assert y.shape == ref.shape
+    assert rel_err(y.numpy(), ref.numpy()) < 1e-4
+    assert float((y - ref).abs().mean() / ref.abs().mean()) < 2e-5

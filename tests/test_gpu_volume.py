@@ -9,10 +9,10 @@ from tests.util import check_digest, rel_err, volume_input, volume_target
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def engine(seed0_state_dict):
+@pytest.fixture(scope="module", params=["FP32", "BF16X3"])
+def engine(request, seed0_state_dict):
     import dcl_b200
-    eng = dcl_b200.Engine(dcl_b200.Precision.FP32)
+    eng = dcl_b200.Engine(dcl_b200.Precision[request.param])
     eng.load_state_dict(seed0_state_dict)
     yield eng
     eng.close()
