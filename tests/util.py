@@ -42,3 +42,30 @@ def volume_input(i=0):
 
 def volume_target(i=0):
     return np.random.RandomState(i).randint(0, 4, (240, 240, 155))
+
+
+COUPLER_ORDER = {"coupler_01": ("01_ee", "01_ss"), "coupler_02": ("02_ee", "02_ss"), "coupler_04": ("04_ee", "04_ss"),
+                 "coupler_fusion": ("fusion",)}
+
+
+def coupler_rows_in_golden_order(name, t, topk, golden):
+    """A coupler output is (1, blocks x 129, 512): per block one class-token row, then one row per SELECTED token in the
+    order torch.topk returned them (cls_wise_former.py:345-376).  Only the selected SET is defined by the algorithm's
+    result (attention is permutation invariant in its keys and the scatter-back goes by index, :458-543); two
+    near-tied scores may come out in either order.  This puts our token rows into the golden's order (rows whose token
+    the golden did not select are reported back) so that stage digests can be compared row by row."""
+    t = t.reshape(-1, 512).clone()
+    missing = 0
+    for b, tag in enumerate(COUPLER_ORDER[name]):
+        ours = topk[tag].tolist()
+        want = golden["topk_" + tag].tolist()
+        pos = {tok: i for i, tok in enumerate(ours)}
+        base = b * 129 + 1
+        block = t[base:base + 128].clone()
+        for i, tok in enumerate(want):
+            if tok in pos:
+                t[base + i] = block[pos[tok]]
+            else:
+                missing += 1
+                t[base + i] = float("nan")
+    return t.reshape(1, -1, 512), missing
