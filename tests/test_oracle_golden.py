@@ -88,3 +88,38 @@ def test_tokenise_roundtrip():
     t = O.tokenise(x, O.SEM_GRID, O.SEM_PATCH)
     assert t.shape == (1, 1024, 512)
     assert torch.equal(O.untokenise(t, 128, O.SEM_GRID, O.SEM_PATCH), x)
+
+
+def test_oracle_matches_overlap50_golden_where_one_patch_covers():
+    """tests/golden/overlap50_seed1000.npz (the benchmarked workload, from the unmodified reference): the corner box
+    x < 64, y < 64, z < 27 of the stride-64 plan is covered by the first patch alone, so there the blend is that patch's
+    output: the oracle's forward must reproduce the golden label map exactly on those 110 592 voxels, and the golden's
+    probability samples that fall into the box to 1e-6.  Also pins the plan (patch origins and order)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "overlap50_seed1000.npz")
+    g = np.load(path)
+    starts = S.patch_starts((240, 240, 155), 64)
+    assert [tuple(int(v) for v in s) for s in g["starts"]] == starts
+    assert starts[0] == (0, 0, 0)
+    x = volume_input(0)[..., :128, :128, :128]
+    probs = O.forward(seed0_state_dict_cached(), x, torch.from_numpy(g["keep_scale"][:1]), want_aux=False)[0][0].numpy()
+    a = g["labels_packed"]
+    labels = np.stack([a & 3, (a >> 2) & 3, (a >> 4) & 3, (a >> 6) & 3], 1).ravel()[:240 * 240 * 155].reshape(240, 240, 155)
+    assert int(g["labels_step"]) == 1
+    assert np.array_equal(labels[:64, :64, :27], probs.argmax(0)[:64, :64, :27])
+    # strided sample k of the flattened (1,4,240,240,155) blend sits at flat index k * step
+    n = 4 * 240 * 240 * 155
+    step = n // 4096
+    idx = np.arange(4096) * step
+    c, rem = np.divmod(idx, 240 * 240 * 155)
+    xx, rem = np.divmod(rem, 240 * 155)
+    yy, zz = np.divmod(rem, 155)
+    box = (xx < 64) & (yy < 64) & (zz < 27)
+    assert box.sum() >= 40
+    got = probs[c[box], xx[box], yy[box], zz[box]]
+    assert np.abs(got - g["blend/sample"][box]).max() <= 1e-6
+
+
+def seed0_state_dict_cached():
+    from models.clswiseformer.cls_wise_former import get_cls_wise_former
+    torch.manual_seed(0)
+    return {k: v.detach().clone() for k, v in get_cls_wise_former("brats", True, "fixed", 0).state_dict().items()}
