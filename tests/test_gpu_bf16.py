@@ -11,7 +11,13 @@ from tests.util import config1_input, coupler_rows_in_golden_order, rel_err, str
 pytestmark = pytest.mark.gpu
 
 BF16_TOL = 2e-2
-COUPLED_TOL = 1.0      # placeholder until measured
+# Stages downstream of the 13 discrete top-k selections.  Measured on B200 (gpurun_out/r02b_tests.log): region couplers
+# (shared token rows) 1.8-2.2e-2, enc_out 1.9e-2, dec3 1.3e-2, dec2 8.5e-3 - gated at 5e-2; the cross-region coupler, dec8
+# and dec4 carry the swapped tokens themselves (a token selected here but not by the reference is a REPLACED 512-vector
+# = a 2x2x1 block of the 16^3 feature map, cls_wise_former.py:458-543, :565-577): max-norm 2.1e-1 / 9.5e-2 / 3.1e-2,
+# gated at 3e-1.  None of these meets the 2e-2 of north_star in bf16 mode; DCL_BF16X3 runs the same stages at 1e-3.
+COUPLED_TOL = {"coupler_01": 5e-2, "coupler_02": 5e-2, "coupler_04": 5e-2, "enc_out": 5e-2, "dec3": 5e-2, "dec2": 5e-2,
+               "coupler_fusion": 3e-1, "dec8": 3e-1, "dec4": 3e-1}
 
 
 @pytest.fixture(scope="module")
@@ -64,7 +70,7 @@ def test_bf16_forward_within_tolerance_of_reference_goldens(engine_bf16, golden_
     for name in ("init", "x1_1", "x2_1", "x3_1", "x4", "edge_1", "edge_2", "edge_4", "sem_1", "sem_2", "sem_4"):
         assert errs[name] < BF16_TOL, (name, errs[name])       # no discrete selection upstream
     for name in ("coupler_01", "coupler_02", "coupler_04", "coupler_fusion", "enc_out", "dec8", "dec4", "dec3", "dec2"):
-        assert errs[name] < COUPLED_TOL, (name, errs[name])     # downstream of the top-k selections
+        assert errs[name] < COUPLED_TOL[name], (name, errs[name])     # downstream of the top-k selections
     assert min(overlap.values()) >= 112                       # at most a few boundary tokens swap
     assert (probs.sum(1) - 1).abs().max().item() < 1e-5
     lab = probs[0].argmax(0).to(torch.uint8).cpu().numpy()
