@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -1251,6 +1252,36 @@ static int build_plan(int mode, const int32_t shape[3], int n_patches, const int
     }
     plan->push_back(p);
   }
+  // Every voxel must lie in at least one patch: an uncovered voxel has weight sum 0 and would come out as 0/0.
+  // Exact test on the grid cut at every patch face: cell (i,j,k) is covered iff some patch covers interval i of x,
+  // j of y and k of z - one AND of three per-interval patch bitsets per cell.
+  {
+    const int P = n_patches, words = (P + 63) / 64;
+    std::vector<int> cuts[3];
+    std::vector<std::vector<uint64_t>> bits[3];
+    for (int a = 0; a < 3; ++a) {
+      std::vector<int>& c = cuts[a];
+      c.push_back(0); c.push_back(shape[a]);
+      for (int i = 0; i < P; ++i) { c.push_back((*plan)[i].start[a]); c.push_back((*plan)[i].start[a] + 128); }
+      std::sort(c.begin(), c.end());
+      c.erase(std::unique(c.begin(), c.end()), c.end());
+      bits[a].assign(c.size() - 1, std::vector<uint64_t>(words, 0));
+      for (size_t k = 0; k + 1 < c.size(); ++k)
+        for (int i = 0; i < P; ++i)
+          if ((*plan)[i].start[a] <= c[k] && c[k + 1] <= (*plan)[i].start[a] + 128) bits[a][k][i / 64] |= 1ull << (i % 64);
+    }
+    for (size_t i = 0; i < bits[0].size(); ++i)
+      for (size_t j = 0; j < bits[1].size(); ++j)
+        for (size_t k = 0; k < bits[2].size(); ++k) {
+          uint64_t any = 0;
+          for (int w = 0; w < words; ++w) any |= bits[0][i][w] & bits[1][j][w] & bits[2][k][w];
+          if (!any) {
+            set_error("patch list does not cover the volume: voxel (" + std::to_string(cuts[0][i]) + "," + std::to_string(cuts[1][j]) +
+                      "," + std::to_string(cuts[2][k]) + ") lies in no patch");
+            return DCL_ERR_ARG;
+          }
+        }
+  }
   return 0;
 }
 
@@ -1314,6 +1345,15 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
   }
   int up_have[dcl_handle::MAX_LANES] = {-1, -1, -1, -1};     // staged upload: highest x-slab each lane already waits for
   int lane = 0;
+  // an error half-way through the plan must not leave the lane streams forked from the caller's stream
+  struct LaneJoin {
+    dcl_handle* h; cudaStream_t st; int L; bool armed;
+    ~LaneJoin() {
+      if (!armed) return;
+      for (int l = 0; l < L; ++l)
+        if (cudaEventRecord(h->ev_lane_acc[l], h->lane_stream[l]) == cudaSuccess) cudaStreamWaitEvent(st, h->ev_lane_acc[l], 0);
+    }
+  } lane_join{h, st, L, two};
   for (int i = first; i < first + count; ++i) {
     const PlanItem& p = plan[i];
     lane = two ? (i - first) % L : 0;
@@ -1359,6 +1399,7 @@ static int run_patches(dcl_handle* h, const float* vol, const int32_t shape[3], 
     if (h->profiling) h->prof_end(ev, 1, bytes, s);
     if (two) DCL_CUDA_OK(cudaEventRecord(h->ev_lane_acc[lane], s));
   }
+  lane_join.armed = false;      // regular exit: the joins below are the minimal ones
   if (two && gather) {
     for (int l = 0; l < L; ++l) DCL_CUDA_OK(cudaStreamWaitEvent(st, h->ev_lane_acc[l], 0));   // every lane's last patch
   } else if (two) {

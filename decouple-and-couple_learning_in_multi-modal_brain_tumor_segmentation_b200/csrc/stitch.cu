@@ -167,7 +167,12 @@ finalize_labels_kernel(const float* __restrict__ acc, const float* __restrict__ 
   LabelCounts k;
 #pragma unroll
   for (int i = 0; i < 13; ++i) k.v[i] = 0;
-  const bool vec_ok = ((total | v0) & 3) == 0;
+  // 128-bit path: plane stride, range start AND every base pointer must keep 16-byte (4-byte for the byte maps) alignment
+  const bool vec_ok = ((total | v0) & 3) == 0 && (reinterpret_cast<uintptr_t>(acc) & 15) == 0 &&
+                      (wsum == nullptr || (reinterpret_cast<uintptr_t>(wsum) & 15) == 0) &&
+                      (probs_out == nullptr || (reinterpret_cast<uintptr_t>(probs_out) & 15) == 0) &&
+                      (labels == nullptr || (reinterpret_cast<uintptr_t>(labels) & 3) == 0) &&
+                      (target == nullptr || (reinterpret_cast<uintptr_t>(target) & 3) == 0);
   const int64_t nvec = vec_ok ? nvox / 4 : 0;
   for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < nvec; g += (int64_t)gridDim.x * 256) {
     const int64_t v = v0 + g * 4;

@@ -15,6 +15,16 @@ AUX_ORDER = [(head, key) for head in ("supervise", "edge", "mid_semantic", "mid_
 TOPK_TAGS = [f"{k}_{s}" for k in ("01", "02", "04") for s in ("ee", "es", "ss", "se")] + ["fusion"]
 
 
+def _single(t, what):
+    """(1,4,...) -> (4,...).  The C ABI takes ONE volume / patch per call; the reference's drivers use batch_size=1
+    (test_overlap.py:94-97).  A larger batch is refused rather than silently truncated."""
+    if t.dim() == 5:
+        if t.shape[0] != 1:
+            raise DclError(f"{what}: batch of {int(t.shape[0])} given, one volume per call (loop over the batch)")
+        t = t[0]
+    return t
+
+
 def reference_starts():
     """The 8 fixed corners of predict_overlap.py:34-41 in the reference's order."""
     return [(x, y, z) for z in (0, 27) for x in (0, 112) for y in (0, 112)]
@@ -141,8 +151,7 @@ class Engine:
                        want_probs=True, want_labels=True):
         """tailor_and_concat + arg-max + Dice counters on a CUDA (4,X,Y,Z) / (1,4,X,Y,Z) fp32 volume.
         Returns dict(probs (1,4,X,Y,Zout) | None, labels uint8 (X,Y,Zout) | None, counts int64[13] tensor)."""
-        if vol.dim() == 5:
-            vol = vol[0]
+        vol = _single(vol, "vol")
         if vol.dim() != 4 or vol.shape[0] != 4 or vol.dtype != torch.float32 or not vol.is_cuda:
             raise DclError("vol must be a CUDA fp32 (4,X,Y,Z) tensor")
         vol = vol.contiguous()
@@ -171,8 +180,7 @@ class Engine:
         'supervise' and 'edge': dicts of (1,2,X,Y,Z) tensors keyed like the reference's outputs."""
         if not self.want_aux:
             raise DclError("engine was created without want_aux")
-        if vol.dim() == 5:
-            vol = vol[0]
+        vol = _single(vol, "vol")
         if vol.dim() != 4 or vol.shape[0] != 4 or vol.dtype != torch.float32 or not vol.is_cuda:
             raise DclError("vol must be a CUDA fp32 (4,X,Y,Z) tensor")
         vol = vol.contiguous()
@@ -187,6 +195,8 @@ class Engine:
         counts = torch.zeros(13, dtype=torch.int64, device=vol.device)
         if target is not None:
             target = target.to(device=vol.device, dtype=torch.uint8).contiguous()
+            if tuple(target.shape) != (X, Y, Z):
+                raise DclError(f"target must have shape {(X, Y, Z)}")
         N.check(self._lib.dcl_predict_volume_aux(
             self._h, _ptr(vol), shape, int(mode), n, s_arr.ctypes.data_as(C.c_void_p),
             k_arr.ctypes.data_as(C.c_void_p) if k_arr is not None else C.c_void_p(0),
@@ -200,8 +210,7 @@ class Engine:
         """8-flip test-time augmentation around the reference tiling (predict_cls.py:180-203) on a CUDA
         (4,240,240,>=155) / (1,4,...) fp32 volume.  keep_scales: None or (8 flips, 8 patches, 16).
         Returns dict(probs (1,4,240,240,155) | None, labels uint8 (240,240,155) | None, counts int64[13])."""
-        if vol.dim() == 5:
-            vol = vol[0]
+        vol = _single(vol, "vol")
         if vol.dim() != 4 or vol.shape[0] != 4 or vol.dtype != torch.float32 or not vol.is_cuda:
             raise DclError("vol must be a CUDA fp32 (4,X,Y,Z) tensor")
         vol = vol.contiguous()
@@ -226,8 +235,7 @@ class Engine:
                             target_host=None, labels_out=None, probs_out=None):
         """The end-to-end call: HOST (ideally pinned) fp32 volume in, HOST uint8 labels + 13 counters out;
         both copies happen inside the library on the current stream, which is synchronised on return."""
-        if vol_host.dim() == 5:
-            vol_host = vol_host[0]
+        vol_host = _single(vol_host, "vol_host")
         if vol_host.is_cuda or vol_host.dtype != torch.float32 or vol_host.shape[0] != 4:
             raise DclError("vol_host must be a CPU fp32 (4,X,Y,Z) tensor")
         vol_host = vol_host.contiguous()
@@ -240,6 +248,10 @@ class Engine:
         counts = np.zeros(13, dtype=np.uint64)
         if target_host is not None:
             target_host = target_host.to(torch.uint8).contiguous()
+            if tuple(target_host.shape) != (X, Y, zout):
+                raise DclError(f"target_host must have shape {(X, Y, zout)}")
+        if tuple(labels_out.shape) != (X, Y, zout) or labels_out.dtype != torch.uint8 or not labels_out.is_contiguous():
+            raise DclError(f"labels_out must be a contiguous uint8 tensor of shape {(X, Y, zout)}")
         N.check(self._lib.dcl_predict_volume_host(
             self._h, _ptr(vol_host), shape, int(mode), n,
             s_arr.ctypes.data_as(C.c_void_p) if s_arr is not None else C.c_void_p(0),
@@ -249,8 +261,7 @@ class Engine:
 
     # ---- multi-GPU building blocks -----------------------------------------------
     def accumulate_patches(self, vol, mode, starts, keep_scales, first, count, acc, wsum):
-        if vol.dim() == 5:
-            vol = vol[0]
+        vol = _single(vol, "vol")
         vol = vol.contiguous()
         mode, n, s_arr, k_arr = self._plan_args(mode, starts, keep_scales)
         shape = (C.c_int32 * 3)(*[int(v) for v in vol.shape[1:]])
