@@ -263,3 +263,21 @@ def test_tta_reference_golden(engine, vol):
     samp = out["labels"].cpu().numpy().ravel()[:: V // 4096][:4096]
     assert (samp != g["labels_sample"]).mean() <= 1e-3
     assert np.allclose(dice_from_counts(counts), g["dice"], atol=1e-3)
+
+
+def test_bad_arguments_are_refused(engine, vol):
+    """A patch list that leaves voxels uncovered (weight sum 0 -> 0/0), a batch of more than one volume and a target of
+    the wrong shape are errors, not silent garbage."""
+    import dcl_b200
+    from dcl_b200 import StitchMode, patch_starts
+    starts = patch_starts((240, 240, 155), 64)
+    with pytest.raises(dcl_b200.DclError, match="does not cover"):
+        engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts[:-1])
+    with pytest.raises(dcl_b200.DclError, match="does not cover"):
+        engine.predict_volume(vol, StitchMode.GAUSSIAN, starts=[(0, 0, 0), (112, 112, 27)])
+    with pytest.raises(dcl_b200.DclError, match="batch of 2"):
+        engine.predict_volume(torch.cat([vol, vol]), StitchMode.REFERENCE)
+    with pytest.raises(dcl_b200.DclError, match="target"):
+        engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, target=torch.zeros(240, 240, 150, dtype=torch.uint8))
+    out = engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, want_probs=False)      # the handle still works
+    assert out["labels"].shape == (240, 240, 155)
