@@ -313,6 +313,76 @@ def profile_pass(eng, step_dev, prof_steps):
             "per_kind": {k: eng.profile_read(k) for k in KINDS}}
 
 
+def measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barrier):
+    """ONE volume per step, its patches split over the ranks (dcl_b200/sharded.py, owner-computes form): device-resident
+    and end-to-end (every rank uploads only the x-slab its patches read, rank 0 downloads the label map), timed like the
+    main loop (CUDA events / wall clock between barriers, max over ranks).  All ranks work on the same volumes."""
+    import torch.distributed as dist
+    from dcl_b200 import sharded
+    n_rot = 3
+    vols_h = [synth_volume(i)[0].pin_memory() for i in range(n_rot)]
+    tgts_h = [synth_target(i).pin_memory() for i in range(n_rot)]
+    vols_d = [v.cuda() for v in vols_h]
+    tgts_d = [t.cuda() for t in tgts_h]
+    keeps = [keep_scales(i, n_patches) for i in range(n_rot)]
+    stage = torch.empty_like(vols_d[0])
+    lab_h = torch.empty(SHAPE, dtype=torch.uint8).pin_memory()
+
+    def step_dev(i):
+        j = i % n_rot
+        return sharded.predict_volume_sharded(eng, vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j])
+
+    up_bytes = [0]
+
+    def step_e2e(i):
+        j = i % n_rot
+        up_bytes[0] = sharded.upload_own_region(vols_h[j], stage, starts)
+        out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j],
+                                             target=tgts_h[j].cuda(non_blocking=True))
+        if rank == 0:
+            lab_h.copy_(out["labels"], non_blocking=True)
+            out["counts"].cpu()
+        torch.cuda.synchronize()
+        return out
+
+    for i in range(max(2, args.warmup)):
+        step_dev(i)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        out = step_dev(i)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    # the sharded label map equals the one-GPU label map bit for bit: checked here on the last volume, outside the timing
+    j = (args.steps - 1) % n_rot
+    one = eng.predict_volume(vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j], want_probs=False)
+    identical = bool(torch.equal(one["labels"], out["labels"]) and torch.equal(one["counts"], out["counts"]))
+    for i in range(2):
+        step_e2e(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step_e2e(i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([ms, e2e_ms, float(up_bytes[0])], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms, up_max = t.tolist()
+    parts = sharded.partition_patches(n_patches, world)
+    slot = 4 * 128 ** 3 * 4
+    return {"scaling": "strong", "value": args.steps / (ms / 1e3), "unit": "volumes/s", "ms_per_volume": ms / args.steps,
+            "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "volumes/s", "ms_per_volume": e2e_ms / args.steps,
+                    "h2d_bytes_per_step_max_rank": int(up_max) + VOXELS, "d2h_bytes_per_step_rank0": VOXELS + 13 * 8},
+            "patches_per_rank": [c for _, c in parts], "load_balance_bound": n_patches / (world * max(c for _, c in parts)),
+            "exchange": "owner-computes: gather_finalize_kernel reads the covering patches' probability slots in place - "
+                        "local HBM or a peer's through CUDA IPC over NVLink; collectives: 1 x all_reduce(int32) barrier, "
+                        "1 x all_gather(uint8 label rows), 1 x all_reduce(13 x int64)",
+            "nvlink_bytes_pulled_per_volume": f"<= {n_patches * slot} (every remote probability at most once), about 1/{world} of it per rank",
+            "labels_bit_identical_to_one_gpu": identical}
+
+
 def unpack2(packed, n):
     a = np.asarray(packed, dtype=np.uint8)
     out = np.stack([a & 3, (a >> 2) & 3, (a >> 4) & 3, (a >> 6) & 3], 1).ravel()
@@ -402,9 +472,9 @@ def run_ours(args):
             j = i % n_rot
             return sharded.predict_volume_sharded(eng, vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j])
 
-        def step_e2e(i):     # every rank uploads the volume over its own PCIe link; rank 0 downloads the label map
+        def step_e2e(i):     # a rank uploads the x-slab its patches read over its own PCIe link; rank 0 downloads the label map
             j = i % n_rot
-            stage.copy_(vols_h[j], non_blocking=True)
+            sharded.upload_own_region(vols_h[j], stage, starts)
             tgt = tgts_h[j].cuda(non_blocking=True)
             out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j], target=tgt)
             if rank == 0:
@@ -535,6 +605,12 @@ def run_ours(args):
         for e in engines[1:]:
             e.close()
 
+    # ---- N > 1: the SAME run also measures ONE volume sharded by patch slab over the ranks (BASELINE configs 3 / 5:
+    # strong scaling, owner-computes exchange over NVLink), attached as a sub-record ----
+    sharded_rec = None
+    if world > 1 and not by_patch and mode != "TTA" and starts is not None and not args.no_sharded:
+        sharded_rec = measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barrier)
+
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -577,6 +653,8 @@ def run_ours(args):
         }
         if bf16_rec is not None:
             line["bf16"] = bf16_rec
+        if sharded_rec is not None:
+            line["single_volume_sharded"] = sharded_rec
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             n_cpu = min(6, n_patches)
@@ -645,6 +723,7 @@ def main():
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="bf16x3 (default) = the parity-grade tensor-core mode; bf16 = the 2e-2 class mode")
     ap.add_argument("--no-bf16", action="store_true", help="skip the plain-bf16 sub-record of a bf16x3 run")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the single-volume-sharded sub-record")
     ap.add_argument("--workload", default="overlap50", choices=sorted(WORKLOADS))
     ap.add_argument("--sharding", default="volume", choices=["volume", "patch"],
                     help="N > 1: 'volume' = one volume per rank per step (no collective, weak scaling); "

@@ -75,6 +75,14 @@ _SIGNATURES = {
     "dcl_accumulate_patches": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
+    "dcl_slots_ensure": (C.c_int, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]),
+    "dcl_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "dcl_ipc_import": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "dcl_ipc_release": (C.c_int, [C.c_void_p]),
+    "dcl_forward_patches_to_slots": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.c_int32, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "dcl_gather_finalize_range": (C.c_int, [C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.c_void_p, C.POINTER(C.c_void_p),
+                                            C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcl_finalize_labels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "dcl_export_labels": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

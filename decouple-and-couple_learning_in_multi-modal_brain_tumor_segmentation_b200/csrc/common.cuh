@@ -157,6 +157,13 @@ struct GatherPlan {
 int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,
                            float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
                            cudaStream_t st);
+// The same blend from one slot POINTER per patch (a slot may live in a peer GPU's memory, mapped through CUDA IPC and
+// read over NVLink: the multi-GPU owner-computes exchange) restricted to the rows x in [x0, x1) of the volume.
+// slots[i] = first float of patch i's (slot_planes x 128^3) slot; outputs are indexed like the whole volume.
+struct GatherSlots { const float* ptr[GatherPlan::MAX]; };
+int launch_gather_finalize_slots(const GatherSlots& slots, const GatherPlan& plan, int gaussian, int X, int Y, int Z, int x0,
+                                 int x1, float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                                 cudaStream_t st);
 // probs (4 x total) [+ wsum] -> labels / normalised probs / 13 counters over voxels [v0, v0+nvox)
 int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, int64_t v0, int64_t nvox,
                            float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,

@@ -233,6 +233,7 @@ struct dcl_handle {
   float* vol_probs = nullptr;  int64_t vol_probs_cap = 0;
   float* vol_wsum = nullptr;   int64_t vol_wsum_cap = 0;
   float* gather_buf = nullptr; int64_t gather_cap = 0;      // gather-form stitch: one probability slot per patch
+  float* shard_buf = nullptr;  int64_t shard_cap = 0;       // multi-GPU: this rank's slots, exported to the peers (CUDA IPC)
   float* tta_vol = nullptr;    int64_t tta_vol_cap = 0;      // flipped copy of the volume (TTA)
   float* tta_sum = nullptr;    int64_t tta_sum_cap = 0;      // running sum of the un-flipped softmaxes (TTA)
   float* stage_vol = nullptr;  int64_t stage_vol_cap = 0;
@@ -1421,7 +1422,6 @@ static int predict_volume_gather(dcl_handle* h, const float* vol_dev, const int3
   const int np = (int)plan.size();
   const int planes = aux_out_dev ? 16 : 4;
   const int64_t V = (int64_t)shape[0] * shape[1] * zout;
-  if ((int64_t)np * planes * P3 >= ((int64_t)1 << 31)) { set_error("predict_volume: too many patches for the gather form"); return DCL_ERR_ARG; }
   DCL_TRY(grow(h, (void**)&h->gather_buf, &h->gather_cap, (int64_t)np * planes * P3 * 4));
   const int64_t before = g_launches;
   int rc = run_patches(h, vol_dev, shape, mode, plan, 0, np, keep_scale_host, zout, nullptr, nullptr, st, h->gather_buf, planes);
@@ -1528,6 +1528,7 @@ DCL_API int dcl_destroy(dcl_handle* h) {
   if (h->vol_probs) cudaFree(h->vol_probs);
   if (h->vol_wsum) cudaFree(h->vol_wsum);
   if (h->gather_buf) cudaFree(h->gather_buf);
+  if (h->shard_buf) cudaFree(h->shard_buf);
   if (h->tta_vol) cudaFree(h->tta_vol);
   if (h->tta_sum) cudaFree(h->tta_sum);
   if (h->stage_vol) cudaFree(h->stage_vol);
@@ -1616,6 +1617,81 @@ DCL_API int dcl_accumulate_patches(dcl_handle* h, const float* vol_dev, const in
                        (cudaStream_t)stream);
   h->launches += g_launches - before;
   return rc;
+}
+
+// ---- single volume over several GPUs, owner-computes: every rank keeps the probabilities of ITS patches in
+// slots of its own memory, exports the slot buffer through CUDA IPC, and blends / labels the x-range it owns by reading
+// the covering patches' slots where they live - local memory or a peer's over NVLink - inside gather_finalize_kernel.
+DCL_API int dcl_slots_ensure(dcl_handle* h, int32_t n_slots, void** slots_dev_out) {
+  if (!h || n_slots < 1 || !slots_dev_out) { set_error("dcl_slots_ensure: bad argument"); return DCL_ERR_ARG; }
+  DCL_TRY(grow(h, (void**)&h->shard_buf, &h->shard_cap, (int64_t)n_slots * 4 * P3 * 4));
+  *slots_dev_out = h->shard_buf;
+  return DCL_OK;
+}
+
+DCL_API int dcl_ipc_export(const void* dev_ptr, void* handle64_out) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+  if (!dev_ptr || !handle64_out) { set_error("dcl_ipc_export: null argument"); return DCL_ERR_ARG; }
+  cudaIpcMemHandle_t hd;
+  DCL_CUDA_OK(cudaIpcGetMemHandle(&hd, const_cast<void*>(dev_ptr)));
+  memcpy(handle64_out, &hd, 64);
+  return DCL_OK;
+}
+
+DCL_API int dcl_ipc_import(const void* handle64, void** dev_ptr_out) {
+  if (!handle64 || !dev_ptr_out) { set_error("dcl_ipc_import: null argument"); return DCL_ERR_ARG; }
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle64, 64);
+  DCL_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr_out, hd, cudaIpcMemLazyEnablePeerAccess));
+  return DCL_OK;
+}
+
+DCL_API int dcl_ipc_release(void* dev_ptr) {
+  if (dev_ptr) DCL_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
+  return DCL_OK;
+}
+
+DCL_API int dcl_forward_patches_to_slots(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                                         int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                                         int32_t first, int32_t count, void* stream) {
+  DCL_TRY(check_handle(h));
+  if (!vol_dev || !shape) { set_error("dcl_forward_patches_to_slots: null argument"); return DCL_ERR_ARG; }
+  if (mode != DCL_STITCH_UNIFORM && mode != DCL_STITCH_GAUSSIAN) { set_error("dcl_forward_patches_to_slots: weighted stitch modes only"); return DCL_ERR_ARG; }
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  DCL_TRY(build_plan(mode, shape, n_patches, starts_host, &plan, &zout));
+  if (first < 0 || count < 0 || first + count > (int)plan.size()) { set_error("patch range outside the plan"); return DCL_ERR_ARG; }
+  if (count == 0) return DCL_OK;
+  if (h->shard_cap < (int64_t)count * 4 * P3 * 4) { set_error("dcl_forward_patches_to_slots: call dcl_slots_ensure first"); return DCL_ERR_STATE; }
+  const int64_t before = g_launches;
+  int rc = run_patches(h, vol_dev, shape, mode, plan, first, count, keep_scale_host, zout, nullptr, nullptr, (cudaStream_t)stream,
+                       h->shard_buf, 4);
+  h->launches += g_launches - before;
+  return rc;
+}
+
+DCL_API int dcl_gather_finalize_range(const int32_t shape[3], int32_t mode, int32_t n_patches, const int32_t* starts_host,
+                                      const void* const* slot_ptrs_host, int32_t x0, int32_t x1, float* probs_out_dev,
+                                      uint8_t* labels_out_dev, const uint8_t* target_dev, uint64_t* counts_out_dev, void* stream) {
+  if (!shape || !slot_ptrs_host) { set_error("dcl_gather_finalize_range: null argument"); return DCL_ERR_ARG; }
+  if (mode != DCL_STITCH_UNIFORM && mode != DCL_STITCH_GAUSSIAN) { set_error("dcl_gather_finalize_range: weighted stitch modes only"); return DCL_ERR_ARG; }
+  std::vector<PlanItem> plan;
+  int zout = 0;
+  DCL_TRY(build_plan(mode, shape, n_patches, starts_host, &plan, &zout));
+  if ((int)plan.size() > GatherPlan::MAX) { set_error("dcl_gather_finalize_range: at most 128 patches"); return DCL_ERR_ARG; }
+  GatherPlan gp;
+  GatherSlots sl;
+  gp.n = (int)plan.size();
+  gp.slot_planes = 4;
+  for (int i = 0; i < GatherPlan::MAX; ++i) {
+    sl.ptr[i] = i < gp.n ? reinterpret_cast<const float*>(slot_ptrs_host[i]) : nullptr;
+    if (i < gp.n) {
+      if (!sl.ptr[i]) { set_error("dcl_gather_finalize_range: null slot pointer"); return DCL_ERR_ARG; }
+      for (int a = 0; a < 3; ++a) gp.start[i][a] = plan[i].start[a];
+    }
+  }
+  return launch_gather_finalize_slots(sl, gp, mode == DCL_STITCH_GAUSSIAN, shape[0], shape[1], zout, x0, x1, probs_out_dev,
+                                      labels_out_dev, target_dev, (unsigned long long*)counts_out_dev, (cudaStream_t)stream);
 }
 
 DCL_API int dcl_finalize_labels(const float* acc_dev, const float* wsum_dev, int64_t voxels_total, int64_t v0, int64_t nvox,

@@ -254,10 +254,12 @@ int launch_finalize_labels(const float* acc, const float* wsum, int64_t total, i
 // ---------------------------------------------------------------------------------------------
 constexpr int GATHER_WARPS = 8;
 __global__ void __launch_bounds__(GATHER_WARPS * 32)
-gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussian, int rows, int Y, int Z,
+gather_finalize_kernel(GatherSlots slots, GatherPlan plan, int gaussian, int row0, int row1, int rows, int Y, int Z,
                        float* __restrict__ probs_out, uint8_t* __restrict__ labels, const uint8_t* __restrict__ target,
                        unsigned long long* __restrict__ counts) {
-  __shared__ int s_base[GATHER_WARPS][GatherPlan::MAX];     // slot offset of (x, y, z = 0) relative to pp, in floats
+  // this launch covers the (x,y) rows [row0, row1) of the volume; `rows` = X * Y of the whole volume (plane stride)
+  __shared__ const float* s_row[GATHER_WARPS][GatherPlan::MAX];   // address of (x, y, z = 0) in the covering patch's slot
+                                                                   // (local or peer memory; may point before the slot: z >= sz only)
   __shared__ short s_sz[GATHER_WARPS][GatherPlan::MAX];     // z origin of the patch
   __shared__ float s_wxy[GATHER_WARPS][GatherPlan::MAX];
   __shared__ unsigned s_cnt[13];
@@ -270,7 +272,7 @@ gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussi
   LabelCounts k;
 #pragma unroll
   for (int i = 0; i < 13; ++i) k.v[i] = 0;
-  for (int row = blockIdx.x * GATHER_WARPS + w; row < rows; row += gridDim.x * GATHER_WARPS) {
+  for (int row = row0 + blockIdx.x * GATHER_WARPS + w; row < row1; row += gridDim.x * GATHER_WARPS) {
     const int x = row / Y, y = row - x * Y;
     int n = 0;
     for (int i0 = 0; i0 < plan.n; i0 += 32) {
@@ -284,7 +286,7 @@ gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussi
       const unsigned m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int j = n + __popc(m & ((1u << lane) - 1u));
-        s_base[w][j] = i * (plan.slot_planes * (int)P3) + (lx * P + ly) * P - plan.start[i][2];
+        s_row[w][j] = slots.ptr[i] + ((lx * P + ly) * P - plan.start[i][2]);
         s_sz[w][j] = (short)plan.start[i][2];
         s_wxy[w][j] = blend_w1(lx, gaussian) * blend_w1(ly, gaussian);
       }
@@ -306,7 +308,7 @@ gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussi
             const int lz = z - s_sz[w][j];
             if ((unsigned)lz < (unsigned)P) {
               wt[u] = s_wxy[w][j] * s_wz[lz];
-              const float* q = pp + ((int64_t)s_base[w][j] + z);
+              const float* q = s_row[w][j] + z;
               p[u][0] = ld_stream1(q); p[u][1] = ld_stream1(q + P3); p[u][2] = ld_stream1(q + 2 * P3); p[u][3] = ld_stream1(q + 3 * P3);
             }
           }
@@ -339,15 +341,15 @@ gather_finalize_kernel(const float* __restrict__ pp, GatherPlan plan, int gaussi
   }
 }
 
-int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,
-                           float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
-                           cudaStream_t st) {
-  if (plan.n < 1 || plan.n > GatherPlan::MAX || plan.slot_planes < 4 ||
-      (int64_t)plan.n * plan.slot_planes * P3 >= ((int64_t)1 << 31)) {
-    set_error("gather_finalize: 1..128 patches and fewer than 2^31 floats of slots");
+int launch_gather_finalize_slots(const GatherSlots& slots, const GatherPlan& plan, int gaussian, int X, int Y, int Z, int x0,
+                                 int x1, float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                                 cudaStream_t st) {
+  if (plan.n < 1 || plan.n > GatherPlan::MAX || plan.slot_planes < 4 || x0 < 0 || x1 > X || x0 > x1) {
+    set_error("gather_finalize: 1..128 patches, 0 <= x0 <= x1 <= X");
     return -1;
   }
-  const int rows = X * Y;
+  if (x0 == x1) return 0;
+  const int rows = (x1 - x0) * Y;
   int blocks = (rows + GATHER_WARPS - 1) / GATHER_WARPS;
   static const int resident = [] {                 // persistent: exactly one wave of resident CTAs
     int per_sm = 0, dev = 0, sms = 148;
@@ -357,11 +359,20 @@ int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int
     return per_sm * sms;
   }();
   if (blocks > resident) blocks = resident;
-  gather_finalize_kernel<<<blocks, GATHER_WARPS * 32, 0, st>>>(patch_probs, plan, gaussian, rows, Y, Z, probs_out, labels,
-                                                              target, counts);
+  gather_finalize_kernel<<<blocks, GATHER_WARPS * 32, 0, st>>>(slots, plan, gaussian, x0 * Y, x1 * Y, X * Y, Y, Z, probs_out,
+                                                              labels, target, counts);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int launch_gather_finalize(const float* patch_probs, const GatherPlan& plan, int gaussian, int X, int Y, int Z,
+                           float* probs_out, uint8_t* labels, const uint8_t* target, unsigned long long* counts,
+                           cudaStream_t st) {
+  GatherSlots sl;
+  for (int i = 0; i < GatherPlan::MAX; ++i)
+    sl.ptr[i] = i < plan.n ? patch_probs + (int64_t)i * plan.slot_planes * P3 : nullptr;
+  return launch_gather_finalize_slots(sl, plan, gaussian, X, Y, Z, 0, X, probs_out, labels, target, counts, st);
 }
 
 // ---------------------------------------------------------------------------------------------

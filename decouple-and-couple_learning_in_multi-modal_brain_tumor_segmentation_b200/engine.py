@@ -276,6 +276,43 @@ class Engine:
         N.check(self._lib.dcl_finalize_labels(_ptr(acc), _ptr(wsum), total, int(v0), int(nvox), _ptr(probs_out),
                                               _ptr(labels), _ptr(target), _ptr(counts), _stream()))
 
+    # ---- multi-GPU, owner-computes form (sharded.py) ----------------------------------------------
+    def slots_ensure(self, n_slots):
+        """Device address of this handle's exportable slot buffer, sized for n_slots patches (4 x 128^3 fp32 each)."""
+        p = C.c_void_p()
+        N.check(self._lib.dcl_slots_ensure(self._h, int(n_slots), C.byref(p)))
+        return int(p.value)
+
+    def ipc_export(self, dev_ptr):
+        buf = C.create_string_buffer(64)
+        N.check(self._lib.dcl_ipc_export(C.c_void_p(int(dev_ptr)), buf))
+        return buf.raw
+
+    def ipc_import(self, handle):
+        p = C.c_void_p()
+        N.check(self._lib.dcl_ipc_import(C.create_string_buffer(bytes(handle), 64), C.byref(p)))
+        return int(p.value)
+
+    def ipc_release(self, dev_ptr):
+        N.check(self._lib.dcl_ipc_release(C.c_void_p(int(dev_ptr))))
+
+    def forward_patches_to_slots(self, vol, mode, starts, keep_scales, first, count):
+        vol = _single(vol, "vol").contiguous()
+        mode, n, s_arr, k_arr = self._plan_args(mode, starts, keep_scales)
+        shape = (C.c_int32 * 3)(*[int(v) for v in vol.shape[1:]])
+        N.check(self._lib.dcl_forward_patches_to_slots(
+            self._h, _ptr(vol), shape, int(mode), n, s_arr.ctypes.data_as(C.c_void_p),
+            k_arr.ctypes.data_as(C.c_void_p) if k_arr is not None else C.c_void_p(0), int(first), int(count), _stream()))
+
+    def gather_finalize_range(self, shape, mode, starts, slot_ptrs, x0, x1, labels, target=None, counts=None, probs_out=None):
+        """Blend + normalise + arg-max + counters of the rows x0 <= x < x1 from one slot pointer per patch (local or
+        IPC-mapped peer memory).  labels / target / probs_out are whole-volume tensors."""
+        mode, n, s_arr, _ = self._plan_args(mode, starts, None)
+        ptrs = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in slot_ptrs])
+        shp = (C.c_int32 * 3)(*[int(v) for v in shape])
+        N.check(self._lib.dcl_gather_finalize_range(shp, int(mode), n, s_arr.ctypes.data_as(C.c_void_p), ptrs, int(x0), int(x1),
+                                                    _ptr(probs_out), _ptr(labels), _ptr(target), _ptr(counts), _stream()))
+
     # ---- introspection -------------------------------------------------------------------
     def read_stage(self, name):
         n = N.check(self._lib.dcl_read_stage(self._h, name.encode(), C.c_void_p(0), 0, _stream()))

@@ -1,16 +1,25 @@
 """One volume sharded over the GPUs of a box (BASELINE.json configs 3 and 5).
 
-A patch is indivisible (InstanceNorm and the top-k selections are global over it), so the unit of
-sharding is the patch: the z-major patch list is cut into `world` contiguous chunks ("slabs"), each rank
-accumulates its patches into a private full-size fp32 accumulator (`dcl_accumulate_patches`), ONE exchange
-step sums the overlapped logits so that rank g owns voxel range g (NCCL reduce-scatter over NVLink; an
-all-reduce where the backend has no reduce-scatter), the owner normalises + arg-maxes + counts its range
-(`dcl_finalize_labels`), and the uint8 labels are all-gathered / the 13 counters all-reduced.
+A patch is indivisible (InstanceNorm and the top-k selections are global over it), so the unit of sharding is the
+patch: the z-major patch list is cut into `world` contiguous chunks ("slabs").
 
-The reference has no counterpart (its inference is single-GPU, test_overlap.py:78); the stitched result is
-defined by predict_overlap.py:31-58 and must not depend on the number of ranks, which the tests check.
-The arithmetic callables default to the CUDA engine; tests inject CPU stand-ins to exercise this host
-logic under the `gloo` backend.
+predict_volume_sharded - the default, OWNER-COMPUTES form.  Rank r forwards its patches into probability slots in its
+own HBM; rank g owns the rows x in owned_x_range(X, g, world) of the output and produces them with ONE kernel
+(`dcl_gather_finalize_range`) that reads, for every owned voxel, the covering patches' probabilities from the slot they
+were written to - local memory or a PEER's, mapped through CUDA IPC and pulled over NVLink inside the kernel.  Nothing is
+accumulated across ranks and no accumulator is exchanged: each probability crosses NVLink at most once (about
+604 MB / world per rank for the 18-patch plan instead of 179 MB x 5 reduce-scatters), the sums run in patch order exactly
+as on one GPU, so the label map is BIT-IDENTICAL to the single-GPU result (tests assert equality).  Collectives:
+one tiny all-reduce as the stream-ordered "slots written" barrier, one all-gather of the uint8 label rows (8.9 MB in
+total) and one all-reduce of the 13 counters (which is also the "slots free again" barrier of the next volume).
+
+predict_volume_sharded_accumulate - the round-1 form, kept for comparison: private full-size fp32 accumulators
+(`dcl_accumulate_patches`) summed by NCCL reduce-scatter, owner finalises a flat voxel range.
+
+The reference has no counterpart (its inference is single-GPU, test_overlap.py:78); the stitched result is defined by
+predict_overlap.py:31-58 (+ the sum-then-divide blend of predict_cls.py:184-203) and must not depend on the number of
+ranks.  The arithmetic callables default to the CUDA engine; tests inject CPU stand-ins to exercise this host logic
+under the `gloo` backend.
 """
 from __future__ import annotations
 
@@ -66,8 +75,8 @@ def _exchange(acc, wsum, rank, world, group):
     return (acc[:, v0:v0 + n].contiguous(), wsum[v0:v0 + n].contiguous() if wsum is not None else None, v0, n)
 
 
-def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, keep_scales=None, target=None,
-                           group=None, accumulate=None, finalize=None):
+def predict_volume_sharded_accumulate(engine, vol, mode=StitchMode.UNIFORM, starts=None, keep_scales=None, target=None,
+                                      group=None, accumulate=None, finalize=None):
     """All ranks call this with the SAME volume / plan; returns dict(labels uint8 (X,Y,Zout), counts int64[13])
     identical on every rank.
 
@@ -113,3 +122,153 @@ def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, ke
     else:
         labels = labels_l[:total]
     return {"labels": labels.reshape(X, Y, zout), "counts": counts, "patches": (first, count)}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# owner-computes form
+# ------------------------------------------------------------------------------------------------------------------
+PATCH = 128
+SLOT_FLOATS = 4 * PATCH ** 3
+
+
+def owned_x_range(X: int, rank: int, world: int):
+    """Rows x0 <= x < x1 of the output volume owned by `rank`: contiguous blocks of ceil(X / world) x-planes (X is the
+    slowest axis, so an owned block is one contiguous voxel range and the label all-gather needs no packing)."""
+    step = -(-X // world)
+    x0 = min(rank * step, X)
+    return x0, min(x0 + step, X)
+
+
+def patch_owner(n_patches: int, world: int):
+    """[(rank, local slot index)] per patch of the plan, consistent with partition_patches."""
+    out = []
+    for r, (first, count) in enumerate(partition_patches(n_patches, world)):
+        out += [(r, i) for i in range(count)]
+    return out
+
+
+class _PeerSlots:
+    """This rank's slot buffer and the IPC-mapped slot buffers of its peers (set up once per engine / group / plan size
+    and reused for every volume)."""
+
+    def __init__(self, engine, group, n_patches):
+        self.engine, self.group, self.n_patches = engine, group, n_patches
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        parts = partition_patches(n_patches, self.world)
+        self.first, self.count = parts[self.rank]
+        self.local = engine.slots_ensure(max(1, max(c for _, c in parts)))
+        self.bases = [self.local] * self.world
+        self.imported = []
+        if self.world > 1:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, engine.ipc_export(self.local), group=group)
+            for r in range(self.world):
+                if r != self.rank:
+                    self.bases[r] = engine.ipc_import(handles[r])
+                    self.imported.append(self.bases[r])
+        self.ptrs = [self.bases[r] + i * SLOT_FLOATS * 4 for r, i in patch_owner(n_patches, self.world)]
+
+    def close(self):
+        for p in self.imported:
+            try:
+                self.engine.ipc_release(p)
+            except Exception:
+                pass
+        self.imported = []
+
+
+def _peer_slots(engine, group, n_patches):
+    cache = engine.__dict__.setdefault("_shard_ctx", {})
+    key = (id(group), n_patches)
+    ctx = cache.get(key)
+    if ctx is None or ctx.local != engine.slots_ensure(max(1, ctx.count)):     # (the buffer only ever grows)
+        if ctx is not None:
+            ctx.close()
+        ctx = cache[key] = _PeerSlots(engine, group, n_patches)
+    return ctx
+
+
+def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, keep_scales=None, target=None, group=None,
+                           forward_to_slots=None, finalize_range=None):
+    """All ranks call this with the SAME plan (and the same volume, of which a rank reads only its patches' boxes);
+    returns dict(labels uint8 (X,Y,Z), counts int64[13]) identical on every rank and bit-identical to one GPU.
+
+    Test hooks (CPU / gloo): forward_to_slots(vol, mode, starts, keep_scales, first, count) -> (count, 4, 128, 128, 128)
+    tensor; finalize_range(slots: list of per-patch tensors, x0, x1, labels (X,Y,Z), target | None, counts).  With the
+    hooks the slots travel by all_gather (the CPU stand-in for peer memory); without them the CUDA engine is used."""
+    mode = StitchMode(mode)
+    if mode not in (StitchMode.UNIFORM, StitchMode.GAUSSIAN) or not starts:
+        raise DclError("predict_volume_sharded: weighted stitch modes with a patch list (the reference's 8-corner "
+                       "crop-overwrite plan has no overlap to exchange: use predict_volume_sharded_accumulate)")
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if vol.dim() == 5:
+        if vol.shape[0] != 1:
+            raise DclError("one volume per call")
+        vol = vol[0]
+    X, Y, Z = (int(v) for v in vol.shape[1:])
+    n_patches = len(starts)
+    first, count = partition_patches(n_patches, world)[rank]
+    x0, x1 = owned_x_range(X, rank, world)
+    dev = vol.device
+    step = -(-X // world)
+    labels = torch.empty((world * step, Y, Z), dtype=torch.uint8, device=dev)      # padded to whole blocks for the gather
+    counts = torch.zeros(13, dtype=torch.int64, device=dev)
+    if target is not None:
+        target = target.to(device=dev, dtype=torch.uint8).contiguous()
+        if tuple(target.shape) != (X, Y, Z):
+            raise DclError(f"target must have shape {(X, Y, Z)}")
+    hooks = forward_to_slots is not None or finalize_range is not None
+    if hooks:
+        mine = forward_to_slots(vol, mode, starts, keep_scales, first, count)
+        slots = [None] * n_patches
+        if world > 1:
+            cmax = max(c for _, c in partition_patches(n_patches, world))
+            pad = torch.zeros((cmax, 4, PATCH, PATCH, PATCH), dtype=torch.float32, device=dev)
+            pad[:count] = mine
+            allp = [torch.empty_like(pad) for _ in range(world)]
+            dist.all_gather(allp, pad, group=group)
+            for i, (r, j) in enumerate(patch_owner(n_patches, world)):
+                slots[i] = allp[r][j]
+        else:
+            slots = list(mine)
+        if x1 > x0:
+            finalize_range(slots, x0, x1, labels[:X], target, counts)
+    else:
+        ctx = _peer_slots(engine, group, n_patches)
+        if count > 0:
+            engine.forward_patches_to_slots(vol, mode, starts, keep_scales, first, count)
+        if world > 1:      # stream-ordered barrier: every rank's slots are written before anybody reads them
+            flag = torch.ones(1, dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=group)
+        if x1 > x0:
+            engine.gather_finalize_range((X, Y, Z), mode, starts, ctx.ptrs, x0, x1, labels[:X], target=target, counts=counts)
+    if world > 1:
+        dist.all_gather_into_tensor(labels.view(-1), labels[rank * step:(rank + 1) * step].reshape(-1).clone(), group=group)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return {"labels": labels[:X], "counts": counts, "patches": (first, count), "rows": (x0, x1)}
+
+
+def own_x_box(starts, first, count, X):
+    """x range [xa, xb) of the input volume that the patches [first, first+count) of the plan read."""
+    if count == 0:
+        return 0, 0
+    xs = [int(starts[i][0]) for i in range(first, first + count)]
+    return max(0, min(xs)), min(X, max(xs) + PATCH)
+
+
+def upload_own_region(vol_host, stage_dev, starts, group=None):
+    """Host-to-device copy of ONLY the x-slab of the (pinned) host volume that this rank's patches read, into the same
+    place of a full-size device staging volume (X is the slowest axis: one contiguous copy per modality).  Returns the
+    number of bytes copied.  With 18 patches on 8 ranks a rank uploads 53-78 MB instead of 143 MB."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if vol_host.dim() == 5:
+        vol_host = vol_host[0]
+    X = int(vol_host.shape[1])
+    first, count = partition_patches(len(starts), world)[rank]
+    xa, xb = own_x_box(starts, first, count, X)
+    if xb > xa:
+        stage_dev[:, xa:xb].copy_(vol_host[:, xa:xb], non_blocking=True)
+    return 4 * (xb - xa) * int(vol_host.shape[2]) * int(vol_host.shape[3]) * 4

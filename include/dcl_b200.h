@@ -154,7 +154,29 @@ DCL_API int dcl_predict_volume_tta(dcl_handle* h, const float* vol_dev, const in
                            float* probs_out_dev, uint8_t* labels_out_dev, const uint8_t* target_dev,
                            uint64_t* counts_out_dev, void* stream);
 
-/* ---- multi-GPU: a rank runs only patches [first, first+count) of the plan into its
+/* ---- multi-GPU, owner-computes (BASELINE.json configs 3 and 5): the reference runs single-GPU
+ * (test_overlap.py:78); this is the sharded form of predict_overlap.tailor_and_concat + the arg-max tail
+ * (predict_overlap.py:31-58, :141-153).  Rank r forwards patches [first, first+count) of the z-major plan into slots of
+ * ITS OWN memory (dcl_slots_ensure + dcl_forward_patches_to_slots), exports the slot buffer to its peers through CUDA
+ * IPC (dcl_ipc_export / dcl_ipc_import: one process per GPU, one node), and after a stream-ordered barrier blends,
+ * normalises and labels the x-range [x0, x1) it owns with dcl_gather_finalize_range, whose kernel reads every covering
+ * patch's probabilities where they live - local HBM or a peer's over NVLink.  No accumulator is exchanged, every
+ * probability crosses NVLink at most once, and the label map is bit-identical to the single-GPU gather form. */
+DCL_API int dcl_slots_ensure(dcl_handle* h, int32_t n_slots, void** slots_dev_out);
+DCL_API int dcl_ipc_export(const void* dev_ptr, void* handle64_out);
+DCL_API int dcl_ipc_import(const void* handle64, void** dev_ptr_out);
+DCL_API int dcl_ipc_release(void* dev_ptr);
+DCL_API int dcl_forward_patches_to_slots(dcl_handle* h, const float* vol_dev, const int32_t shape[3], int32_t mode,
+                                         int32_t n_patches, const int32_t* starts_host, const float* keep_scale_host,
+                                         int32_t first, int32_t count, void* stream);
+/* slot_ptrs_host: n_patches device pointers (slot of patch i = 4 x 128^3 floats, local or IPC-mapped); outputs are
+ * whole-volume buffers of which only the rows x0 <= x < x1 are written; counts_out_dev += the 13 counters of the range */
+DCL_API int dcl_gather_finalize_range(const int32_t shape[3], int32_t mode, int32_t n_patches, const int32_t* starts_host,
+                                      const void* const* slot_ptrs_host, int32_t x0, int32_t x1, float* probs_out_dev,
+                                      uint8_t* labels_out_dev, const uint8_t* target_dev, uint64_t* counts_out_dev, void* stream);
+
+/* ---- multi-GPU building blocks of the accumulate form (kept for the reduce-scatter variant and the tests): a rank runs
+ * only patches [first, first+count) of the plan into its
  * private fp32 accumulator (acc: 4 x X x Y x Zout weighted sums, wsum: X x Y x Zout); the
  * accumulators are then summed across ranks by the caller (NCCL reduce-scatter / all-reduce
  * through torch.distributed) and finalised into labels. */

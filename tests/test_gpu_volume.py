@@ -165,13 +165,14 @@ def test_sharded_path_world1_equals_predict_volume(engine, vol):
     keeps = np.ones((len(starts), 16), np.float32)
     tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
     want = engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt, want_probs=False)
-    got = sharded.predict_volume_sharded(engine, vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
-    torch.cuda.synchronize()
-    assert torch.equal(got["labels"], want["labels"])
-    assert torch.equal(got["counts"], want["counts"])
+    for fn in (sharded.predict_volume_sharded, sharded.predict_volume_sharded_accumulate):     # owner-computes / reduce-scatter
+        got = fn(engine, vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
+        torch.cuda.synchronize()
+        assert torch.equal(got["labels"], want["labels"]), fn.__name__
+        assert torch.equal(got["counts"], want["counts"]), fn.__name__
 
 
-def _sharded_rank(rank, world, port, out_dir, sd):
+def _sharded_rank(rank, world, port, out_dir, sd, precision="FP32"):
     import os
     import torch.distributed as dist
     import dcl_b200
@@ -181,16 +182,19 @@ def _sharded_rank(rank, world, port, out_dir, sd):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        eng = dcl_b200.Engine(dcl_b200.Precision.FP32)
+        eng = dcl_b200.Engine(dcl_b200.Precision[precision])
         eng.load_state_dict(sd)
         starts = patch_starts((240, 240, 155), 96)
         keeps = np.ones((len(starts), 16), np.float32)
         v = volume_input(0).cuda()
         tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
         out = sharded.predict_volume_sharded(eng, v, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
+        out2 = sharded.predict_volume_sharded(eng, v, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)   # reuse of the slots
+        acc = sharded.predict_volume_sharded_accumulate(eng, v, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
         torch.cuda.synchronize()
+        assert torch.equal(out["labels"], out2["labels"]) and torch.equal(out["counts"], out2["counts"])
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), labels=out["labels"].cpu().numpy(),
-                 counts=out["counts"].cpu().numpy())
+                 counts=out["counts"].cpu().numpy(), acc_labels=acc["labels"].cpu().numpy(), acc_counts=acc["counts"].cpu().numpy())
         eng.close()
     finally:
         dist.destroy_process_group()
@@ -198,8 +202,10 @@ def _sharded_rank(rank, world, port, out_dir, sd):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_sharded_two_gpus_nccl_equals_one_gpu(engine, vol, seed0_state_dict, tmp_path):
-    """One volume, patches split over 2 ranks, NCCL reduce-scatter of the accumulators: the label map may differ from
-    the single-GPU result only where fp32 re-association of the overlap sums flips a near-tie (<= 1e-4 of voxels)."""
+    """One volume, patches split over 2 ranks.  Owner-computes form (per-rank slots, peer reads over NVLink inside
+    gather_finalize_kernel): the label map and the counters EQUAL the single-GPU result bit for bit.  Accumulate form
+    (NCCL reduce-scatter of the accumulators): may differ only where fp32 re-association of the overlap sums flips a
+    near-tie (<= 1e-4 of voxels)."""
     import socket
     import torch.multiprocessing as mp
     from dcl_b200 import StitchMode, patch_starts
@@ -215,8 +221,9 @@ def test_sharded_two_gpus_nccl_equals_one_gpu(engine, vol, seed0_state_dict, tmp
     r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
     assert np.array_equal(r0["labels"], r1["labels"]) and np.array_equal(r0["counts"], r1["counts"])
     wl = want["labels"].cpu().numpy()
-    assert (r0["labels"] != wl).mean() <= 1e-4
-    assert np.abs(r0["counts"][:4] - want["counts"].cpu().numpy()[:4]).sum() <= 2e-4 * wl.size
+    assert np.array_equal(r0["labels"], wl) and np.array_equal(r0["counts"], want["counts"].cpu().numpy())
+    assert (r0["acc_labels"] != wl).mean() <= 1e-4
+    assert np.abs(r0["acc_counts"][:4] - want["counts"].cpu().numpy()[:4]).sum() <= 2e-4 * wl.size
 
 
 def test_tta_matches_oracle_algebra(engine, vol):

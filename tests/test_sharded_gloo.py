@@ -44,6 +44,29 @@ def _cpu_finalize(acc_l, wsum_l, labels_l, tgt_l, counts):
     counts += torch.tensor(c, dtype=torch.int64)
 
 
+def _cpu_forward_to_slots(vol, mode, starts, keep_scales, first, count):
+    return torch.from_numpy(np.stack([_patch_probs(i) for i in range(first, first + count)])) if count else torch.zeros((0, 4, 128, 128, 128))
+
+
+def _cpu_finalize_range(slots, x0, x1, labels, target, counts):
+    """Owner-computes stand-in: blend of the rows x0 <= x < x1 from per-patch slots (here tensors that travelled by
+    all_gather; on the GPU pointers into local / peer memory), in patch order like gather_finalize_kernel."""
+    X, Y, Z = SHAPE
+    starts = S.patch_starts(SHAPE, 16)
+    acc = np.zeros((4, x1 - x0, Y, Z), np.float32)
+    w = np.zeros((x1 - x0, Y, Z), np.float32)
+    for p, (sx, sy, sz) in zip(slots, starts):
+        a, b = max(sx, x0), min(sx + 128, x1)
+        if a < b:
+            acc[:, a - x0:b - x0, sy:sy + 128, sz:sz + 128] += p.numpy()[:, a - sx:b - sx]
+            w[a - x0:b - x0, sy:sy + 128, sz:sz + 128] += 1.0
+    lab = (acc / w[None]).argmax(0)
+    labels[x0:x1] = torch.from_numpy(lab.astype(np.uint8))
+    c = [int((lab == k).sum()) for k in range(4)]
+    c += [v for trip in S.region_counts(lab, target[x0:x1].numpy()) for v in trip] if target is not None else [0] * 9
+    counts += torch.tensor(c, dtype=torch.int64)
+
+
 def _expected(starts, target):
     want = S.accumulate_from_probs([_patch_probs(i) for i in range(len(starts))], starts, "uniform", shape=SHAPE)
     lab = S.labels_from_probs(want)
@@ -60,11 +83,14 @@ def _worker(rank, world, port, out_dir):
         starts = S.patch_starts(SHAPE, 16)
         target = np.random.RandomState(7).randint(0, 4, SHAPE)
         vol = torch.zeros((4,) + SHAPE)
-        out = sharded.predict_volume_sharded(None, vol, StitchMode.UNIFORM, starts=starts,
-                                             target=torch.from_numpy(target), accumulate=_cpu_accumulate,
-                                             finalize=_cpu_finalize)
+        out = sharded.predict_volume_sharded_accumulate(None, vol, StitchMode.UNIFORM, starts=starts,
+                                                        target=torch.from_numpy(target), accumulate=_cpu_accumulate,
+                                                        finalize=_cpu_finalize)
+        own = sharded.predict_volume_sharded(None, vol, StitchMode.UNIFORM, starts=starts, target=torch.from_numpy(target),
+                                             forward_to_slots=_cpu_forward_to_slots, finalize_range=_cpu_finalize_range)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), labels=out["labels"].numpy(), counts=out["counts"].numpy(),
-                 patches=np.array(out["patches"]))
+                 patches=np.array(out["patches"]), own_labels=own["labels"].numpy(), own_counts=own["counts"].numpy(),
+                 own_rows=np.array(own["rows"]))
     finally:
         dist.destroy_process_group()
 
@@ -73,6 +99,18 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+def test_owner_ranges_and_patch_owners():
+    for world in (1, 2, 3, 7, 8):
+        for X in (240, 144, 10):
+            rs = [sharded.owned_x_range(X, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == X
+            for (a, b), (c, _) in zip(rs, rs[1:]):
+                assert a <= b == c
+    assert sharded.owned_x_range(240, 7, 8) == (210, 240)
+    owners = sharded.patch_owner(18, 8)
+    assert owners[:4] == [(0, 0), (0, 1), (0, 2), (1, 0)] and owners[-1] == (7, 1) and len(owners) == 18
 
 
 def test_partition_and_ranges():
@@ -98,14 +136,22 @@ def test_two_rank_gloo_equals_single_process_oracle(tmp_path):
     want_labels, want_counts = _expected(starts, target)
     got = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     assert got[0]["patches"].tolist() == [0, 4] and got[1]["patches"].tolist() == [4, 4]
-    for g in got:                                   # every rank ends with the full, identical result
+    for g in got:                                   # every rank ends with the full, identical result - in both forms
         assert np.array_equal(g["labels"], want_labels)
         assert g["counts"].tolist() == want_counts
+        assert np.array_equal(g["own_labels"], want_labels)
+        assert g["own_counts"].tolist() == want_counts
+    assert got[0]["own_rows"].tolist() == [0, 72] and got[1]["own_rows"].tolist() == [72, 144]
 
 
 def test_single_process_path_needs_no_process_group():
     starts = S.patch_starts(SHAPE, 16)[:2]
     vol = torch.zeros((4,) + SHAPE)
-    out = sharded.predict_volume_sharded(None, vol, StitchMode.UNIFORM, starts=starts, accumulate=_cpu_accumulate,
-                                         finalize=lambda a, w, l, t, c: l.zero_())
+    out = sharded.predict_volume_sharded_accumulate(None, vol, StitchMode.UNIFORM, starts=starts, accumulate=_cpu_accumulate,
+                                                    finalize=lambda a, w, l, t, c: l.zero_())
     assert out["patches"] == (0, 2) and out["labels"].shape == SHAPE
+    full = S.patch_starts(SHAPE, 16)
+    own = sharded.predict_volume_sharded(None, vol, StitchMode.UNIFORM, starts=full, forward_to_slots=_cpu_forward_to_slots,
+                                         finalize_range=_cpu_finalize_range)
+    want_labels, _ = _expected(full, np.zeros(SHAPE, np.int64))
+    assert own["patches"] == (0, 8) and own["rows"] == (0, 144) and np.array_equal(own["labels"].numpy(), want_labels)
