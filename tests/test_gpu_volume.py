@@ -213,7 +213,7 @@ def test_sharded_two_gpus_nccl_equals_one_gpu(engine, vol, seed0_state_dict, tmp
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     sd = {k: v.cpu() for k, v in seed0_state_dict.items()}
-    mp.spawn(_sharded_rank, args=(2, port, str(tmp_path), sd), nprocs=2, join=True)
+    mp.spawn(_sharded_rank, args=(2, port, str(tmp_path), sd, engine.precision.name), nprocs=2, join=True)
     starts = patch_starts((240, 240, 155), 96)
     keeps = np.ones((len(starts), 16), np.float32)
     tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
