@@ -897,7 +897,8 @@ int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st) {
   p.out_mode = g.out_mode; p.gelu = g.gelu;
   p.x3 = g.x3 ? 1 : 0;
   p.w_lo = w.lo_off / 16;
-  if (g.x3 && (w.lo_off == 0 || (w.cin % 16) != 0 && g.a1 != nullptr)) { set_error("gemm_conv: split-bf16 needs split weights"); return -1; }
+  if (w.layout != 0) { set_error("gemm_conv: weights packed for the rolling kernel"); return -1; }
+  if (g.x3 && (w.lo_off == 0 || ((w.cin % 16) != 0 && g.a1 != nullptr))) { set_error("gemm_conv: split-bf16 needs split weights"); return -1; }
   p.OD = (g.D - 1) / g.stride + 1; p.OH = (g.H - 1) / g.stride + 1; p.OW = (g.W - 1) / g.stride + 1;
   if (p.out_mode == 1 && (p.cout % 16) != 0) { set_error("gemm_conv: row-major output needs cout % 16 == 0"); return -1; }
   return launch_gemm_params(p, st);
@@ -952,6 +953,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   p.out_mode = g.out_mode; p.gelu = g.gelu;
   p.x3 = g.x3 ? 1 : 0;
   p.w_lo = w.lo_off / 16;
+  if (w.layout != 0) { set_error("slab_conv: weights packed for the rolling kernel"); return -1; }
   if (g.x3 && w.lo_off == 0) { set_error("slab_conv: split-bf16 needs split weights"); return -1; }
   const int xs = p.x3;
   sp.sums = norm ? norm->sums : nullptr;

@@ -29,13 +29,21 @@ using namespace tc;
 
 cudaError_t trace_set_conv_tc(long long* p, int cta) { return trace_set_local(p, cta); }
 
-// X3_: split-bf16 (DCL_BF16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (exactly
-// the global layout, so a plane is still one bulk copy per chunk), the weights a hi image followed by a lo image, and
-// every (tap, K step) issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo into the same accumulator.
-template <int C_, int G_, int TH_, bool KHN_, int NSLOT_, bool X3_ = false>
+// X3_: split-bf16 (DCL_BF16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (a plane is
+// still one bulk copy per chunk).  The weights hold, per K chunk, the hi rows followed by the lo rows of every output
+// row block: B' = [W_hi | W_lo] stacked along N, so that ONE MMA A x B' fills two accumulators D1 (x W_hi) and D2
+// (x W_lo).  Per (tap, K step) two MMAs are issued, A_hi x B' and A_lo x B':
+//     D1 = a_hi*w_hi + a_lo*w_hi,   D2 = a_hi*w_lo + a_lo*w_lo,   result = D1 + D2 (formed by the epilogue)
+// - all four partial products for two operand reads (a narrow-N MMA is bound by its A read, so three separate MMAs
+// cost 1.5x as much; measured 193 -> us per 16-channel layer).
+// CI_ < CO_: the kernel covers CI_ of the layer's input channels per launch (the split weights of a 32 -> 32 layer do
+// not fit next to the staged planes); the layer then runs as CO_/CI_ launches, the later ones adding to the earlier
+// ones' output through the residual input.
+template <int CI_, int CO_, int G_, int TH_, bool KHN_, int NSLOT_, bool X3_ = false>
 struct RollCfg {
-  static constexpr int C = C_, G = G_, TH = TH_;
+  static constexpr int CI = CI_, CO = CO_, G = G_, TH = TH_;
   static constexpr bool X3 = X3_;
+  static constexpr int NP = X3 ? 2 : 1;           // accumulator parts per output (D1, D2)
   static constexpr bool KHN = KHN_;               // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
   static constexpr int W = G;                     // staged rows have NO halo columns (kw = 0/2 use lane masks)
   static constexpr int ROWS = TH + 2;
@@ -43,21 +51,20 @@ struct RollCfg {
                                                   // (and the bulk copies that fill them) stay 128-byte aligned - a 16-byte offset
                                                   // destination made the plane copies land at ~9 instead of ~45 B/clk
   static constexpr int NPOS = ROWS * W + 2 * PAD; // positions per channel chunk of one plane
-  static constexpr int KC = C / 8;                // 16-byte channel chunks
+  static constexpr int KC = CI / 8;               // 16-byte channel chunks
   static constexpr int KCS = X3 ? 2 * KC : KC;    // staged chunks per plane
-  static constexpr int KS = C / 16;               // K = 16 MMA steps per tap
+  static constexpr int KS = CI / 16;              // K = 16 MMA steps per tap
   static constexpr int SLOT_BYTES = KCS * NPOS * 16;
   static constexpr int NSLOT = NSLOT_;            // staged planes: 3 feeding the MMAs + (NSLOT-3) in flight
   static constexpr int TROWS = 128 / W;           // output rows per 128-voxel M tile (1 for W=128, 2 for W=64)
   static constexpr int NT = TH / TROWS;           // M tiles per plane
-  static constexpr int ACC_COLS = NT * C;         // TMEM columns of one accumulator buffer
+  static constexpr int ACC_COLS = NT * CO * NP;   // TMEM columns of one accumulator buffer
   static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128
                                    : 2 * ACC_COLS <= 256 ? 256 : 512;
-  static constexpr int W_HALF = 27 * C * C * 2;   // one weight image
-  static constexpr int W_BYTES = X3 ? 2 * W_HALF : W_HALF;
+  static constexpr int W_BYTES = 27 * CI * CO * NP * 2;
   static constexpr int OFF_W = NSLOT * SLOT_BYTES;
-  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // scale[C], shift[C], bias[C], out_scale[C] floats
-  static constexpr int OFF_BAR = OFF_SMALL + 4 * C * 4;      // 16-byte aligned (C multiple of 16)
+  static constexpr int OFF_SMALL = OFF_W + W_BYTES;          // scale[CI], shift[CI], bias[CO], out_scale[CO] floats
+  static constexpr int OFF_BAR = OFF_SMALL + (2 * CI + 2 * CO) * 4;   // 16-byte aligned (channel counts are multiples of 16)
   static constexpr int SMEM_BYTES = OFF_BAR + (3 * NSLOT + 5) * 8 + 16;
   static_assert(W == 64 || W == 128, "rows must tile 128-voxel M tiles");
   static_assert(!KHN || TROWS == 1, "kh stacking needs one-row M tiles");
@@ -100,6 +107,8 @@ struct RollParams {
   uint4* yb;                // B-format output
   stat_t* stats;            // 2*C fixed-point sums += (sum, sum of squares) of the fp32 outputs, or nullptr
   int dsplit;
+  int cin_off;              // first input channel this launch covers (CI < layer Cin: one launch per CI channels)
+  int cin_total;            // channels of the input tensor xb (its lo planes start cin_total / 8 chunks in)
 };
 
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
@@ -111,14 +120,14 @@ __global__ void __launch_bounds__(ROLL_THREADS, 1)
 conv3d_k3_roll_kernel(RollParams prm) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
-  constexpr int C = Cfg::C, G = Cfg::G, TH = Cfg::TH, W = Cfg::W, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
-  constexpr int ROWS = Cfg::ROWS, KC = Cfg::KC, KCS = Cfg::KCS;
+  constexpr int CI = Cfg::CI, CO = Cfg::CO, G = Cfg::G, TH = Cfg::TH, W = Cfg::W, NPOS = Cfg::NPOS, NSLOT = Cfg::NSLOT;
+  constexpr int ROWS = Cfg::ROWS, KC = Cfg::KC, KCS = Cfg::KCS, NP = Cfg::NP;
   constexpr bool X3 = Cfg::X3;
   extern __shared__ __align__(128) uint8_t smem[];
-  float* s_scale = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);   // rstd
-  float* s_shift = s_scale + C;                                        // -mean * rstd
-  float* s_bias = s_shift + C;
-  float* s_oscale = s_bias + C;
+  float* s_scale = reinterpret_cast<float*>(smem + Cfg::OFF_SMALL);   // rstd of the CI input channels of this launch
+  float* s_shift = s_scale + CI;                                       // -mean * rstd
+  float* s_bias = s_shift + CI;
+  float* s_oscale = s_bias + CO;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);   // plane staged + transformed
   uint64_t* bar_empty = bar_full + NSLOT;                                  // MMAs reading the slot are done
   uint64_t* bar_land = bar_empty + NSLOT;                                  // bulk copies of the plane landed
@@ -151,18 +160,21 @@ conv3d_k3_roll_kernel(RollParams prm) {
         make_uint4(0u, 0u, 0u, 0u);
   }
   const bool has_norm = prm.sums != nullptr || prm.mean != nullptr;
-  if (tid < C) {
+  if (tid < CI) {
     float m = 0.f, r = 1.f;
+    const int c = prm.cin_off + tid;
     if (prm.sums != nullptr) {
-      stat_mean_rstd(prm.sums, tid, prm.inv_n, &m, &r);
+      stat_mean_rstd(prm.sums, c, prm.inv_n, &m, &r);
     } else if (prm.mean != nullptr) {
-      m = prm.mean[tid];
-      r = prm.rstd[tid];
+      m = prm.mean[c];
+      r = prm.rstd[c];
     }
     s_scale[tid] = r;
     s_shift[tid] = -m * r;
-    s_bias[tid] = prm.bias ? prm.bias[tid] : 0.f;
-    s_oscale[tid] = prm.out_scale ? prm.out_scale[tid] : 1.f;
+  }
+  if (tid >= 64 && tid < 64 + CO) {
+    s_bias[tid - 64] = prm.bias ? prm.bias[tid - 64] : 0.f;
+    s_oscale[tid - 64] = prm.out_scale ? prm.out_scale[tid - 64] : 1.f;
   }
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) { mbar_init(&bar_full[s], NPROD); mbar_init(&bar_empty[s], 1); mbar_init(&bar_land[s], 1); }
@@ -211,8 +223,9 @@ conv3d_k3_roll_kernel(RollParams prm) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(d_ok ? (uint32_t)KCS * run_bytes : 0u), "r"(bar)
                        : "memory");
         __syncwarp();
-        if (d_ok && lane < KCS) {      // split-bf16: chunk KC + k (lo) follows chunk k (hi) in global memory as in the slot
-          const uint4* src = prm.xb + (int64_t)lane * SP + ((int64_t)d_in * G + (h0 - 1 + r_lo)) * G;
+        if (d_ok && lane < KCS) {      // staged chunks: the KC hi chunks of this launch's channels, then (split-bf16) their lo chunks
+          const int gchunk = (lane < KC ? 0 : prm.cin_total / 8) + prm.cin_off / 8 + (lane < KC ? lane : lane - KC);
+          const uint4* src = prm.xb + (int64_t)gchunk * SP + ((int64_t)d_in * G + (h0 - 1 + r_lo)) * G;
           const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (lane * NPOS + Cfg::PAD + r_lo * W) * 16);
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                        "l"(src), "r"(run_bytes), "r"(bar)
@@ -353,7 +366,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ==================================================
     {   // all 32 lanes run the loop; the elected lane issues (see umma_bf16_ws)
-      constexpr uint32_t idesc = umma_idesc_bf16(128, C);
+      constexpr uint32_t idesc = umma_idesc_bf16(128, CO * NP);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t w_base = smem_base + Cfg::OFF_W;
       const bool x4_src = prm.xb == nullptr;
@@ -380,8 +393,9 @@ conv3d_k3_roll_kernel(RollParams prm) {
           // stacked N = 3C operand, so one MMA (one read of the 4 KB A tile) does the work of three.
           // Fully unrolled: every descriptor is (one of 3 per-plane bases) + a compile-time constant.
           // kw runs 1,0,2 so that the MMA that initialises an accumulator (accumulate = 0) is unmasked.
-          constexpr uint32_t WB = 3 * C * C * 2;            // bytes of one (kd,kw) stacked weight matrix
-          constexpr uint32_t B_LBO = 3 * C * 16;
+          constexpr int CN = CO * NP;                       // accumulator columns per output row (split-bf16: D1 | D2)
+          constexpr uint32_t WB = 3 * CN * CI * 2;          // bytes of one (kd,kw) stacked weight matrix
+          constexpr uint32_t B_LBO = 3 * CN * 16;
           const uint64_t b_base = umma_desc(w_base, B_LBO, 128);
 #pragma unroll
           for (int rho = 0; rho < TH + 2; ++rho) {
@@ -403,28 +417,29 @@ conv3d_k3_roll_kernel(RollParams prm) {
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
 #pragma unroll
-                  for (int v = 0; v < (X3 ? 3 : 1); ++v) {      // split-bf16: a_hi*w_hi, a_lo*w_hi, a_hi*w_lo
-                    // (the 4-channel fp32 source packs hi and lo into ONE chunk and pairs it with two weight images)
+                  for (int v = 0; v < NP; ++v) {      // split-bf16: A_hi x [W_hi | W_lo], then A_lo x [W_hi | W_lo]
+                    // (the 4-channel fp32 source packs hi and lo into ONE chunk whose weights carry w at k = ci and ci + 4)
                     if (X3 && v == 1 && x4_src) continue;
                     const uint64_t ad = a_kd[kd] + (uint64_t)(Cfg::PAD + rho * W + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
-                    const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * C * 16 + ks * 2 * B_LBO + (v == 2 ? Cfg::W_HALF : 0)) >> 4);
+                    const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * CN * 16 + ks * 2 * B_LBO) >> 4);
                     if (n_acc > 0) {
-                      if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u);
-                      else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * C), ad, bd, umma_idesc_bf16(128, n_acc * C), 1u, m0, m1, m2, m3);
+                      if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * CN), ad, bd, umma_idesc_bf16(128, n_acc * CN), 1u);
+                      else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * CN), ad, bd, umma_idesc_bf16(128, n_acc * CN), 1u, m0, m1, m2, m3);
                     }
                     if (first)
-                      umma_bf16_ws(acc0 + (uint32_t)(rho * C), ad, bd + (uint64_t)((n_acc * C * 16) >> 4),
-                                   umma_idesc_bf16(128, C), (ks | v) == 0 ? 0u : 1u);
+                      umma_bf16_ws(acc0 + (uint32_t)(rho * CN), ad, bd + (uint64_t)((n_acc * CN * 16) >> 4),
+                                   umma_idesc_bf16(128, CN), (ks | v) == 0 ? 0u : 1u);
                   }
                 }
               }
             }
           }
         } else {
-          const uint64_t b_base = umma_desc(w_base, C * 16, 128);
+          constexpr int CN = CO * NP;                       // B rows per K chunk: split-bf16 stacks [W_hi | W_lo] along N
+          const uint64_t b_base = umma_desc(w_base, CN * 16, 128);
 #pragma unroll 1
           for (int t = 0; t < Cfg::NT; ++t) {
-            const uint32_t d_tmem = acc0 + (uint32_t)(t * C);
+            const uint32_t d_tmem = acc0 + (uint32_t)(t * CN);
 #pragma unroll
             for (int kd = 0; kd < 3; ++kd) {
 #pragma unroll
@@ -440,9 +455,9 @@ conv3d_k3_roll_kernel(RollParams prm) {
 #pragma unroll
                   for (int ks = 0; ks < Cfg::KS; ++ks) {
 #pragma unroll
-                    for (int v = 0; v < (X3 ? 3 : 1); ++v) {
+                    for (int v = 0; v < NP; ++v) {
                       const uint64_t ad = a_kd[kd] + (uint64_t)(uint32_t)(Cfg::PAD + (t * Cfg::TROWS + kh) * W + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
-                      const uint64_t bd = b_base + (uint64_t)((tap * C * C * 2 + ks * 2 * C * 16 + (v == 2 ? Cfg::W_HALF : 0)) >> 4);
+                      const uint64_t bd = b_base + (uint64_t)((tap * CI * CN * 2 + ks * 2 * CN * 16) >> 4);
                       const uint32_t accum = (kd | kh | kwi | ks | v) != 0 ? 1u : 0u;
                       if (kw == 1) umma_bf16_ws(d_tmem, ad, bd, idesc, accum);
                       else umma_bf16_masked_ws(d_tmem, ad, bd, idesc, accum, m0, m1, m2, m3);
@@ -463,7 +478,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
     // =============================== epilogue ====================================================
     // Work item = (tile, 16-channel group); the two epilogue groups take alternate items, so with C = 32 a group owns
     // a fixed channel half (16 statistics accumulators per thread) and with C = 16 it owns every other tile.
-    constexpr int G16 = C / 16;
+    constexpr int G16 = CO / 16;
     constexpr int ITEMS = Cfg::NT * G16;                // items per plane
     static_assert(ITEMS % EPI_GROUPS == 0, "items must split evenly over the epilogue groups");
     const int grp_id = warp >> 3;                       // 0: warps 0-3, 1: warps 8-11
@@ -503,8 +518,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
           rv0 = __ldg(res0 + off);
           rv1 = __ldg(res0 + SP + off);
           if constexpr (X3) {
-            rl0 = __ldg(res0 + (int64_t)KC * SP + off);
-            rl1 = __ldg(res0 + (int64_t)(KC + 1) * SP + off);
+            rl0 = __ldg(res0 + (int64_t)(CO / 8) * SP + off);
+            rl1 = __ldg(res0 + (int64_t)(CO / 8 + 1) * SP + off);
           }
         }
         if (!waited) {
@@ -514,7 +529,14 @@ conv3d_k3_roll_kernel(RollParams prm) {
           if (tid == 0) trace_event(tbuf, 6, i);   // epilogue: accumulator of plane i complete
         }
         uint32_t acc[16];
-        tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * C + 16 * g16), acc);
+        tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * CO * NP + 16 * g16), acc);
+        if constexpr (X3) {      // result = D1 + D2
+          uint32_t acc2[16];
+          tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * CO * NP + CO + 16 * g16), acc2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) acc[k] = __float_as_uint(__uint_as_float(acc[k]) + __uint_as_float(acc2[k]));
+        }
         tmem_ld_wait();
         if (it + EPI_GROUPS >= ITEMS) {   // all of this thread's TMEM reads of buffer b are done
           tc_fence_before();
@@ -555,8 +577,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
           split_bf16x2(val[4], val[5], o0.z, l0.z);     split_bf16x2(val[6], val[7], o0.w, l0.w);
           split_bf16x2(val[8], val[9], o1.x, l1.x);     split_bf16x2(val[10], val[11], o1.y, l1.y);
           split_bf16x2(val[12], val[13], o1.z, l1.z);   split_bf16x2(val[14], val[15], o1.w, l1.w);
-          y0[(int64_t)KC * SP + off] = l0;
-          y0[(int64_t)(KC + 1) * SP + off] = l1;
+          y0[(int64_t)(CO / 8) * SP + off] = l0;
+          y0[(int64_t)(CO / 8 + 1) * SP + off] = l1;
         } else {
           o0.x = pack_bf16x2(val[0], val[1]);   o0.y = pack_bf16x2(val[2], val[3]);
           o0.z = pack_bf16x2(val[4], val[5]);   o0.w = pack_bf16x2(val[6], val[7]);
@@ -584,7 +606,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
         if (lane == 0) { s_red[(ewarp * 16 + c) * 2] = a; s_red[(ewarp * 16 + c) * 2 + 1] = q; }
       }
       asm volatile("bar.sync 1, %0;" ::"n"(EPI_GROUPS * EPI_WARPS * 32) : "memory");
-      if (warp == 0 && lane < C) {
+      if (warp == 0 && lane < CO) {
         const int c = lane;
         float a = 0.f, q = 0.f;
         if (G16 == 1) {
@@ -622,9 +644,16 @@ static uint16_t f32_to_bf16_rn(float f) {
 }
 
 // B operand tiles, bf16, K-major no-swizzle (core matrix = 8 couts x 8 cins, 128 contiguous bytes):
-//   layout 0  [tap][cin/8][cout][8]                     one N = cout matrix per tap
-//   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]      one stacked N = 3*cout matrix per (kd,kw)
-static int tc_weight_layout(int cin, int cout) { return (cin <= 16 && cout == 16) ? 1 : 0; }
+//   layout 0  [tap][cin/8][cout][8]                            one N = cout matrix per tap (split-bf16: hi image, then lo image)
+//   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]             one stacked N = 3*cout matrix per (kd,kw)
+//   layout 2  [kd][kw][cin/8][kh = 2,1,0][hi|lo][cout][8]      split-bf16 rolling kernel, 16-channel layers: N = 3*2*cout
+//   layout 3  [cin half][tap][2 chunks][hi|lo][cout][8]        split-bf16 rolling kernel, 32 -> 32 layers: one image of
+//                                                              N = 2*cout per 16 input channels (one launch each)
+static int tc_weight_layout(int cin, int cout, bool x3) {
+  if (cin <= 16 && cout == 16) return x3 ? 2 : 1;
+  if (x3 && cin == 32 && cout == 32) return 3;
+  return 0;
+}
 
 static float bf16_to_f32(uint16_t h) {
   const uint32_t u = (uint32_t)h << 16;
@@ -638,28 +667,36 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;   // zero padded
   const int kcs = cin_pad / 8;
   const size_t image = (size_t)taps * cin_pad * cout_pad;
-  std::vector<uint16_t> packed(x3 ? 2 * image : image, 0);       // split-bf16: hi image, then lo image
-  const int layout = (roll_layout && taps == 27) ? tc_weight_layout(cin, cout) : 0;
+  std::vector<uint16_t> packed(x3 ? 2 * image : image, 0);       // split-bf16: twice the elements in every layout
+  const int layout = (roll_layout && taps == 27) ? tc_weight_layout(cin, cout, x3) : 0;
+  out->layout = layout;
   // InitConv in split-bf16 mode: the rolling kernel stages the four input channels as [hi0..3 | lo0..3] in ONE chunk,
-  // so image 0 carries w_hi at k = ci AND k = ci + 4 (a_hi*w_hi + a_lo*w_hi) and image 1 carries w_lo at k = ci
-  const bool init_x3 = x3 && layout == 1 && cin == 4;
+  // so the weights of channel ci sit at k = ci AND k = ci + 4
+  const bool init_x3 = layout == 2 && cin == 4;
   for (int tap = 0; tap < taps; ++tap)
     for (int ci = 0; ci < cin; ++ci)
       for (int n = 0; n < cout; ++n) {
         const int kc = ci / 8, k = ci % 8;
-        size_t dst;
-        if (layout == 0) {
-          dst = (((size_t)tap * kcs + kc) * cout_pad + n) * 8 + k;
-        } else {
-          const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-          dst = (((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * cout_pad) + n) * 8 + k;
-        }
+        const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
         const float wv = w_host[((size_t)n * cin + ci) * taps + tap];
         const uint16_t hi = f32_to_bf16_rn(wv);
-        packed[dst] = hi;
-        if (x3) {
-          packed[image + dst] = f32_to_bf16_rn(wv - bf16_to_f32(hi));
-          if (init_x3) packed[dst + 4] = hi;
+        const uint16_t lo = f32_to_bf16_rn(wv - bf16_to_f32(hi));
+        if (layout == 0) {
+          const size_t dst = (((size_t)tap * kcs + kc) * cout_pad + n) * 8 + k;
+          packed[dst] = hi;
+          if (x3) packed[image + dst] = lo;
+        } else if (layout == 1) {
+          packed[(((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * cout_pad) + n) * 8 + k] = hi;
+        } else if (layout == 2) {
+          const size_t row = ((((size_t)(kd * 3 + kw) * kcs + kc) * 3 + (2 - kh)) * 2) * cout_pad;      // [hi rows | lo rows]
+          packed[(row + n) * 8 + k] = hi;
+          packed[(row + cout_pad + n) * 8 + k] = lo;
+          if (init_x3) { packed[(row + n) * 8 + k + 4] = hi; packed[(row + cout_pad + n) * 8 + k + 4] = lo; }
+        } else {
+          const int half = ci / 16, c16 = ci % 16;
+          const size_t row = ((((size_t)half * 27 + tap) * 2 + c16 / 8) * 2) * cout_pad;
+          packed[(row + n) * 8 + c16 % 8] = hi;
+          packed[(row + cout_pad + n) * 8 + c16 % 8] = lo;
         }
       }
   out->bytes = (int64_t)packed.size() * 2;
@@ -669,15 +706,16 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
   return 0;
 }
 
-using RollC16 = RollCfg<16, 128, 8, true, 5>;
-using RollC32 = RollCfg<32, 64, 8, false, 4>;
-// split-bf16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory); the
-// 32-channel layers (110 KB of split weights) run on the slab kernel instead
-using RollC16X3 = RollCfg<16, 128, 4, true, 4, true>;
+using RollC16 = RollCfg<16, 16, 128, 8, true, 5>;
+using RollC32 = RollCfg<32, 32, 64, 8, false, 4>;
+// split-bf16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory) for the
+// 16-channel layers; a 32 -> 32 layer (110 KB of split weights) runs as two launches over 16 input channels each
+using RollC16X3 = RollCfg<16, 16, 128, 4, true, 4, true>;
+using RollC32X3 = RollCfg<16, 32, 64, 8, false, 4, true>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
+  (void)split;     // both modes cover the same layers
   if (stride != 1) return false;
-  if (split) return (cin == 16 || cin == 4) && cout == 16 && g == 128;
   return (cin == 16 && cout == 16 && g == 128) || (cin == 32 && cout == 32 && g == 64) || (cin == 4 && cout == 16 && g == 128);
 }
 
@@ -702,7 +740,7 @@ static int launch_roll(RollParams& prm, cudaStream_t st) {
 
 int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cudaStream_t st) {
   const int cin = w.cin;
-  if (!tc_conv_supported(cin, cout, g, 1, a.x3) || w.dev == nullptr || (a.x3 && w.lo_off == 0) || (a.xb == nullptr) == (a.x4 == nullptr && a.desc == nullptr) ||
+  if (!tc_conv_supported(cin, cout, g, 1, a.x3) || w.dev == nullptr || w.layout != tc_weight_layout(cin, cout, a.x3) || (a.xb == nullptr) == (a.x4 == nullptr && a.desc == nullptr) ||
       (cin == 4) != (a.x4 != nullptr || a.desc != nullptr)) {
     set_error("roll_conv: unsupported shape / source");
     return -1;
@@ -717,6 +755,18 @@ int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cud
   p.yb = reinterpret_cast<uint4*>(a.yb);
   p.stats = a.stats;
   p.dsplit = 1;
+  p.cin_off = 0; p.cin_total = cin == 4 ? 16 : cin;
+  if (a.x3 && cout == 32) {
+    // 16 input channels per launch: y1 = conv(x[0:16]) + bias + residual, then y = conv(x[16:32]) + y1 (+ statistics)
+    p.stats = nullptr;
+    { const int rc = launch_roll<RollC32X3>(p, st); if (rc != 0) return rc; }
+    p.cin_off = 16;
+    p.w = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(w.dev) + RollC32X3::W_BYTES);
+    p.bias = nullptr; p.out_scale = nullptr;
+    p.resb = p.yb;
+    p.stats = a.stats;
+    return launch_roll<RollC32X3>(p, st);
+  }
   if (a.x3) return launch_roll<RollC16X3>(p, st);
   if (cout == 16) return launch_roll<RollC16>(p, st);
   return launch_roll<RollC32>(p, st);

@@ -10,6 +10,7 @@ struct TcWeights {
   int cout = 0, cin = 0;
   int64_t bytes = 0;
   int64_t lo_off = 0;   // bf16x3: byte offset of the "lo" image (same layout as the "hi" image at dev); 0 = plain bf16
+  int layout = 0;       // 0 canonical [tap][cin/8][cout][8] (+ lo image); 1-3: rolling-kernel orders (tc_pack_weights)
   // lazily built copy in the slab kernel's streaming order for one tile width (launch_slab_conv)
   mutable void* slab_dev = nullptr;
   mutable int slab_ntile = 0;

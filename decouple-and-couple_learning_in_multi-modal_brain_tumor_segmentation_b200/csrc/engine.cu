@@ -883,8 +883,7 @@ struct Fwd16 {
       if (norm) a.norm = *norm;
       a.bias = w.b; a.out_scale = out_scale; a.resb = resb; a.yb = y; a.stats = stats;
       rc = launch_roll_conv(a, w.tc, w.cout, g, st);
-    } else if (taps == 27 && slab_conv_supported(c0 + c1, w.cout, g, g, g, stride, taps) && (g <= 32 || (x3 && g == 64))) {
-      // (split-bf16: the 32-channel 64^3 layers come here too - their split weights do not fit the rolling kernel)
+    } else if (taps == 27 && slab_conv_supported(c0 + c1, w.cout, g, g, g, stride, taps) && g <= 32) {
       kind = 4;
       GemmArgs ga;
       ga.x3 = x3;
@@ -1993,7 +1992,7 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
       ga.bias = bias; ga.out_mode = 2; ga.y = y;
       if (mode & 2) ga.residual = r;
       if (mode & 4) ga.stats = sout;
-      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && (g <= 32 || (x3 && g == 64))) rc = launch_slab_conv(ga, (mode & 1) ? &bn : nullptr, tw, 0);
+      if (stride == 1 && slab_conv_supported(cin, cout, g, g, g, 1, 27) && g <= 32) rc = launch_slab_conv(ga, (mode & 1) ? &bn : nullptr, tw, 0);
       else if (stride == 2 && (x3 ? s2_roll_supported_x3(cin, cout, g) : s2_roll_supported(cin, cout, g)))
         rc = launch_s2_roll_conv(x, tw, bias, y, (mode & 7) ? sout : nullptr, 0, x3);
       else rc = launch_gemm_conv(ga, tw, 0);
