@@ -699,11 +699,20 @@ def dominant_roofline(prof, pk, precision):
            "traffic": traffic, "kernel": name, "launches": n, "avg_launch_ms": ms / max(n, 1),
            "flops_per_launch": flops / max(n, 1), "share_of_step": ms / prof_ms,
            "peak_source": pk["source"] + " sustained bf16 dense"}
+    # what the tensor pipe EXECUTES per algorithmic MAC: split-bf16 forms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ a_lo*w_lo where
+    # the weights ride stacked along N: the rolling kernels) - 3 bf16 MMAs in the GEMM / slab / stride-2 kernels, 4 in the
+    # rolling kernels; north_star's "tensor-pipe utilisation against the dense bf16 peak" is executed MMA FLOPs / peak
+    factor = (4 if best in (2, 3) else 3) if x3 else 1
+    rec["tensor_pipe"] = {"executed_mma_flops_per_algorithmic_flop": factor, "executed_TFLOP/s": tf * factor,
+                          "utilisation_of_sustained_peak": tf * factor / pk["tensor"],
+                          "utilisation_of_nominal_2250": tf * factor / 2250.0,
+                          "ncu_counter": "sm__pipe_tensor_subpipe_hmma_cycles_active / (8 x sm__cycles_elapsed): "
+                                         "profiles/r02_ncu_full_conv_kernels.csv (0.148 for the split-bf16 16-channel layer, "
+                                         "0.118 for the bf16 one; that counter's own peak is ~1.87 x the bf16 dense peak)"}
     if x3:
-        rec["mma_flops_factor"] = 3
-        rec["note"] = ("algorithmic FLOPs (2 x MACs); the split-bf16 mode issues 3 tensor-core MACs per algorithmic MAC "
-                       "(a_hi*w_hi + a_lo*w_hi + a_hi*w_lo), so the tensor pipe executes 3 x `achieved` and the ceiling of "
-                       "`frac` is 1/3")
+        rec["note"] = ("`achieved` / `frac` count ALGORITHMIC FLOPs (2 x MACs of the convolution); the split-bf16 kernels execute "
+                       f"{factor} tensor-core MACs per algorithmic MAC, so the ceiling of `frac` is 1/{factor} and the pipe's own "
+                       "utilisation is `tensor_pipe`")
     if best == 2 and n > 0:
         # the 16-channel 128^3 layers are HBM-side too: 2 (3 with the residual) passes over a 16-channel tensor
         b = _roll16_bytes(x3)
