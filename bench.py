@@ -337,8 +337,7 @@ def measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barri
     def step_e2e(i):
         j = i % n_rot
         up_bytes[0] = sharded.upload_own_region(vols_h[j], stage, starts)
-        out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j],
-                                             target=tgts_h[j].cuda(non_blocking=True))
+        out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j], target=tgts_h[j])
         if rank == 0:
             lab_h.copy_(out["labels"], non_blocking=True)
             out["counts"].cpu()
@@ -374,7 +373,8 @@ def measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barri
     slot = 4 * 128 ** 3 * 4
     return {"scaling": "strong", "value": args.steps / (ms / 1e3), "unit": "volumes/s", "ms_per_volume": ms / args.steps,
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "volumes/s", "ms_per_volume": e2e_ms / args.steps,
-                    "h2d_bytes_per_step_max_rank": int(up_max) + VOXELS, "d2h_bytes_per_step_rank0": VOXELS + 13 * 8},
+                    "h2d_bytes_per_step_max_rank": int(up_max) + -(-SHAPE[0] // world) * SHAPE[1] * SHAPE[2],
+                    "d2h_bytes_per_step_rank0": VOXELS + 13 * 8},
             "patches_per_rank": [c for _, c in parts], "load_balance_bound": n_patches / (world * max(c for _, c in parts)),
             "exchange": "owner-computes: gather_finalize_kernel reads the covering patches' probability slots in place - "
                         "local HBM or a peer's through CUDA IPC over NVLink; collectives: 1 x all_reduce(int32) barrier, "
@@ -475,8 +475,7 @@ def run_ours(args):
         def step_e2e(i):     # a rank uploads the x-slab its patches read over its own PCIe link; rank 0 downloads the label map
             j = i % n_rot
             sharded.upload_own_region(vols_h[j], stage, starts)
-            tgt = tgts_h[j].cuda(non_blocking=True)
-            out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j], target=tgt)
+            out = sharded.predict_volume_sharded(eng, stage, mode, starts=starts, keep_scales=keeps[j], target=tgts_h[j])
             if rank == 0:
                 lab_h.copy_(out["labels"], non_blocking=True)
                 out["counts"].cpu()
