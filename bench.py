@@ -37,7 +37,10 @@ SHAPE = (240, 240, 155)
 VOXELS = SHAPE[0] * SHAPE[1] * SHAPE[2]
 FLOPS_PER_PATCH = 523.35e9 + 0.44e9      # conv+linear without aux heads + attention
 WORKLOADS = {"overlap50": ("UNIFORM", 64), "overlap75": ("UNIFORM", 32), "reference8": ("REFERENCE", None),
-             "tta8": ("TTA", None)}
+             "tta8": ("TTA", None),
+             # BASELINE.json configs[3]: the sliding window whose output carries WT/TC/ET class probabilities AND the six
+             # auxiliary region / edge heads (cls_wise_former.py:545-546, :585-592), 16 blended channels per voxel
+             "overlap50_aux": ("UNIFORM", 64)}
 
 
 def seed0_weights():
@@ -201,7 +204,7 @@ def cpu_reference_volumes_per_s(workload, n_sample_patches, threads, steps=1, wa
         for j in range(n_sample_patches):
             sx, sy, sz = starts[j]
             probs.append(O.forward(sd, x[..., sx:sx + 128, sy:sy + 128, sz:sz + 128],
-                                   torch.from_numpy(ks[j:j + 1]), want_aux=False)[0][0].numpy())
+                                   torch.from_numpy(ks[j:j + 1]), want_aux=workload == "overlap50_aux")[0][0].numpy())
         t_patch = (time.perf_counter() - t0) / n_sample_patches
         t1 = time.perf_counter()
         full = [probs[j % n_sample_patches] for j in range(len(starts))]
@@ -269,7 +272,9 @@ def workload_name(w):
                          "(stride 64, 18 patches, uniform blend)",
             "overlap75": "4x240x240x155 volume, 128^3 patches at 75% overlap (stride 32, 50 patches, uniform blend)",
             "reference8": "predict_overlap.py 8-corner tiling + crop-overwrite stitch, one 4x240x240x155 volume",
-            "tta8": "predict_cls.py 8-flip TTA around the 8-corner tiling (64 patch forwards), one 4x240x240x155 volume"}[w]
+            "tta8": "predict_cls.py 8-flip TTA around the 8-corner tiling (64 patch forwards), one 4x240x240x155 volume",
+            "overlap50_aux": "sliding window with WT/TC/ET + edge outputs (4 class + 6 x 2 auxiliary-head channels blended per "
+                             "voxel), one 4x240x240x155 volume, 128^3 patches at 50% overlap (18 patches, uniform blend)"}[w]
 
 
 def measure_device(eng, step_dev, args, barrier, sampler):
@@ -449,7 +454,8 @@ def run_ours(args):
 
     prec = {"fp32": dcl_b200.Precision.FP32, "bf16x3": dcl_b200.Precision.BF16X3, "bf16": dcl_b200.Precision.BF16}[
         args.precision]
-    eng = dcl_b200.Engine(prec)
+    with_aux = args.workload == "overlap50_aux"
+    eng = dcl_b200.Engine(prec, want_aux=with_aux)
     eng.load_state_dict(seed0_weights())
     mode, starts, n_patches = workload_plan(args.workload)
     n_rot = 3     # rotating inputs: 3 x 143 MB per rank, each larger than the 126 MB L2
@@ -479,6 +485,22 @@ def run_ours(args):
             if rank == 0:
                 lab_h.copy_(out["labels"], non_blocking=True)
                 out["counts"].cpu()
+            torch.cuda.synchronize()
+            return out
+    elif with_aux:
+        stage = torch.empty_like(vols_d[0])
+
+        def step_dev(i):
+            j = i % n_rot
+            return eng.predict_volume_aux(vols_d[j], mode, starts=starts, keep_scales=keeps[j], target=tgts_d[j], want_probs=False)
+
+        def step_e2e(i):     # host volume + target in, host labels + counters out; the 12 blended auxiliary channels stay on the device
+            j = i % n_rot
+            stage.copy_(vols_h[j], non_blocking=True)
+            out = eng.predict_volume_aux(stage, mode, starts=starts, keep_scales=keeps[j], target=tgts_h[j].cuda(non_blocking=True),
+                                         want_probs=False)
+            lab_h.copy_(out["labels"], non_blocking=True)
+            out["counts"].cpu()
             torch.cuda.synchronize()
             return out
     elif mode == "TTA":
@@ -539,7 +561,7 @@ def run_ours(args):
 
     # ---- the plain bf16 mode beside the parity-grade headline (same workload, same run) ----
     bf16_rec = None
-    if rank == 0 and world == 1 and args.precision == "bf16x3" and mode != "TTA" and not args.no_bf16:
+    if rank == 0 and world == 1 and args.precision == "bf16x3" and mode != "TTA" and not args.no_bf16 and not with_aux:
         e16 = dcl_b200.Engine(dcl_b200.Precision.BF16)
         e16.load_state_dict(seed0_weights())
 
@@ -563,7 +585,7 @@ def run_ours(args):
     # The call is synchronous (upload, compute, download, sync), so a throughput-minded caller keeps two volumes in
     # flight: two worker threads, each with its own handle and stream (ctypes drops the GIL during the call), so the
     # host-to-device copy of one volume overlaps the compute of the other.  --e2e-workers 1 is the plain serial loop.
-    workers = 1 if (by_patch or mode == "TTA") else max(1, args.e2e_workers)
+    workers = 1 if (by_patch or mode == "TTA" or with_aux) else max(1, args.e2e_workers)
     if workers == 1:
         for i in range(max(1, args.warmup // 2)):
             step_e2e(i)
@@ -607,7 +629,7 @@ def run_ours(args):
     # ---- N > 1: the SAME run also measures ONE volume sharded by patch slab over the ranks (BASELINE configs 3 / 5:
     # strong scaling, owner-computes exchange over NVLink), attached as a sub-record ----
     sharded_rec = None
-    if world > 1 and not by_patch and mode != "TTA" and starts is not None and not args.no_sharded:
+    if world > 1 and not by_patch and mode != "TTA" and starts is not None and not args.no_sharded and not with_aux:
         sharded_rec = measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barrier)
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -634,7 +656,7 @@ def run_ours(args):
                     "d2h_bytes_per_step": VOXELS + 13 * 8, "workers": workers,
                     "call": "dcl_predict_volume_host (pinned host volume + target in, host labels + 13 counters out)"},
             "gpu_launches": launches,
-            "model_tflops": vols_per_step * args.steps * n_patches * FLOPS_PER_PATCH / (ms / 1e3) / 1e12,
+            "model_tflops": vols_per_step * args.steps * n_patches * (FLOPS_PER_PATCH + (8.40e9 if with_aux else 0.0)) / (ms / 1e3) / 1e12,
             "roofline": dominant_roofline(prof, pk, args.precision),
             "roofline_all_k3_convs": all_convs_roofline(prof, pk),
             "roofline_accumulate": {"bound": "hbm", "achieved": tail_gbs, "peak": pk["hbm"], "unit": "GB/s",

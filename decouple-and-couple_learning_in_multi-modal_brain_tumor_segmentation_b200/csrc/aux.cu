@@ -15,7 +15,9 @@ __device__ __forceinline__ void src_index(int dst, float inv_scale, int size, in
 }
 
 __global__ void __launch_bounds__(256)
-upsample_softmax2_kernel(const float* __restrict__ x, float* __restrict__ y, int g, int scale) {
+upsample_softmax2_kernel(const float* __restrict__ x, float* __restrict__ y_fixed, int g, int scale,
+                         const PatchDesc* __restrict__ desc, int slot) {
+  float* __restrict__ y = desc != nullptr ? desc->aux[slot] : y_fixed;
   const int og = g * scale;
   const int64_t n = (int64_t)og * og * og;
   const int64_t e = (int64_t)blockIdx.x * 256 + threadIdx.x;
@@ -47,9 +49,9 @@ upsample_softmax2_kernel(const float* __restrict__ x, float* __restrict__ y, int
   y[n + e] = e1 / s;
 }
 
-int launch_upsample_softmax2(const float* x, float* y, int g, int scale, cudaStream_t st) {
+int launch_upsample_softmax2(const float* x, float* y, int g, int scale, cudaStream_t st, const PatchDesc* desc, int slot) {
   int64_t n = (int64_t)g * scale * g * scale * g * scale;
-  upsample_softmax2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, g, scale);
+  upsample_softmax2_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, g, scale, desc, slot);
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;

@@ -126,6 +126,7 @@ struct PatchDesc {
   long long sc, sd, sh;     // element strides of (C, X, Y); the Z stride is 1
   float keep[16];
   float* probs;             // nullptr, or where this patch's probabilities go instead of the handle's buffer
+  float* aux[12];           // destinations of the auxiliary heads of this patch (nullptr = head not requested)
 };
 // debug: dst[idx] = %globaltimer (ns); DCL_STAMPS=1 places these between the stages of the forward
 int launch_stamp(unsigned long long* dst, int idx, cudaStream_t st);
@@ -136,7 +137,9 @@ int launch_fill16(float* dst, const Floats16& v, cudaStream_t st);
 
 // ---- aux heads (aux.cu) --------------------------------------------------------------------
 // x: (2, g,g,g) logits -> y: (2, g*s, g*s, g*s) = softmax_c(trilinear_upsample(x, align_corners=False))
-int launch_upsample_softmax2(const float* x, float* y, int g, int scale, cudaStream_t st);
+// desc != nullptr: the destination is desc->aux[slot] (read on the device: the launch is graph-replayable)
+int launch_upsample_softmax2(const float* x, float* y, int g, int scale, cudaStream_t st, const PatchDesc* desc = nullptr,
+                             int slot = 0);
 
 // ---- stitch / label tail (stitch.cu) -------------------------------------------------------
 struct StitchBox {      // one rectangular copy of the crop-and-overwrite plan

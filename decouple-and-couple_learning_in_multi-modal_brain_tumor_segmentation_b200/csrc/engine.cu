@@ -203,8 +203,8 @@ struct dcl_handle {
   float* keep_dev;                               // (16)  (bf16 mode: aliases patch_desc->keep)
   PatchDesc* patch_desc = nullptr;               // per-patch arguments of the graph-replayed bf16 forward
   unsigned long long* stamps = nullptr;          // debug (DCL_STAMPS=1): %globaltimer between the stages of the forward
-  cudaGraphExec_t fwd_graph = nullptr;           // the captured bf16 forward (no aux outputs)
-  int64_t fwd_graph_launches = 0;
+  struct FwdGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int eager_runs = 0; };
+  std::map<int, FwdGraph> fwd_graphs;            // captured tensor-core forwards, keyed by the mask of requested auxiliary heads
   int fwd_eager_runs = 0;
   bool fwd_graph_off = false;
   double* stat_accum;                            // (2*512)
@@ -460,7 +460,8 @@ static int pack_conv(dcl_handle* h, WKind kind, const std::vector<const std::vec
 static bool needed(const dcl_handle* h, const WSpec& s) { return !s.aux || h->cfg.want_aux; }
 
 static int prepare(dcl_handle* h) {
-  if (h->fwd_graph) { cudaGraphExecDestroy(h->fwd_graph); h->fwd_graph = nullptr; }   // weights are about to move
+  for (auto& kv : h->fwd_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);      // weights are about to move
+  h->fwd_graphs.clear();
   h->fwd_eager_runs = 0;
   for (const auto& s : catalogue())
     if (needed(h, s) && !h->host_w.count(s.name)) {
@@ -722,12 +723,13 @@ struct Fwd {
   }
 
   // one auxiliary head branch: conv k3 -> conv k3 (2 classes) -> trilinear upsample -> softmax
-  int aux_branch(const float* x, int c, int g, const std::string& first, const std::string& second, float* out) {
+  // slot >= 0: the destination is read from the device-side patch descriptor (graph-replayable tensor-core forward)
+  int aux_branch(const float* x, int c, int g, const std::string& first, const std::string& second, float* out, int slot = -1) {
     const ConvW& w1 = h->conv.at(first);
     DCL_TRY(conv3(x, c, nullptr, 0, g, w1, 1, nullptr, ACT_NONE, nullptr, nullptr, h->aux_t1));
     DCL_TRY(conv3(h->aux_t1, w1.cout, nullptr, 0, g, h->conv.at(second), 1, nullptr, ACT_NONE, nullptr, nullptr,
                   h->aux_t2));
-    DCL_TRY(launch_upsample_softmax2(h->aux_t2, out, g, 128 / g, st));
+    DCL_TRY(launch_upsample_softmax2(h->aux_t2, out, g, 128 / g, st, slot >= 0 ? h->patch_desc : nullptr, slot >= 0 ? slot : 0));
     return 0;
   }
 
@@ -949,13 +951,20 @@ struct Fwd16 {
     d.x = x; d.sc = xs[0]; d.sd = xs[1]; d.sh = xs[2];
     for (int i = 0; i < 16; ++i) d.keep[i] = keep_host ? keep_host[i] : 1.f;
     d.probs = probs_out;      // endconv writes here (the captured graph only knows h->probs)
+    int mask = 0;             // requested auxiliary heads: their destinations travel in the descriptor too
+    for (int j = 0; j < DCL_NUM_AUX; ++j) {
+      d.aux[j] = aux ? aux[j] : nullptr;
+      if (d.aux[j]) mask |= 1 << j;
+    }
     DCL_TRY(launch_patch_desc(h->patch_desc, d, st));
-    const bool graphable = aux == nullptr && !h->profiling && !h->fwd_graph_off;
+    const bool graphable = !h->profiling && !h->fwd_graph_off;
     if (!graphable) return body(probs_out, aux);
-    if (h->fwd_graph == nullptr) {
-      if (h->fwd_eager_runs < 1) {     // the first forward runs eagerly: one-time attribute calls and weight repacks
+    dcl_handle::FwdGraph& fg = h->fwd_graphs[mask];
+    if (fg.exec == nullptr) {
+      if (fg.eager_runs < 1) {         // the first forward of a kind runs eagerly: one-time attribute calls and weight repacks
+        ++fg.eager_runs;
         ++h->fwd_eager_runs;
-        return body(probs_out, nullptr);
+        return body(probs_out, aux);
       }
       // capture the whole forward (including the three concurrent coupler streams) into a graph writing h->probs
       // (captured on a private stream: the caller's stream may be the legacy default stream, which cannot capture)
@@ -966,28 +975,28 @@ struct Fwd16 {
         cudaGetLastError();
         h->fwd_graph_off = true;
         if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: stream capture unavailable\n");
-        return body(probs_out, nullptr);
+        return body(probs_out, aux);
       }
       Fwd16 cap{h, cs};
-      const int rc = cap.body(h->probs, nullptr);
+      const int rc = cap.body(h->probs, aux);       // aux: only WHICH heads are present matters to the captured launches
       const cudaError_t e = cudaStreamEndCapture(cs, &graph);
       if (rc != 0 || e != cudaSuccess || graph == nullptr ||
-          cudaGraphInstantiate(&h->fwd_graph, graph, 0) != cudaSuccess) {
+          cudaGraphInstantiate(&fg.exec, graph, 0) != cudaSuccess) {
         cudaGetLastError();
         if (graph) cudaGraphDestroy(graph);
-        h->fwd_graph = nullptr;
+        fg.exec = nullptr;
         h->fwd_graph_off = true;       // stay on the eager launches (same kernels)
         if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: graph capture failed rc=%d e=%d (%s)\n", rc, (int)e, g_error.c_str());
         g_launches = before;
-        return body(probs_out, nullptr);
+        return body(probs_out, aux);
       }
       cudaGraphDestroy(graph);
-      if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: forward captured, %lld launches\n", (long long)(g_launches - before));
-      h->fwd_graph_launches = g_launches - before;
+      if (getenv("DCL_DEBUG")) fprintf(stderr, "dcl: forward captured (aux mask %x), %lld launches\n", mask, (long long)(g_launches - before));
+      fg.launches = g_launches - before;
       g_launches = before;
     }
-    DCL_CUDA_OK(cudaGraphLaunch(h->fwd_graph, st));
-    g_launches += h->fwd_graph_launches;
+    DCL_CUDA_OK(cudaGraphLaunch(fg.exec, st));
+    g_launches += fg.launches;
     return 0;
   }
 
@@ -1048,10 +1057,10 @@ struct Fwd16 {
         std::string n = REGION_NUM[r];
         if (aux[6 + r] != nullptr)
           DCL_TRY(f.aux_branch(h->sem_dense[r], 128, 16, "mid_supervise_label.supervise_label_" + n,
-                             "mid_supervise_label.down_label_" + n, aux[6 + r]));
+                             "mid_supervise_label.down_label_" + n, aux[6 + r], 6 + r));
         if (aux[9 + r] != nullptr)
           DCL_TRY(f.aux_branch(h->edge_dense[r], 32, 32, "mid_edge_supervise_label.edge_supervise_label_" + n,
-                             "mid_edge_supervise_label.edge_down_label_" + n, aux[9 + r]));
+                             "mid_edge_supervise_label.edge_down_label_" + n, aux[9 + r], 9 + r));
       }
     }
 
@@ -1108,10 +1117,10 @@ struct Fwd16 {
         std::string n = REGION_NUM[r];
         if (aux[0 + r] != nullptr)
           DCL_TRY(f.aux_branch(h->sup_sem[r], 128, 16, "supervise_label.supervise_label_" + n,
-                             "supervise_label.down_label_" + n, aux[0 + r]));
+                             "supervise_label.down_label_" + n, aux[0 + r], 0 + r));
         if (aux[3 + r] != nullptr)
           DCL_TRY(f.aux_branch(h->sup_edge[r], 32, 32, "edge_supervise_label.edge_supervise_label_" + n,
-                             "edge_supervise_label.edge_down_label_" + n, aux[3 + r]));
+                             "edge_supervise_label.edge_down_label_" + n, aux[3 + r], 3 + r));
       }
     }
 
@@ -1502,7 +1511,7 @@ DCL_API int dcl_destroy(dcl_handle* h) {
   if (!h) return DCL_OK;
   cudaDeviceSynchronize();
   free_lanes(h);
-  if (h->fwd_graph) cudaGraphExecDestroy(h->fwd_graph);
+  for (auto& kv : h->fwd_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   for (void* p : h->allocs) cudaFree(p);
   for (auto& kv : h->conv)
     if (kv.second.tc.slab_dev) cudaFree(kv.second.tc.slab_dev);

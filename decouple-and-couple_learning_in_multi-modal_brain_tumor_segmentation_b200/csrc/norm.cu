@@ -191,6 +191,7 @@ int launch_stamp(unsigned long long* dst, int idx, cudaStream_t st) {
 __global__ void patch_desc_kernel(PatchDesc* __restrict__ dst, PatchDesc v) {
   if (threadIdx.x == 0) { dst->x = v.x; dst->sc = v.sc; dst->sd = v.sd; dst->sh = v.sh; dst->probs = v.probs; }
   if (threadIdx.x < 16) dst->keep[threadIdx.x] = v.keep[threadIdx.x];
+  if (threadIdx.x >= 16 && threadIdx.x < 28) dst->aux[threadIdx.x - 16] = v.aux[threadIdx.x - 16];
 }
 
 int launch_patch_desc(PatchDesc* dst, const PatchDesc& v, cudaStream_t st) {
