@@ -17,7 +17,8 @@ class DclError(RuntimeError):
 
 class Precision(enum.IntEnum):
     FP32 = 0
-    BF16X3 = 1
+    F16X3 = 1       # split operands: fp16 hi + fp16 lo, 3-4 tcgen05 MMAs per product (the parity-grade tensor-core mode)
+    BF16X3 = 1      # the name the mode was specified under; same value
     BF16 = 2
 
 

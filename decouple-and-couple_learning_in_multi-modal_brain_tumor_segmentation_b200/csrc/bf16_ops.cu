@@ -27,8 +27,12 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 
 // B-format load / store of one (chunk, voxel) vector; lo_off != 0 = split-bf16 (the lo planes sit lo_off vectors behind)
 __device__ __forceinline__ void load8(const uint4* __restrict__ p, int64_t lo_off, float (&f)[8]) {
-  unpack8(__ldg(p), f);
-  if (lo_off != 0) unpack8_acc<true>(__ldg(p + lo_off), f);
+  if (lo_off != 0) {        // split mode: two fp16 halves
+    unpack8_x3<false>(__ldg(p), f);
+    unpack8_x3<true>(__ldg(p + lo_off), f);
+  } else {
+    unpack8(__ldg(p), f);
+  }
 }
 __device__ __forceinline__ void store8(uint4* __restrict__ p, int64_t lo_off, const float (&f)[8]) {
   if (lo_off != 0) {
@@ -211,10 +215,17 @@ int launch_untokenise_b(const float* tokens, const float* class_token, void* y, 
 // no shared-memory staging of activations is needed.  A CTA serves one (kd,kh); a warp walks tiles of 16 parent
 // voxels along w and produces their 2 x 16 outputs (kw = 0, 1).  Weights: bf16 in shared memory, rows padded by
 // 8 elements (conflict-free fragment reads).
+// F16: fp16 operands (the split-operand mode), else bf16
+template <bool F16>
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  if constexpr (F16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
 // X3: split-bf16 tensors and weights (hi image followed by the lo image): every product is hi*hi + lo*hi + hi*lo.
@@ -297,26 +308,26 @@ deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, c
         const __nv_bfloat16* wr = s_wm + (kw * CH + nt * 8 + g) * LDM + 2 * c;   // B fragment: n = g, k = 2c (+8)
 #pragma unroll
         for (int ks = 0; ks < KX; ++ks) {
-          mma_bf16_16816(acc, ax[0][ks], *reinterpret_cast<const uint32_t*>(wr + ks * 16), *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8));
+          mma_bf16_16816<X3>(acc, ax[0][ks], *reinterpret_cast<const uint32_t*>(wr + ks * 16), *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8));
           if constexpr (X3) {
-            mma_bf16_16816(acc, ax[NIMG - 1][ks], *reinterpret_cast<const uint32_t*>(wr + ks * 16), *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8));
-            mma_bf16_16816(acc, ax[0][ks], *reinterpret_cast<const uint32_t*>(wr + WM_IMG + ks * 16), *reinterpret_cast<const uint32_t*>(wr + WM_IMG + ks * 16 + 8));
+            mma_bf16_16816<X3>(acc, ax[NIMG - 1][ks], *reinterpret_cast<const uint32_t*>(wr + ks * 16), *reinterpret_cast<const uint32_t*>(wr + ks * 16 + 8));
+            mma_bf16_16816<X3>(acc, ax[0][ks], *reinterpret_cast<const uint32_t*>(wr + WM_IMG + ks * 16), *reinterpret_cast<const uint32_t*>(wr + WM_IMG + ks * 16 + 8));
           }
         }
         const __nv_bfloat16* wsr = s_ws + (nt * 8 + g) * LDS_ + 2 * c;
 #pragma unroll
         for (int ks = 0; ks < KS; ++ks) {
-          mma_bf16_16816(acc, as[0][ks], *reinterpret_cast<const uint32_t*>(wsr + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + ks * 16 + 8));
+          mma_bf16_16816<X3>(acc, as[0][ks], *reinterpret_cast<const uint32_t*>(wsr + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + ks * 16 + 8));
           if constexpr (X3) {
-            mma_bf16_16816(acc, as[NIMG - 1][ks], *reinterpret_cast<const uint32_t*>(wsr + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + ks * 16 + 8));
-            mma_bf16_16816(acc, as[0][ks], *reinterpret_cast<const uint32_t*>(wsr + WS_IMG + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + WS_IMG + ks * 16 + 8));
+            mma_bf16_16816<X3>(acc, as[NIMG - 1][ks], *reinterpret_cast<const uint32_t*>(wsr + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + ks * 16 + 8));
+            mma_bf16_16816<X3>(acc, as[0][ks], *reinterpret_cast<const uint32_t*>(wsr + WS_IMG + ks * 16), *reinterpret_cast<const uint32_t*>(wsr + WS_IMG + ks * 16 + 8));
           }
         }
         // D fragment: (row g, n = 2c, 2c+1), (row g+8, same n) -> word c of the voxel's 16-byte vector of chunk nt
         if constexpr (X3) {
           uint32_t h0, l0, h1, l1;
-          tc::split_bf16x2(acc[0], acc[1], h0, l0);
-          tc::split_bf16x2(acc[2], acc[3], h1, l1);
+          tc::split_x2(acc[0], acc[1], h0, l0);
+          tc::split_x2(acc[2], acc[3], h1, l1);
           yw[((int64_t)nt * sp_out + qa) * 4 + c] = h0;
           yw[((int64_t)nt * sp_out + qb) * 4 + c] = h1;
           yw[((int64_t)(NT + nt) * sp_out + qa) * 4 + c] = l0;
@@ -412,8 +423,8 @@ endconv_softmax_b_kernel(const uint4* __restrict__ x, BNorm n, const uint4* __re
       if (lo_off != 0) {       // the rounding of the stored (split) tensor
         uint4 qh, ql;
         split8(t, qh, ql);
-        unpack8(qh, t);
-        unpack8_acc<true>(ql, t);
+        unpack8_x3<false>(qh, t);
+        unpack8_x3<true>(ql, t);
       } else {
         const uint4 q = pack8(t);
         unpack8(q, t);

@@ -238,18 +238,24 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint
                 const uint32_t* pr = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                  v[8 * hf + 2 * k] += __uint_as_float(pr[k] << 16);
-                  v[8 * hf + 2 * k + 1] += __uint_as_float(pr[k] & 0xffff0000u);
+                  if (p.x3) {       // split mode: fp16 halves
+                    const float2 t = unpack_f16x2(pr[k]);
+                    v[8 * hf + 2 * k] += t.x;
+                    v[8 * hf + 2 * k + 1] += t.y;
+                  } else {
+                    v[8 * hf + 2 * k] += __uint_as_float(pr[k] << 16);
+                    v[8 * hf + 2 * k + 1] += __uint_as_float(pr[k] & 0xffff0000u);
+                  }
                 }
               }
             }
             uint4 o;
             if (p.x3) {
               uint4 l;
-              split_bf16x2(v[8 * hf], v[8 * hf + 1], o.x, l.x);
-              split_bf16x2(v[8 * hf + 2], v[8 * hf + 3], o.y, l.y);
-              split_bf16x2(v[8 * hf + 4], v[8 * hf + 5], o.z, l.z);
-              split_bf16x2(v[8 * hf + 6], v[8 * hf + 7], o.w, l.w);
+              split_x2(v[8 * hf], v[8 * hf + 1], o.x, l.x);
+              split_x2(v[8 * hf + 2], v[8 * hf + 3], o.y, l.y);
+              split_x2(v[8 * hf + 4], v[8 * hf + 5], o.z, l.z);
+              split_x2(v[8 * hf + 6], v[8 * hf + 7], o.w, l.w);
               yb[lo_off + (int64_t)kc * m_total + m] = l;
             } else {
               o.x = pack_bf16x2(v[8 * hf], v[8 * hf + 1]);
@@ -464,7 +470,7 @@ conv_gemm_kernel(GemmConvParams p) {
   } else if (warp == G_EPI_WARPS) {
     // =============================== MMA issuer ==================================================
     {   // all 32 lanes run the loop; the elected lane issues
-      const uint32_t idesc = umma_idesc_bf16(128, p.n_tile);
+      const uint32_t idesc = umma_idesc_16(128, p.n_tile, p.x3 != 0);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t b_lbo = (uint32_t)p.n_tile * 16;
       const uint64_t a_desc0 = umma_desc(smem_base, 2048, 128);
@@ -574,8 +580,8 @@ template <int ACT>
 __device__ __forceinline__ void slab_xf_run_x3(uint4* bh, uint4* bl, int n_vec, int lane, const float (&sc)[8], const float (&sh)[8]) {
   for (int i = lane; i < n_vec; i += 32) {
     float f[8];
-    unpack8_acc<false>(bh[i], f);
-    unpack8_acc<true>(bl[i], f);
+    unpack8_x3<false>(bh[i], f);
+    unpack8_x3<true>(bl[i], f);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float v = fmaf(f[k], sc[k], sh[k]);
@@ -997,7 +1003,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   }
   if (best_mt == 0) { set_error("slab_conv: tile does not fit shared memory"); return -1; }
   sp.mt = best_mt; p.n_tile = best_nt; sp.npass = best_pass; sp.nb = best_nb;
-  sp.idesc = umma_idesc_bf16(128, 3 * best_nt);
+  sp.idesc = umma_idesc_16(128, 3 * best_nt, xs != 0);
   sp.rows = best_mt * 128 / g.W;
   sp.kc_pass = cin_pad / 8 / best_pass;
   const int64_t n16 = (int64_t)27 * (cin_pad / 8) * p.cout_pad;
@@ -1120,10 +1126,10 @@ prep_rows_kernel(PrepRowsSrc s0, PrepRowsSrc s1, int x3) {
     uint4 o;
     if (x3) {
       uint4 l;
-      split_bf16x2(v[8 * c], v[8 * c + 1], o.x, l.x);
-      split_bf16x2(v[8 * c + 2], v[8 * c + 3], o.y, l.y);
-      split_bf16x2(v[8 * c + 4], v[8 * c + 5], o.z, l.z);
-      split_bf16x2(v[8 * c + 6], v[8 * c + 7], o.w, l.w);
+      split_x2(v[8 * c], v[8 * c + 1], o.x, l.x);
+      split_x2(v[8 * c + 2], v[8 * c + 3], o.y, l.y);
+      split_x2(v[8 * c + 4], v[8 * c + 5], o.z, l.z);
+      split_x2(v[8 * c + 6], v[8 * c + 7], o.w, l.w);
       out[(int64_t)(TOKEN_DIM / 8 + lane * 2 + c) * rows + row] = l;
     } else {
       o.x = pack_bf16x2(v[8 * c], v[8 * c + 1]);

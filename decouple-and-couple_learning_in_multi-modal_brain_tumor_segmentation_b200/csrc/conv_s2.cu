@@ -160,7 +160,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
     }
   } else if (warp == EPI_WARPS) {
     // =============================== MMA issuer ====================================================
-    constexpr uint32_t idesc = umma_idesc_bf16(128, CO);
+    constexpr uint32_t idesc = umma_idesc_16(128, CO, X3);
     const uint32_t smem_base = smem_u32(smem);
     const uint64_t b_base = umma_desc(smem_base + C::OFF_W, CO * 16, 128);
     for (int i = 0; i < n_out; ++i) {
@@ -250,10 +250,10 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
             uint4 o;
             if constexpr (X3) {
               uint4 l;
-              split_bf16x2(val[h8 * 8 + 0], val[h8 * 8 + 1], o.x, l.x);
-              split_bf16x2(val[h8 * 8 + 2], val[h8 * 8 + 3], o.y, l.y);
-              split_bf16x2(val[h8 * 8 + 4], val[h8 * 8 + 5], o.z, l.z);
-              split_bf16x2(val[h8 * 8 + 6], val[h8 * 8 + 7], o.w, l.w);
+              split_x2(val[h8 * 8 + 0], val[h8 * 8 + 1], o.x, l.x);
+              split_x2(val[h8 * 8 + 2], val[h8 * 8 + 3], o.y, l.y);
+              split_x2(val[h8 * 8 + 4], val[h8 * 8 + 5], o.z, l.z);
+              split_x2(val[h8 * 8 + 6], val[h8 * 8 + 7], o.w, l.w);
               prm.yb[(int64_t)(CO / 8 + g16 * 2 + h8) * SPO + off] = l;
             } else {
               o.x = pack_bf16x2(val[h8 * 8 + 0], val[h8 * 8 + 1]);

@@ -273,8 +273,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
 #pragma unroll
                 for (int i = 0; i < W / 32; ++i) {
                   float f[8];
-                  unpack8_acc<false>(q[lane + 32 * i], f);
-                  unpack8_acc<true>(ql[lane + 32 * i], f);
+                  unpack8_x3<false>(q[lane + 32 * i], f);
+                  unpack8_x3<true>(ql[lane + 32 * i], f);
 #pragma unroll
                   for (int k = 0; k < 8; ++k) {
                     float t = fmaf(f[k], sc[k], sh[k]);
@@ -350,8 +350,8 @@ conv3d_k3_roll_kernel(RollParams prm) {
           if (e < ROWS * W) {
             uint4 o = make_uint4(pack_bf16x2(v[it][0], v[it][1]), pack_bf16x2(v[it][2], v[it][3]), 0u, 0u);
             if constexpr (X3) {   // the four lo halves ride in elements 4-7 of the same chunk (weights: see tc_pack_weights)
-              split_bf16x2(v[it][0], v[it][1], o.x, o.z);
-              split_bf16x2(v[it][2], v[it][3], o.y, o.w);
+              split_x2(v[it][0], v[it][1], o.x, o.z);
+              split_x2(v[it][2], v[it][3], o.y, o.w);
             }
             *reinterpret_cast<uint4*>(slot + (size_t)(Cfg::PAD + e) * 16) = o;
 #pragma unroll
@@ -366,7 +366,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   } else if (warp == MMA_WARP) {
     // =============================== MMA issuer ==================================================
     {   // all 32 lanes run the loop; the elected lane issues (see umma_bf16_ws)
-      constexpr uint32_t idesc = umma_idesc_bf16(128, CO * NP);
+      constexpr uint32_t idesc = umma_idesc_16(128, CO * NP, X3);
       const uint32_t smem_base = smem_u32(smem);
       const uint32_t w_base = smem_base + Cfg::OFF_W;
       const bool x4_src = prm.xb == nullptr;
@@ -423,12 +423,12 @@ conv3d_k3_roll_kernel(RollParams prm) {
                     const uint64_t ad = a_kd[kd] + (uint64_t)(Cfg::PAD + rho * W + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
                     const uint64_t bd = b_base + (uint64_t)(((kd * 3 + kw) * WB + blk0 * CN * 16 + ks * 2 * B_LBO) >> 4);
                     if (n_acc > 0) {
-                      if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * CN), ad, bd, umma_idesc_bf16(128, n_acc * CN), 1u);
-                      else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * CN), ad, bd, umma_idesc_bf16(128, n_acc * CN), 1u, m0, m1, m2, m3);
+                      if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(q_lo * CN), ad, bd, umma_idesc_16(128, n_acc * CN, X3), 1u);
+                      else umma_bf16_masked_ws(acc0 + (uint32_t)(q_lo * CN), ad, bd, umma_idesc_16(128, n_acc * CN, X3), 1u, m0, m1, m2, m3);
                     }
                     if (first)
                       umma_bf16_ws(acc0 + (uint32_t)(rho * CN), ad, bd + (uint64_t)((n_acc * CN * 16) >> 4),
-                                   umma_idesc_bf16(128, CN), (ks | v) == 0 ? 0u : 1u);
+                                   umma_idesc_16(128, CN, X3), (ks | v) == 0 ? 0u : 1u);
                   }
                 }
               }
@@ -550,7 +550,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
           const uint32_t* p1 = reinterpret_cast<const uint32_t*>(&rv1);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 f0 = unpack_bf16x2(p0[k]), f1 = unpack_bf16x2(p1[k]);
+            const float2 f0 = X3 ? unpack_f16x2(p0[k]) : unpack_bf16x2(p0[k]), f1 = X3 ? unpack_f16x2(p1[k]) : unpack_bf16x2(p1[k]);
             val[2 * k] += f0.x; val[2 * k + 1] += f0.y;
             val[8 + 2 * k] += f1.x; val[8 + 2 * k + 1] += f1.y;
           }
@@ -559,7 +559,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
             const uint32_t* q1 = reinterpret_cast<const uint32_t*>(&rl1);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const float2 f0 = unpack_bf16x2(q0[k]), f1 = unpack_bf16x2(q1[k]);
+              const float2 f0 = unpack_f16x2(q0[k]), f1 = unpack_f16x2(q1[k]);
               val[2 * k] += f0.x; val[2 * k + 1] += f0.y;
               val[8 + 2 * k] += f1.x; val[8 + 2 * k + 1] += f1.y;
             }
@@ -573,10 +573,10 @@ conv3d_k3_roll_kernel(RollParams prm) {
         uint4 o0, o1;
         if constexpr (X3) {
           uint4 l0, l1;
-          split_bf16x2(val[0], val[1], o0.x, l0.x);     split_bf16x2(val[2], val[3], o0.y, l0.y);
-          split_bf16x2(val[4], val[5], o0.z, l0.z);     split_bf16x2(val[6], val[7], o0.w, l0.w);
-          split_bf16x2(val[8], val[9], o1.x, l1.x);     split_bf16x2(val[10], val[11], o1.y, l1.y);
-          split_bf16x2(val[12], val[13], o1.z, l1.z);   split_bf16x2(val[14], val[15], o1.w, l1.w);
+          split_x2(val[0], val[1], o0.x, l0.x);     split_x2(val[2], val[3], o0.y, l0.y);
+          split_x2(val[4], val[5], o0.z, l0.z);     split_x2(val[6], val[7], o0.w, l0.w);
+          split_x2(val[8], val[9], o1.x, l1.x);     split_x2(val[10], val[11], o1.y, l1.y);
+          split_x2(val[12], val[13], o1.z, l1.z);   split_x2(val[14], val[15], o1.w, l1.w);
           y0[(int64_t)(CO / 8) * SP + off] = l0;
           y0[(int64_t)(CO / 8 + 1) * SP + off] = l1;
         } else {
@@ -655,13 +655,6 @@ static int tc_weight_layout(int cin, int cout, bool x3) {
   return 0;
 }
 
-static float bf16_to_f32(uint16_t h) {
-  const uint32_t u = (uint32_t)h << 16;
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-
 int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_layout, TcWeights* out, bool x3) {
   out->dev = nullptr; out->cout = cout; out->cin = cin; out->bytes = 0; out->lo_off = 0;
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;   // zero padded
@@ -679,8 +672,16 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
         const int kc = ci / 8, k = ci % 8;
         const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
         const float wv = w_host[((size_t)n * cin + ci) * taps + tap];
-        const uint16_t hi = f32_to_bf16_rn(wv);
-        const uint16_t lo = f32_to_bf16_rn(wv - bf16_to_f32(hi));
+        uint16_t hi, lo;
+        if (x3) {          // split mode: fp16 hi + fp16 lo (22 significant bits; tc_common.cuh)
+          const __half hh = __float2half_rn(wv);
+          const __half hl = __float2half_rn(wv - __half2float(hh));
+          memcpy(&hi, &hh, 2);
+          memcpy(&lo, &hl, 2);
+        } else {
+          hi = f32_to_bf16_rn(wv);
+          lo = 0;
+        }
         if (layout == 0) {
           const size_t dst = (((size_t)tap * kcs + kc) * cout_pad + n) * 8 + k;
           packed[dst] = hi;

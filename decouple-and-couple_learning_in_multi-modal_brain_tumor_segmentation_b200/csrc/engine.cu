@@ -6,6 +6,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_fp16.h>
+
 #include <algorithm>
 #include <map>
 #include <string>
@@ -578,12 +580,13 @@ static int prepare(dcl_handle* h) {
         for (int r = 0; r < rows; ++r)
           for (int c = 0; c < cols; ++c) {
             const float f = src[(size_t)r * cols + c];
-            const uint16_t hi = rn(f);
-            o[(size_t)r * (cols + 8) + c] = hi;
-            if (x3) {
-              const uint32_t hu = (uint32_t)hi << 16;
-              float hf; memcpy(&hf, &hu, 4);
-              o[image + (size_t)r * (cols + 8) + c] = rn(f - hf);
+            if (x3) {        // split mode: fp16 hi image, fp16 lo image
+              const __half hh = __float2half_rn(f);
+              const __half hl = __float2half_rn(f - __half2float(hh));
+              memcpy(&o[(size_t)r * (cols + 8) + c], &hh, 2);
+              memcpy(&o[image + (size_t)r * (cols + 8) + c], &hl, 2);
+            } else {
+              o[(size_t)r * (cols + 8) + c] = rn(f);
             }
           }
         return out;

@@ -2,6 +2,7 @@
 // layers, 8-head attention over 129-token sequences, row scatter.  All fp32 (the discrete
 // top-k makes low precision fragile here).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <float.h>
 #include "common.cuh"
 
@@ -316,9 +317,12 @@ attention_kernel(const float* __restrict__ q, const float* __restrict__ kv, floa
         const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
         out_blocked[((int64_t)(c0 >> 3) * mq + row) * 8 + (c0 & 7)] = __bfloat16_as_ushort(h0);
         out_blocked[((int64_t)(c1 >> 3) * mq + row) * 8 + (c1 & 7)] = __bfloat16_as_ushort(h1);
-        if (x3) {      // split-bf16: the lo planes follow the 64 hi chunks
-          out_blocked[((int64_t)(64 + (c0 >> 3)) * mq + row) * 8 + (c0 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(v0 - __bfloat162float(h0)));
-          out_blocked[((int64_t)(64 + (c1 >> 3)) * mq + row) * 8 + (c1 & 7)] = __bfloat16_as_ushort(__float2bfloat16_rn(v1 - __bfloat162float(h1)));
+        if (x3) {      // split mode: fp16 hi + fp16 lo, the lo planes follow the 64 hi chunks
+          const __half g0 = __float2half_rn(v0), g1 = __float2half_rn(v1);
+          out_blocked[((int64_t)(c0 >> 3) * mq + row) * 8 + (c0 & 7)] = __half_as_ushort(g0);
+          out_blocked[((int64_t)(c1 >> 3) * mq + row) * 8 + (c1 & 7)] = __half_as_ushort(g1);
+          out_blocked[((int64_t)(64 + (c0 >> 3)) * mq + row) * 8 + (c0 & 7)] = __half_as_ushort(__float2half_rn(v0 - __half2float(g0)));
+          out_blocked[((int64_t)(64 + (c1 >> 3)) * mq + row) * 8 + (c1 & 7)] = __half_as_ushort(__float2half_rn(v1 - __half2float(g1)));
         }
       } else {
         out[(int64_t)row * TOKEN_DIM + head * ATT_HD + lane] = o[r][0] * inv[r];

@@ -55,9 +55,10 @@ typedef enum dcl_status {
 /* Arithmetic mode of the convolution / GEMM kernels. */
 typedef enum dcl_precision {
   DCL_FP32 = 0,            /* fp32 FFMA kernels: the parity mode (1e-3 rel. to the reference) */
-  DCL_BF16X3 = 1,          /* split-bf16 on tcgen05: every activation / weight is a bf16 hi + lo pair, every product
-                              a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in the fp32 TMEM accumulator: the fast parity mode
-                              (same 1e-3 / 1e-4-label gates as DCL_FP32) */
+  DCL_F16X3 = 1,           /* split operands on tcgen05: every activation / weight is a 16-bit hi + lo pair (fp16 + fp16 = 22
+                              significant bits), every product a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ a_lo*w_lo) in the fp32
+                              TMEM accumulator: the fast parity mode (same 1e-3 / 1e-4-label gates as DCL_FP32) */
+  DCL_BF16X3 = 1,          /* the name the mode was specified under; same value */
   DCL_BF16 = 2             /* tcgen05 bf16 MMA, fp32 accumulate (2e-2 rel.) */
 } dcl_precision;
 

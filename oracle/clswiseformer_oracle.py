@@ -138,6 +138,7 @@ class _Net:
         score = token @ feats.transpose(2, 1).contiguous()
         idx = score.topk(TOP_NUM, dim=2, largest=True, sorted=True)[1][0, 0]
         self.tap("topk_" + tag, idx)
+        self.tap("score_" + tag, score[0, 0])      # tests size the near-tie margin of the selection with these
         picked = torch.index_select(feats, 1, idx) + pe_row      # PositionalEncoding.py:20-22: row 0 only
         return torch.cat((token, picked), dim=1), idx
 

@@ -69,3 +69,20 @@ def coupler_rows_in_golden_order(name, t, topk, golden):
                 missing += 1
                 t[base + i] = float("nan")
     return t.reshape(1, -1, 512), missing
+
+
+def topk_disagreement(ours, oracle_stages, tags):
+    """Compares our 13 top-k index sets with the oracle's.  Returns (n_differing_selections, worst_margin): for every
+    token that one side selected and the other did not, |score(token) - score(128th selected)| / std(score) in the
+    ORACLE's fp32 scores - how close to a tie the disagreement is (0 = exact tie)."""
+    n_diff, worst = 0, 0.0
+    for tag in tags:
+        a, b = set(int(v) for v in ours[tag]), set(int(v) for v in oracle_stages["topk_" + tag].tolist())
+        if a == b:
+            continue
+        n_diff += 1
+        sc = oracle_stages["score_" + tag].double()
+        kth = sc[oracle_stages["topk_" + tag][-1]]
+        for tok in a ^ b:
+            worst = max(worst, float((sc[tok] - kth).abs() / sc.std()))
+    return n_diff, worst
