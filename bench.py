@@ -2,14 +2,14 @@
 """Benchmark of the sliding-window ClsWiseFormer inference path (BASELINE.json metric: BraTS
 4x240x240x155 volumes/sec).
 
-    python bench.py [--gpus N --steps K --warmup W] [--precision fp32|bf16x3|bf16] [--workload overlap50|reference8|overlap75]
+    python bench.py [--gpus N --steps K --warmup W] [--precision f16x3|bf16|fp32] [--workload overlap50|reference8|overlap75]
     python bench.py --impl reference ...      # the CPU oracle port of the reference path on the host cores
 
 A step = one full volume: patch gather -> clswiseformer forward per 128^3 patch -> overlap
 accumulate / stitch -> normalise + arg-max + label histogram + Dice counters.  Default workload is
 BASELINE.json configs[1]: 50 % overlap (stride 64 -> 18 patches, uniform blend).  Prints ONE JSON line.
 
-The headline (`value`, `e2e`, `roofline`) is the PARITY-GRADE mode DCL_BF16X3 (split-bf16 operands on the tcgen05
+The headline (`value`, `e2e`, `roofline`) is the PARITY-GRADE mode DCL_BF16X3 (split-fp16 operands on the tcgen05
 kernels: meets the fp32 tolerances of north_star); the plain bf16 mode (2e-2 class) is measured in the same run and
 reported beside it under "bf16".  "parity" holds the observed error of each mode on this very workload against the
 golden minted from the unmodified reference (tests/golden/make_golden_overlap50.py), computed outside the timed region.
@@ -452,7 +452,9 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    prec = {"fp32": dcl_b200.Precision.FP32, "bf16x3": dcl_b200.Precision.BF16X3, "bf16": dcl_b200.Precision.BF16}[
+    if args.precision == "f16x3":
+        args.precision = "f16x3"
+    prec = {"fp32": dcl_b200.Precision.FP32, "f16x3": dcl_b200.Precision.F16X3, "bf16": dcl_b200.Precision.BF16}[
         args.precision]
     with_aux = args.workload == "overlap50_aux"
     eng = dcl_b200.Engine(prec, want_aux=with_aux)
@@ -561,7 +563,7 @@ def run_ours(args):
 
     # ---- the plain bf16 mode beside the parity-grade headline (same workload, same run) ----
     bf16_rec = None
-    if rank == 0 and world == 1 and args.precision == "bf16x3" and mode != "TTA" and not args.no_bf16 and not with_aux:
+    if rank == 0 and world == 1 and args.precision == "f16x3" and mode != "TTA" and not args.no_bf16 and not with_aux:
         e16 = dcl_b200.Engine(dcl_b200.Precision.BF16)
         e16.load_state_dict(seed0_weights())
 
@@ -648,7 +650,7 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if by_patch else "weak", "vs_baseline": None,
             "dtype": {"fp32": "fp32 (FFMA)",
-                      "bf16x3": "bf16x3: split-bf16 operands (hi+lo), 3 tcgen05 MMAs per product, fp32 accumulate - parity-grade",
+                      "f16x3": "f16x3: split operands (fp16 hi + fp16 lo), 3-4 tcgen05 MMAs per product, fp32 accumulate - parity-grade",
                       "bf16": "bf16"}[args.precision],
             "data": "synthetic",
             "config": config_dict(args, n_patches, by_patch),
@@ -714,13 +716,13 @@ def dominant_roofline(prof, pk, precision):
         t = json.load(open(tpath))
         if t.get("kind") == best:
             traffic = t.get("dram_bytes_per_launch")
-    x3 = precision == "bf16x3"
+    x3 = precision == "f16x3"
     rec = {"bound": "tensor", "achieved": tf, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": tf / pk["tensor"],
            "frac_of_burst_peak": tf / pk["tensor_burst"], "frac_of_nominal_2250": tf / 2250.0,
            "traffic": traffic, "kernel": name, "launches": n, "avg_launch_ms": ms / max(n, 1),
            "flops_per_launch": flops / max(n, 1), "share_of_step": ms / prof_ms,
            "peak_source": pk["source"] + " sustained bf16 dense"}
-    # what the tensor pipe EXECUTES per algorithmic MAC: split-bf16 forms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ a_lo*w_lo where
+    # what the tensor pipe EXECUTES per algorithmic MAC: split-fp16 forms a_hi*w_hi + a_lo*w_hi + a_hi*w_lo (+ a_lo*w_lo where
     # the weights ride stacked along N: the rolling kernels) - 3 bf16 MMAs in the GEMM / slab / stride-2 kernels, 4 in the
     # rolling kernels; north_star's "tensor-pipe utilisation against the dense bf16 peak" is executed MMA FLOPs / peak
     factor = (4 if best in (2, 3) else 3) if x3 else 1
@@ -728,10 +730,10 @@ def dominant_roofline(prof, pk, precision):
                           "utilisation_of_sustained_peak": tf * factor / pk["tensor"],
                           "utilisation_of_nominal_2250": tf * factor / 2250.0,
                           "ncu_counter": "sm__pipe_tensor_subpipe_hmma_cycles_active / (8 x sm__cycles_elapsed): "
-                                         "profiles/r02_ncu_full_conv_kernels.csv (0.148 for the split-bf16 16-channel layer, "
+                                         "profiles/r02_ncu_full_conv_kernels.csv (0.148 for the split-fp16 16-channel layer, "
                                          "0.118 for the bf16 one; that counter's own peak is ~1.87 x the bf16 dense peak)"}
     if x3:
-        rec["note"] = ("`achieved` / `frac` count ALGORITHMIC FLOPs (2 x MACs of the convolution); the split-bf16 kernels execute "
+        rec["note"] = ("`achieved` / `frac` count ALGORITHMIC FLOPs (2 x MACs of the convolution); the split-fp16 kernels execute "
                        f"{factor} tensor-core MACs per algorithmic MAC, so the ceiling of `frac` is 1/{factor} and the pipe's own "
                        "utilisation is `tensor_pipe`")
     if best == 2 and n > 0:
@@ -750,9 +752,10 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
-                    help="bf16x3 (default) = the parity-grade tensor-core mode; bf16 = the 2e-2 class mode")
-    ap.add_argument("--no-bf16", action="store_true", help="skip the plain-bf16 sub-record of a bf16x3 run")
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3", "bf16x3", "bf16"],
+                    help="f16x3 (default; bf16x3 is the same mode's first name) = the parity-grade split-operand tensor-core mode; "
+                         "bf16 = the 2e-2 class mode")
+    ap.add_argument("--no-bf16", action="store_true", help="skip the plain-bf16 sub-record of an f16x3 run")
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the single-volume-sharded sub-record")
     ap.add_argument("--workload", default="overlap50", choices=sorted(WORKLOADS))
     ap.add_argument("--sharding", default="volume", choices=["volume", "patch"],

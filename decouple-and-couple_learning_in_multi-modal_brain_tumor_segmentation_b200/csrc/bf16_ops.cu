@@ -25,7 +25,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return o;
 }
 
-// B-format load / store of one (chunk, voxel) vector; lo_off != 0 = split-bf16 (the lo planes sit lo_off vectors behind)
+// B-format load / store of one (chunk, voxel) vector; lo_off != 0 = split-fp16 (the lo planes sit lo_off vectors behind)
 __device__ __forceinline__ void load8(const uint4* __restrict__ p, int64_t lo_off, float (&f)[8]) {
   if (lo_off != 0) {        // split mode: two fp16 halves
     unpack8_x3<false>(__ldg(p), f);
@@ -228,7 +228,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// X3: split-bf16 tensors and weights (hi image followed by the lo image): every product is hi*hi + lo*hi + hi*lo.
+// X3: split-fp16 tensors and weights (hi image followed by the lo image): every product is hi*hi + lo*hi + hi*lo.
 template <int CIN, bool X3>
 __global__ void __launch_bounds__(256)
 deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, const float* __restrict__ mt,

@@ -110,7 +110,7 @@ int launch_linear(const float* x, const float* w, const float* bias, const float
                   int k, bool gelu, cudaStream_t st);
 // 8 heads x 64; q: (mq,512), kv: (mk,1024) = [K | V]; out (mq,512)
 // out_blocked != nullptr: the result is written as bf16 [64][mq][8] (GEMM A operand) instead of fp32 `out`
-// x3: out_blocked is split-bf16 ([64 hi chunks][64 lo chunks] x mq rows)
+// x3: out_blocked is split-fp16 ([64 hi chunks][64 lo chunks] x mq rows)
 int launch_attention(const float* q, const float* kv, float* out, int mq, int mk, cudaStream_t st, void* out_blocked = nullptr,
                      bool x3 = false);
 // feats[idx[i]] = rows[i]   (i < 128)

@@ -60,7 +60,7 @@ prep_blocked_kernel(ConvSrc src, int64_t spatial, int in_h, int in_w, uint4* __r
     v[k] = x;
   }
   uint4 o;
-  if (lo_off != 0) {      // split-bf16: hi planes, then lo planes
+  if (lo_off != 0) {      // split-fp16: hi planes, then lo planes
     uint4 l;
     split8(v, o, l);
     out[lo_off + (int64_t)kc * spatial + p] = l;
@@ -101,7 +101,7 @@ struct GemmConvParams {
   int D, H, W, OD, OH, OW, stride, taps, kstage;
   int out_mode;            // 0: fp32 NCDHW [cout][m]   1: fp32 row-major [m][cout]   2: B-format bf16
   int gelu;                // exact (erf) GELU after the bias
-  // split-bf16 (DCL_BF16X3): the lo planes of a source follow its hi planes (chunk kc of source 0 at + c0_chunks *
+  // split-fp16 (DCL_BF16X3): the lo planes of a source follow its hi planes (chunk kc of source 0 at + c0_chunks *
   // spatial, of source 1 at + c1 chunks * spatial), the lo weight image sits w_lo 16-byte units behind the hi image,
   // B-format outputs / residuals carry their lo planes cout_pad / 8 chunks behind the hi planes
   int x3;
@@ -327,7 +327,7 @@ conv_gemm_kernel(GemmConvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int a_half = 2 * p.kstage * 2048;                // [chunk][128 rows][16 B]
   const int b_half = 2 * p.kstage * p.n_tile * 16;       // [chunk][n_tile rows][16 B]
-  const int a_bytes = a_half << p.x3;                    // split-bf16: the lo chunks follow the hi chunks
+  const int a_bytes = a_half << p.x3;                    // split-fp16: the lo chunks follow the hi chunks
   const int b_bytes = b_half << p.x3;
   const int stage_bytes = a_bytes + b_bytes;
   uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + G_NS * stage_bytes);
@@ -543,7 +543,7 @@ conv_gemm_kernel(GemmConvParams p) {
 struct SlabParams {
   GemmConvParams g;         // a / a1 / c0_chunks / bias / residual / y / stats / cout / n_tile / D,H,W / out_mode
   const uint4* wslab;       // repacked weights
-  int64_t wslab_lo;         // split-bf16: 16-byte units from the hi image to the lo image
+  int64_t wslab_lo;         // split-fp16: 16-byte units from the hi image to the lo image
   const stat_t* sums;       // fused input InstanceNorm (+ activation), as in the rolling kernel
   float inv_n;
   const float* mean;
@@ -575,7 +575,7 @@ __device__ __forceinline__ uint4 slab_xf(uint4 v, const float (&sc)[8], const fl
   return v;
 }
 
-// split-bf16 variant: value = hi + lo -> norm + act -> split again
+// split-fp16 variant: value = hi + lo -> norm + act -> split again
 template <int ACT>
 __device__ __forceinline__ void slab_xf_run_x3(uint4* bh, uint4* bl, int n_vec, int lane, const float (&sc)[8], const float (&sh)[8]) {
   for (int i = lane; i < n_vec; i += 32) {
@@ -619,7 +619,7 @@ conv_slab_kernel(SlabParams sp) {
   const int R = sp.rows;
   const int npos = 3 * (R + 2) * W;                      // 16-byte positions per channel chunk
   const int kcp = sp.kc_pass;                            // channel chunks per pass
-  const int kcs = kcp << p.x3;                           // staged chunks per pass: split-bf16 keeps the lo chunks behind the hi chunks
+  const int kcs = kcp << p.x3;                           // staged chunks per pass: split-fp16 keeps the lo chunks behind the hi chunks
   const int slab_bytes = kcs * npos * 16;
   const int nst = 3 * p.n_tile;                          // stacked N
   const int b_stage = kcs * nst * 16;                    // ring stage = one (kd,kh): [hi|lo][chunk][kw][n_tile] x 16 B
@@ -904,7 +904,7 @@ int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st) {
   p.x3 = g.x3 ? 1 : 0;
   p.w_lo = w.lo_off / 16;
   if (w.layout != 0) { set_error("gemm_conv: weights packed for the rolling kernel"); return -1; }
-  if (g.x3 && (w.lo_off == 0 || ((w.cin % 16) != 0 && g.a1 != nullptr))) { set_error("gemm_conv: split-bf16 needs split weights"); return -1; }
+  if (g.x3 && (w.lo_off == 0 || ((w.cin % 16) != 0 && g.a1 != nullptr))) { set_error("gemm_conv: split-fp16 needs split weights"); return -1; }
   p.OD = (g.D - 1) / g.stride + 1; p.OH = (g.H - 1) / g.stride + 1; p.OW = (g.W - 1) / g.stride + 1;
   if (p.out_mode == 1 && (p.cout % 16) != 0) { set_error("gemm_conv: row-major output needs cout % 16 == 0"); return -1; }
   return launch_gemm_params(p, st);
@@ -960,7 +960,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   p.x3 = g.x3 ? 1 : 0;
   p.w_lo = w.lo_off / 16;
   if (w.layout != 0) { set_error("slab_conv: weights packed for the rolling kernel"); return -1; }
-  if (g.x3 && w.lo_off == 0) { set_error("slab_conv: split-bf16 needs split weights"); return -1; }
+  if (g.x3 && w.lo_off == 0) { set_error("slab_conv: split-fp16 needs split weights"); return -1; }
   const int xs = p.x3;
   sp.sums = norm ? norm->sums : nullptr;
   sp.inv_n = norm ? norm->inv_n : 0.f;
@@ -1010,7 +1010,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   if (w.slab_dev == nullptr || w.slab_ntile != best_nt) {   // one-time repack for this tile width (cached in w)
     if (w.slab_dev) { cudaStreamSynchronize(st); cudaFree(w.slab_dev); w.slab_dev = nullptr; }
     DCL_CUDA_OK(cudaMalloc(&w.slab_dev, (size_t)(n16 << xs) * 16));
-    for (int part = 0; part <= xs; ++part)     // split-bf16: the lo image is repacked the same way, behind the hi image
+    for (int part = 0; part <= xs; ++part)     // split-fp16: the lo image is repacked the same way, behind the hi image
       slab_repack_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, st>>>(p.w + (part ? p.w_lo : 0),
                                                                      reinterpret_cast<uint4*>(w.slab_dev) + (part ? n16 : 0),
                                                                      cin_pad / 8, p.cout_pad, best_nt);
@@ -1052,7 +1052,7 @@ static int launch_gemm_params(GemmConvParams& p, cudaStream_t st) {
   const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
   const int64_t m_tiles = (m_total + 127) / 128;
   p.n_tile = pick_n_tile(p.cout_pad, m_tiles);
-  // split-bf16 stages are twice as large: halve the K depth of a stage until three of them fit
+  // split-fp16 stages are twice as large: halve the K depth of a stage until three of them fit
   while (p.x3 && p.kstage % 2 == 0 && ((2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16) << 1) > 64 * 1024) p.kstage /= 2;
   const int stage_bytes = (2 * p.kstage * 2048 + 2 * p.kstage * p.n_tile * 16) << p.x3;
   // deep enough to cover the L2 round trip with small stages; short K loops (linears) take all stages at once

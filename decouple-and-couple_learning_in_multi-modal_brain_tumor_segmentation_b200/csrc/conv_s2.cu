@@ -25,7 +25,7 @@ namespace dcl {
 
 using namespace tc;
 
-// X3_: split-bf16 (DCL_BF16X3): staged planes and weights carry their lo halves behind the hi halves (as in global
+// X3_: split-fp16 (DCL_BF16X3): staged planes and weights carry their lo halves behind the hi halves (as in global
 // memory), every (tap, K step) issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
 template <int CI_, int CO_, int GI_, int NT_, int NSLOT_, bool X3_ = false>
 struct S2Cfg {
@@ -131,7 +131,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
       const bool d_ok = d_in >= 0;                  // the high side never leaves the volume (2*(GO-1)+1 = GI-1)
       uint8_t* slot = smem + (size_t)s * SLOT_BYTES;
       // item = (chunk, staged row, w): consecutive threads read consecutive 16-byte vectors of one row
-      constexpr int ITEMS = KCS * ROWS * GI;      // (split-bf16: global chunk KC + k is the lo half of chunk k, as in the slot)
+      constexpr int ITEMS = KCS * ROWS * GI;      // (split-fp16: global chunk KC + k is the lo half of chunk k, as in the slot)
       for (int e0 = pt; e0 < ITEMS; e0 += 4 * NPROD) {
         uint4 v[4];
         int pos[4];
@@ -325,7 +325,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
 using S2EnDown1 = S2Cfg<16, 32, 128, 2, 5>;     // 16 -> 32 @ 128^3
 using S2EnDown2 = S2Cfg<32, 64, 64, 1, 3>;      // 32 -> 64 @ 64^3: 110 KB of weights leave room for three staged planes
 using S2Edge = S2Cfg<32, 32, 64, 1, 4>;         // conv_64_to_32: 32 -> 32 @ 64^3
-using S2EnDown1X3 = S2Cfg<16, 32, 128, 1, 4, true>;   // split-bf16: two output rows per CTA, 221 KB (the 64^3 layers' split
+using S2EnDown1X3 = S2Cfg<16, 32, 128, 1, 4, true>;   // split-fp16: two output rows per CTA, 221 KB (the 64^3 layers' split
                                                       // weights alone are 221 KB: they stay on the GEMM kernel)
 
 static bool s2_general_enabled() {      // DCL_S2GEN=0 sends the 64^3 layers back to the im2col GEMM
@@ -369,7 +369,7 @@ static int launch_s2(const void* xb, const TcWeights& w, const float* bias, void
 int launch_s2_roll_conv(const void* xb, const TcWeights& w, const float* bias, void* yb, stat_t* stats, cudaStream_t st, bool x3) {
   if (w.dev == nullptr) { set_error("s2_roll_conv: weights not packed"); return -1; }
   if (x3) {
-    if (w.lo_off == 0 || !(w.cin == 16 && w.cout == 32)) { set_error("s2_roll_conv: unsupported split-bf16 layer"); return -1; }
+    if (w.lo_off == 0 || !(w.cin == 16 && w.cout == 32)) { set_error("s2_roll_conv: unsupported split-fp16 layer"); return -1; }
     return launch_s2<S2EnDown1X3>(xb, w, bias, yb, stats, st);
   }
   if (w.cin == 16 && w.cout == 32) return launch_s2<S2EnDown1>(xb, w, bias, yb, stats, st);

@@ -29,7 +29,7 @@ using namespace tc;
 
 cudaError_t trace_set_conv_tc(long long* p, int cta) { return trace_set_local(p, cta); }
 
-// X3_: split-bf16 (DCL_BF16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (a plane is
+// X3_: split-fp16 (DCL_BF16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (a plane is
 // still one bulk copy per chunk).  The weights hold, per K chunk, the hi rows followed by the lo rows of every output
 // row block: B' = [W_hi | W_lo] stacked along N, so that ONE MMA A x B' fills two accumulators D1 (x W_hi) and D2
 // (x W_lo).  Per (tap, K step) two MMAs are issued, A_hi x B' and A_lo x B':
@@ -223,7 +223,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(d_ok ? (uint32_t)KCS * run_bytes : 0u), "r"(bar)
                        : "memory");
         __syncwarp();
-        if (d_ok && lane < KCS) {      // staged chunks: the KC hi chunks of this launch's channels, then (split-bf16) their lo chunks
+        if (d_ok && lane < KCS) {      // staged chunks: the KC hi chunks of this launch's channels, then (split-fp16) their lo chunks
           const int gchunk = (lane < KC ? 0 : prm.cin_total / 8) + prm.cin_off / 8 + (lane < KC ? lane : lane - KC);
           const uint4* src = prm.xb + (int64_t)gchunk * SP + ((int64_t)d_in * G + (h0 - 1 + r_lo)) * G;
           const uint32_t dst = smem_base + (uint32_t)(s * Cfg::SLOT_BYTES + (lane * NPOS + Cfg::PAD + r_lo * W) * 16);
@@ -393,7 +393,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
           // stacked N = 3C operand, so one MMA (one read of the 4 KB A tile) does the work of three.
           // Fully unrolled: every descriptor is (one of 3 per-plane bases) + a compile-time constant.
           // kw runs 1,0,2 so that the MMA that initialises an accumulator (accumulate = 0) is unmasked.
-          constexpr int CN = CO * NP;                       // accumulator columns per output row (split-bf16: D1 | D2)
+          constexpr int CN = CO * NP;                       // accumulator columns per output row (split-fp16: D1 | D2)
           constexpr uint32_t WB = 3 * CN * CI * 2;          // bytes of one (kd,kw) stacked weight matrix
           constexpr uint32_t B_LBO = 3 * CN * 16;
           const uint64_t b_base = umma_desc(w_base, B_LBO, 128);
@@ -417,7 +417,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
 #pragma unroll
                 for (int ks = 0; ks < Cfg::KS; ++ks) {
 #pragma unroll
-                  for (int v = 0; v < NP; ++v) {      // split-bf16: A_hi x [W_hi | W_lo], then A_lo x [W_hi | W_lo]
+                  for (int v = 0; v < NP; ++v) {      // split-fp16: A_hi x [W_hi | W_lo], then A_lo x [W_hi | W_lo]
                     // (the 4-channel fp32 source packs hi and lo into ONE chunk whose weights carry w at k = ci and ci + 4)
                     if (X3 && v == 1 && x4_src) continue;
                     const uint64_t ad = a_kd[kd] + (uint64_t)(Cfg::PAD + rho * W + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
@@ -435,7 +435,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
             }
           }
         } else {
-          constexpr int CN = CO * NP;                       // B rows per K chunk: split-bf16 stacks [W_hi | W_lo] along N
+          constexpr int CN = CO * NP;                       // B rows per K chunk: split-fp16 stacks [W_hi | W_lo] along N
           const uint64_t b_base = umma_desc(w_base, CN * 16, 128);
 #pragma unroll 1
           for (int t = 0; t < Cfg::NT; ++t) {
@@ -644,10 +644,10 @@ static uint16_t f32_to_bf16_rn(float f) {
 }
 
 // B operand tiles, bf16, K-major no-swizzle (core matrix = 8 couts x 8 cins, 128 contiguous bytes):
-//   layout 0  [tap][cin/8][cout][8]                            one N = cout matrix per tap (split-bf16: hi image, then lo image)
+//   layout 0  [tap][cin/8][cout][8]                            one N = cout matrix per tap (split-fp16: hi image, then lo image)
 //   layout 1  [kd][kw][cin/8][kh = 2,1,0][cout][8]             one stacked N = 3*cout matrix per (kd,kw)
-//   layout 2  [kd][kw][cin/8][kh = 2,1,0][hi|lo][cout][8]      split-bf16 rolling kernel, 16-channel layers: N = 3*2*cout
-//   layout 3  [cin half][tap][2 chunks][hi|lo][cout][8]        split-bf16 rolling kernel, 32 -> 32 layers: one image of
+//   layout 2  [kd][kw][cin/8][kh = 2,1,0][hi|lo][cout][8]      split-fp16 rolling kernel, 16-channel layers: N = 3*2*cout
+//   layout 3  [cin half][tap][2 chunks][hi|lo][cout][8]        split-fp16 rolling kernel, 32 -> 32 layers: one image of
 //                                                              N = 2*cout per 16 input channels (one launch each)
 static int tc_weight_layout(int cin, int cout, bool x3) {
   if (cin <= 16 && cout == 16) return x3 ? 2 : 1;
@@ -660,10 +660,10 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;   // zero padded
   const int kcs = cin_pad / 8;
   const size_t image = (size_t)taps * cin_pad * cout_pad;
-  std::vector<uint16_t> packed(x3 ? 2 * image : image, 0);       // split-bf16: twice the elements in every layout
+  std::vector<uint16_t> packed(x3 ? 2 * image : image, 0);       // split-fp16: twice the elements in every layout
   const int layout = (roll_layout && taps == 27) ? tc_weight_layout(cin, cout, x3) : 0;
   out->layout = layout;
-  // InitConv in split-bf16 mode: the rolling kernel stages the four input channels as [hi0..3 | lo0..3] in ONE chunk,
+  // InitConv in split-fp16 mode: the rolling kernel stages the four input channels as [hi0..3 | lo0..3] in ONE chunk,
   // so the weights of channel ci sit at k = ci AND k = ci + 4
   const bool init_x3 = layout == 2 && cin == 4;
   for (int tap = 0; tap < taps; ++tap)
@@ -709,7 +709,7 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
 
 using RollC16 = RollCfg<16, 16, 128, 8, true, 5>;
 using RollC32 = RollCfg<32, 32, 64, 8, false, 4>;
-// split-bf16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory) for the
+// split-fp16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory) for the
 // 16-channel layers; a 32 -> 32 layer (110 KB of split weights) runs as two launches over 16 input channels each
 using RollC16X3 = RollCfg<16, 16, 128, 4, true, 4, true>;
 using RollC32X3 = RollCfg<16, 32, 64, 8, false, 4, true>;

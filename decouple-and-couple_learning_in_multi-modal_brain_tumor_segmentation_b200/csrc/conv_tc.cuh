@@ -19,7 +19,7 @@ void tc_free_weights(TcWeights* w);   // frees dev and slab_dev
 
 // Packs a PyTorch (cout, cin, taps) fp32 weight (host) into the kernel's B-operand layout (taps = 27 | 1).
 // roll_layout: the conv will run on the rolling kernel (stacked-kh weight order for 16-channel outputs)
-// x3: split every weight into bf16 hi + lo images (precision mode DCL_BF16X3)
+// x3: split every weight into fp16 hi + lo images (precision mode DCL_F16X3)
 int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_layout, TcWeights* out, bool x3 = false);
 // fp32 NCDHW (two-source concat, fused norm + activation) -> bf16 channel-blocked [cin_pad/8][D][H][W][8]
 // x3: out holds 2 * cin_pad / 8 chunks, the hi planes followed by the lo planes
@@ -28,8 +28,8 @@ int launch_prep_blocked(const ConvSrc& src, int in_d, int in_h, int in_w, void* 
 int launch_conv_gemm(const void* a_blocked, const TcWeights& w, const ConvDst& dst, int in_d, int in_h, int in_w,
                      int stride, int taps, cudaStream_t st, bool x3 = false);
 // ---- "B-format" activations of the bf16 pipeline: bf16, channel-blocked [C/8][spatial][8] ------------------
-// Split-bf16 mode (DCL_BF16X3, `x3` below): every B-format tensor is [2][C/8][spatial][8] - the bf16 "hi" planes
-// followed by the bf16 "lo" planes (value = hi + lo, 16 significant bits); every MMA kernel forms
+// Split-fp16 mode (DCL_F16X3, `x3` below): every B-format tensor is [2][C/8][spatial][8] - the fp16 "hi" planes
+// followed by the fp16 "lo" planes (value = hi + lo, 22 significant bits); every MMA kernel forms
 // a_hi*w_hi + a_lo*w_hi + a_hi*w_lo in its fp32 accumulator.
 // Fused transform of a conv input: InstanceNorm (from raw sums or explicit mean/rstd; all null = none) + activation.
 struct BNorm {
@@ -50,7 +50,7 @@ struct RollArgs {
   const void* resb = nullptr;        // B-format residual
   void* yb = nullptr;                // B-format output
   stat_t* stats = nullptr;           // 2*cout fixed-point sums += (sum, sum of squares) of the outputs
-  bool x3 = false;                   // split-bf16 tensors and weights
+  bool x3 = false;                   // split-fp16 tensors and weights
 };
 // General implicit-GEMM convolution / linear layer on B-format input (conv_gemm.cu).
 struct GemmArgs {
@@ -64,7 +64,7 @@ struct GemmArgs {
   const void* residual = nullptr;            // same format as y
   stat_t* stats = nullptr;                   // 2*cout fixed-point sums += (sum, sum of squares) of the outputs
   int gelu = 0;
-  bool x3 = false;                           // split-bf16 sources / weights / B-format output and residual
+  bool x3 = false;                           // split-fp16 sources / weights / B-format output and residual
 };
 int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st);
 // stride-1 3x3x3 conv with the input tile staged once ("slab" kernel, fused input norm); W in {16,32,64,128}
@@ -88,7 +88,7 @@ int launch_norm_act_b(const void* x, const BNorm& n, const void* res, void* y, i
 // B-format -> fp32 NCDHW
 int launch_unblock(const void* x, float* y, int channels, int64_t spatial, cudaStream_t st, bool x3 = false);
 // tokens = convert_dim(act(norm(x[chunk0*8 : chunk0*8 + channels]))) (+ dense fp32 NCDHW copy)
-// x3_chunks: 0, or the chunk count (C_total / 8) of the split-bf16 tensor x (its lo planes start there)
+// x3_chunks: 0, or the chunk count (C_total / 8) of the split-fp16 tensor x (its lo planes start there)
 int launch_tokenise_b(const void* x, const BNorm& n, int chunk0, float* tokens, float* dense_or_null, int channels,
                       int grid, int p0, int p1, int p2, cudaStream_t st, int x3_chunks = 0);
 // y (B-format) = split_dim(tokens * class_token)
@@ -112,7 +112,7 @@ int launch_prep_rows2(const float* x0, const float* g0, const float* b0, int row
                       const float* b1, int rows1, void* out1, cudaStream_t st, bool x3 = false);
 // y[m][n] = a[m][:] . w[n][:] + bias (+GELU) (+residual), a blocked bf16, w packed by tc_pack_weights(taps = 1)
 // y_blocked != nullptr: the result goes out as bf16 [n/8][m][8] (the next GEMM's A operand) instead of fp32 `y`
-// x3: a_blocked / y_blocked are split-bf16, w_packed holds the hi image followed by the lo image (n * k * 2 bytes each)
+// x3: a_blocked / y_blocked are split-fp16, w_packed holds the hi image followed by the lo image (n * k * 2 bytes each)
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
                      int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked = nullptr, bool x3 = false);
 

@@ -284,7 +284,7 @@ struct dcl_handle {
 
 namespace dcl {
 
-// tensor-core pipeline (B-format activations, tcgen05 kernels): DCL_BF16 and the split-bf16 mode DCL_BF16X3
+// tensor-core pipeline (B-format activations, tcgen05 kernels): DCL_BF16 and the split-fp16 mode DCL_BF16X3
 static inline bool is_tc(const dcl_handle* h) { return h->cfg.precision == DCL_BF16 || h->cfg.precision == DCL_BF16X3; }
 static inline bool is_x3(const dcl_handle* h) { return h->cfg.precision == DCL_BF16X3; }
 
@@ -342,7 +342,7 @@ static int allocate_workspace(dcl_handle* h) {
   }
   DCL_TRY(falloc(h, &h->probs, 4 * P3));
   if (is_tc(h)) {
-    const int64_t E = is_x3(h) ? 4 : 2;      // bytes per element of a B-format tensor (split-bf16: hi + lo planes)
+    const int64_t E = is_x3(h) ? 4 : 2;      // bytes per element of a B-format tensor (split-fp16: hi + lo planes)
     DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * E));
     DCL_TRY(dev_alloc(h, &h->tok_a, 258 * 512 * E));
     DCL_TRY(dev_alloc(h, &h->tok_b, 258 * 512 * E));
@@ -570,7 +570,7 @@ static int prepare(dcl_handle* h) {
       }
       // the kernel keeps these as bf16 with rows padded by 8 elements (conflict-free fragment reads): store exactly that
       // image, so its prologue is a straight 16-byte copy instead of thousands of scalar loads + conversions per CTA
-      // (split-bf16: the hi image is followed by the lo image = bf16(w - hi))
+      // (split-fp16: the hi image is followed by the lo image = bf16(w - hi))
       const bool x3 = is_x3(h);
       auto to_bf16_padded = [x3](const std::vector<float>& src, int rows, int cols) {
         const size_t image = (size_t)rows * (cols + 8);                  // bf16 elements
@@ -1978,7 +1978,7 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
   std::vector<float> w((size_t)cout * cin * 27);
   for (size_t i = 0; i < w.size(); ++i) w[i] = (float)((i * 2654435761u >> 8) & 0xffff) / 65536.f - 0.5f;
-  const bool x3 = (mode & 8) != 0;     // split-bf16 (DCL_BF16X3) variant of the same layer
+  const bool x3 = (mode & 8) != 0;     // split-fp16 (DCL_BF16X3) variant of the same layer
   const int E = x3 ? 4 : 2;
   const bool roll = stride == 1 && tc_conv_supported(cin, cout, g, 1, x3) && cin != 4;
   TcWeights tw;
@@ -2104,7 +2104,7 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
     cudaStreamSynchronize(st);
     cudaFree(wp);
   } else {
-    const bool x3 = impl == 1;           // split-bf16 operands (DCL_BF16X3)
+    const bool x3 = impl == 1;           // split-fp16 operands (DCL_BF16X3)
     const int E = x3 ? 4 : 2;            // bytes per B-format element
     TcWeights tw;
     const bool cubic = in_dhw[0] == in_dhw[1] && in_dhw[1] == in_dhw[2];

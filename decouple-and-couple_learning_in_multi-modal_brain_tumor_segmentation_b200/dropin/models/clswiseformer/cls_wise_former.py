@@ -166,7 +166,7 @@ class ClsWiseFormer(nn.Module):
 
         # ---- engine state (not part of state_dict) ----
         self.deterministic = False          # True: skip the always-on dropout3d draw (mask = 1)
-        self.precision = Precision.BF16X3     # split-bf16 on the tensor cores: fp32-class results
+        self.precision = Precision.BF16X3     # split-fp16 on the tensor cores: fp32-class results
         self.compute_aux = True             # forward() returns the 4 aux dicts like the reference
         self._engine = None
         self._engine_key = None

@@ -21,7 +21,7 @@ for _k in ("01", "02", "04"):
 FP32_TOL = 1e-3     # north_star: fp32 logits within 1e-3 relative of the reference forward
 
 
-# Both parity-grade modes run the whole file: DCL_FP32 (FFMA kernels) and DCL_BF16X3 (split-bf16 operands on the
+# Both parity-grade modes run the whole file: DCL_FP32 (FFMA kernels) and DCL_BF16X3 (split-fp16 operands on the
 # tcgen05 kernels, the fast path) are gated at the SAME fp32 tolerances of north_star.
 @pytest.fixture(scope="module", params=["FP32", "BF16X3"])
 def engine(request, seed0_state_dict):

@@ -184,7 +184,7 @@ def test_conv3d_k3_gemm_bf16(case):
     dict(c0=8, c1=0, cout=2, dims=(20, 12, 36), stride=1, norm=False, act=0, residual=False),
 ])
 def test_conv3d_k3_split_bf16(case):
-    """DCL_BF16X3 kernels (split-bf16 operands: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05, fp32 accumulate) against
+    """DCL_BF16X3 kernels (split-fp16 operands: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05, fp32 accumulate) against
     the PLAIN fp32 torch convolution - no operand rounding is granted: 16 significant bits per operand leave ~2^-16
     per product, and B-format outputs are stored as hi + lo (2^-17)."""
     y, ref = _conv_case(seed=31, impl=1, **case)

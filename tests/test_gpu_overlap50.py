@@ -57,7 +57,7 @@ def engine_mode(request, seed0_state_dict):
 def test_overlap50_volume_against_unmodified_reference(engine_mode, i):
     eng, mode = engine_mode
     if mode == "FP32" and i > 0:
-        pytest.skip("the FFMA mode runs one seed (0.6 s per volume); the split-bf16 mode runs all three")
+        pytest.skip("the FFMA mode runs one seed (0.6 s per volume); the split-fp16 mode runs all three")
     r = run_volume(eng, i)
     print(f"overlap50 seed {1000 + i} [{mode}]: probs_rel {r['probs_rel']:.2e}  label flips {r['flips']:.2e} of {r['voxels']} voxels  "
           f"hist L1 {r['hist_l1']:.2e}  dice delta {r['dice_delta']:.2e}")

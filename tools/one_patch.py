@@ -1,5 +1,5 @@
 """Runs N forwards of one 128^3 patch through dcl_forward (for ncu launch lists / quick timing).
-usage: python tools/one_patch.py [precision: fp32|bf16x3|bf16] [n_forwards]"""
+usage: python tools/one_patch.py [precision: fp32|f16x3|bf16x3|bf16] [n_forwards]"""
 import os
 import sys
 import time
@@ -14,7 +14,7 @@ from models.clswiseformer.cls_wise_former import get_cls_wise_former  # noqa: E4
 
 
 def main():
-    prec = {"fp32": dcl_b200.Precision.FP32, "bf16x3": dcl_b200.Precision.BF16X3, "bf16": dcl_b200.Precision.BF16}[
+    prec = {"fp32": dcl_b200.Precision.FP32, "bf16x3": dcl_b200.Precision.F16X3, "f16x3": dcl_b200.Precision.F16X3, "bf16": dcl_b200.Precision.BF16}[
         sys.argv[1] if len(sys.argv) > 1 else "fp32"]
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2
     torch.manual_seed(0)

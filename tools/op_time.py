@@ -14,7 +14,7 @@ lib.dcl_bench_conv.restype = C.c_double
 lib.dcl_bench_conv.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
 for (cin, cout, g, stride) in [(16, 16, 128, 1), (32, 32, 64, 1), (64, 64, 32, 1), (128, 128, 16, 1), (96, 96, 32, 1), (256, 384, 16, 1),
                                (128, 256, 16, 1), (16, 32, 128, 2), (32, 64, 64, 2), (64, 128, 32, 2), (32, 32, 64, 2)]:
-    x3 = 8 if len(sys.argv) > 1 and sys.argv[1] == "x3" else 0      # python tools/op_time.py x3: the split-bf16 kernels
+    x3 = 8 if len(sys.argv) > 1 and sys.argv[1] == "x3" else 0      # python tools/op_time.py x3: the split-fp16 kernels
     for mode in ((0, 1, 2, 4, 7) if stride == 1 and g >= 64 and not x3 else (0, 7)):
         mode |= x3
         us = lib.dcl_bench_conv(cin, cout, g, stride, mode, 20)
