@@ -711,7 +711,7 @@ def dominant_roofline(prof, pk, precision):
         (ms, n, flops), name = per_kind[best], KINDS[best]
     tf = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", f"r02_ncu_full_dominant_{precision}.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_full_dominant_%s.json" % ("bf16x3" if precision == "f16x3" else precision))
     if best is not None and os.path.exists(tpath):
         t = json.load(open(tpath))
         if t.get("kind") == best:
