@@ -288,3 +288,36 @@ def test_bad_arguments_are_refused(engine, vol):
         engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, target=torch.zeros(240, 240, 150, dtype=torch.uint8))
     out = engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, want_probs=False)      # the handle still works
     assert out["labels"].shape == (240, 240, 155)
+
+
+def test_owner_computes_building_blocks_on_one_gpu(engine, vol):
+    """dcl_forward_patches_to_slots + dcl_gather_finalize_range (the multi-GPU owner-computes blocks) on ONE GPU: the
+    volume blended in three x-ranges from explicit slot pointers - the second half of the patches living in a second
+    buffer, as a peer's slots would - equals dcl_predict_volume bit for bit (labels, counters, probabilities)."""
+    from dcl_b200 import StitchMode, patch_starts
+    starts = patch_starts((240, 240, 155), 96)
+    n = len(starts)
+    keeps = np.ones((n, 16), np.float32)
+    keeps[2, 4] = 0.0
+    tgt = torch.from_numpy(volume_target(0).astype(np.uint8)).cuda()
+    want = engine.predict_volume(vol, StitchMode.UNIFORM, starts=starts, keep_scales=keeps, target=tgt)
+    slot_bytes = 4 * 128 ** 3 * 4
+    base = engine.slots_ensure(n)
+    engine.forward_patches_to_slots(vol, StitchMode.UNIFORM, starts, keeps, 0, n)
+    torch.cuda.synchronize()
+    other = torch.empty((n - n // 2) * slot_bytes // 4, dtype=torch.float32, device="cuda")      # "peer" memory
+    import ctypes as C
+    from dcl_b200 import _native as N
+    cudart = C.CDLL("libcudart.so")
+    assert cudart.cudaMemcpy(C.c_void_p(other.data_ptr()), C.c_void_p(base + (n // 2) * slot_bytes),
+                             C.c_size_t(other.numel() * 4), 3) == 0          # cudaMemcpyDeviceToDevice
+    ptrs = [base + i * slot_bytes if i < n // 2 else other.data_ptr() + (i - n // 2) * slot_bytes for i in range(n)]
+    labels = torch.zeros((240, 240, 155), dtype=torch.uint8, device="cuda")
+    probs = torch.zeros((1, 4, 240, 240, 155), dtype=torch.float32, device="cuda")
+    counts = torch.zeros(13, dtype=torch.int64, device="cuda")
+    for x0, x1 in ((0, 77), (77, 78), (78, 240)):
+        engine.gather_finalize_range((240, 240, 155), StitchMode.UNIFORM, starts, ptrs, x0, x1, labels, target=tgt, counts=counts,
+                                     probs_out=probs)
+    torch.cuda.synchronize()
+    assert torch.equal(labels, want["labels"]) and torch.equal(counts, want["counts"]) and torch.equal(probs, want["probs"])
+    _ = N

@@ -113,6 +113,15 @@ def test_owner_ranges_and_patch_owners():
     assert owners[:4] == [(0, 0), (0, 1), (0, 2), (1, 0)] and owners[-1] == (7, 1) and len(owners) == 18
 
 
+def test_own_x_ranges_merge_overlaps():
+    starts = S.patch_starts((240, 240, 155), 64)
+    parts = sharded.partition_patches(len(starts), 8)
+    rs = [sharded.own_x_ranges(starts, f, c, 240) for f, c in parts]
+    assert rs[0] == [(0, 128)] and rs[3] == [(0, 240)] and rs[7] == [(112, 240)]
+    assert sharded.own_x_ranges([(0, 0, 0), (200, 0, 0)], 0, 2, 400) == [(0, 128), (200, 328)]
+    assert sharded.own_x_ranges(starts, 0, 0, 240) == []
+
+
 def test_partition_and_ranges():
     assert sharded.partition_patches(18, 8) == [(0, 3), (3, 3), (6, 2), (8, 2), (10, 2), (12, 2), (14, 2), (16, 2)]
     assert sharded.partition_patches(8, 8) == [(i, 1) for i in range(8)]
