@@ -36,6 +36,9 @@ def show(title, recs, names):
         print(f"  {t - t0:9d}  {str(names.get(tag, tag)):28s} {step}")
 
 
+IMPL = 1 if os.environ.get("TRACE_X3") else 2      # TRACE_X3=1: the split-fp16 kernels
+
+
 def conv_case(c, g, cout=None, stride=1, norm=True):
     cout = cout or c
     gen = torch.Generator().manual_seed(1)
@@ -45,10 +48,10 @@ def conv_case(c, g, cout=None, stride=1, norm=True):
     mean = torch.zeros(c).cuda()
     rstd = torch.ones(c).cuda()
     for _ in range(2):
-        op_conv3d_k3(x, w, b, None, stride, (mean, rstd) if norm else None, 1 if norm else 0, None, impl=2)
+        op_conv3d_k3(x, w, b, None, stride, (mean, rstd) if norm else None, 1 if norm else 0, None, impl=IMPL)
     torch.cuda.synchronize()
     read_trace()
-    op_conv3d_k3(x, w, b, None, stride, (mean, rstd) if norm else None, 1 if norm else 0, None, impl=2)
+    op_conv3d_k3(x, w, b, None, stride, (mean, rstd) if norm else None, 1 if norm else 0, None, impl=IMPL)
     torch.cuda.synchronize()
     return read_trace()
 
