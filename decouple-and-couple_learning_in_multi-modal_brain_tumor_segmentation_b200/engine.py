@@ -70,6 +70,9 @@ class Engine:
         self._h = h
 
     def close(self):
+        for ctx in getattr(self, "_shard_ctx", {}).values():      # peers' slot buffers mapped through CUDA IPC (sharded.py)
+            ctx.close()
+        self.__dict__.pop("_shard_ctx", None)
         if getattr(self, "_h", None):
             self._lib.dcl_destroy(self._h)
             self._h = None
