@@ -232,7 +232,7 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
 template <int CIN, bool X3>
 __global__ void __launch_bounds__(256)
 deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, const float* __restrict__ mt,
-                  const float* __restrict__ w3a, const float* __restrict__ bt, uint4* __restrict__ y, int gi) {
+                  const float* __restrict__ w3a, const float* __restrict__ bt, uint4* __restrict__ y, int gi, float out_mul) {
   pdl_wait();      // programmatic dependent launch: the predecessor kernel has completed past this point
   pdl_trigger();
   constexpr int CH = CIN / 2;                       // skip / output channels
@@ -325,9 +325,10 @@ deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, c
         }
         // D fragment: (row g, n = 2c, 2c+1), (row g+8, same n) -> word c of the voxel's 16-byte vector of chunk nt
         if constexpr (X3) {
+          // (split mode: mt / w3a / bt are stored times 2^k, out_mul = 2^-k)
           uint32_t h0, l0, h1, l1;
-          tc::split_x2(acc[0], acc[1], h0, l0);
-          tc::split_x2(acc[2], acc[3], h1, l1);
+          tc::split_x2(acc[0] * out_mul, acc[1] * out_mul, h0, l0);
+          tc::split_x2(acc[2] * out_mul, acc[3] * out_mul, h1, l1);
           yw[((int64_t)nt * sp_out + qa) * 4 + c] = h0;
           yw[((int64_t)nt * sp_out + qb) * 4 + c] = h1;
           yw[((int64_t)(NT + nt) * sp_out + qa) * 4 + c] = l0;
@@ -343,7 +344,7 @@ deup_mma_b_kernel(const uint4* __restrict__ x, const uint4* __restrict__ skip, c
 
 template <int CIN, bool X3>
 static int launch_deup_mma(const uint4* x, const uint4* skip, const float* mt, const float* w3a, const float* bt, uint4* y,
-                           int gi, cudaStream_t st) {
+                           int gi, cudaStream_t st, float out_mul) {
   constexpr int CH = CIN / 2;
   constexpr int smem = (2 * CH * (CIN + 8) + CH * (CH + 8)) * 2 * (X3 ? 2 : 1) + 2 * CH * 4;
   static bool configured = false;
@@ -354,26 +355,26 @@ static int launch_deup_mma(const uint4* x, const uint4* skip, const float* mt, c
   const int64_t n_tiles = (int64_t)gi * gi * gi / 16;
   int gx = (int)((n_tiles + 7) / 8);
   if (gx > 148) gx = 148;                          // x 4 (kd,kh) CTAs of 8 warps: persistent over the parent tiles
-  DCL_CUDA_OK(launch_pdl(deup_mma_b_kernel<CIN, X3>, dim3(dim3(gx, 4)), dim3(256), (size_t)(smem), st, x, skip, mt, w3a, bt, y, gi));
+  DCL_CUDA_OK(launch_pdl(deup_mma_b_kernel<CIN, X3>, dim3(dim3(gx, 4)), dim3(256), (size_t)(smem), st, x, skip, mt, w3a, bt, y, gi, out_mul));
   ++g_launches;
   DCL_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const float* w3a, const float* bt, void* y,
-                        int cin, int gi, cudaStream_t st, bool x3) {
+                        int cin, int gi, cudaStream_t st, bool x3, float out_mul) {
   const uint4* xp = reinterpret_cast<const uint4*>(x);
   const uint4* sp = reinterpret_cast<const uint4*>(skip);
   uint4* yp = reinterpret_cast<uint4*>(y);
   if (gi % 16 != 0) { set_error("deup_fused: grid must be a multiple of 16"); return -1; }
   if (x3) {
-    if (cin == 32) return launch_deup_mma<32, true>(xp, sp, mt, w3a, bt, yp, gi, st);
-    if (cin == 64) return launch_deup_mma<64, true>(xp, sp, mt, w3a, bt, yp, gi, st);
-    if (cin == 128) return launch_deup_mma<128, true>(xp, sp, mt, w3a, bt, yp, gi, st);
+    if (cin == 32) return launch_deup_mma<32, true>(xp, sp, mt, w3a, bt, yp, gi, st, out_mul);
+    if (cin == 64) return launch_deup_mma<64, true>(xp, sp, mt, w3a, bt, yp, gi, st, out_mul);
+    if (cin == 128) return launch_deup_mma<128, true>(xp, sp, mt, w3a, bt, yp, gi, st, out_mul);
   } else {
-    if (cin == 32) return launch_deup_mma<32, false>(xp, sp, mt, w3a, bt, yp, gi, st);
-    if (cin == 64) return launch_deup_mma<64, false>(xp, sp, mt, w3a, bt, yp, gi, st);
-    if (cin == 128) return launch_deup_mma<128, false>(xp, sp, mt, w3a, bt, yp, gi, st);
+    if (cin == 32) return launch_deup_mma<32, false>(xp, sp, mt, w3a, bt, yp, gi, st, 1.f);
+    if (cin == 64) return launch_deup_mma<64, false>(xp, sp, mt, w3a, bt, yp, gi, st, 1.f);
+    if (cin == 128) return launch_deup_mma<128, false>(xp, sp, mt, w3a, bt, yp, gi, st, 1.f);
   }
   set_error("deup_fused: cin must be 32, 64 or 128");
   return -1;

@@ -106,6 +106,7 @@ struct GemmConvParams {
   // B-format outputs / residuals carry their lo planes cout_pad / 8 chunks behind the hi planes
   int x3;
   int64_t w_lo;
+  float acc_mul;           // accumulators are multiplied by this (split mode: 2^-k of the power-of-two weight scale; else 1)
 };
 
 constexpr int G_EPI_WARPS = 4;
@@ -204,7 +205,7 @@ __device__ __forceinline__ void gemm_epilogue_tile(const GemmConvParams& p, uint
     float v[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const float val = (__uint_as_float(acc[k]) + bs[k]) * os[k];
+      const float val = (__uint_as_float(acc[k]) * p.acc_mul + bs[k]) * os[k];
       v[k] = (row_ok && n0 + c0 + k < p.cout) ? val : 0.f;
     }
     if (p.gelu) {
@@ -903,6 +904,7 @@ int launch_gemm_conv(const GemmArgs& g, const TcWeights& w, cudaStream_t st) {
   p.out_mode = g.out_mode; p.gelu = g.gelu;
   p.x3 = g.x3 ? 1 : 0;
   p.w_lo = w.lo_off / 16;
+  p.acc_mul = g.x3 ? w.out_mul : 1.f;
   if (w.layout != 0) { set_error("gemm_conv: weights packed for the rolling kernel"); return -1; }
   if (g.x3 && (w.lo_off == 0 || ((w.cin % 16) != 0 && g.a1 != nullptr))) { set_error("gemm_conv: split-fp16 needs split weights"); return -1; }
   p.OD = (g.D - 1) / g.stride + 1; p.OH = (g.H - 1) / g.stride + 1; p.OW = (g.W - 1) / g.stride + 1;
@@ -959,6 +961,7 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
   p.out_mode = g.out_mode; p.gelu = g.gelu;
   p.x3 = g.x3 ? 1 : 0;
   p.w_lo = w.lo_off / 16;
+  p.acc_mul = g.x3 ? w.out_mul : 1.f;
   if (w.layout != 0) { set_error("slab_conv: weights packed for the rolling kernel"); return -1; }
   if (g.x3 && w.lo_off == 0) { set_error("slab_conv: split-fp16 needs split weights"); return -1; }
   const int xs = p.x3;
@@ -1161,11 +1164,12 @@ int launch_prep_rows2(const float* x0, const float* g0, const float* b0, int row
 }
 
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
-                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked, bool x3) {
+                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked, bool x3, float acc_mul) {
   if (n % 16 != 0 || k % 16 != 0) { set_error("linear_tc: n and k must be multiples of 16"); return -1; }
   TcWeights w;
   w.dev = const_cast<void*>(w_packed); w.cin = k; w.cout = n;
   w.lo_off = x3 ? (int64_t)n * k * 2 : 0;
+  w.out_mul = acc_mul;
   GemmArgs g;
   g.x3 = x3;
   g.a0 = a_blocked; g.c0 = k;

@@ -71,6 +71,7 @@ struct S2Params {
   const float* bias;
   uint4* yb;            // B-format output, CO channels @ GO^3
   stat_t* stats;        // 2*CO fixed-point sums or nullptr
+  float acc_mul;        // accumulators are multiplied by this (split mode: 2^-k of the weight scale; else 1)
   int dsplit;
 };
 
@@ -244,7 +245,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
           }
           float val[16];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) val[k] = __uint_as_float(acc[k]) + s_bias[g16 * 16 + k];
+          for (int k = 0; k < 16; ++k) val[k] = __uint_as_float(acc[k]) * prm.acc_mul + s_bias[g16 * 16 + k];
 #pragma unroll
           for (int h8 = 0; h8 < 2; ++h8) {
             uint4 o;
@@ -354,6 +355,7 @@ static int launch_s2(const void* xb, const TcWeights& w, const float* bias, void
   p.bias = bias;
   p.yb = reinterpret_cast<uint4*>(yb);
   p.stats = stats;
+  p.acc_mul = C::X3 ? w.out_mul : 1.f;
   const int htiles = C::GO / C::TH;
   p.dsplit = 148 / htiles;
   if (p.dsplit > C::GO) p.dsplit = C::GO;

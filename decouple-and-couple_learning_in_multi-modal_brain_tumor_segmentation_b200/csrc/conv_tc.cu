@@ -19,8 +19,10 @@
 #include "conv_tc.cuh"
 #include "tc_common.cuh"
 
+#include <math.h>
 #include <string.h>
 
+#include <cmath>
 #include <vector>
 
 namespace dcl {
@@ -107,6 +109,7 @@ struct RollParams {
   uint4* yb;                // B-format output
   stat_t* stats;            // 2*C fixed-point sums += (sum, sum of squares) of the fp32 outputs, or nullptr
   int dsplit;
+  float acc_mul;            // accumulators are multiplied by this (2^-k of the power-of-two weight scale; 1 otherwise)
   int cin_off;              // first input channel this launch covers (CI < layer Cin: one launch per CI channels)
   int cin_total;            // channels of the input tensor xb (its lo planes start cin_total / 8 chunks in)
 };
@@ -535,7 +538,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
           tmem_ld16(lane_addr + (uint32_t)(b * Cfg::ACC_COLS + t * CO * NP + CO + 16 * g16), acc2);
           tmem_ld_wait();
 #pragma unroll
-          for (int k = 0; k < 16; ++k) acc[k] = __float_as_uint(__uint_as_float(acc[k]) + __uint_as_float(acc2[k]));
+          for (int k = 0; k < 16; ++k) acc[k] = __float_as_uint((__uint_as_float(acc[k]) + __uint_as_float(acc2[k])) * prm.acc_mul);
         }
         tmem_ld_wait();
         if (it + EPI_GROUPS >= ITEMS) {   // all of this thread's TMEM reads of buffer b are done
@@ -663,6 +666,23 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
   std::vector<uint16_t> packed(x3 ? 2 * image : image, 0);       // split-fp16: twice the elements in every layout
   const int layout = (roll_layout && taps == 27) ? tc_weight_layout(cin, cout, x3) : 0;
   out->layout = layout;
+  // split mode: |w| ~ 0.02 would put w_lo ~ 1e-5 deep into fp16's subnormal range (an absolute 6e-8: only ~19 bits of w,
+  // measured as 1.3e-5 on the deepest encoder stage against 2.5e-6 for fp32 FFMA): store w * 2^k with max|w| * 2^k in
+  // [2^13, 2^14) and give the exact 2^-k back to the epilogue
+  float wscale = 1.f;
+  out->out_mul = 1.f;
+  if (x3) {
+    float mx = 0.f;
+    for (size_t i = 0; i < (size_t)cout * cin * taps; ++i) mx = fmaxf(mx, fabsf(w_host[i]));
+    if (mx > 0.f && std::isfinite(mx)) {
+      int e = 0;
+      frexpf(mx, &e);                       // mx = f * 2^e, f in [0.5, 1)
+      int k = 14 - e;
+      k = k < -8 ? -8 : (k > 30 ? 30 : k);
+      wscale = ldexpf(1.f, k);
+      out->out_mul = ldexpf(1.f, -k);
+    }
+  }
   // InitConv in split-fp16 mode: the rolling kernel stages the four input channels as [hi0..3 | lo0..3] in ONE chunk,
   // so the weights of channel ci sit at k = ci AND k = ci + 4
   const bool init_x3 = layout == 2 && cin == 4;
@@ -671,7 +691,7 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
       for (int n = 0; n < cout; ++n) {
         const int kc = ci / 8, k = ci % 8;
         const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
-        const float wv = w_host[((size_t)n * cin + ci) * taps + tap];
+        const float wv = w_host[((size_t)n * cin + ci) * taps + tap] * wscale;
         uint16_t hi, lo;
         if (x3) {          // split mode: fp16 hi + fp16 lo (22 significant bits; tc_common.cuh)
           const __half hh = __float2half_rn(wv);
@@ -757,6 +777,7 @@ int launch_roll_conv(const RollArgs& a, const TcWeights& w, int cout, int g, cud
   p.stats = a.stats;
   p.dsplit = 1;
   p.cin_off = 0; p.cin_total = cin == 4 ? 16 : cin;
+  p.acc_mul = a.x3 ? w.out_mul : 1.f;
   if (a.x3 && cout == 32) {
     // 16 input channels per launch: y1 = conv(x[0:16]) + bias + residual, then y = conv(x[16:32]) + y1 (+ statistics)
     p.stats = nullptr;

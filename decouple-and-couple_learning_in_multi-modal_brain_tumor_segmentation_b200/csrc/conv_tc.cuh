@@ -10,6 +10,8 @@ struct TcWeights {
   int cout = 0, cin = 0;
   int64_t bytes = 0;
   int64_t lo_off = 0;   // bf16x3: byte offset of the "lo" image (same layout as the "hi" image at dev); 0 = plain bf16
+  float out_mul = 1.f;  // split mode: the weights are stored times 2^k (so that their fp16 lo halves stay normal numbers);
+                        // every accumulator read is multiplied by out_mul = 2^-k (exact)
   int layout = 0;       // 0 canonical [tap][cin/8][cout][8] (+ lo image); 1-3: rolling-kernel orders (tc_pack_weights)
   // lazily built copy in the slab kernel's streaming order for one tile width (launch_slab_conv)
   mutable void* slab_dev = nullptr;
@@ -97,7 +99,7 @@ int launch_untokenise_b(const float* tokens, const float* class_token, void* y, 
 // DeUp_Cat as one kernel: mt [8][cin/2][cin], w3a [cin/2][cin/2], bt [8][cin/2] (composed on the host)
 // x3: mt / w3a hold the hi image followed by the lo image
 int launch_deup_fused_b(const void* x, const void* skip, const float* mt, const float* w3a, const float* bt, void* y,
-                        int cin, int gi, cudaStream_t st, bool x3 = false);
+                        int cin, int gi, cudaStream_t st, bool x3 = false, float out_mul = 1.f);
 // probs (fp32 NCDHW, 4 classes) = softmax(endconv(x)), x B-format 16 channels
 // norm != nullptr: the input is act(norm(x)) + res, i.e. the DeBlock tail is applied while loading (bit-identical to
 // running launch_norm_act_b first, including its bf16 rounding)
@@ -114,6 +116,7 @@ int launch_prep_rows2(const float* x0, const float* g0, const float* b0, int row
 // y_blocked != nullptr: the result goes out as bf16 [n/8][m][8] (the next GEMM's A operand) instead of fp32 `y`
 // x3: a_blocked / y_blocked are split-fp16, w_packed holds the hi image followed by the lo image (n * k * 2 bytes each)
 int launch_linear_tc(const void* a_blocked, const void* w_packed, const float* bias, const float* residual, float* y,
-                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked = nullptr, bool x3 = false);
+                     int m, int n, int k, bool gelu, cudaStream_t st, void* y_blocked = nullptr, bool x3 = false,
+                     float acc_mul = 1.f);
 
 }  // namespace dcl

@@ -151,7 +151,8 @@ struct ConvW {          // packed conv weights on the device
 
 struct Transformer {
   float *n1w, *n1b, *n2w, *n2b, *wqkv, *wout, *bout, *fnw, *fnb, *w0, *b0, *w3, *b3;
-  void *pq = nullptr, *pkv = nullptr, *pout = nullptr, *p0 = nullptr, *p3 = nullptr;   // bf16 UMMA operand tiles (DCL_BF16)
+  void *pq = nullptr, *pkv = nullptr, *pout = nullptr, *p0 = nullptr, *p3 = nullptr;   // 16-bit UMMA operand tiles (tensor-core modes)
+  float mq = 1.f, mkv = 1.f, mout = 1.f, m0 = 1.f, m3 = 1.f;                           // their accumulator multipliers (split mode)
 };
 
 struct StatSlot { float* mean; float* rstd; };
@@ -224,7 +225,7 @@ struct dcl_handle {
   void *b_dl[3][5];                              // decoder levels: in, a, b, 1, 2
   stat_t* stat_arena = nullptr;                  // STAT_SLOTS x 1024 fixed-point sums, zeroed once per forward
   int stat_used = 0;
-  struct DeUpW { float *mt, *w3a, *bt; } deup[3];     // mt / w3a: bf16 rows padded by 8 elements (the kernel's smem image)
+  struct DeUpW { float *mt, *w3a, *bt; float out_mul = 1.f; } deup[3];     // mt / w3a: bf16 rows padded by 8 elements (the kernel's smem image)
   float *end_w = nullptr, *end_b = nullptr;
   struct BStage { const void* p; int c; int64_t spatial; };
   std::map<std::string, BStage> bstages;
@@ -512,18 +513,19 @@ static int prepare(dcl_handle* h) {
     t.w3 = R(f + "fn.net.3.weight"); t.b3 = R(f + "fn.net.3.bias");
     if (is_tc(h)) {
       const std::vector<float>& qkv = h->host_w.at(a + "fn.qkv.weight");
-      auto pack = [&](const float* w, int n, void** out) -> int {
+      auto pack = [&](const float* w, int n, void** out, float* mul) -> int {
         TcWeights tw;
         DCL_TRY(tc_pack_weights(w, n, 512, 1, false, &tw, is_x3(h)));
         h->allocs.push_back(tw.dev);
         *out = tw.dev;
+        *mul = tw.out_mul;
         return 0;
       };
-      DCL_TRY(pack(qkv.data(), 512, &t.pq));
-      DCL_TRY(pack(qkv.data() + 512 * 512, 1024, &t.pkv));
-      DCL_TRY(pack(h->host_w.at(a + "fn.out_proj.weight").data(), 512, &t.pout));
-      DCL_TRY(pack(h->host_w.at(f + "fn.net.0.weight").data(), 512, &t.p0));
-      DCL_TRY(pack(h->host_w.at(f + "fn.net.3.weight").data(), 512, &t.p3));
+      DCL_TRY(pack(qkv.data(), 512, &t.pq, &t.mq));
+      DCL_TRY(pack(qkv.data() + 512 * 512, 1024, &t.pkv, &t.mkv));
+      DCL_TRY(pack(h->host_w.at(a + "fn.out_proj.weight").data(), 512, &t.pout, &t.mout));
+      DCL_TRY(pack(h->host_w.at(f + "fn.net.0.weight").data(), 512, &t.p0, &t.m0));
+      DCL_TRY(pack(h->host_w.at(f + "fn.net.3.weight").data(), 512, &t.p3, &t.m3));
     }
   }
   for (int r = 0; r < 3; ++r) {
@@ -591,6 +593,23 @@ static int prepare(dcl_handle* h) {
           }
         return out;
       };
+      h->deup[l].out_mul = 1.f;
+      if (x3) {      // one power-of-two scale for both maps and the bias (they share the accumulator): fp16 lo halves stay normal
+        float mx = 0.f;
+        for (float v : mt) mx = fmaxf(mx, fabsf(v));
+        for (float v : w3a) mx = fmaxf(mx, fabsf(v));
+        if (mx > 0.f) {
+          int e = 0;
+          frexpf(mx, &e);
+          int k = 14 - e;
+          k = k < -8 ? -8 : (k > 30 ? 30 : k);
+          const float sc = ldexpf(1.f, k);
+          for (float& v : mt) v *= sc;
+          for (float& v : w3a) v *= sc;
+          for (float& v : btc) v *= sc;
+          h->deup[l].out_mul = ldexpf(1.f, -k);
+        }
+      }
       DCL_TRY(upload(h, to_bf16_padded(mt, 8 * CH, C), &h->deup[l].mt));
       DCL_TRY(upload(h, to_bf16_padded(w3a, CH, CH), &h->deup[l].w3a));
       DCL_TRY(upload(h, btc, &h->deup[l].bt));
@@ -687,10 +706,10 @@ struct Fwd {
     if (is_tc(h)) {   // LayerNorm fused into the bf16 operand prep, linears on tcgen05
       const bool x3 = is_x3(h);
       DCL_TRY(launch_prep_rows2(x, t.n1w, t.n1b, mq, ts->tok_a, x2, t.n2w, t.n2b, mk, ts->tok_b, st, x3));
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.pq, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st, nullptr, x3));
-      DCL_TRY(launch_linear_tc(ts->tok_b, t.pkv, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st, nullptr, x3));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.pq, nullptr, nullptr, ts->qbuf, mq, 512, 512, false, st, nullptr, x3, t.mq));
+      DCL_TRY(launch_linear_tc(ts->tok_b, t.pkv, nullptr, nullptr, ts->kvbuf, mk, 1024, 512, false, st, nullptr, x3, t.mkv));
       DCL_TRY(launch_attention(ts->qbuf, ts->kvbuf, nullptr, mq, mk, st, ts->tok_a, x3));     // bf16 blocked, straight into the GEMM
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st, nullptr, x3));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.pout, t.bout, x, out, mq, 512, 512, false, st, nullptr, x3, t.mout));
       return 0;
     }
     DCL_TRY(launch_layernorm(x, t.n1w, t.n1b, ts->ln_a, mq, st));
@@ -707,8 +726,8 @@ struct Fwd {
     if (is_tc(h)) {
       const bool x3 = is_x3(h);
       DCL_TRY(launch_prep_rows(x, t.fnw, t.fnb, m, ts->tok_a, st, x3));
-      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, nullptr, m, 512, 512, true, st, ts->tok_b, x3));   // GELU, bf16 blocked out
-      DCL_TRY(launch_linear_tc(ts->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st, nullptr, x3));
+      DCL_TRY(launch_linear_tc(ts->tok_a, t.p0, t.b0, nullptr, nullptr, m, 512, 512, true, st, ts->tok_b, x3, t.m0));   // GELU, blocked out
+      DCL_TRY(launch_linear_tc(ts->tok_b, t.p3, t.b3, x, out, m, 512, 512, false, st, nullptr, x3, t.m3));
       return 0;
     }
     DCL_TRY(launch_layernorm(x, t.fnw, t.fnb, ts->ffn_ln, m, st));
@@ -1157,7 +1176,8 @@ struct Fwd16 {
       void** b = h->b_dl[l];
       {
         dcl_handle::ProfScope ps(h, st, 6);
-        DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st, is_x3(h)));
+        DCL_TRY(launch_deup_fused_b(cur, h->b_x[2 - l], h->deup[l].mt, h->deup[l].w3a, h->deup[l].bt, b[0], cin, g_in, st, is_x3(h),
+                                    h->deup[l].out_mul));
       }
       DCL_TRY(post_block(b[0], c, g, dbn[l][0], b[1], b[2], b[3]));
       // the very last DeBlock tail (16 channels @ 128^3) is folded into endconv's load unless the stage is to be kept
