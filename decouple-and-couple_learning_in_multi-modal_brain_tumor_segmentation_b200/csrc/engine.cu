@@ -304,15 +304,23 @@ static const int LVL_G[4] = {128, 64, 32, 16};
 static const int STAT_SLOTS = 64;
 
 static int allocate_workspace(dcl_handle* h) {
+  // the dense fp32 NCDHW activations of the convolutional path exist only in the FFMA mode: the tensor-core modes keep
+  // those tensors in B-format (below) - 2.0 GB less per handle, and a volume call runs three handles (lanes)
+  const bool dense = !is_tc(h);
   for (int l = 0; l < 4; ++l) {
+    h->l_t0[l] = h->l_a[l] = h->l_t1[l] = h->l_x[l] = nullptr;
+    if (!dense) continue;
     int64_t n = (int64_t)LVL_C[l] * LVL_G[l] * LVL_G[l] * LVL_G[l];
     DCL_TRY(falloc(h, &h->l_t0[l], n)); DCL_TRY(falloc(h, &h->l_a[l], n));
     DCL_TRY(falloc(h, &h->l_t1[l], n)); DCL_TRY(falloc(h, &h->l_x[l], n));
   }
   const int64_t g16 = 16 * 16 * 16, g32 = 32 * 32 * 32;
-  DCL_TRY(falloc(h, &h->x4, 256 * g16));
-  DCL_TRY(falloc(h, &h->e_down, 32 * g32)); DCL_TRY(falloc(h, &h->e_raw, 96 * g32));
-  DCL_TRY(falloc(h, &h->s_raw, 384 * g16));
+  h->x4 = h->e_down = h->e_raw = h->s_raw = nullptr;
+  if (dense) {
+    DCL_TRY(falloc(h, &h->x4, 256 * g16));
+    DCL_TRY(falloc(h, &h->e_down, 32 * g32)); DCL_TRY(falloc(h, &h->e_raw, 96 * g32));
+    DCL_TRY(falloc(h, &h->s_raw, 384 * g16));
+  }
   for (int r = 0; r < 3; ++r) {
     DCL_TRY(falloc(h, &h->E[r], 2048 * 512)); DCL_TRY(falloc(h, &h->S[r], 1024 * 512));
     DCL_TRY(falloc(h, &h->edge_dense[r], 32 * g32)); DCL_TRY(falloc(h, &h->sem_dense[r], 128 * g16));
@@ -330,11 +338,16 @@ static int allocate_workspace(dcl_handle* h) {
   DCL_TRY(falloc(h, &h->ffn_h, 258 * 512));
   for (int i = 0; i < 4; ++i) DCL_TRY(falloc(h, &h->coupler_out[i], 258 * 512));
   DCL_TRY(falloc(h, &h->f_tok, 512)); DCL_TRY(falloc(h, &h->f_fea, 1024 * 512));
-  DCL_TRY(falloc(h, &h->fused_dense, 128 * g16)); DCL_TRY(falloc(h, &h->enc, 256 * g16));
-  DCL_TRY(falloc(h, &h->d8_0, 128 * g16)); DCL_TRY(falloc(h, &h->d8_a, 128 * g16));
-  DCL_TRY(falloc(h, &h->d8_b, 128 * g16)); DCL_TRY(falloc(h, &h->d8_1, 128 * g16));
-  DCL_TRY(falloc(h, &h->d8_2, 128 * g16));
+  h->fused_dense = h->enc = h->d8_0 = h->d8_a = h->d8_b = h->d8_1 = h->d8_2 = nullptr;
+  if (dense) {
+    DCL_TRY(falloc(h, &h->fused_dense, 128 * g16)); DCL_TRY(falloc(h, &h->enc, 256 * g16));
+    DCL_TRY(falloc(h, &h->d8_0, 128 * g16)); DCL_TRY(falloc(h, &h->d8_a, 128 * g16));
+    DCL_TRY(falloc(h, &h->d8_b, 128 * g16)); DCL_TRY(falloc(h, &h->d8_1, 128 * g16));
+    DCL_TRY(falloc(h, &h->d8_2, 128 * g16));
+  }
   for (int l = 0; l < 3; ++l) {   // decoder level l: channels 64/32/16 at 32/64/128
+    h->up_u1[l] = h->up_u2[l] = h->dl_in[l] = h->dl_a[l] = h->dl_b[l] = h->dl_1[l] = h->dl_2[l] = nullptr;
+    if (!dense) continue;
     int c = 64 >> l, g = 32 << l;
     int64_t n = (int64_t)c * g * g * g;
     DCL_TRY(falloc(h, &h->up_u1[l], n / 8)); DCL_TRY(falloc(h, &h->up_u2[l], n));
@@ -344,7 +357,7 @@ static int allocate_workspace(dcl_handle* h) {
   DCL_TRY(falloc(h, &h->probs, 4 * P3));
   if (is_tc(h)) {
     const int64_t E = is_x3(h) ? 4 : 2;      // bytes per element of a B-format tensor (split-fp16: hi + lo planes)
-    DCL_TRY(dev_alloc(h, &h->blk, 32 * P3 * E));
+    DCL_TRY(dev_alloc(h, &h->blk, 2 * 1024 * 1024 * E));      // blocked input of an auxiliary-head convolution (<= 128 ch @ 16^3, 32 ch @ 32^3)
     DCL_TRY(dev_alloc(h, &h->tok_a, 258 * 512 * E));
     DCL_TRY(dev_alloc(h, &h->tok_b, 258 * 512 * E));
     for (int l = 0; l < 4; ++l) {
