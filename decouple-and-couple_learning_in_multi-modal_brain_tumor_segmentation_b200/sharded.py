@@ -139,6 +139,15 @@ def owned_x_range(X: int, rank: int, world: int):
     return x0, min(x0 + step, X)
 
 
+def assignment_order(starts):
+    """The order in which the patches of a plan are DEALT to the ranks (contiguous chunks of this order): x-major, so
+    that the patches of a rank share their x-range and the rank uploads one 128-plane slab of the input (76 MB of the
+    143 MB volume for the 18-patch plan on 8 ranks; the z-major plan order itself would hand rank 3 the patches at
+    x = 112 and x = 0, i.e. the whole volume).  Which rank computes a patch changes nothing in the result: the blend
+    reads the slots by patch index, in plan order."""
+    return sorted(range(len(starts)), key=lambda i: (int(starts[i][0]), int(starts[i][2]), int(starts[i][1])))
+
+
 def patch_owner(n_patches: int, world: int):
     """[(rank, local slot index)] per patch of the plan, consistent with partition_patches."""
     out = []
@@ -151,7 +160,7 @@ class _PeerSlots:
     """This rank's slot buffer and the IPC-mapped slot buffers of its peers (set up once per engine / group / plan size
     and reused for every volume)."""
 
-    def __init__(self, engine, group, n_patches):
+    def __init__(self, engine, group, n_patches, order):
         self.engine, self.group, self.n_patches = engine, group, n_patches
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -167,7 +176,9 @@ class _PeerSlots:
                 if r != self.rank:
                     self.bases[r] = engine.ipc_import(handles[r])
                     self.imported.append(self.bases[r])
-        self.ptrs = [self.bases[r] + i * SLOT_FLOATS * 4 for r, i in patch_owner(n_patches, self.world)]
+        owner = patch_owner(n_patches, self.world)             # by position in the assignment order
+        pos = {p: k for k, p in enumerate(order)}
+        self.ptrs = [self.bases[owner[pos[i]][0]] + owner[pos[i]][1] * SLOT_FLOATS * 4 for i in range(n_patches)]
 
     def close(self):
         for p in self.imported:
@@ -178,14 +189,14 @@ class _PeerSlots:
         self.imported = []
 
 
-def _peer_slots(engine, group, n_patches):
+def _peer_slots(engine, group, n_patches, order):
     cache = engine.__dict__.setdefault("_shard_ctx", {})
-    key = (id(group), n_patches)
+    key = (id(group), n_patches, tuple(order))
     ctx = cache.get(key)
     if ctx is None or ctx.local != engine.slots_ensure(max(1, ctx.count)):     # (the buffer only ever grows)
         if ctx is not None:
             ctx.close()
-        ctx = cache[key] = _PeerSlots(engine, group, n_patches)
+        ctx = cache[key] = _PeerSlots(engine, group, n_patches, order)
     return ctx
 
 
@@ -195,7 +206,7 @@ def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, ke
     returns dict(labels uint8 (X,Y,Z), counts int64[13]) identical on every rank and bit-identical to one GPU.
 
     Test hooks (CPU / gloo): forward_to_slots(vol, mode, starts, keep_scales, first, count) -> (count, 4, 128, 128, 128)
-    tensor; finalize_range(slots: list of per-patch tensors, x0, x1, labels (X,Y,Z), target | None, counts).  With the
+    tensor (starts / keep_scales arrive in assignment_order); finalize_range(slots: list of per-patch tensors, x0, x1, labels (X,Y,Z), target | None, counts).  With the
     hooks the slots travel by all_gather (the CPU stand-in for peer memory); without them the CUDA engine is used."""
     mode = StitchMode(mode)
     if mode not in (StitchMode.UNIFORM, StitchMode.GAUSSIAN) or not starts:
@@ -209,6 +220,10 @@ def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, ke
         vol = vol[0]
     X, Y, Z = (int(v) for v in vol.shape[1:])
     n_patches = len(starts)
+    order = assignment_order(starts)                        # patches are dealt to the ranks x-major ...
+    starts_a = [tuple(int(v) for v in starts[i]) for i in order]
+    keep_a = None if keep_scales is None else np.asarray(keep_scales, dtype=np.float32).reshape(n_patches, 16)[order]
+    pos = {p: k for k, p in enumerate(order)}               # ... and read back by plan index
     first, count = partition_patches(n_patches, world)[rank]
     x0, x1 = owned_x_range(X, rank, world)
     dev = vol.device
@@ -227,7 +242,7 @@ def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, ke
             target = target.to(dtype=torch.uint8).contiguous()
     hooks = forward_to_slots is not None or finalize_range is not None
     if hooks:
-        mine = forward_to_slots(vol, mode, starts, keep_scales, first, count)
+        mine = forward_to_slots(vol, mode, starts_a, keep_a, first, count)
         slots = [None] * n_patches
         if world > 1:
             cmax = max(c for _, c in partition_patches(n_patches, world))
@@ -235,16 +250,18 @@ def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, ke
             pad[:count] = mine
             allp = [torch.empty_like(pad) for _ in range(world)]
             dist.all_gather(allp, pad, group=group)
-            for i, (r, j) in enumerate(patch_owner(n_patches, world)):
+            owner = patch_owner(n_patches, world)
+            for i in range(n_patches):
+                r, j = owner[pos[i]]
                 slots[i] = allp[r][j]
         else:
-            slots = list(mine)
+            slots = [mine[pos[i]] for i in range(n_patches)]
         if x1 > x0:
             finalize_range(slots, x0, x1, labels[:X], target, counts)
     else:
-        ctx = _peer_slots(engine, group, n_patches)
+        ctx = _peer_slots(engine, group, n_patches, order)
         if count > 0:
-            engine.forward_patches_to_slots(vol, mode, starts, keep_scales, first, count)
+            engine.forward_patches_to_slots(vol, mode, starts_a, keep_a, first, count)
         if world > 1:      # stream-ordered barrier: every rank's slots are written before anybody reads them
             flag = torch.ones(1, dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.SUM, group=group)
@@ -253,7 +270,8 @@ def predict_volume_sharded(engine, vol, mode=StitchMode.UNIFORM, starts=None, ke
     if world > 1:
         dist.all_gather_into_tensor(labels.view(-1), labels[rank * step:(rank + 1) * step].reshape(-1).clone(), group=group)
         dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-    return {"labels": labels[:X], "counts": counts, "patches": (first, count), "rows": (x0, x1)}
+    return {"labels": labels[:X], "counts": counts, "patches": (first, count), "patch_ids": order[first:first + count],
+            "rows": (x0, x1)}
 
 
 def own_x_ranges(starts, first, count, X):
@@ -279,8 +297,9 @@ def upload_own_region(vol_host, stage_dev, starts, group=None):
         vol_host = vol_host[0]
     X = int(vol_host.shape[1])
     first, count = partition_patches(len(starts), world)[rank]
+    starts_a = [starts[i] for i in assignment_order(starts)]
     total = 0
-    for xa, xb in own_x_ranges(starts, first, count, X):
+    for xa, xb in own_x_ranges(starts_a, first, count, X):
         for c in range(int(vol_host.shape[0])):
             stage_dev[c, xa:xb].copy_(vol_host[c, xa:xb], non_blocking=True)
         total += int(vol_host.shape[0]) * (xb - xa) * int(vol_host.shape[2]) * int(vol_host.shape[3]) * 4

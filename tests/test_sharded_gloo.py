@@ -45,7 +45,10 @@ def _cpu_finalize(acc_l, wsum_l, labels_l, tgt_l, counts):
 
 
 def _cpu_forward_to_slots(vol, mode, starts, keep_scales, first, count):
-    return torch.from_numpy(np.stack([_patch_probs(i) for i in range(first, first + count)])) if count else torch.zeros((0, 4, 128, 128, 128))
+    """`starts` arrives in the assignment order of sharded.py; the stand-in probabilities go by PLAN index."""
+    plan = S.patch_starts(SHAPE, 16)
+    ids = [plan.index(tuple(starts[k])) for k in range(first, first + count)]
+    return torch.from_numpy(np.stack([_patch_probs(i) for i in ids])) if count else torch.zeros((0, 4, 128, 128, 128))
 
 
 def _cpu_finalize_range(slots, x0, x1, labels, target, counts):
@@ -164,3 +167,13 @@ def test_single_process_path_needs_no_process_group():
                                          finalize_range=_cpu_finalize_range)
     want_labels, _ = _expected(full, np.zeros(SHAPE, np.int64))
     assert own["patches"] == (0, 8) and own["rows"] == (0, 144) and np.array_equal(own["labels"].numpy(), want_labels)
+    assert sorted(own["patch_ids"]) == list(range(8))
+
+
+def test_assignment_order_groups_patches_by_x():
+    starts = S.patch_starts((240, 240, 155), 64)
+    order = sharded.assignment_order(starts)
+    assert sorted(order) == list(range(18)) and [starts[i][0] for i in order] == [0] * 6 + [64] * 6 + [112] * 6
+    dealt = [starts[i] for i in order]
+    for rank, (f, c) in enumerate(sharded.partition_patches(18, 8)):
+        assert sharded.own_x_ranges(dealt, f, c, 240) in ([(0, 128)], [(64, 192)], [(112, 240)]), rank
