@@ -101,7 +101,7 @@ struct GemmConvParams {
   int D, H, W, OD, OH, OW, stride, taps, kstage;
   int out_mode;            // 0: fp32 NCDHW [cout][m]   1: fp32 row-major [m][cout]   2: B-format bf16
   int gelu;                // exact (erf) GELU after the bias
-  // split-fp16 (DCL_BF16X3): the lo planes of a source follow its hi planes (chunk kc of source 0 at + c0_chunks *
+  // split-fp16 (DCL_F16X3): the lo planes of a source follow its hi planes (chunk kc of source 0 at + c0_chunks *
   // spatial, of source 1 at + c1 chunks * spatial), the lo weight image sits w_lo 16-byte units behind the hi image,
   // B-format outputs / residuals carry their lo planes cout_pad / 8 chunks behind the hi planes
   int x3;

@@ -25,7 +25,7 @@ namespace dcl {
 
 using namespace tc;
 
-// X3_: split-fp16 (DCL_BF16X3): staged planes and weights carry their lo halves behind the hi halves (as in global
+// X3_: split-fp16 (DCL_F16X3): staged planes and weights carry their lo halves behind the hi halves (as in global
 // memory), every (tap, K step) issues a_hi*w_hi + a_lo*w_hi + a_hi*w_lo.
 template <int CI_, int CO_, int GI_, int NT_, int NSLOT_, bool X3_ = false>
 struct S2Cfg {

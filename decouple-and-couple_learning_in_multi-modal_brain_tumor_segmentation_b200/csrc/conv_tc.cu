@@ -31,7 +31,7 @@ using namespace tc;
 
 cudaError_t trace_set_conv_tc(long long* p, int cta) { return trace_set_local(p, cta); }
 
-// X3_: split-fp16 (DCL_BF16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (a plane is
+// X3_: split-fp16 (DCL_F16X3).  The staged planes hold the KC "hi" chunks followed by the KC "lo" chunks (a plane is
 // still one bulk copy per chunk).  The weights hold, per K chunk, the hi rows followed by the lo rows of every output
 // row block: B' = [W_hi | W_lo] stacked along N, so that ONE MMA A x B' fills two accumulators D1 (x W_hi) and D2
 // (x W_lo).  Per (tap, K step) two MMAs are issued, A_hi x B' and A_lo x B':

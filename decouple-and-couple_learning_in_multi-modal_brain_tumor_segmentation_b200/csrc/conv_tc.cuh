@@ -1,4 +1,4 @@
-// tcgen05 / TMEM implicit-GEMM 3x3x3 convolution (precision modes DCL_BF16X3 and DCL_BF16).
+// tcgen05 / TMEM implicit-GEMM 3x3x3 convolution (precision modes DCL_F16X3 and DCL_BF16).
 #pragma once
 #include "common.cuh"
 
@@ -9,7 +9,7 @@ struct TcWeights {
   void* dev = nullptr;
   int cout = 0, cin = 0;
   int64_t bytes = 0;
-  int64_t lo_off = 0;   // bf16x3: byte offset of the "lo" image (same layout as the "hi" image at dev); 0 = plain bf16
+  int64_t lo_off = 0;   // split mode: byte offset of the "lo" image (same layout as the "hi" image at dev); 0 = plain bf16
   float out_mul = 1.f;  // split mode: the weights are stored times 2^k (so that their fp16 lo halves stay normal numbers);
                         // every accumulator read is multiplied by out_mul = 2^-k (exact)
   int layout = 0;       // 0 canonical [tap][cin/8][cout][8] (+ lo image); 1-3: rolling-kernel orders (tc_pack_weights)

@@ -145,7 +145,7 @@ struct ConvW {          // packed conv weights on the device
   float* w = nullptr;   // k3: [cin][27][cout_pad]   k1: [cin][cout]   convT: [cin][8][cout]
   float* b = nullptr;
   float* raw = nullptr; // PyTorch layout (used by the tensor-core path, which packs its own operand tiles)
-  TcWeights tc;         // bf16 hi/lo canonical tiles (built when precision != FP32)
+  TcWeights tc;         // 16-bit operand tiles: bf16 (DCL_BF16) or fp16 hi + lo images (DCL_F16X3); built when precision != FP32
   int cout = 0, cin = 0, cout_pad = 0;
 };
 
@@ -285,9 +285,9 @@ struct dcl_handle {
 
 namespace dcl {
 
-// tensor-core pipeline (B-format activations, tcgen05 kernels): DCL_BF16 and the split-fp16 mode DCL_BF16X3
-static inline bool is_tc(const dcl_handle* h) { return h->cfg.precision == DCL_BF16 || h->cfg.precision == DCL_BF16X3; }
-static inline bool is_x3(const dcl_handle* h) { return h->cfg.precision == DCL_BF16X3; }
+// tensor-core pipeline (B-format activations, tcgen05 kernels): DCL_BF16 and the split-fp16 mode DCL_F16X3
+static inline bool is_tc(const dcl_handle* h) { return h->cfg.precision == DCL_BF16 || h->cfg.precision == DCL_F16X3; }
+static inline bool is_x3(const dcl_handle* h) { return h->cfg.precision == DCL_F16X3; }
 
 static int dev_alloc(dcl_handle* h, void** p, int64_t bytes) {
   h->alloc_bytes += (bytes + 255) / 256 * 256;
@@ -2011,7 +2011,7 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
   const int cin_pad = (cin + 15) / 16 * 16, cout_pad = (cout + 15) / 16 * 16;
   std::vector<float> w((size_t)cout * cin * 27);
   for (size_t i = 0; i < w.size(); ++i) w[i] = (float)((i * 2654435761u >> 8) & 0xffff) / 65536.f - 0.5f;
-  const bool x3 = (mode & 8) != 0;     // split-fp16 (DCL_BF16X3) variant of the same layer
+  const bool x3 = (mode & 8) != 0;     // split-fp16 (DCL_F16X3) variant of the same layer
   const int E = x3 ? 4 : 2;
   const bool roll = stride == 1 && tc_conv_supported(cin, cout, g, 1, x3) && cin != 4;
   TcWeights tw;
@@ -2137,7 +2137,7 @@ DCL_API int dcl_op_conv3d_k3(const float* x0, int32_t c0, const float* x1, int32
     cudaStreamSynchronize(st);
     cudaFree(wp);
   } else {
-    const bool x3 = impl == 1;           // split-fp16 operands (DCL_BF16X3)
+    const bool x3 = impl == 1;           // split-fp16 operands (DCL_F16X3)
     const int E = x3 ? 4 : 2;            // bytes per B-format element
     TcWeights tw;
     const bool cubic = in_dhw[0] == in_dhw[1] && in_dhw[1] == in_dhw[2];

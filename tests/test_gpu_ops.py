@@ -183,11 +183,11 @@ def test_conv3d_k3_gemm_bf16(case):
     dict(c0=32, c1=0, cout=8, dims=(16, 16, 16), stride=1, norm=True, act=2, residual=False),       # auxiliary-head shapes
     dict(c0=8, c1=0, cout=2, dims=(20, 12, 36), stride=1, norm=False, act=0, residual=False),
 ])
-def test_conv3d_k3_split_bf16(case):
-    """DCL_BF16X3 kernels (split-fp16 operands: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05, fp32 accumulate) against
-    the PLAIN fp32 torch convolution - no operand rounding is granted: 16 significant bits per operand leave ~2^-16
-    per product, and B-format outputs are stored as hi + lo (2^-17)."""
+def test_conv3d_k3_split_fp16(case):
+    """DCL_F16X3 kernels (split operands, fp16 hi + fp16 lo: a_hi*w_hi + a_lo*w_hi + a_hi*w_lo on tcgen05, fp32 accumulate)
+    against the PLAIN fp32 torch convolution - no operand rounding is granted: 22 significant bits per operand, B-format
+    outputs stored as hi + lo."""
     y, ref = _conv_case(seed=31, impl=1, **case)
     assert y.shape == ref.shape
-    assert rel_err(y.numpy(), ref.numpy()) < 1e-4
-    assert float((y - ref).abs().mean() / ref.abs().mean()) < 2e-5
+    assert rel_err(y.numpy(), ref.numpy()) < 2e-5
+    assert float((y - ref).abs().mean() / ref.abs().mean()) < 3e-6
