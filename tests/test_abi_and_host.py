@@ -81,3 +81,25 @@ def test_dice_from_counts_agrees_with_oracle():
     assert np.allclose(E.dice_from_counts(counts), S.softmax_output_dice(o, t), atol=1e-12)
     from utils.tools import softmax_output_dice
     assert np.allclose(softmax_output_dice(o, t), S.softmax_output_dice(o, t), atol=0)
+
+
+def test_bench_helpers_roundtrip_and_configs_match():
+    """bench.py host logic: the 2-bit label packing of the overlap50 goldens round-trips, both arms print the same
+    `config` dict (the driver compares them), and the committed goldens decode to a full label map."""
+    import argparse
+    import os
+    import sys
+    import numpy as np
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_overlap50 import pack2
+    lab = np.random.RandomState(0).randint(0, 4, 1001).astype(np.uint8)
+    assert np.array_equal(bench.unpack2(pack2(lab), lab.size), lab)
+    args = argparse.Namespace(workload="overlap50", sharding="volume", gpus=1)
+    assert bench.config_dict(args, 18, False) == bench.config_dict(args, 18, args.sharding == "patch" and args.gpus > 1)
+    g = np.load(os.path.join(root, "tests", "golden", "overlap50_seed1000.npz"))
+    full = bench.unpack2(g["labels_packed"], 240 * 240 * 155)
+    assert int(g["labels_step"]) == 1 and np.array_equal(np.bincount(full, minlength=4), g["labels_hist"])
+    assert g["keep_scale"].shape == (18, 16) and g["starts"].shape == (18, 3)
