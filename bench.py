@@ -632,7 +632,10 @@ def run_ours(args):
     # strong scaling, owner-computes exchange over NVLink), attached as a sub-record ----
     sharded_rec = None
     if world > 1 and not by_patch and mode != "TTA" and starts is not None and not args.no_sharded and not with_aux:
-        sharded_rec = measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barrier)
+        try:
+            sharded_rec = measure_patch_sharded(eng, args, mode, starts, n_patches, rank, world, barrier)
+        except Exception as exc:      # e.g. CUDA IPC unavailable in this container: the weak-scaling line must still be printed
+            sharded_rec = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
