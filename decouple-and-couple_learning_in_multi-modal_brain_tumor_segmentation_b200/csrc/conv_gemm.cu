@@ -338,7 +338,7 @@ conv_gemm_kernel(GemmConvParams p) {
   float* s_stat = reinterpret_cast<float*>(s_tmem + 2);     // [4 warps][2][n_tile] partial sums
   float* s_bo = s_stat + 8 * p.n_tile;                      // [n_tile] bias, [n_tile] channel scale
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform role index
   long long* const tbuf = trace_begin();
   if (tid == 0) trace_event(tbuf, 0, 0);     // kernel entry
   const int64_t m_total = (int64_t)p.OD * p.OH * p.OW;
@@ -364,7 +364,7 @@ conv_gemm_kernel(GemmConvParams p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
   if (tid == 0) trace_event(tbuf, 1, 0);   // setup done
 
   if (warp >= G_EPI_WARPS + 1) {
@@ -637,7 +637,7 @@ conv_slab_kernel(SlabParams sp) {
   float* s_xchg = s_shift + p.cin_pad;                   // [2 groups][2 buffers][4 warps][2][16]
   float* s_bo = s_xchg + 4 * G_EPI_WARPS * 32;           // [n_tile] bias, [n_tile] channel scale
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform role index
   long long* const tbuf = trace_begin();
   if (tid == 0) trace_event(tbuf, 0, 0);
   const int64_t m_total = (int64_t)D * H * W;
@@ -677,7 +677,7 @@ conv_slab_kernel(SlabParams sp) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
   const uint32_t smem_base = smem_u32(smem);
   const int kcs_total = p.cin_pad / 8;
   if (tid == 0) trace_event(tbuf, 1, 0);

@@ -93,7 +93,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
   uint64_t* bar_acc_empty = bar_acc_full + 2;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_acc_empty + 2);
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;   // provably warp-uniform role index
   const int dsplit = prm.dsplit;
   const int ht = blockIdx.x / dsplit;
   const int ds = blockIdx.x - ht * dsplit;
@@ -120,7 +120,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
 
   if (warp >= EPI_WARPS + 1) {
     // =============================== producers: de-interleaving stage ==============================

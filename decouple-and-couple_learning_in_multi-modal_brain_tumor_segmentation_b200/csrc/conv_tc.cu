@@ -140,7 +140,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bar_w + 1);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform: role branches stay convergent
   const int lane = tid & 31;
   long long* const tbuf = trace_begin();
   if (tid == 0) trace_grid_extent(false);
@@ -196,7 +196,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *s_tmem, 0);
   if (tid == 0) trace_event(tbuf, 1, 0);     // setup done
 
   if (warp != MMA_WARP && !roll_is_epilogue(warp)) {
