@@ -942,10 +942,19 @@ void tc_free_weights(TcWeights* w) {
   w->dev = nullptr; w->slab_dev = nullptr; w->slab_ntile = 0;
 }
 
+// Tuning runs (tools/slab_sweep.py): DCL_SLAB_DEBUG=1 prints the chosen configuration and re-reads DCL_SLAB_FORCE=mt,nt,npass
+// (a pinned configuration) at every launch
+static int g_slab_force[3] = {0, 0, 0};
+static const bool g_slab_debug = []() { const char* e = getenv("DCL_SLAB_DEBUG"); return e && e[0] == '1'; }();
+
 int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, cudaStream_t st) {
   if (!slab_conv_supported(w.cin, w.cout, g.D, g.H, g.W, g.stride, g.taps) || w.dev == nullptr || g.a0 == nullptr) {
     set_error("slab_conv: unsupported shape");
     return -1;
+  }
+  if (g_slab_debug) {
+    g_slab_force[0] = 0;
+    if (const char* f = getenv("DCL_SLAB_FORCE")) sscanf(f, "%d,%d,%d", &g_slab_force[0], &g_slab_force[1], &g_slab_force[2]);
   }
   SlabParams sp;
   GemmConvParams& p = sp.g;
@@ -1000,12 +1009,16 @@ int launch_slab_conv(const GemmArgs& g, const BNorm* norm, const TcWeights& w, c
         const double wstream = 27.0 * cin_pad * nt * 2 / 40.0 * (xs ? 2.0 : 1.0);
         const double cost = waves * (6000.0 + (double)npass * (slab / 40.0 + slab / 60.0) + (mma > wstream ? mma : wstream) +
                                      (nb < 3 ? 3000.0 : 0.0) + mt * nt * 6.0);
+        if (g_slab_force[0] > 0 && !(mt == g_slab_force[0] && nt == g_slab_force[1] && npass == g_slab_force[2])) continue;
         if (cost < best_cost) { best_cost = cost; best_mt = mt; best_nt = nt; best_pass = npass; best_nb = nb; }
       }
     }
   }
   if (best_mt == 0) { set_error("slab_conv: tile does not fit shared memory"); return -1; }
   sp.mt = best_mt; p.n_tile = best_nt; sp.npass = best_pass; sp.nb = best_nb;
+  if (g_slab_debug)
+    fprintf(stderr, "slab %d->%d @%dx%dx%d x3=%d: mt %d nt %d npass %d nb %d cost %.0f\n", w.cin, w.cout, g.D, g.H, g.W, xs, best_mt, best_nt,
+            best_pass, best_nb, best_cost);
   sp.idesc = umma_idesc_16(128, 3 * best_nt, xs != 0);
   sp.rows = best_mt * 128 / g.W;
   sp.kc_pass = cin_pad / 8 / best_pass;

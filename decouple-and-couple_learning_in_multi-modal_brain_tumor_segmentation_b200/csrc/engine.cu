@@ -2043,12 +2043,17 @@ DCL_API double dcl_bench_conv(int32_t cin, int32_t cout, int32_t g, int32_t stri
       else rc = launch_gemm_conv(ga, tw, 0);
     }
   }
-  cudaEventRecord(e1, 0);
-  cudaEventSynchronize(e1);
-  float ms = 0.f; cudaEventElapsedTime(&ms, e0, e1);
+  float ms = 0.f;
+  if (rc == 0) {     // a refused configuration never recorded e0
+    cudaEventRecord(e1, 0);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+  }
+  cudaDeviceSynchronize();
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   cudaFree(x); cudaFree(y); cudaFree(r); cudaFree(bias); cudaFree(sin); cudaFree(sout);
   tc_free_weights(&tw);
+  if (cudaGetLastError() != cudaSuccess) rc = -1;
   return rc == 0 ? (double)ms * 1e3 / reps : -1.0;
 }
 
