@@ -714,7 +714,7 @@ def dominant_roofline(prof, pk, precision):
         (ms, n, flops), name = per_kind[best], KINDS[best]
     tf = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r02_ncu_full_dominant_%s.json" % ("bf16x3" if precision == "f16x3" else precision))
+    tpath = os.path.join(ROOT, "profiles", "r02n_ncu_full_dominant_f16x3.json" if precision == "f16x3" else "r02_ncu_full_dominant_%s.json" % precision)
     if best is not None and os.path.exists(tpath):
         t = json.load(open(tpath))
         if t.get("kind") == best:
@@ -733,8 +733,9 @@ def dominant_roofline(prof, pk, precision):
                           "utilisation_of_sustained_peak": tf * factor / pk["tensor"],
                           "utilisation_of_nominal_2250": tf * factor / 2250.0,
                           "ncu_counter": "sm__pipe_tensor_subpipe_hmma_cycles_active / (8 x sm__cycles_elapsed): "
-                                         "profiles/r02_ncu_full_conv_kernels.csv (0.148 for the split-fp16 16-channel layer, "
-                                         "0.118 for the bf16 one; that counter's own peak is ~1.87 x the bf16 dense peak)"}
+                                         "profiles/r02n_ncu_full_roll16_f16x3.csv (0.200 for the split-fp16 16-channel layer; "
+                                         "0.148 before the issue loop moved to the uniform datapath and 0.118 for the bf16 one, "
+                                         "profiles/r02_ncu_full_conv_kernels.csv; that counter's own peak is ~1.87 x the bf16 dense peak)"}
     if x3:
         rec["note"] = ("`achieved` / `frac` count ALGORITHMIC FLOPs (2 x MACs of the convolution); the split-fp16 kernels execute "
                        f"{factor} tensor-core MACs per algorithmic MAC, so the ceiling of `frac` is 1/{factor} and the pipe's own "

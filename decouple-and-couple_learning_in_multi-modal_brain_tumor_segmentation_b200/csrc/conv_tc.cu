@@ -591,6 +591,7 @@ conv3d_k3_roll_kernel(RollParams prm) {
         y0[off] = o0;
         y0[SP + off] = o1;
       }
+      if (tid == 0) trace_event(tbuf, 11, i);    // epilogue: items of plane i stored (this thread)
     }
     if (tid == 0) trace_event(tbuf, 7, n_out);   // epilogue: all planes stored
     if (prm.stats != nullptr) {
