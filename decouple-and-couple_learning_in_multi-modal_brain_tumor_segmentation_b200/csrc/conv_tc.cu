@@ -41,12 +41,14 @@ cudaError_t trace_set_conv_tc(long long* p, int cta) { return trace_set_local(p,
 // CI_ < CO_: the kernel covers CI_ of the layer's input channels per launch (the split weights of a 32 -> 32 layer do
 // not fit next to the staged planes); the layer then runs as CO_/CI_ launches, the later ones adding to the earlier
 // ones' output through the residual input.
-template <int CI_, int CO_, int G_, int TH_, bool KHN_, int NSLOT_, bool X3_ = false>
+template <int CI_, int CO_, int G_, int TH_, bool KHN_, int NSLOT_, bool X3_ = false, bool KH2_ = false>
 struct RollCfg {
   static constexpr int CI = CI_, CO = CO_, G = G_, TH = TH_;
   static constexpr bool X3 = X3_;
   static constexpr int NP = X3 ? 2 : 1;           // accumulator parts per output (D1, D2)
   static constexpr bool KHN = KHN_;               // the 3 kh taps stacked along N (one MMA feeds 3 output rows)
+  static constexpr bool KH2 = KH2_;               // two-row M tiles: an A tile on an EVEN staged row feeds tile t (kh = 0) and tile t-1
+                                                  // (kh = 2) at once through a stacked [W_kh2 | W_kh0] operand; odd rows carry kh = 1
   static constexpr int W = G;                     // staged rows have NO halo columns (kw = 0/2 use lane masks)
   static constexpr int ROWS = TH + 2;
   static constexpr int PAD = 8;                   // pad positions in front of / behind the rows: 128 bytes, so that the staged rows
@@ -70,6 +72,7 @@ struct RollCfg {
   static constexpr int SMEM_BYTES = OFF_BAR + (3 * NSLOT + 5) * 8 + 16;
   static_assert(W == 64 || W == 128, "rows must tile 128-voxel M tiles");
   static_assert(!KHN || TROWS == 1, "kh stacking needs one-row M tiles");
+  static_assert(!KH2 || (TROWS == 2 && !KHN), "kh pairing is the two-row-tile form");
   static_assert(2 * ACC_COLS <= 512, "accumulators exceed tensor memory");
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   // output lanes switched off for kw = 0 (their w == 0) and kw = 2 (w == W-1): exactly zero padding
@@ -437,6 +440,55 @@ conv3d_k3_roll_kernel(RollParams prm) {
               }
             }
           }
+        } else if constexpr (Cfg::KH2) {
+          // Two-row M tiles (W = 64).  The A tile that starts on staged row s covers input rows (s, s+1): for EVEN s = 2t it is
+          // the kh = 0 operand of output tile t AND the kh = 2 operand of tile t-1, whose accumulators are adjacent TMEM column
+          // blocks, so one MMA against the stacked [W_kh2 | W_kh0] matrix (N = 2 CN) feeds both from one read of the 4 KB A
+          // tile; for ODD s = 2t+1 it is the kh = 1 operand of tile t.  9 MMAs per (kd, kw, K step, operand half) instead of
+          // 12; the odd-row MMAs of the first (kd, kw) go first and initialise the accumulators.
+          constexpr int CN = CO * NP;
+          constexpr int NT = Cfg::NT;
+          constexpr uint32_t QB = 3 * CI * CN * 2;            // bytes of the three kh matrices of one (kd,kw)
+          constexpr uint32_t P_LBO = 2 * CN * 16, S_LBO = CN * 16;
+          const uint64_t bp_base = umma_desc(w_base, P_LBO, 128);                         // pair images [kh2 | kh0]
+          const uint64_t bs_base = umma_desc(w_base + (uint32_t)KC * P_LBO, S_LBO, 128);  // kh = 1 images, behind the pair
+          constexpr uint32_t id1 = umma_idesc_16(128, CN, X3), id2 = umma_idesc_16(128, 2 * CN, X3);
+#pragma unroll
+          for (int kd = 0; kd < 3; ++kd) {
+#pragma unroll
+            for (int kwi = 0; kwi < 3; ++kwi) {
+              const int kw = kwi == 0 ? 1 : (kwi == 1 ? 0 : 2);
+              const uint32_t m0 = kw == 0 ? Cfg::mask0(0) : (kw == 2 ? Cfg::mask2(0) : 0u);
+              const uint32_t m1 = kw == 0 ? Cfg::mask0(1) : (kw == 2 ? Cfg::mask2(1) : 0u);
+              const uint32_t m2 = kw == 0 ? Cfg::mask0(2) : (kw == 2 ? Cfg::mask2(2) : 0u);
+              const uint32_t m3 = kw == 0 ? Cfg::mask0(3) : (kw == 2 ? Cfg::mask2(3) : 0u);
+#pragma unroll
+              for (int ks = 0; ks < Cfg::KS; ++ks) {
+#pragma unroll
+                for (int v = 0; v < NP; ++v) {
+                  const uint64_t a0 = a_kd[kd] + (uint64_t)(uint32_t)(Cfg::PAD + (kw - 1) + ks * 2 * NPOS + (v == 1 ? KC * NPOS : 0));
+                  const uint64_t bp = bp_base + (uint64_t)(((kd * 3 + kw) * QB + ks * 2 * P_LBO) >> 4);
+                  const uint64_t bs = bs_base + (uint64_t)(((kd * 3 + kw) * QB + ks * 2 * S_LBO) >> 4);
+                  const uint32_t init = (kd | kwi | ks | v) != 0 ? 1u : 0u;
+#pragma unroll
+                  for (int t = 0; t < NT; ++t) {          // odd rows: kh = 1 -> tile t
+                    const uint64_t ad = a0 + (uint64_t)((2 * t + 1) * W);
+                    if (kw == 1) umma_bf16_ws(acc0 + (uint32_t)(t * CN), ad, bs, id1, init);
+                    else umma_bf16_masked_ws(acc0 + (uint32_t)(t * CN), ad, bs, id1, init, m0, m1, m2, m3);
+                  }
+#pragma unroll
+                  for (int t = 0; t <= NT; ++t) {         // even rows: kh = 2 -> tile t-1, kh = 0 -> tile t
+                    const uint64_t ad = a0 + (uint64_t)(2 * t * W);
+                    const uint32_t d = acc0 + (uint32_t)((t == 0 ? 0 : t - 1) * CN);
+                    const uint64_t bd = t == 0 ? bp + (uint64_t)((CN * 16) >> 4) : bp;     // first tile: the kh = 0 rows only
+                    const uint32_t id = (t == 0 || t == NT) ? id1 : id2;                   // last tile: the kh = 2 rows only
+                    if (kw == 1) umma_bf16_ws(d, ad, bd, id, 1u);
+                    else umma_bf16_masked_ws(d, ad, bd, id, 1u, m0, m1, m2, m3);
+                  }
+                }
+              }
+            }
+          }
         } else {
           constexpr int CN = CO * NP;                       // B rows per K chunk: split-fp16 stacks [W_hi | W_lo] along N
           const uint64_t b_base = umma_desc(w_base, CN * 16, 128);
@@ -653,9 +705,12 @@ static uint16_t f32_to_bf16_rn(float f) {
 //   layout 2  [kd][kw][cin/8][kh = 2,1,0][hi|lo][cout][8]      split-fp16 rolling kernel, 16-channel layers: N = 3*2*cout
 //   layout 3  [cin half][tap][2 chunks][hi|lo][cout][8]        split-fp16 rolling kernel, 32 -> 32 layers: one image of
 //                                                              N = 2*cout per 16 input channels (one launch each)
+//   layout 4  [cin half][kd][kw]{[2 chunks][kh2 | kh0][hi|lo][cout][8], [2 chunks][kh1: hi|lo][cout][8]}
+//                                                              the same layers with the kh = 2 / kh = 0 matrices paired along N
+//                                                              (RollCfg::KH2)
 static int tc_weight_layout(int cin, int cout, bool x3) {
   if (cin <= 16 && cout == 16) return x3 ? 2 : 1;
-  if (x3 && cin == 32 && cout == 32) return 3;
+  if (x3 && cin == 32 && cout == 32) return 4;
   return 0;
 }
 
@@ -714,9 +769,16 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
           packed[(row + n) * 8 + k] = hi;
           packed[(row + cout_pad + n) * 8 + k] = lo;
           if (init_x3) { packed[(row + n) * 8 + k + 4] = hi; packed[(row + cout_pad + n) * 8 + k + 4] = lo; }
-        } else {
+        } else if (layout == 3) {
           const int half = ci / 16, c16 = ci % 16;
           const size_t row = ((((size_t)half * 27 + tap) * 2 + c16 / 8) * 2) * cout_pad;
+          packed[(row + n) * 8 + c16 % 8] = hi;
+          packed[(row + cout_pad + n) * 8 + c16 % 8] = lo;
+        } else {         // layout 4: per (kd,kw) the [kh2 | kh0] pair (N = 4*cout rows per chunk), then kh1 (N = 2*cout)
+          const int half = ci / 16, c16 = ci % 16, chunk = c16 / 8;
+          const size_t cn = 2 * (size_t)cout_pad;                             // rows of one matrix: hi | lo
+          const size_t q_rows = ((size_t)half * 9 + (size_t)(kd * 3 + kw)) * (2 * 3 * cn);   // 2 chunks x 3 matrices
+          const size_t row = kh == 1 ? q_rows + 2 * 2 * cn + chunk * cn : q_rows + chunk * 2 * cn + (kh == 2 ? 0 : cn);
           packed[(row + n) * 8 + c16 % 8] = hi;
           packed[(row + cout_pad + n) * 8 + c16 % 8] = lo;
         }
@@ -733,7 +795,7 @@ using RollC32 = RollCfg<32, 32, 64, 8, false, 4>;
 // split-fp16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory) for the
 // 16-channel layers; a 32 -> 32 layer (110 KB of split weights) runs as two launches over 16 input channels each
 using RollC16X3 = RollCfg<16, 16, 128, 4, true, 4, true>;
-using RollC32X3 = RollCfg<16, 32, 64, 8, false, 4, true>;
+using RollC32X3 = RollCfg<16, 32, 64, 8, false, 4, true, true>;
 
 bool tc_conv_supported(int cin, int cout, int g, int stride, bool split) {
   (void)split;     // both modes cover the same layers
