@@ -705,12 +705,12 @@ static uint16_t f32_to_bf16_rn(float f) {
 //   layout 2  [kd][kw][cin/8][kh = 2,1,0][hi|lo][cout][8]      split-fp16 rolling kernel, 16-channel layers: N = 3*2*cout
 //   layout 3  [cin half][tap][2 chunks][hi|lo][cout][8]        split-fp16 rolling kernel, 32 -> 32 layers: one image of
 //                                                              N = 2*cout per 16 input channels (one launch each)
-//   layout 4  [cin half][kd][kw]{[2 chunks][kh2 | kh0][hi|lo][cout][8], [2 chunks][kh1: hi|lo][cout][8]}
-//                                                              the same layers with the kh = 2 / kh = 0 matrices paired along N
-//                                                              (RollCfg::KH2)
+//   layout 4  [cin half][kd][kw]{[chunks][kh2 | kh0][hi|lo][cout][8], [chunks][kh1: hi|lo][cout][8]}
+//                                                              32 -> 32 layers with the kh = 2 / kh = 0 matrices paired along N
+//                                                              (RollCfg::KH2); bf16: one image of all 32 input channels, no lo rows
 static int tc_weight_layout(int cin, int cout, bool x3) {
   if (cin <= 16 && cout == 16) return x3 ? 2 : 1;
-  if (x3 && cin == 32 && cout == 32) return 4;
+  if (cin == 32 && cout == 32) return 4;
   return 0;
 }
 
@@ -774,13 +774,15 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
           const size_t row = ((((size_t)half * 27 + tap) * 2 + c16 / 8) * 2) * cout_pad;
           packed[(row + n) * 8 + c16 % 8] = hi;
           packed[(row + cout_pad + n) * 8 + c16 % 8] = lo;
-        } else {         // layout 4: per (kd,kw) the [kh2 | kh0] pair (N = 4*cout rows per chunk), then kh1 (N = 2*cout)
-          const int half = ci / 16, c16 = ci % 16, chunk = c16 / 8;
-          const size_t cn = 2 * (size_t)cout_pad;                             // rows of one matrix: hi | lo
-          const size_t q_rows = ((size_t)half * 9 + (size_t)(kd * 3 + kw)) * (2 * 3 * cn);   // 2 chunks x 3 matrices
-          const size_t row = kh == 1 ? q_rows + 2 * 2 * cn + chunk * cn : q_rows + chunk * 2 * cn + (kh == 2 ? 0 : cn);
-          packed[(row + n) * 8 + c16 % 8] = hi;
-          packed[(row + cout_pad + n) * 8 + c16 % 8] = lo;
+        } else {         // layout 4: per (kd,kw) the [kh2 | kh0] pair (2 matrices per chunk), then kh1; split-fp16: a matrix is
+                         // hi | lo rows and an image covers 16 input channels (one launch), bf16: all 32 in one image
+          const int cl = x3 ? 16 : 32;                                        // input channels per launch
+          const int half = ci / cl, cc = ci % cl, chunk = cc / 8, kcl = cl / 8;
+          const size_t cn = (x3 ? 2 : 1) * (size_t)cout_pad;                  // rows of one matrix
+          const size_t q_rows = ((size_t)half * 9 + (size_t)(kd * 3 + kw)) * ((size_t)kcl * 3 * cn);
+          const size_t row = kh == 1 ? q_rows + (size_t)kcl * 2 * cn + chunk * cn : q_rows + chunk * 2 * cn + (kh == 2 ? 0 : cn);
+          packed[(row + n) * 8 + cc % 8] = hi;
+          if (x3) packed[(row + cout_pad + n) * 8 + cc % 8] = lo;
         }
       }
   out->bytes = (int64_t)packed.size() * 2;
@@ -791,7 +793,7 @@ int tc_pack_weights(const float* w_host, int cout, int cin, int taps, bool roll_
 }
 
 using RollC16 = RollCfg<16, 16, 128, 8, true, 5>;
-using RollC32 = RollCfg<32, 32, 64, 8, false, 4>;
+using RollC32 = RollCfg<32, 32, 64, 8, false, 4, false, true>;
 // split-fp16: twice the staged bytes per plane, so strips of 4 rows and a 4-deep ring (228 KB of shared memory) for the
 // 16-channel layers; a 32 -> 32 layer (110 KB of split weights) runs as two launches over 16 input channels each
 using RollC16X3 = RollCfg<16, 16, 128, 4, true, 4, true>;
