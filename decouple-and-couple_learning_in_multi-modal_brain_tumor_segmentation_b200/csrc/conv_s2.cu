@@ -133,11 +133,12 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
       uint8_t* slot = smem + (size_t)s * SLOT_BYTES;
       // item = (chunk, staged row, w): consecutive threads read consecutive 16-byte vectors of one row
       constexpr int ITEMS = KCS * ROWS * GI;      // (split-fp16: global chunk KC + k is the lo half of chunk k, as in the slot)
-      for (int e0 = pt; e0 < ITEMS; e0 += 4 * NPROD) {
-        uint4 v[4];
-        int pos[4];
+      constexpr int U = 8;                        // 16-byte loads in flight per producer thread (the stage is load-latency bound)
+      for (int e0 = pt; e0 < ITEMS; e0 += U * NPROD) {
+        uint4 v[U];
+        int pos[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
           const int e = e0 + u * NPROD;
           v[u] = make_uint4(0u, 0u, 0u, 0u);
           pos[u] = -1;
@@ -153,7 +154,7 @@ conv3d_k3s2_roll_kernel(S2Params prm) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
           if (pos[u] >= 0) *reinterpret_cast<uint4*>(slot + (size_t)pos[u] * 16) = v[u];
       }
       fence_proxy_async();
